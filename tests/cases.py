@@ -1,0 +1,133 @@
+"""Seeded test cases shared by oracle/gen_golden.py (reference run), the oracle tests (CPU) and the
+GPU parity tests.  A case is regenerated from its name alone, so fixtures store only outputs."""
+import zlib
+
+import numpy as np
+
+from planer_b200 import zoo
+
+
+def _rng(name):
+    return np.random.default_rng(zlib.crc32(name.encode()))
+
+
+def _x(rng, shape, dtype):
+    return rng.standard_normal(shape).astype(dtype)
+
+
+def _conv(name, xs, ks, bias=True, dtype='float32', **kw):
+    rng = _rng(name)
+    fan = ks[1] * ks[2] * ks[3]
+    args = [_x(rng, xs, dtype), (rng.standard_normal(ks) * np.sqrt(2.0 / fan)).astype(dtype)]
+    if bias:
+        args.append((rng.standard_normal(ks[0]) * 0.1).astype(dtype))
+    return 'conv', args, kw
+
+
+# name -> builder;  every builder returns (op kind, positional args, attrs)
+OP_CASES = {
+    # BASELINE config 1: README Conv2d(3, 64, 3, 1) on 1x3x32x32, both paddings
+    'c1_conv_p0': lambda n: _conv(n, (1, 3, 32, 32), (64, 3, 3, 3), strides=(1, 1), pads=(0, 0, 0, 0)),
+    'c1_conv_p1': lambda n: _conv(n, (1, 3, 32, 32), (64, 3, 3, 3), strides=(1, 1), pads=(1, 1, 1, 1)),
+    'conv_s2_p1': lambda n: _conv(n, (2, 16, 17, 19), (32, 16, 3, 3), strides=(2, 2), pads=(1, 1, 1, 1)),
+    'conv_d2_p2': lambda n: _conv(n, (2, 16, 14, 14), (16, 16, 3, 3), dilations=(2, 2), pads=(2, 2, 2, 2)),
+    'conv_7x7_s2_p3': lambda n: _conv(n, (2, 3, 64, 64), (64, 3, 7, 7), bias=False, strides=(2, 2), pads=(3, 3, 3, 3)),
+    'conv_1x1_s2': lambda n: _conv(n, (2, 64, 14, 14), (128, 64, 1, 1), bias=False, strides=(2, 2)),
+    'conv_g2': lambda n: _conv(n, (2, 16, 9, 9), (8, 8, 3, 3), group=2, pads=(1, 1, 1, 1)),
+    'conv_dw8': lambda n: _conv(n, (1, 8, 10, 10), (8, 1, 3, 3), group=8, pads=(1, 1, 1, 1)),
+    'conv_1x3_asym': lambda n: _conv(n, (1, 4, 8, 8), (6, 4, 1, 3), pads=(0, 1, 0, 1)),
+    'conv_pad_tl_only': lambda n: _conv(n, (1, 8, 8, 8), (8, 8, 3, 3), pads=(1, 1, 0, 0)),
+    'conv_64_64_3x3': lambda n: _conv(n, (2, 64, 14, 14), (64, 64, 3, 3), bias=False, pads=(1, 1, 1, 1)),
+    'conv_64_64_3x3_f16': lambda n: _conv(n, (2, 64, 14, 14), (64, 64, 3, 3), dtype='float16', pads=(1, 1, 1, 1)),
+    'conv_s2_p1_f16': lambda n: _conv(n, (2, 32, 17, 19), (64, 32, 3, 3), dtype='float16', strides=(2, 2), pads=(1, 1, 1, 1)),
+    'conv_255_f16': lambda n: _conv(n, (1, 64, 13, 13), (255, 64, 1, 1), dtype='float16'),
+    'dense': lambda n: ('dense', [_x(_rng(n), (4, 512), 'float32'),
+                                 (_rng(n + 'w').standard_normal((1000, 512)) / 22.6).astype('float32'),
+                                 _x(_rng(n + 'b'), (1000,), 'float32')], {}),
+    'dense_f16': lambda n: ('dense', [_x(_rng(n), (4, 512), 'float16'),
+                                     (_rng(n + 'w').standard_normal((1000, 512)) / 22.6).astype('float16'),
+                                     _x(_rng(n + 'b'), (1000,), 'float16')], {}),
+    'relu': lambda n: ('relu', [_x(_rng(n), (2, 8, 5, 7), 'float32')], {}),
+    'relu_f16': lambda n: ('relu', [_x(_rng(n), (2, 8, 5, 7), 'float16')], {}),
+    'leakyrelu': lambda n: ('leakyrelu', [_x(_rng(n), (2, 8, 5, 7), 'float32')], {'alpha': 0.1}),
+    'leakyrelu_f16': lambda n: ('leakyrelu', [_x(_rng(n), (2, 8, 5, 7), 'float16')], {'alpha': 0.1}),
+    'sigmoid': lambda n: ('sigmoid', [_x(_rng(n), (2, 8, 5, 7), 'float32') * 3], {}),
+    'sigmoid_f16': lambda n: ('sigmoid', [_x(_rng(n), (2, 8, 5, 7), 'float16') * 3], {}),
+    'add': lambda n: ('add', [_x(_rng(n), (2, 8, 5, 7), 'float32'), _x(_rng(n + '2'), (2, 8, 5, 7), 'float32')], {}),
+    'batchnorm': lambda n: ('batchnorm', [_x(_rng(n), (2, 8, 5, 7), 'float32'),
+                                         _rng(n + 'k').uniform(0.5, 1.5, (1, 8, 1, 1)).astype('float32'),
+                                         _x(_rng(n + 'b'), (1, 8, 1, 1), 'float32')], {}),
+    'batchnorm_f16': lambda n: ('batchnorm', [_x(_rng(n), (2, 8, 5, 7), 'float16'),
+                                             _rng(n + 'k').uniform(0.5, 1.5, (1, 8, 1, 1)).astype('float16'),
+                                             _x(_rng(n + 'b'), (1, 8, 1, 1), 'float16')], {}),
+    # quirk Q2: zero padding + -1e4 floor on signed data
+    'maxpool_k3s2p1_signed': lambda n: ('maxpool', [_x(_rng(n), (2, 8, 13, 15), 'float32') - 2.0],
+                                        {'w': (3, 3), 'pads': (1, 1, 1, 1), 'strides': (2, 2)}),
+    'maxpool_k2s2': lambda n: ('maxpool', [_x(_rng(n), (2, 8, 9, 11), 'float32')], {}),
+    'maxpool_k3s2p1_f16': lambda n: ('maxpool', [_x(_rng(n), (2, 16, 12, 12), 'float16')],
+                                     {'w': (3, 3), 'pads': (1, 1, 1, 1), 'strides': (2, 2)}),
+    'maxpool_floor': lambda n: ('maxpool', [np.full((1, 8, 4, 4), -3e4, 'float32')], {}),
+    'upsample_x2': lambda n: ('upsample', [_x(_rng(n), (2, 8, 5, 7), 'float32'), np.array([1, 1, 2, 2], 'float32')],
+                              {'mode': 'nearest'}),
+    'upsample_2x3_f16': lambda n: ('upsample', [_x(_rng(n), (1, 8, 4, 5), 'float16'), np.array([1, 1, 2, 3], 'float32')],
+                                   {'mode': 'nearest'}),
+    'concat_c': lambda n: ('concat', [_x(_rng(n), (2, 8, 5, 7), 'float32'), _x(_rng(n + '2'), (2, 16, 5, 7), 'float32')],
+                           {'axis': 1}),
+    'gap': lambda n: ('gap', [_x(_rng(n), (2, 16, 7, 7), 'float32')], {}),
+    'gap_f16': lambda n: ('gap', [_x(_rng(n), (2, 16, 7, 7), 'float16')], {}),
+    'flatten': lambda n: ('flatten', [_x(_rng(n), (2, 16, 1, 1), 'float32')], {}),
+}
+
+
+def make_case(name):
+    return OP_CASES[name](name)
+
+
+# ---------------------------------------------------------------------------------------------
+# whole-graph cases: name -> (builder, input shape, dtype/half)
+# ---------------------------------------------------------------------------------------------
+BUILDERS = {
+    'readme': lambda: zoo.readme_net(0),
+    'resnet18': lambda: zoo.resnet18(0),
+    'yolov3_quarter': lambda: zoo.yolov3(0, width=0.25),
+    'yolov3': lambda: zoo.yolov3(0),
+}
+GRAPH_CASES = {
+    'readme_f32': ('readme', (2, 3, 32, 32), False),
+    'readme_f16': ('readme', (2, 3, 32, 32), True),
+    'resnet18_f32_n1': ('resnet18', (1, 3, 224, 224), False),     # BASELINE config 2
+    'resnet18_f32_n2': ('resnet18', (2, 3, 224, 224), False),
+    'resnet18_f16_n1': ('resnet18', (1, 3, 224, 224), True),      # true numpy-fp16 path (slow: no BLAS)
+    'resnet18_small_f32': ('resnet18', (3, 3, 64, 64), False),
+    'yolov3_quarter_f32': ('yolov3_quarter', (2, 3, 96, 96), False),
+    'yolov3_416_f32_n1': ('yolov3', (1, 3, 416, 416), False),     # BASELINE config 4 graph
+}
+
+_model_cache = {}
+
+
+def get_model(key):
+    if key not in _model_cache:
+        _model_cache.clear()          # blobs are big (YOLOv3: 248 MB); keep one at a time
+        _model_cache[key] = BUILDERS[key]()
+    return _model_cache[key]
+
+
+def make_graph_case(name):
+    key, shape, half = GRAPH_CASES[name]
+    model, blob = get_model(key)
+    x = np.random.default_rng(1).standard_normal(shape).astype('float16' if half else 'float32')
+    return model, blob, x, half
+
+
+def sample(t, limit=20000):
+    """Deterministic strided sample of a flattened tensor (whole tensor if small)."""
+    flat = np.ascontiguousarray(t).reshape(-1)
+    step = max(1, flat.size // limit)
+    return flat[::step].copy()
+
+
+def rel_err(y, ref):
+    """Range-relative error  max|y - ref| / max|ref|  (SURVEY 8d primary metric)."""
+    y, ref = np.asarray(y, np.float64), np.asarray(ref, np.float64)
+    return float(np.abs(y - ref).max() / max(np.abs(ref).max(), 1e-30))
