@@ -1,0 +1,276 @@
+"""Headline benchmark: ResNet-18 224x224 forward images/sec on N B200s (BASELINE.json metric), fp16,
+batch 128 per GPU (configs[2]; configs[4] = 8 x 128 is the same workload weak-scaled to 8 GPUs).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  A "step" is one forward of the whole graph over one batch of synthetic
+NCHW input.  `value` is device-timed with inputs resident in HBM; `e2e` goes through the public
+``net(numpy_array)`` call with pinned-host H2D and the D2H of the logits inside the timed region.
+The reference arm times the numpy restatement of the reference (oracle/planer_oracle.py, "port") on the
+host cores -- the only place outside tests/ and smoke() where oracle/ is executed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'resnet18_224_fwd_images_per_sec'
+UNIT = 'images/s'
+BATCH = 128                       # per GPU
+IN_SHAPE = (3, 224, 224)
+N_INPUT_BUFFERS = 8               # 8 x 38.5 MB = 308 MB of rotating inputs > 126 MB L2
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {'tflops_burst': p['bf16_tflops'], 'tflops_sustained': p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                'hbm_gbs': p['hbm_gbs'], 'source': 'measured (MEASURED_PEAKS.json)'}
+    return {'tflops_burst': 1590.0, 'tflops_sustained': 1400.0, 'hbm_gbs': 6650.0,
+            'source': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def cpu_baseline_run(steps, warmup, batch=8):
+    """Reference numpy path (restated in oracle/planer_oracle.py) on the host cores: ResNet-18 fp32."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import planer_oracle as oracle
+    from planer_b200 import zoo
+    model, blob = zoo.resnet18(0)
+    net = oracle.build_net(model, blob)
+    x = np.random.default_rng(1).standard_normal((batch,) + IN_SHAPE).astype(np.float32)
+    for _ in range(warmup):
+        net(x.copy())
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        net(x.copy())
+    dt = time.perf_counter() - t0
+    cores = len(os.sched_getaffinity(0))
+    return {'value': batch * steps / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': 'ResNet-18 fp32 (numpy fp16 matmul has no BLAS: 18 s/img) batch %d x %d forwards, numpy %s '
+                      'BLAS threads=all cores' % (batch, steps, np.__version__)}, dt / steps
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    cb, sec = cpu_baseline_run(steps, max(1, min(args.warmup, 2)))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': max(1, min(args.warmup, 2)), 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'ResNet-18 224x224 forward, reference numpy path on host cores, bounded sample: '
+                                   'batch 8 per step'},
+            'cpu_baseline': cb,
+            'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def per_kernel_profile(net, x_dev, flops_by_step, reps=3):
+    """Un-graphed pass with a CUDA event pair around every launch: durations per step (ms)."""
+    import ctypes as C
+    from planer_b200 import _capi, backend as B
+    ex = net.executor([x_dev.shape])
+    lib, ctx = B.lib(), B.ctx()
+    n = len(ex.launches)
+    best = [float('inf')] * n
+    for _ in range(reps):
+        ex._load_inputs([x_dev])
+        evs = []
+        for fn in ex.launches:
+            a, b = C.c_void_p(), C.c_void_p()
+            lib.plnr_event_create(C.byref(a)); lib.plnr_event_create(C.byref(b))
+            lib.plnr_event_record(ctx, a)
+            fn()
+            lib.plnr_event_record(ctx, b)
+            evs.append((a, b))
+        B.synchronize()
+        for i, (a, b) in enumerate(evs):
+            ms = C.c_float()
+            lib.plnr_event_elapsed_ms(a, b, C.byref(ms))
+            best[i] = min(best[i], ms.value)
+            lib.plnr_event_destroy(a); lib.plnr_event_destroy(b)
+    return [{'kind': k, 'ms': t} for k, t in zip(ex.kinds, best)]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=BATCH, help='images per GPU (the headline config is 128)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--dump', default=None, help='write the per-kernel table to this JSON file')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        return run_reference(args, rank)
+
+    import torch
+    import planer_b200 as planer
+    from planer_b200 import zoo, dist, backend as B
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local)
+        torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local))
+    warmup, steps = max(args.warmup, 3), args.steps
+    planer.core(planer.b200)
+    B.init(local)
+
+    # ---- model: rank 0 builds the blob, ONE NCCL broadcast hands it to the other ranks ----
+    model, blob = zoo.resnet18(0)
+    net = planer.Net()
+    net.load_json(model['input'], model['inits'], model['layers'], model['flow'])
+    net.load_weights(blob if rank == 0 else None) if world > 1 else net.load_weights(blob)
+    net.half()
+    del blob
+
+    rng = np.random.default_rng(100 + rank)
+    shape = (args.batch,) + IN_SHAPE
+    hosts = [rng.standard_normal(shape).astype(np.float16) for _ in range(2)]
+    xs = [B.asarray(hosts[i % 2] if i < 2 else np.roll(hosts[i % 2], i, axis=0)) for i in range(N_INPUT_BUFFERS)]
+    B.synchronize()
+
+    ex = net.executor([shape])
+    flops = ex.plan.flops
+    for i in range(warmup):
+        net.forward(xs[i % N_INPUT_BUFFERS])
+    B.synchronize()
+
+    # ---- timed region: device events on the library stream, barrier + sync on both sides ----
+    stream = B.stream()
+    clocks = ClockSampler(local)
+    dist.barrier(); torch.cuda.synchronize()
+    if rank == 0:
+        clocks.start()
+    l0 = B.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for i in range(steps):
+            net.forward(xs[i % N_INPUT_BUFFERS])
+        e1.record(stream)
+    torch.cuda.synchronize(); dist.barrier()
+    ms_total = dist.max_over_ranks(e0.elapsed_time(e1))
+    launches = B.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    value = world * args.batch * steps / (ms_total / 1e3)
+
+    # ---- e2e: public API with host buffers (pinned), H2D + forward + D2H inside the timed region ----
+    pinned = [torch.from_numpy(h).pin_memory().numpy() for h in hosts]
+    for i in range(3):
+        net(pinned[i % 2])
+    dist.barrier(); torch.cuda.synchronize()
+    e2e_steps = max(5, steps // 2)
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        y = net(pinned[i % 2])
+    torch.cuda.synchronize()
+    e2e_sec = dist.max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * args.batch * e2e_steps / e2e_sec
+    h2d, d2h = int(hosts[0].nbytes), int(y.nbytes)
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), timed live per launch ----
+    table = per_kernel_profile(net, xs[0], None)
+    conv_ms = sum(r['ms'] for r in table if r['kind'] in ('conv', 'dense'))
+    all_ms = sum(r['ms'] for r in table)
+    conv_nodes = [n for n in ex.plan.nodes if n.kind in ('conv', 'dense')]
+    pk = peaks()
+    achieved = flops / (conv_ms / 1e3) / 1e12
+    roofline = {'bound': 'tensor', 'kernel': 'conv_igemm_f16_kernel (TMA-im2col + tcgen05, %d launches/step)' % len(conv_nodes),
+                'achieved': achieved, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
+                'frac': achieved / pk['tflops_sustained'], 'traffic': None,
+                'peak_source': pk['source'] + ', sustained figure (kernel timed inside a long step)',
+                'flops_per_step': flops, 'kernel_ms_per_step': conv_ms, 'kernel_share_of_step': conv_ms / all_ms,
+                'whole_step_frac': (flops * steps / (ms_total / 1e3) / 1e12) / pk['tflops_sustained']}
+    if args.dump:
+        convs = iter(conv_nodes)
+        for r in table:
+            if r['kind'] in ('conv', 'dense'):
+                nd = next(convs)
+                r.update(name=nd.name, gflop=nd.flops / 1e9, tflops=nd.flops / (r['ms'] / 1e3) / 1e12)
+        with open(args.dump, 'w') as f:
+            json.dump({'batch': args.batch, 'table': table}, f, indent=1)
+
+    cb = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_baseline_run(steps=8, warmup=1)
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warmup,
+            'ms_per_step': ms_total / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f16', 'data': 'synthetic',
+            'config': {'workload': 'ResNet-18 224x224 fp16 forward, batch %d per GPU (BASELINE configs[2]; x8 = configs[4])'
+                                   % args.batch, 'global_batch': world * args.batch, 'parallelism': 'dp%d batch split, no forward collective' % world,
+                       'l2': 'inputs rotate over %d device buffers (%.0f MB > 126 MB L2)' % (N_INPUT_BUFFERS, N_INPUT_BUFFERS * h2d / 1e6),
+                       'launch': '1 layout kernel + 1 CUDA graph (%d fused kernels) per step' % len(ex.launches)},
+            'clocks': clk, 'gpu_launches': int(launches),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'steps': e2e_steps},
+            'roofline': roofline, 'cpu_baseline': cb}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == '__main__':
+    main()
+    try:
+        import torch.distributed as _d
+        if _d.is_available() and _d.is_initialized():
+            _d.destroy_process_group()
+    except Exception:
+        pass

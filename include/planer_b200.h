@@ -1,0 +1,173 @@
+/* planer_b200.h -- C ABI of libplaner_b200.so: the B200 (sm_100a) forward hot path of Planer.
+ *
+ * The reference (Image-Py/planer @ 39174495) is pure Python and has NO foreign-function boundary;
+ * its only native call site is the destination-passing cuDNN call in planer/util.py:74-76.  This
+ * ABI is modelled on that call: every tensor argument is a raw device pointer plus explicit
+ * extents, outputs are pre-allocated by the caller, the library never allocates or frees user
+ * tensors.  Each entry point names the reference function it replaces (file:line under
+ * /root/reference).  A host binds it with ctypes (planer_b200/_capi.py; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, <0 = error; plnr_last_error() gives a thread-local text.
+ *   - no exceptions or aborts cross the boundary.
+ *   - a plnr_ctx binds one device and one stream; it is not thread-safe; different ctxs are
+ *     independent.  All work is enqueued on the ctx stream and is asynchronous.
+ *   - INTERNAL ACTIVATION LAYOUT IS NHWC ("pixel-major"): a tensor of logical shape (N,C,H,W) is
+ *     stored as N*H*W pixel rows, each `ld` elements long, the tensor's channels occupying
+ *     [coff, coff+C) of the row.  (The reference itself hands non-contiguous CNHW views between
+ *     layers -- planer/util.py:44 -- so inter-layer layout is not part of its contract; NCHW is
+ *     restored at the graph boundary by plnr_nhwc_to_nchw.)
+ *   - dtype codes: PLNR_F32 / PLNR_F16.
+ */
+#ifndef PLANER_B200_H
+#define PLANER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLNR_ABI_VERSION 1
+
+enum { PLNR_F32 = 0, PLNR_F16 = 1 };
+enum { PLNR_ACT_NONE = 0, PLNR_ACT_RELU = 1, PLNR_ACT_LEAKY = 2, PLNR_ACT_SIGMOID = 3 };
+enum { PLNR_ALGO_AUTO = 0, PLNR_ALGO_TCGEN05 = 1, PLNR_ALGO_DIRECT = 2 };
+enum {
+  PLNR_OK = 0, PLNR_ERR_INVALID = -1, PLNR_ERR_UNSUPPORTED = -2, PLNR_ERR_CUDA = -3, PLNR_ERR_DRIVER = -4
+};
+/* elementwise op codes for plnr_eltwise */
+enum {
+  PLNR_EW_RELU = 0,        /* y = x * (x > 0)                    planer/layer.py:44-46  */
+  PLNR_EW_LEAKY = 1,       /* y = x * ((x>0)*(1-a) + a)          planer/layer.py:48-51  */
+  PLNR_EW_SIGMOID = 2,     /* y = 1 / (1 + exp(-x))              planer/layer.py:61-64  */
+  PLNR_EW_ADD = 3,         /* y = x + x2                         planer/layer.py:93-95  */
+  PLNR_EW_SCALE_SHIFT = 4  /* y = x * K[c] + B[c]  (folded BN)   planer/layer.py:125-127 */
+};
+
+typedef struct plnr_ctx plnr_ctx;
+typedef struct plnr_graph plnr_graph;
+typedef struct plnr_event plnr_event;
+
+/* A pixel-major (NHWC) activation view: see "INTERNAL ACTIVATION LAYOUT" above. */
+typedef struct {
+  void* ptr;      /* device pointer to pixel row 0, channel 0 of the underlying buffer */
+  int32_t n, h, w, c;
+  int32_t ld;     /* elements per pixel row of the underlying buffer (>= coff + c) */
+  int32_t coff;   /* first channel of this view inside the row */
+} plnr_tensor;
+
+/* Fused epilogue of conv/dense: y = act(acc * scale[c] + shift[c] + residual)  [or act(..) + residual].  The caller folds
+ * bias and BatchNorm into (scale, shift) with plnr_fold_affine.  Order follows the reference graph
+ * conv(+bias) -> batchnorm -> add -> relu  (planer/layer.py:26, :125-127, :93-95, :44-51). */
+typedef struct {
+  const float* scale;       /* [Cout] fp32 or NULL (=1) */
+  const float* shift;       /* [Cout] fp32 or NULL (=0) */
+  const plnr_tensor* residual; /* same (n,h,w,c) and dtype as y, or NULL */
+  int32_t act;              /* PLNR_ACT_* */
+  float alpha;              /* leaky slope */
+  int32_t res_after_act;    /* 0: act(v + residual) (ResNet);  1: act(v) + residual (Darknet shortcut) */
+} plnr_epilogue;
+
+typedef struct {
+  int32_t dtype;            /* PLNR_F32 | PLNR_F16: dtype of x, w_packed, y, residual */
+  int32_t kh, kw;
+  int32_t pad_t, pad_l, pad_b, pad_r;
+  int32_t stride_h, stride_w, dil_h, dil_w;
+  int32_t groups;
+  int32_t algo;             /* PLNR_ALGO_* */
+} plnr_conv_desc;
+
+/* ---- library / context ------------------------------------------------------------------ */
+int plnr_abi_version(void);
+const char* plnr_last_error(void);
+/* stream: a cudaStream_t to adopt (e.g. torch's current stream), or NULL to create an own one. */
+int plnr_create(int device, void* stream, plnr_ctx** out);
+int plnr_destroy(plnr_ctx* ctx);
+int plnr_set_stream(plnr_ctx* ctx, void* stream);
+int plnr_stream_sync(plnr_ctx* ctx);
+/* number of kernels this ctx has enqueued so far (graph replays add the graph's node count). */
+int plnr_launch_count(plnr_ctx* ctx, int64_t* out);
+/* sm count, compute capability major/minor, L2 bytes -> out[4] */
+int plnr_device_info(plnr_ctx* ctx, int64_t* out4);
+
+/* ---- raw memory for hosts that do not bring their own allocator (replaces np.zeros / np.asarray /
+ *      .get() of the backend module: planer/net.py:21,98,100) -------------------------------- */
+int plnr_malloc(plnr_ctx* ctx, size_t bytes, void** out);
+int plnr_free(plnr_ctx* ctx, void* ptr);
+int plnr_memcpy_h2d(plnr_ctx* ctx, void* dst, const void* src, size_t bytes);
+int plnr_memcpy_d2h(plnr_ctx* ctx, void* dst, const void* src, size_t bytes);
+int plnr_memset(plnr_ctx* ctx, void* dst, int value, size_t bytes);
+
+/* ---- layout / dtype --------------------------------------------------------------------- */
+/* NCHW (dense, x_dtype) -> pixel-major view y (y_dtype); channels [c, y.c) of y are zero-filled
+ * (channel padding for the tensor-core path).  Graph entry: planer/net.py:96-98. */
+int plnr_nchw_to_nhwc(plnr_ctx* ctx, const void* x, int x_dtype, int c_src, const plnr_tensor* y, int y_dtype);
+/* pixel-major view x -> NCHW dense y.  Graph exit: planer/net.py:100. */
+int plnr_nhwc_to_nchw(plnr_ctx* ctx, const plnr_tensor* x, int x_dtype, void* y, int y_dtype);
+/* flat cast, n elements (Net.half, planer/net.py:26-29). */
+int plnr_cast(plnr_ctx* ctx, const void* x, int x_dtype, void* y, int y_dtype, int64_t n);
+/* OIHW weight (w_dtype) -> packed [Cout][kh][kw][cin_pad] (out_dtype), zero-filling padded input
+ * channels.  One-off at load (K = core.reshape(Co,-1) of planer/util.py:41, re-ordered so the
+ * contraction index is (r,s,c) with c innermost). */
+int plnr_pack_conv_weight(plnr_ctx* ctx, const void* w, int w_dtype, void* out, int out_dtype,
+                          int cout, int cin_g, int kh, int kw, int cin_pad);
+/* scale[c] = bn_k ? bn_k[c] : 1 ; shift[c] = (bias ? bias[c] : 0) * scale[c] + (bn_b ? bn_b[c] : 0).
+ * Inputs have dtype `dtype`; outputs are fp32.  Folds planer/layer.py:26 and :125-127. */
+int plnr_fold_affine(plnr_ctx* ctx, const void* bias, const void* bn_k, const void* bn_b, int dtype,
+                     float* scale, float* shift, int c);
+
+/* ---- the FLOPs --------------------------------------------------------------------------- */
+/* Conv2d forward.  Replaces planer/layer.py:22-26 (Conv2d) + planer/util.py:17-44 (conv_for:
+ * zero-pad, im2col, one GEMM M=Co K=C*kh*kw N=N*oh*ow) and, through `ep`, the following
+ * batchnorm / add / relu layers.  x: (n,h,w,c) view; w_packed from plnr_pack_conv_weight with
+ * cin_pad == x.c / groups; y: (n,oh,ow,cout) view, oh/ow by the formula of planer/util.py:25-26.
+ * fp16 + groups==1 + x.c%16==0 runs the TMA-im2col / tcgen05 implicit GEMM; everything else runs
+ * the direct CUDA-core kernel (fp32 accumulate in both). */
+int plnr_conv2d_fwd(plnr_ctx* ctx, const plnr_conv_desc* desc, const plnr_tensor* x, const void* w_packed,
+                    const plnr_tensor* y, const plnr_epilogue* ep);
+/* Dense forward  y[M,N] = x[M,K] @ w[N,K]^T (+ epilogue).  Replaces planer/layer.py:15-18 (Dense);
+ * w is the reference's (out,in) matrix as stored.  Runs as a 1x1 convolution over M pixels. */
+int plnr_dense_fwd(plnr_ctx* ctx, int dtype, const void* x, const void* w, void* y, int m, int n, int k,
+                   const plnr_epilogue* ep, int algo);
+
+/* ---- HBM-bound companions ---------------------------------------------------------------- */
+/* Maxpool with the reference's semantics: ZERO padding and a -1e4 floor (planer/util.py:79-95). */
+int plnr_maxpool2d(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y,
+                   int kh, int kw, int pad_t, int pad_l, int stride_h, int stride_w);
+/* Integer-factor nearest upsample, zero pixel shift (planer/util.py:184-192 with the default mode
+ * strings of planer/util.py:212). */
+int plnr_upsample_nearest(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y, int fh, int fw);
+/* Channel-slice copy x -> y (same n,h,w,c; different ld/coff): the building block of
+ * np.concatenate(axis=1) (planer/layer.py:90-91). */
+int plnr_copy_channels(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y);
+/* Elementwise family on dense pixel-major data of `npix` rows x `c` channels (ld == c).
+ * p0/p1: second operand (ADD: x2) or per-channel K/B of dtype `dtype` (SCALE_SHIFT). */
+int plnr_eltwise(plnr_ctx* ctx, int op, int dtype, const void* x, const void* p0, const void* p1, void* y,
+                 int64_t npix, int c, float alpha);
+/* Global average pool (n, hw, c) -> (n, c), fp32 accumulate (planer/layer.py:77-78). */
+int plnr_global_avgpool(plnr_ctx* ctx, int dtype, const plnr_tensor* x, void* y);
+
+/* ---- CUDA-graph capture of a planned forward (replaces the Python interpreter loop of
+ *      planer/net.py:43-70 by one replayable launch) ------------------------------------- */
+int plnr_graph_begin(plnr_ctx* ctx);
+int plnr_graph_end(plnr_ctx* ctx, plnr_graph** out);
+int plnr_graph_launch(plnr_ctx* ctx, plnr_graph* g);
+int plnr_graph_destroy(plnr_graph* g);
+
+/* ---- device timers (feeds Net.timer, planer/net.py:67-70, with real device time) -------- */
+int plnr_event_create(plnr_event** out);
+int plnr_event_record(plnr_ctx* ctx, plnr_event* ev);
+int plnr_event_elapsed_ms(plnr_event* start, plnr_event* stop, float* ms);   /* syncs on stop */
+int plnr_event_destroy(plnr_event* ev);
+
+/* ---- diagnostics -------------------------------------------------------------------------- */
+/* Which kernel plnr_conv2d_fwd would pick for this problem: PLNR_ALGO_TCGEN05 or PLNR_ALGO_DIRECT. */
+int plnr_conv2d_algo(const plnr_conv_desc* desc, const plnr_tensor* x, const plnr_tensor* y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLANER_B200_H */

@@ -1,0 +1,466 @@
+// fp16 implicit-GEMM convolution for sm_100a:  TMA-im2col -> shared memory -> tcgen05.mma -> TMEM -> fused epilogue.
+//
+// Replaces planer/layer.py:22-26 (Conv2d) + planer/util.py:17-44 (conv_for) and the batchnorm / add / relu layers
+// that follow it (planer/layer.py:125-127, :93-95, :44-51).  The reference materialises the im2col matrix
+// (9-12x the input) and runs one GEMM  M=Co, K=C*kh*kw, N=N*oh*ow;  here the same contraction is tiled as
+//
+//     D[128 output pixels, n_tile output channels] += A[128 pixels, 64 k] * B[n_tile channels, 64 k]^T
+//
+// with the activation operand A fetched straight from the NHWC tensor by the TMA unit in im2col mode (zero fill
+// = padding, element strides = conv stride, per-load filter-tap offsets = dilation), the packed weights B by a
+// tiled TMA load, both landing in swizzled shared memory that tcgen05.mma reads through matrix descriptors;
+// fp32 accumulators live in TMEM (double buffered: the epilogue of tile i overlaps the main loop of tile i+1).
+//
+// CTA = 8 warps, persistent over output tiles (grid = #SMs):
+//   warp 0  lane 0 : TMA producer            (waits empty[s], arms full[s] with the stage's byte count)
+//   warp 1  lane 0 : tcgen05.mma issuer      (waits full[s], issues 64/16 MMAs, commits -> empty[s] / tmem_full[a])
+//   warp 2         : TMEM allocator / deallocator
+//   warps 4-7      : epilogue, one TMEM lane quarter each: tcgen05.ld -> *scale+shift (+residual) -> act -> fp16
+//
+// K is walked in "units" of kc input channels of one filter tap (kc = 64/32/16 -> 128B/64B/32B swizzle); a
+// pipeline stage holds 64/kc units, i.e. always 64 k-values = one 128-byte row per pixel / per output channel.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 256;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kAStageBytes = kTileM * 64 * 2;  // 16 KB: 128 pixels x 64 k x fp16
+constexpr uint32_t kEpiBytes = 2 * 2 * 256 * 4;     // [tile parity][scale|shift][256] fp32
+constexpr long long kWatchdogCycles = 4000000000ll; // ~2 s: a stuck barrier becomes an error, not a hang
+
+struct IgemmParams {
+  int M, OW, OH;
+  int pad_t, pad_l, sh, sw, dh, dw;
+  int S;          // filter width
+  int kc;         // input channels per unit
+  int cchunks;    // Cin / kc
+  int units;      // kh * kw * cchunks
+  int tps;        // units per stage (64 / kc)
+  int kstages;    // ceil(units / tps)
+  int n_tile, num_m_tiles, num_tiles;
+  int stages;
+  uint32_t a_layout, a_sbo, a_unit_bytes, b_stage_bytes, idesc, tmem_cols;
+  __half* y; int yld, ycoff, Cout;
+  const float* scale; const float* shift;
+  const __half* res; int rld, rcoff;
+  int act; float alpha; int res_after;
+  int vec_ok;
+  int* err;
+};
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int role) {
+  if (ptx::mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFF) == 0) {
+      if (*reinterpret_cast<volatile int*>(err) != 0) return;       // somebody else already gave up
+      if (clock64() - t0 > kWatchdogCycles) {
+        if (atomicCAS(err, 0, 1) == 0) { err[1] = blockIdx.x; err[2] = role; err[3] = (int)parity; }
+        __threadfence();
+        return;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                      const IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;           // 128B-swizzle atoms need 1024-byte alignment
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t stages = (uint32_t)p.stages;
+  const uint32_t sA = base;
+  const uint32_t sB = sA + stages * kAStageBytes;
+  const uint32_t epi_off = stages * (kAStageBytes + p.b_stage_bytes);
+  float* epi = reinterpret_cast<float*>(base_ptr + epi_off);
+  const uint32_t sBar = base + epi_off + kEpiBytes;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * stages;
+  const uint32_t bar_tfull = sBar + 16 * stages, bar_tempty = bar_tfull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + epi_off + kEpiBytes + 16 * stages + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&mapA);
+    ptx::prefetch_tmap(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (uint32_t i = 0; i < stages; ++i) {
+      ptx::mbar_init(bar_full + 8 * i, 1);    // producer's arrive.expect_tx (+ TMA transaction bytes)
+      ptx::mbar_init(bar_empty + 8 * i, 1);   // tcgen05.commit
+    }
+    for (uint32_t a = 0; a < 2; ++a) {
+      ptx::mbar_init(bar_tfull + 8 * a, 1);   // tcgen05.commit after the last k-stage of a tile
+      ptx::mbar_init(bar_tempty + 8 * a, 128);  // every epilogue thread
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
+        const int m0 = m_idx * kTileM;
+        const int q0 = m0 % p.OW;
+        const int t1 = m0 / p.OW;
+        const int p0 = t1 % p.OH, img = t1 / p.OH;
+        const int cw = q0 * p.sw - p.pad_l, chh = p0 * p.sh - p.pad_t;   // base input coordinate of the tile's first pixel
+        int r = 0, sx = 0, cc = 0;                                       // filter row / column / channel chunk of the next unit
+        int u = 0;
+        for (int j = 0; j < p.kstages; ++j) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1, p.err, 0);
+          const int nu = min(p.tps, p.units - u);
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)nu * p.a_unit_bytes + p.b_stage_bytes);
+          const uint32_t a_dst = sA + s * kAStageBytes;
+          for (int t = 0; t < nu; ++t) {
+            ptx::tma_load_im2col_4d(a_dst + t * p.a_unit_bytes, &mapA, bar_full + 8 * s, cc * p.kc, cw, chh, img,
+                                    (uint16_t)(sx * p.dw), (uint16_t)(r * p.dh));
+            if (++cc == p.cchunks) { cc = 0; if (++sx == p.S) { sx = 0; ++r; } }
+          }
+          u += nu;
+          ptx::tma_load_2d(sB + s * p.b_stage_bytes, &mapB, bar_full + 8 * s, j * 64, n_idx * p.n_tile);
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =========================================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0, it = 0;
+      const int kper = p.kc >> 4;   // MMAs (K=16) per unit
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t a = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * a, aph ^ 1, p.err, 1);   // epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * (uint32_t)p.n_tile;
+        uint32_t accumulate = 0;
+        int u = 0;
+        for (int j = 0; j < p.kstages; ++j) {
+          mbar_wait(bar_full + 8 * s, ph, p.err, 2);        // TMA bytes have landed
+          ptx::tc_fence_after();
+          const int nu = min(p.tps, p.units - u);
+          const uint32_t a_src = sA + s * kAStageBytes, b_src = sB + s * p.b_stage_bytes;
+          for (int t = 0; t < nu; ++t) {
+            for (int k = 0; k < kper; ++k) {
+              const uint64_t da = ptx::make_smem_desc(a_src + t * p.a_unit_bytes + k * 32, p.a_sbo, p.a_layout);
+              const uint64_t db = ptx::make_smem_desc(b_src + (t * p.kc + k * 16) * 2, 1024, 2);
+              ptx::umma_f16(d_tmem, da, db, p.idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          u += nu;
+          ptx::umma_commit(bar_empty + 8 * s);              // smem slot reusable once these MMAs retire
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+        ptx::umma_commit(bar_tfull + 8 * a);                // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================================== epilogue ===========================================
+    const int ew = warp - 4;                 // == warp % 4: the TMEM lane quarter this warp may read
+    const int et = threadIdx.x - 128;        // 0..127
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t a = it & 1, aph = (it >> 1) & 1;
+      const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
+      const int n0 = n_idx * p.n_tile;
+      // stage this tile's per-channel scale/shift in shared memory (double buffered by tile parity)
+      float* ep_scale = epi + a * 512, *ep_shift = ep_scale + 256;
+      for (int i = et; i < p.n_tile; i += 128) {
+        const int c = n0 + i;
+        float sc = 0.f, sf = 0.f;
+        if (c < p.Cout) { sc = p.scale ? __ldg(p.scale + c) : 1.f; sf = p.shift ? __ldg(p.shift + c) : 0.f; }
+        ep_scale[i] = sc; ep_shift[i] = sf;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      mbar_wait(bar_tfull + 8 * a, aph, p.err, 3);
+      ptx::tc_fence_after();
+
+      const int m = m_idx * kTileM + ew * 32 + lane;
+      const bool mvalid = m < p.M;
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + a * (uint32_t)p.n_tile;
+      __half* yrow = p.y + (size_t)(mvalid ? m : 0) * p.yld + p.ycoff;
+      const __half* rrow = p.res ? p.res + (size_t)(mvalid ? m : 0) * p.rld + p.rcoff : nullptr;
+
+      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+        __syncwarp();                       // tcgen05.ld is warp-collective: re-converge after the guarded stores
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(t_row + c0, v);
+        const int cb = n0 + c0;
+        const bool fast = p.vec_ok && (cb + 32 <= p.Cout);
+        uint4 rv[4];
+        if (fast && rrow && mvalid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rv[q] = *reinterpret_cast<const uint4*>(rrow + cb + q * 8);
+        }
+        ptx::tmem_ld_wait();
+        if (c0 + 32 >= p.n_tile) {          // accumulator fully read: hand it back to the MMA warp
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(bar_tempty + 8 * a);
+        }
+        if (mvalid && fast) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float sc[8], sf[8], o[8];
+            *reinterpret_cast<float4*>(&sc[0]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8);
+            *reinterpret_cast<float4*>(&sc[4]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8 + 4);
+            *reinterpret_cast<float4*>(&sf[0]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8);
+            *reinterpret_cast<float4*>(&sf[4]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8 + 4);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fmaf(__uint_as_float(v[q * 8 + e]), sc[e], sf[e]);
+            float rf[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) rf[e] = 0.f;
+            if (rrow) {
+              const __half2* rh = reinterpret_cast<const __half2*>(&rv[q]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(rh[e]);
+                rf[2 * e] = f.x; rf[2 * e + 1] = f.y;
+              }
+            }
+            if (!p.res_after) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] += rf[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = plnr_apply_act(o[e], p.act, p.alpha);
+            if (p.res_after) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] += rf[e];
+            }
+            uint4 pk;
+            pk.x = pack_half2(o[0], o[1]); pk.y = pack_half2(o[2], o[3]);
+            pk.z = pack_half2(o[4], o[5]); pk.w = pack_half2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(yrow + cb + q * 8) = pk;
+          }
+        } else if (mvalid) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int c = cb + e;
+            if (c < p.Cout) {
+              float o = fmaf(__uint_as_float(v[e]), ep_scale[c0 + e], ep_shift[c0 + e]);
+              const float rf = rrow ? __half2float(rrow[c]) : 0.f;
+              if (!p.res_after) o += rf;
+              o = plnr_apply_act(o, p.act, p.alpha);
+              if (p.res_after) o += rf;
+              yrow[c] = __float2half_rn(o);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown: everyone is done with TMEM before the allocator warp frees it ----
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: TMA descriptors (driver entry points resolved at run time; no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+static int g_driver_version = 0;
+
+static int resolve_driver() {
+  if (g_encode_tiled && g_encode_im2col) return PLNR_OK;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+    plnr_set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+    return PLNR_ERR_DRIVER;
+  }
+  g_encode_tiled = (EncodeTiledFn)fn;
+  fn = nullptr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+    plnr_set_error("cuTensorMapEncodeIm2col not available from the driver (%s)", cudaGetErrorString(e));
+    return PLNR_ERR_DRIVER;
+  }
+  g_encode_im2col = (EncodeIm2colFn)fn;
+  cudaDriverGetVersion(&g_driver_version);
+  return PLNR_OK;
+}
+
+// Drivers up to CUDA 13.1 mis-encode one descriptor bit for tensors smaller than 128 KiB; CUTLASS clears it
+// (cute/atom/copy_traits_sm90_tma.hpp, copy_traits_sm90_im2col.hpp) and so do we.
+static void small_tensor_fixup(CUtensorMap* m, uint64_t tensor_bytes) {
+  if (g_driver_version <= 13010 && tensor_bytes < 131072) reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static int pick_kc(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16); }
+
+// Estimated main-loop cost of a tile column width: MMA cycles per 64-k stage (N/2 per K=16 MMA at full rate;
+// narrow tiles are shared-memory-read bound: ~48 cycles per MMA at N=64) times the number of waves.
+static int pick_n_tile(int cout, int num_m_tiles, int sm_count) {
+  const int cap = round_up(cout, 32) < 256 ? round_up(cout, 32) : 256;
+  int best = cap;
+  double best_cost = 1e30;
+  for (int n = cap; n >= 32; n -= 32) {
+    if (n != cap && n != 128 && n != 64) continue;
+    const int n_tiles = (cout + n - 1) / n;
+    const long long tiles = (long long)num_m_tiles * n_tiles;
+    const long long waves = (tiles + sm_count - 1) / sm_count;
+    const double per_stage = 4.0 * (n / 2.0 > 48.0 ? n / 2.0 : 48.0) + 40.0;
+    const double cost = (double)waves * per_stage;
+    if (cost < best_cost * 0.97) { best_cost = cost; best = n; }
+  }
+  return best;
+}
+
+}  // namespace
+
+bool plnr_conv2d_tcgen05_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y) {
+  if (d->dtype != PLNR_F16 || d->groups != 1) return false;
+  if (x->c % 16 != 0 || x->ld % 8 != 0 || x->coff % 8 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(x->ptr) & 15) != 0) return false;
+  if (d->stride_h > 8 || d->stride_w > 8) return false;                       // TMA traversal stride limit
+  if ((d->kh - 1) * d->dil_h > 255 || (d->kw - 1) * d->dil_w > 255) return false;   // im2col offsets are 8-bit
+  const int up_w = d->pad_r - (d->kw - 1) * d->dil_w, up_h = d->pad_b - (d->kh - 1) * d->dil_h;
+  if (d->pad_t > 128 || d->pad_l > 128 || up_w < -128 || up_h < -128 || up_w > 127 || up_h > 127) return false;
+  if ((int64_t)y->n * y->h * y->w >= (1ll << 31) - 256) return false;
+  return true;
+}
+
+int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w,
+                        const plnr_tensor* y, const plnr_epilogue* ep) {
+  int rc = resolve_driver();
+  if (rc != PLNR_OK) return rc;
+  PLNR_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, "conv2d(tcgen05): packed weights must be 16-byte aligned");
+
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int Cin = x->c, Cout = y->c;
+  p.M = y->n * y->h * y->w; p.OW = y->w; p.OH = y->h;
+  p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.sh = d->stride_h; p.sw = d->stride_w; p.dh = d->dil_h; p.dw = d->dil_w;
+  p.S = d->kw;
+  p.kc = pick_kc(Cin);
+  p.cchunks = Cin / p.kc;
+  p.units = d->kh * d->kw * p.cchunks;
+  p.tps = 64 / p.kc;
+  p.kstages = (p.units + p.tps - 1) / p.tps;
+  p.num_m_tiles = (p.M + kTileM - 1) / kTileM;
+  p.n_tile = pick_n_tile(Cout, p.num_m_tiles, ctx->sm_count);
+  const int num_n_tiles = (Cout + p.n_tile - 1) / p.n_tile;
+  p.num_tiles = p.num_m_tiles * num_n_tiles;
+  p.a_unit_bytes = (uint32_t)kTileM * p.kc * 2;
+  p.b_stage_bytes = (uint32_t)p.n_tile * 128;
+  p.a_layout = p.kc == 64 ? 2u : (p.kc == 32 ? 4u : 6u);
+  p.a_sbo = 8u * p.kc * 2;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 @4, a/b format F16 (0) @7/@10,
+  // both K-major (0) @15/@16, N>>3 @17, M>>4 @24
+  p.idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  uint32_t cols = 32;
+  while (cols < 2u * p.n_tile) cols <<= 1;
+  p.tmem_cols = cols;
+  const uint32_t stage_bytes = kAStageBytes + p.b_stage_bytes;
+  const uint32_t budget = 232448u - 1024u - kEpiBytes - 256u;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  PLNR_REQUIRE(stages >= 2, "conv2d(tcgen05): tile does not fit shared memory");
+  p.stages = stages;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + kEpiBytes + 16 * stages + 64 + 1024;
+
+  p.y = (__half*)y->ptr; p.yld = y->ld; p.ycoff = y->coff; p.Cout = Cout;
+  bool vec = (y->ld % 8 == 0) && (y->coff % 8 == 0) && ((reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0);
+  if (ep) {
+    p.scale = ep->scale; p.shift = ep->shift; p.act = ep->act; p.alpha = ep->alpha;
+    p.res_after = ep->res_after_act;
+    if (ep->residual) {
+      const plnr_tensor* r = ep->residual;
+      p.res = (const __half*)r->ptr; p.rld = r->ld; p.rcoff = r->coff;
+      vec = vec && (r->ld % 8 == 0) && (r->coff % 8 == 0) && ((reinterpret_cast<uintptr_t>(r->ptr) & 15) == 0);
+    }
+  }
+  p.vec_ok = vec ? 1 : 0;
+  p.err = ctx->dev_error;
+
+  // ---- activation map: im2col over (C, W, H, N) ----
+  CUtensorMap mapA, mapB;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)x->w, (cuuint64_t)x->h, (cuuint64_t)x->n};
+    const cuuint64_t strides[3] = {(cuuint64_t)x->ld * 2, (cuuint64_t)x->w * x->ld * 2,
+                                   (cuuint64_t)x->h * x->w * x->ld * 2};
+    const int lower[2] = {-d->pad_l, -d->pad_t};
+    const int upper[2] = {d->pad_r - (d->kw - 1) * d->dil_w, d->pad_b - (d->kh - 1) * d->dil_h};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1};
+    const CUtensorMapSwizzle sw = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    void* gaddr = (void*)((__half*)x->ptr + x->coff);
+    CUresult r = g_encode_im2col(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, gaddr, dims, strides, lower, upper,
+                                 (cuuint32_t)p.kc, (cuuint32_t)kTileM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      plnr_set_error("cuTensorMapEncodeIm2col failed with CUresult %d (C=%d W=%d H=%d N=%d ld=%d kc=%d)", (int)r, Cin,
+                     x->w, x->h, x->n, x->ld, p.kc);
+      return PLNR_ERR_DRIVER;
+    }
+    small_tensor_fixup(&mapA, (uint64_t)x->n * x->h * x->w * x->ld * 2);
+  }
+  // ---- weight map: tiled over (K, Cout), box 64 x n_tile, 128B swizzle ----
+  {
+    const int Ktot = d->kh * d->kw * Cin;
+    const cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+    const cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)p.n_tile};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      plnr_set_error("cuTensorMapEncodeTiled failed with CUresult %d (K=%d Cout=%d n_tile=%d)", (int)r, Ktot, Cout,
+                     p.n_tile);
+      return PLNR_ERR_DRIVER;
+    }
+    small_tensor_fixup(&mapB, (uint64_t)Ktot * Cout * 2);
+  }
+
+  if (!ctx->igemm_attr_set) {
+    PLNR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    ctx->igemm_attr_set = true;
+  }
+  int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
+  conv_igemm_f16_kernel<<<grid, kThreads, smem_bytes, ctx->stream>>>(mapA, mapB, p);
+  return plnr_after_launch(ctx, "conv2d_tcgen05");
+}

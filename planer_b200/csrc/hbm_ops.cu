@@ -1,0 +1,406 @@
+// HBM-bound companions of the conv/dense path: layout transforms, casts, weight packing, maxpool,
+// nearest upsample, channel-slice copy (concat), the elementwise family and global average pool.
+// All are coalesced, 16-byte-vectorised streaming kernels over the pixel-major (NHWC) layout; their
+// roofline is HBM bandwidth (algorithmic bytes = (elements_in + elements_out) * sizeof(dtype)).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename T, int V> struct alignas(sizeof(T) * V) Vec { T v[V]; };
+
+template <typename T> struct VecWidth { static constexpr int value = 16 / sizeof(T); };
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static inline int grid_for(int64_t work, int sm_count) {
+  int64_t blocks = (work + kThreads - 1) / kThreads;
+  int64_t cap = (int64_t)sm_count * 16;  // grid-stride loops: a few resident waves are enough
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW <-> pixel-major transposes through a 32x33 shared tile (coalesced on both sides)
+// ---------------------------------------------------------------------------------------------
+template <typename Tin, typename Tout>
+__global__ void nchw_to_nhwc_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, int C, int HW, int Cy, int ld,
+                                    int coff) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // (32, 8)
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    int c = c0 + j, p = p0 + tx;
+    float v = 0.f;
+    if (c < C && p < HW) v = ld_f(x + ((size_t)n * C + c) * HW + p);
+    tile[j][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    int p = p0 + j, c = c0 + tx;
+    if (p < HW && c < Cy) st_f(y + ((size_t)n * HW + p) * ld + coff + c, tile[tx][j]);
+  }
+}
+
+template <typename Tin, typename Tout>
+__global__ void nhwc_to_nchw_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, int C, int HW, int ld, int coff) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    int p = p0 + j, c = c0 + tx;
+    float v = 0.f;
+    if (p < HW && c < C) v = ld_f(x + ((size_t)n * HW + p) * ld + coff + c);
+    tile[j][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    int c = c0 + j, p = p0 + tx;
+    if (c < C && p < HW) st_f(y + ((size_t)n * C + c) * HW + p, tile[tx][j]);
+  }
+}
+
+template <typename Tin, typename Tout>
+__global__ void cast_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    st_f(y + i, ld_f(x + i));
+}
+
+template <typename Tin, typename Tout>
+__global__ void pack_weight_kernel(const Tin* __restrict__ w, Tout* __restrict__ out, int cout, int cin_g, int kh,
+                                   int kw, int cin_pad) {
+  int64_t total = (int64_t)cout * kh * kw * cin_pad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int ci = (int)(i % cin_pad);
+    int64_t t = i / cin_pad;
+    int s = (int)(t % kw);
+    t /= kw;
+    int r = (int)(t % kh);
+    int co = (int)(t / kh);
+    float v = 0.f;
+    if (ci < cin_g) v = ld_f(w + (((size_t)co * cin_g + ci) * kh + r) * kw + s);
+    st_f(out + i, v);
+  }
+}
+
+template <typename T>
+__global__ void fold_affine_kernel(const T* __restrict__ bias, const T* __restrict__ bn_k, const T* __restrict__ bn_b,
+                                   float* __restrict__ scale, float* __restrict__ shift, int c) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  float k = bn_k ? ld_f(bn_k + i) : 1.f;
+  float b = bn_b ? ld_f(bn_b + i) : 0.f;
+  float bi = bias ? ld_f(bias + i) : 0.f;
+  scale[i] = k;
+  shift[i] = bi * k + b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// maxpool: zero padding + -1e4 floor (planer/util.py:79-95)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int xld,
+                               int xcoff, int OH, int OW, int yld, int ycoff, int kh, int kw, int pt, int pl, int sh,
+                               int sw) {
+  const int CV = C / V;
+  const int64_t total = (int64_t)N * OH * OW * CV;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    int64_t t = i / CV;
+    int ow = (int)(t % OW);
+    t /= OW;
+    int oh = (int)(t % OH);
+    int n = (int)(t / OH);
+    float m[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) m[k] = -1e4f;
+    for (int r = 0; r < kh; ++r) {
+      int ih = oh * sh + r - pt;
+      for (int s = 0; s < kw; ++s) {
+        int iw = ow * sw + s - pl;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+          const Vec<T, V> v =
+              *reinterpret_cast<const Vec<T, V>*>(x + (((size_t)n * H + ih) * W + iw) * xld + xcoff + cv * V);
+#pragma unroll
+          for (int k = 0; k < V; ++k) m[k] = fmaxf(m[k], ld_f(&v.v[k]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) m[k] = fmaxf(m[k], 0.f);  // the reference pads with ZERO, not -inf
+        }
+      }
+    }
+    Vec<T, V> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k) st_f(&o.v[k], m[k]);
+    *reinterpret_cast<Vec<T, V>*>(y + (((size_t)n * OH + oh) * OW + ow) * yld + ycoff + cv * V) = o;
+  }
+}
+
+template <typename T, int V>
+__global__ void upsample_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int xld,
+                                int xcoff, int yld, int ycoff, int fh, int fw) {
+  const int CV = C / V, OH = H * fh, OW = W * fw;
+  const int64_t total = (int64_t)N * OH * OW * CV;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    int64_t t = i / CV;
+    int ow = (int)(t % OW);
+    t /= OW;
+    int oh = (int)(t % OH);
+    int n = (int)(t / OH);
+    const Vec<T, V> v =
+        *reinterpret_cast<const Vec<T, V>*>(x + (((size_t)n * H + oh / fh) * W + ow / fw) * xld + xcoff + cv * V);
+    *reinterpret_cast<Vec<T, V>*>(y + (((size_t)n * OH + oh) * OW + ow) * yld + ycoff + cv * V) = v;
+  }
+}
+
+template <typename T, int V>
+__global__ void copy_channels_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t npix, int C, int xld,
+                                     int xcoff, int yld, int ycoff) {
+  const int CV = C / V;
+  const int64_t total = npix * CV;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    int64_t p = i / CV;
+    *reinterpret_cast<Vec<T, V>*>(y + p * yld + ycoff + cv * V) =
+        *reinterpret_cast<const Vec<T, V>*>(x + p * xld + xcoff + cv * V);
+  }
+}
+
+template <typename T, int V>
+__global__ void eltwise_kernel(int op, const T* __restrict__ x, const T* __restrict__ p0, const T* __restrict__ p1,
+                               T* __restrict__ y, int64_t total_vec, int C, float alpha) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const Vec<T, V> a = *reinterpret_cast<const Vec<T, V>*>(x + i * V);
+    Vec<T, V> o;
+    if (op == PLNR_EW_ADD) {
+      const Vec<T, V> b = *reinterpret_cast<const Vec<T, V>*>(p0 + i * V);
+#pragma unroll
+      for (int k = 0; k < V; ++k) st_f(&o.v[k], ld_f(&a.v[k]) + ld_f(&b.v[k]));
+    } else if (op == PLNR_EW_SCALE_SHIFT) {
+      int c = (int)((i * V) % C);
+#pragma unroll
+      for (int k = 0; k < V; ++k) st_f(&o.v[k], ld_f(&a.v[k]) * ld_f(p0 + c + k) + ld_f(p1 + c + k));
+    } else {
+      int act = op == PLNR_EW_RELU ? PLNR_ACT_RELU : (op == PLNR_EW_LEAKY ? PLNR_ACT_LEAKY : PLNR_ACT_SIGMOID);
+#pragma unroll
+      for (int k = 0; k < V; ++k) st_f(&o.v[k], plnr_apply_act(ld_f(&a.v[k]), act, alpha));
+    }
+    *reinterpret_cast<Vec<T, V>*>(y + i * V) = o;
+  }
+}
+
+template <typename T, int V>
+__global__ void gap_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int HW, int C, int xld, int xcoff) {
+  const int CV = C / V;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * CV) return;
+  int cv = i % CV, n = i / CV;
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  for (int p = 0; p < HW; ++p) {
+    const Vec<T, V> v = *reinterpret_cast<const Vec<T, V>*>(x + ((size_t)n * HW + p) * xld + xcoff + cv * V);
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] += ld_f(&v.v[k]);
+  }
+  Vec<T, V> o;
+  const float inv = 1.f / (float)HW;
+#pragma unroll
+  for (int k = 0; k < V; ++k) st_f(&o.v[k], acc[k] * inv);
+  *reinterpret_cast<Vec<T, V>*>(y + (size_t)n * C + cv * V) = o;
+}
+
+static inline bool view_vec_ok(const plnr_tensor* t, int V, size_t esz) {
+  return t->c % V == 0 && t->ld % V == 0 && t->coff % V == 0 && aligned16(t->ptr) && (V * esz == 16);
+}
+
+#define DISPATCH_T(dt, ...)                                  \
+  if ((dt) == PLNR_F16) { using T = __half; __VA_ARGS__ }    \
+  else { using T = float; __VA_ARGS__ }
+
+}  // namespace
+
+extern "C" {
+
+int plnr_nchw_to_nhwc(plnr_ctx* ctx, const void* x, int x_dtype, int c_src, const plnr_tensor* y, int y_dtype) {
+  PLNR_REQUIRE(ctx && x && y && y->ptr, "nchw_to_nhwc: NULL argument");
+  PLNR_REQUIRE(c_src >= 1 && c_src <= y->c && y->ld >= y->coff + y->c, "nchw_to_nhwc: bad channel counts");
+  const int HW = y->h * y->w;
+  dim3 grid((HW + 31) / 32, (y->c + 31) / 32, y->n), block(32, 8);
+  PLNR_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "nchw_to_nhwc: batch/channel count too large for one launch");
+#define LAUNCH(TI, TO)                                                                                       \
+  nchw_to_nhwc_kernel<TI, TO><<<grid, block, 0, ctx->stream>>>((const TI*)x, (TO*)y->ptr, c_src, HW, y->c, y->ld, \
+                                                               y->coff)
+  if (x_dtype == PLNR_F32 && y_dtype == PLNR_F32) LAUNCH(float, float);
+  else if (x_dtype == PLNR_F32 && y_dtype == PLNR_F16) LAUNCH(float, __half);
+  else if (x_dtype == PLNR_F16 && y_dtype == PLNR_F16) LAUNCH(__half, __half);
+  else LAUNCH(__half, float);
+#undef LAUNCH
+  return plnr_after_launch(ctx, "nchw_to_nhwc");
+}
+
+int plnr_nhwc_to_nchw(plnr_ctx* ctx, const plnr_tensor* x, int x_dtype, void* y, int y_dtype) {
+  PLNR_REQUIRE(ctx && x && x->ptr && y, "nhwc_to_nchw: NULL argument");
+  const int HW = x->h * x->w;
+  dim3 grid((HW + 31) / 32, (x->c + 31) / 32, x->n), block(32, 8);
+  PLNR_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "nhwc_to_nchw: batch/channel count too large for one launch");
+#define LAUNCH(TI, TO) \
+  nhwc_to_nchw_kernel<TI, TO><<<grid, block, 0, ctx->stream>>>((const TI*)x->ptr, (TO*)y, x->c, HW, x->ld, x->coff)
+  if (x_dtype == PLNR_F32 && y_dtype == PLNR_F32) LAUNCH(float, float);
+  else if (x_dtype == PLNR_F32 && y_dtype == PLNR_F16) LAUNCH(float, __half);
+  else if (x_dtype == PLNR_F16 && y_dtype == PLNR_F16) LAUNCH(__half, __half);
+  else LAUNCH(__half, float);
+#undef LAUNCH
+  return plnr_after_launch(ctx, "nhwc_to_nchw");
+}
+
+int plnr_cast(plnr_ctx* ctx, const void* x, int x_dtype, void* y, int y_dtype, int64_t n) {
+  PLNR_REQUIRE(ctx && x && y && n >= 0, "cast: bad argument");
+  if (n == 0) return PLNR_OK;
+  int grid = grid_for(n, ctx->sm_count);
+  if (x_dtype == PLNR_F32 && y_dtype == PLNR_F16)
+    cast_kernel<float, __half><<<grid, kThreads, 0, ctx->stream>>>((const float*)x, (__half*)y, n);
+  else if (x_dtype == PLNR_F16 && y_dtype == PLNR_F32)
+    cast_kernel<__half, float><<<grid, kThreads, 0, ctx->stream>>>((const __half*)x, (float*)y, n);
+  else if (x_dtype == PLNR_F32)
+    cast_kernel<float, float><<<grid, kThreads, 0, ctx->stream>>>((const float*)x, (float*)y, n);
+  else
+    cast_kernel<__half, __half><<<grid, kThreads, 0, ctx->stream>>>((const __half*)x, (__half*)y, n);
+  return plnr_after_launch(ctx, "cast");
+}
+
+int plnr_pack_conv_weight(plnr_ctx* ctx, const void* w, int w_dtype, void* out, int out_dtype, int cout, int cin_g,
+                          int kh, int kw, int cin_pad) {
+  PLNR_REQUIRE(ctx && w && out, "pack_conv_weight: NULL argument");
+  PLNR_REQUIRE(cin_pad >= cin_g && cout >= 1 && kh >= 1 && kw >= 1, "pack_conv_weight: bad extents");
+  int64_t total = (int64_t)cout * kh * kw * cin_pad;
+  int grid = grid_for(total, ctx->sm_count);
+#define LAUNCH(TI, TO) \
+  pack_weight_kernel<TI, TO><<<grid, kThreads, 0, ctx->stream>>>((const TI*)w, (TO*)out, cout, cin_g, kh, kw, cin_pad)
+  if (w_dtype == PLNR_F32 && out_dtype == PLNR_F32) LAUNCH(float, float);
+  else if (w_dtype == PLNR_F32 && out_dtype == PLNR_F16) LAUNCH(float, __half);
+  else if (w_dtype == PLNR_F16 && out_dtype == PLNR_F16) LAUNCH(__half, __half);
+  else LAUNCH(__half, float);
+#undef LAUNCH
+  return plnr_after_launch(ctx, "pack_conv_weight");
+}
+
+int plnr_fold_affine(plnr_ctx* ctx, const void* bias, const void* bn_k, const void* bn_b, int dtype, float* scale,
+                     float* shift, int c) {
+  PLNR_REQUIRE(ctx && scale && shift && c >= 1, "fold_affine: bad argument");
+  int grid = (c + kThreads - 1) / kThreads;
+  DISPATCH_T(dtype, fold_affine_kernel<T><<<grid, kThreads, 0, ctx->stream>>>((const T*)bias, (const T*)bn_k,
+                                                                              (const T*)bn_b, scale, shift, c);)
+  return plnr_after_launch(ctx, "fold_affine");
+}
+
+int plnr_maxpool2d(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y, int kh, int kw, int pad_t,
+                   int pad_l, int stride_h, int stride_w) {
+  PLNR_REQUIRE(ctx && x && y && x->ptr && y->ptr, "maxpool2d: NULL argument");
+  PLNR_REQUIRE(x->n == y->n && x->c == y->c, "maxpool2d: batch/channel mismatch");
+  PLNR_REQUIRE(kh >= 1 && kw >= 1 && stride_h >= 1 && stride_w >= 1 && pad_t >= 0 && pad_l >= 0, "maxpool2d: bad window");
+  int64_t work;
+  DISPATCH_T(dtype, {
+    constexpr int V = VecWidth<T>::value;
+    if (view_vec_ok(x, V, sizeof(T)) && view_vec_ok(y, V, sizeof(T))) {
+      work = (int64_t)y->n * y->h * y->w * (y->c / V);
+      maxpool_kernel<T, V><<<grid_for(work, ctx->sm_count), kThreads, 0, ctx->stream>>>(
+          (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, kh, kw,
+          pad_t, pad_l, stride_h, stride_w);
+    } else {
+      work = (int64_t)y->n * y->h * y->w * y->c;
+      maxpool_kernel<T, 1><<<grid_for(work, ctx->sm_count), kThreads, 0, ctx->stream>>>(
+          (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, kh, kw,
+          pad_t, pad_l, stride_h, stride_w);
+    }
+  })
+  return plnr_after_launch(ctx, "maxpool2d");
+}
+
+int plnr_upsample_nearest(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y, int fh, int fw) {
+  PLNR_REQUIRE(ctx && x && y && x->ptr && y->ptr, "upsample_nearest: NULL argument");
+  PLNR_REQUIRE(fh >= 1 && fw >= 1 && y->h == x->h * fh && y->w == x->w * fw && y->n == x->n && y->c == x->c,
+               "upsample_nearest: output extents do not match factors (%d,%d)", fh, fw);
+  int64_t work;
+  DISPATCH_T(dtype, {
+    constexpr int V = VecWidth<T>::value;
+    if (view_vec_ok(x, V, sizeof(T)) && view_vec_ok(y, V, sizeof(T))) {
+      work = (int64_t)y->n * y->h * y->w * (y->c / V);
+      upsample_kernel<T, V><<<grid_for(work, ctx->sm_count), kThreads, 0, ctx->stream>>>(
+          (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->ld, y->coff, fh, fw);
+    } else {
+      work = (int64_t)y->n * y->h * y->w * y->c;
+      upsample_kernel<T, 1><<<grid_for(work, ctx->sm_count), kThreads, 0, ctx->stream>>>(
+          (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->ld, y->coff, fh, fw);
+    }
+  })
+  return plnr_after_launch(ctx, "upsample_nearest");
+}
+
+int plnr_copy_channels(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y) {
+  PLNR_REQUIRE(ctx && x && y && x->ptr && y->ptr, "copy_channels: NULL argument");
+  PLNR_REQUIRE(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c, "copy_channels: shape mismatch");
+  const int64_t npix = (int64_t)x->n * x->h * x->w;
+  DISPATCH_T(dtype, {
+    constexpr int V = VecWidth<T>::value;
+    if (view_vec_ok(x, V, sizeof(T)) && view_vec_ok(y, V, sizeof(T))) {
+      copy_channels_kernel<T, V><<<grid_for(npix * (x->c / V), ctx->sm_count), kThreads, 0, ctx->stream>>>(
+          (const T*)x->ptr, (T*)y->ptr, npix, x->c, x->ld, x->coff, y->ld, y->coff);
+    } else {
+      copy_channels_kernel<T, 1><<<grid_for(npix * x->c, ctx->sm_count), kThreads, 0, ctx->stream>>>(
+          (const T*)x->ptr, (T*)y->ptr, npix, x->c, x->ld, x->coff, y->ld, y->coff);
+    }
+  })
+  return plnr_after_launch(ctx, "copy_channels");
+}
+
+int plnr_eltwise(plnr_ctx* ctx, int op, int dtype, const void* x, const void* p0, const void* p1, void* y,
+                 int64_t npix, int c, float alpha) {
+  PLNR_REQUIRE(ctx && x && y, "eltwise: NULL argument");
+  PLNR_REQUIRE(op >= PLNR_EW_RELU && op <= PLNR_EW_SCALE_SHIFT, "eltwise: unknown op %d", op);
+  PLNR_REQUIRE(op != PLNR_EW_ADD || p0, "eltwise: ADD needs a second operand");
+  PLNR_REQUIRE(op != PLNR_EW_SCALE_SHIFT || (p0 && p1), "eltwise: SCALE_SHIFT needs K and B");
+  const int64_t total = npix * c;
+  if (total == 0) return PLNR_OK;
+  DISPATCH_T(dtype, {
+    constexpr int V = VecWidth<T>::value;
+    bool vec = (c % V == 0) && aligned16(x) && aligned16(y) && (op != PLNR_EW_ADD || aligned16(p0));
+    if (vec)
+      eltwise_kernel<T, V><<<grid_for(total / V, ctx->sm_count), kThreads, 0, ctx->stream>>>(
+          op, (const T*)x, (const T*)p0, (const T*)p1, (T*)y, total / V, c, alpha);
+    else
+      eltwise_kernel<T, 1><<<grid_for(total, ctx->sm_count), kThreads, 0, ctx->stream>>>(
+          op, (const T*)x, (const T*)p0, (const T*)p1, (T*)y, total, c, alpha);
+  })
+  return plnr_after_launch(ctx, "eltwise");
+}
+
+int plnr_global_avgpool(plnr_ctx* ctx, int dtype, const plnr_tensor* x, void* y) {
+  PLNR_REQUIRE(ctx && x && x->ptr && y, "global_avgpool: NULL argument");
+  const int HW = x->h * x->w;
+  DISPATCH_T(dtype, {
+    constexpr int V = VecWidth<T>::value;
+    if (view_vec_ok(x, V, sizeof(T)) && aligned16(y)) {
+      int work = x->n * (x->c / V);
+      gap_kernel<T, V><<<(work + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>((const T*)x->ptr, (T*)y, x->n,
+                                                                                     HW, x->c, x->ld, x->coff);
+    } else {
+      int work = x->n * x->c;
+      gap_kernel<T, 1><<<(work + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>((const T*)x->ptr, (T*)y, x->n,
+                                                                                     HW, x->c, x->ld, x->coff);
+    }
+  })
+  return plnr_after_launch(ctx, "global_avgpool");
+}
+
+}  // extern "C"

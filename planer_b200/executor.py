@@ -1,0 +1,245 @@
+"""GraphPlan -> device buffers, kernel launches and one CUDA graph (the replacement of the hot loop of
+planer/net.py:43-70).
+
+Per forward the host issues: one layout/cast kernel per graph input (NCHW -> pixel-major, reading the
+caller's device array in place) and ONE ``plnr_graph_launch`` that replays every fused step and the
+output transposes.  Weights are packed ([Cout][kh][kw][Cin]) and bias/BatchNorm folded into fp32
+(scale, shift) vectors once, on the device, when the executor is built.
+"""
+import numpy as np
+
+from . import _capi, ops, plan as P
+from . import backend as B
+from .backend import DeviceArray
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class Executor:
+    def __init__(self, net, gplan, dtype, use_graph=True):
+        self.net, self.plan, self.dtype = net, gplan, np.dtype(dtype)
+        self.use_graph = use_graph
+        self.values = gplan.values
+        self.arr = {}             # root value id -> DeviceArray
+        self.launches = []        # closures, in order
+        self.kinds = []           # step op per closure (for timers / launch accounting)
+        self.graph = None
+        self.input_ids = list(gplan.inputs)
+        self.in_arrays, self.out_arrays, self.out_flat = [], [], []
+        self._keep = []
+        self._build()
+
+    # ------------------------------------------------------------------------------------------
+    def _root(self, vid):
+        return P._root(self.values, vid)
+
+    def _weight(self, vid):
+        return self.net.weights[self.net.inits.index(self.values[vid].name)]
+
+    def _storage_c(self, vid):
+        v = self.values[vid]
+        if v.kind == 'input' and len(v.shape) == 4:
+            return self._input_cpad(vid)
+        return v.shape[1]
+
+    def _input_cpad(self, vid):
+        """Graph inputs feeding only group-1 convs are channel-padded to a multiple of 16 in fp16 so that the
+        first layer runs on the tensor cores (Cin=3 -> 16; the packed weights carry zeros there)."""
+        c = self.values[vid].shape[1]
+        if self.dtype != np.float16 or c % 16 == 0:
+            return c
+        for st in self.plan.steps:
+            if vid in [self._root(r) for r in st.reads()]:
+                if not (st.op == 'conv' and st.attrs['group'] == 1 and self._root(st.ins[0]) == vid):
+                    return c
+        return _round_up(c, 16)
+
+    def _get(self, vid):
+        return self.arr[self._root(vid)]
+
+    def _view(self, vid):
+        """DeviceArray of value ``vid`` with ITS logical shape on its root's storage."""
+        a, v = self._get(vid), self.values[vid]
+        if a.shape == v.shape:
+            return a
+        if a.layout == 'nhwc' and len(v.shape) == 2:          # flatten of an (N,C,1,1) map
+            return DeviceArray(a.buf, v.shape, a.dtype, 'flat', offset=a.offset)
+        if a.layout == 'nhwc' and len(v.shape) == 4 and a.shape[0] == v.shape[0] and a.shape[2:] == v.shape[2:] \
+                and a.shape[1] >= v.shape[1] and v.kind == 'input':
+            return a                                          # channel-padded graph input (zeros beyond C)
+        raise AssertionError('alias with a different shape: %s vs %s' % (a.shape, v.shape))
+
+    def _build(self):
+        gp, vals, dt = self.plan, self.values, self.dtype
+        P.assign_buffers(gp, dt.itemsize, self._storage_c)
+        pool = [None] * len(gp.buffer_bytes)
+
+        def alloc(vid):
+            r = self._root(vid)
+            if r in self.arr:
+                return self.arr[r]
+            shape = vals[r].shape
+            b = gp.buffer_of[r]
+            if pool[b] is None:
+                pool[b] = B.empty((gp.buffer_bytes[b],), np.uint8).buf
+            layout = 'nhwc' if len(shape) == 4 else 'flat'
+            self.arr[r] = DeviceArray(pool[b], shape, dt, layout)
+            return self.arr[r]
+
+        # graph inputs: pixel-major staging filled by an eager transform at every forward
+        for vid in self.input_ids:
+            shp = vals[vid].shape
+            if len(shp) == 4:
+                cp = self._input_cpad(vid)
+                a = B.empty((shp[0], cp, shp[2], shp[3]), dt, 'nhwc')
+            else:
+                a = B.empty(shp, dt)
+            self.arr[vid] = a
+            self.in_arrays.append(a)
+
+        for st in gp.steps:
+            fn = self._make(st, alloc)
+            if fn is not None:
+                self.launches.append(fn)
+                self.kinds.append(st.op)
+
+        # graph outputs: restore NCHW (planer/net.py:100 hands NCHW arrays back)
+        for o in gp.outputs:
+            a = self._view(o)
+            if a.layout == 'nhwc':
+                flat = B.empty(a.shape, dt)
+                self.launches.append(lambda a=a, flat=flat: ops.nhwc_to_nchw_into(a, flat))
+                self.kinds.append('to_nchw')
+                self.out_flat.append(flat)
+            else:
+                self.out_flat.append(a)
+
+    # ------------------------------------------------------------------------------------------
+    def _make(self, st, alloc):
+        vals, dt = self.values, self.dtype
+        op = st.op
+        if op in ('conv', 'dense'):
+            x = self._view(st.ins[0])
+            K = self._weight(st.w)
+            co = K.shape[0]
+            bias = self._weight(st.bias) if st.bias is not None else None
+            bn_k, bn_b = (self._weight(st.bn[0]), self._weight(st.bn[1])) if st.bn else (None, None)
+            scale = shift = None
+            if bias is not None or bn_k is not None:
+                scale, shift = ops.fold_affine(bias, bn_k, bn_b, co)
+                if bn_k is None:
+                    scale = None
+            res = self._view(st.res) if st.res is not None else None
+            y = alloc(st.out)
+            self._keep += [scale, shift]
+            if op == 'conv':
+                a = st.attrs
+                g = a['group']
+                wp = ops.pack_weight(K, x.shape[1] // g, dt)
+                self._keep.append(wp)
+                kh, kw = K.shape[2], K.shape[3]
+                return lambda: ops.conv2d_into(x, wp, y, kh, kw, a['strides'], a['dilations'], a['pads'], g,
+                                               scale, shift, res, st.act, st.alpha, res_after_act=st.res_after)
+            Kc = K.astype(dt)
+            self._keep.append(Kc)
+            if x.layout != 'flat':
+                raise NotImplementedError('dense %r needs a 2-D input (got %s)' % (st.name, x.shape))
+            return lambda: ops.dense_into(x, Kc, y, scale, shift, res, st.act, st.alpha, res_after_act=st.res_after)
+        if op == 'relu':
+            x = self._get(st.ins[0])                      # in place on the root storage
+            if self._root(st.ins[0]) not in self.arr:
+                raise AssertionError('relu input not materialised')
+            return lambda: ops.eltwise(ops.EW_RELU, _dense(x), _dense(x))
+        if op == 'alias':
+            return None
+        if op in ('leakyrelu', 'sigmoid'):
+            x, y = self._view(st.ins[0]), alloc(st.out)
+            code = ops.EW_LEAKY if op == 'leakyrelu' else ops.EW_SIGMOID
+            alpha = st.attrs.get('alpha', 0.0)
+            return lambda: ops.eltwise(code, _dense(x), y, alpha=alpha)
+        if op == 'add':
+            x1, x2, y = self._view(st.ins[0]), self._view(st.ins[1]), alloc(st.out)
+            return lambda: ops.eltwise(ops.EW_ADD, _dense(x1), y, p0=_dense(x2))
+        if op == 'scale_shift':
+            x, y = self._view(st.ins[0]), alloc(st.out)
+            k, b = self._weight(st.bn[0]).astype(dt), self._weight(st.bn[1]).astype(dt)
+            self._keep += [k, b]
+            return lambda: ops.eltwise(ops.EW_SCALE_SHIFT, _dense(x), y, p0=k, p1=b)
+        if op == 'maxpool':
+            x, y, a = self._view(st.ins[0]), alloc(st.out), st.attrs
+            return lambda: ops.maxpool_into(x, y, a['w'], a['pads'], a['strides'])
+        if op == 'upsample':
+            x, y, a = self._view(st.ins[0]), alloc(st.out), st.attrs
+            return lambda: ops.upsample_into(x, y, a['fh'], a['fw'])
+        if op == 'concat':
+            xs, y = [self._view(i) for i in st.ins], alloc(st.out)
+            offs = np.cumsum([0] + [x.shape[1] for x in xs]).tolist()
+            views = [ops.channel_slice(y, o, x.shape[1]) for x, o in zip(xs, offs)]
+            def run():
+                for x, v in zip(xs, views):
+                    ops.copy_channels(x, v)
+            return run
+        if op == 'gap':
+            x, y = self._view(st.ins[0]), alloc(st.out)
+            return lambda: ops.gap_into(x, y)
+        if op == 'flatten':
+            x = self._view(st.ins[0])
+            if self.values[st.out].alias_of is not None:
+                return None                              # (N,C,1,1) -> (N,C): same memory
+            y = alloc(st.out)
+            flat4 = DeviceArray(y.buf, x.shape, dt, 'flat', offset=y.offset)
+            return lambda: ops.nhwc_to_nchw_into(x, flat4)
+        raise NotImplementedError(op)
+
+    # ------------------------------------------------------------------------------------------
+    def _load_inputs(self, xs):
+        for a, x, vid in zip(self.in_arrays, xs, self.input_ids):
+            shp = self.values[vid].shape
+            if tuple(x.shape) != tuple(shp):
+                raise ValueError('input %r: plan compiled for shape %s, got %s' % (self.values[vid].name, shp, x.shape))
+            if x.layout != 'flat':
+                x = B.to_flat(x)
+            if len(shp) == 4:
+                ops.nchw_to_nhwc_into(x, a, shp[1])
+            else:
+                _capi.check(B.lib().plnr_cast(B.ctx(), x.ptr, _capi.dtype_code(x.dtype), a.ptr,
+                                              _capi.dtype_code(a.dtype), x.size), 'plnr_cast')
+
+    def run(self, xs):
+        """xs: DeviceArrays (flat NCHW) in graph-input order -> tuple of flat (NCHW) output DeviceArrays that
+        stay owned by the executor (valid until the next run)."""
+        self._load_inputs(xs)
+        if not self.use_graph:
+            for fn in self.launches:
+                fn()
+        else:
+            import ctypes as C
+            if self.graph is None:
+                for fn in self.launches:        # one eager pass first: validates every launch outside capture
+                    fn()
+                B.synchronize()
+                lib, ctx = B.lib(), B.ctx()
+                _capi.check(lib.plnr_graph_begin(ctx), 'plnr_graph_begin')
+                try:
+                    for fn in self.launches:
+                        fn()
+                finally:
+                    g = C.c_void_p()
+                    rc = lib.plnr_graph_end(ctx, C.byref(g))
+                _capi.check(rc, 'plnr_graph_end')
+                self.graph = g
+            _capi.check(B.lib().plnr_graph_launch(B.ctx(), self.graph), 'plnr_graph_launch')
+        return tuple(self.out_flat)
+
+    def close(self):
+        if self.graph is not None:
+            B.lib().plnr_graph_destroy(self.graph)
+            self.graph = None
+
+
+def _dense(a):
+    if a.layout == 'nhwc':
+        assert a.ld == a.shape[1] and a.coff == 0
+    return a

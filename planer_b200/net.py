@@ -1,0 +1,225 @@
+"""Graph runtime with the reference's ``Net`` API (planer/net.py:5-101), re-implemented for the B200 path.
+
+Same attributes (``weights, body, flow, life, timer, input, inits, layer``) and methods (``load_json,
+load_weights, half, info, forward, timeit, run, __call__``).  Differences that matter:
+
+  * ``forward`` does not interpret the flow layer by layer; it compiles it once per input shape into a fused
+    launch list captured in a CUDA graph (plan.py / executor.py) and replays that.  ``forward(debug=True)``
+    keeps the reference's per-layer interpreter (net.py:43-70) over the eager operator table, prints the same
+    trace and fills ``timer`` per operator type -- with device time from CUDA events (the reference's timers
+    are unsynchronised wall clock).
+  * weights live in ONE device blob (the uint8 ``.npy`` of planer/io.py:286 uploaded as is); ``self.weights``
+    are views into it.  With ``torch.distributed`` initialised the blob is read by rank 0 only and broadcast
+    once over NCCL (dist.py); there is no collective on the forward path.
+  * operators outside the hot path raise ``NotImplementedError`` at ``load_json`` time.
+"""
+import time
+
+import numpy
+
+from . import backend as B
+from .backend import DeviceArray
+from .layer import wrap, layer_map as key
+
+
+class Net:
+    def __init__(self, table=None, array_module=None):
+        self.weights, self.body, self.flow = [], [], []
+        self.life, self.timer = {}, {}
+        self.input, self.inits, self.layer = [], [], []
+        self._table = key if table is None else table                 # tests may inject another operator table
+        self._array = B if array_module is None else array_module     # ... and array module (Level A protocol)
+        self._init_meta, self._host_blob, self._blob = [], None, None
+        self._executors, self.use_graph = {}, True
+
+    # -- planer/net.py:10-24 ---------------------------------------------------------------------
+    def load_json(self, inputs, inits, body, flow, debug=False):
+        self.body, self.flow, self.life = [], [], {}
+        for i in body:
+            para = i[2]
+            if debug: print(i)
+            self.body.append((i[0], wrap(self._table[i[1]], i[1])(**para)))
+        for i in range(len(flow)):
+            keys = flow[i][0]
+            if isinstance(keys, str): keys = [keys]
+            for j in keys: self.life[j] = i
+        self._init_meta = [(i[0], tuple(i[1]), numpy.dtype(i[2])) for i in inits]
+        self.weights = []            # created by load_weights as views into one blob
+        self.input, self.inits = inputs, [i[0] for i in inits]
+        self.layer, self.flow = body, flow
+        self._executors = {}
+
+    def _model(self):
+        return {'input': self.input, 'inits': [[n, list(s), str(d)] for n, s, d in self._init_meta],
+                'layers': self.layer, 'flow': self.flow}
+
+    # -- planer/net.py:83-88 -----------------------------------------------------------------------
+    def load_weights(self, data, broadcast=None):
+        """``data``: the flat uint8 blob (host numpy array, or an array of the active array module).  Inits are
+        sliced out of it in ``inits`` order, each ``nbytes`` long (scalar inits occupy one element).
+        ``broadcast``: None = automatically when torch.distributed is initialised, True/False to force."""
+        np = self._array
+        total = sum(max(int(numpy.prod(s)), 1) * d.itemsize for _, s, d in self._init_meta)
+        if np is not B:                                   # injected array module (tests): plain slicing
+            blob = np.asarray(data).reshape(-1).view(numpy.uint8)
+            self.weights, s = [], 0
+            for name, shape, dt in self._init_meta:
+                nb = max(int(numpy.prod(shape)), 1) * dt.itemsize
+                w = np.zeros(shape, dtype=dt)
+                w.reshape(-1).view(numpy.uint8)[:] = blob[s:s + nb]
+                self.weights.append(w)
+                s += nb
+            return
+        from . import dist
+        if data is None or isinstance(data, numpy.ndarray):
+            host = None
+            if data is not None:
+                host = numpy.ascontiguousarray(data).reshape(-1).view(numpy.uint8)
+                if host.size < total:
+                    raise ValueError('weight blob has %d bytes, the graph needs %d' % (host.size, total))
+            blob = dist.upload_blob(host, total, broadcast)
+        else:
+            blob = dist.broadcast_device_blob(data) if broadcast else data
+        self._blob = blob
+        self.weights, s = [], 0
+        for name, shape, dt in self._init_meta:
+            nb = max(int(numpy.prod(shape)), 1) * dt.itemsize
+            self.weights.append(DeviceArray(blob.buf, shape, dt, 'flat', offset=blob.offset + s))
+            s += nb
+        self._executors = {}
+
+    # -- planer/net.py:26-29 -----------------------------------------------------------------------
+    def half(self):
+        for i in range(len(self.weights)):
+            if self.weights[i].dtype == numpy.float32:
+                self.weights[i] = self.weights[i].astype('float16')
+        self._executors = {}
+
+    def info(self, obj):
+        if isinstance(obj, list):
+            return [self.info(i) for i in obj]
+        if hasattr(obj, 'shape'): return obj.shape
+        return obj
+
+    def host_const(self, name):
+        """Host copy of a (small) init, e.g. the upsample scales the planner needs as numbers."""
+        w = self.weights[self.inits.index(name)]
+        return w.get() if isinstance(w, DeviceArray) else numpy.asarray(w)
+
+    def compute_dtype(self):
+        dts = {numpy.dtype(w.dtype) for w in self.weights if numpy.dtype(w.dtype).kind == 'f' and w.size > 4}
+        return numpy.dtype(numpy.float16) if dts == {numpy.dtype(numpy.float16)} else numpy.dtype(numpy.float32)
+
+    # -- planer/net.py:37-72 -----------------------------------------------------------------------
+    def forward(self, *x, debug=False):
+        if debug or self._array is not B:
+            return self._forward_layers(*x, debug=debug)
+        xs = [B.asarray(i) for i in x]
+        ex = self.executor([i.shape for i in xs])
+        start = time.time()
+        out = ex.run(xs)
+        self.timer['plan'] = self.timer.get('plan', 0) + time.time() - start
+        return out
+
+    def executor(self, shapes):
+        """Compile (once per input-shape signature) and return the fused executor."""
+        from . import plan as P
+        from .executor import Executor
+        sig = (tuple(tuple(int(v) for v in s) for s in shapes), str(self.compute_dtype()), self.use_graph)
+        if sig not in self._executors:
+            names = [n for n in self.input if n not in self.inits]
+            consts = {}
+            kinds = {l[0]: l[1] for l in self.layer}
+            for xs, ls, y in self.flow:
+                first = ls[0] if isinstance(ls, list) else ls
+                if kinds.get(first) == 'upsample' and not isinstance(xs, str) and len(xs) > 1:
+                    consts[xs[1]] = self.host_const(xs[1])
+            gp = P.compile_graph(self._model(), dict(zip(names, sig[0])), consts)
+            self._executors[sig] = Executor(self, gp, self.compute_dtype(), self.use_graph)
+        return self._executors[sig]
+
+    def _forward_layers(self, *x, debug=False):
+        """The reference interpreter, identical in behaviour (net.py:38-72), over the eager operator table."""
+        np = self._array
+        dic = dict(self.body)
+        rst = {'None': None}
+        for k, v in zip(self.inits, self.weights): rst[k] = v
+        for k, v in zip(self.input, x): rst[k] = v
+        y = None
+        for i in range(len(self.flow)):
+            x, ls, y = self.flow[i]
+            if not isinstance(ls, list): ls = [ls]
+            for l in ls:
+                out = x if l == ls[0] else y
+                if not isinstance(out, str):
+                    p = [rst.get(i) for i in out]
+                else: p = [rst[out]]
+                xs = x if isinstance(x, list) else [x]
+                for k in set(xs):
+                    if k in rst and self.life[k] <= i: del rst[k]
+                obj = dic[l]
+                if debug:
+                    print(l, obj.name, ':', obj.para())
+                    print('\t--> ', out, ':', self.info(p))
+                t0 = _tick(np)
+                if isinstance(y, str): rst[y] = obj(*p)
+                else:
+                    for k, v in zip(y, obj(*p)): rst[k] = v
+                cost = _tock(np, t0)
+                if debug:
+                    for k in (y, [y])[isinstance(y, str)]:
+                        print('\t<-- ', k, ':', self.info(rst[k]))
+                self.timer[obj.name] = self.timer.get(obj.name, 0) + cost
+        out = rst[y]
+        if np is B and isinstance(out, tuple):             # graph boundary: NCHW, like the planned path
+            out = tuple(B.to_flat(o) if isinstance(o, DeviceArray) else o for o in out)
+        return out
+
+    def timeit(self, status='start'):
+        if status == 'start': self.timer = {}
+        if status == 'end':
+            for i in self.timer: print(i, self.timer[i])
+
+    def run(self, output=None, input={}):
+        rst = self(input)   # compatible with onnxruntime (planer/net.py:79-81)
+        return rst if isinstance(rst, tuple) else (rst,)
+
+    def show(self):
+        raise NotImplementedError('Net.show needs planer/plot.py, which the reference snapshot does not ship '
+                                  '(planer/net.py:90-92)')
+
+    # -- planer/net.py:94-101 ----------------------------------------------------------------------
+    def __call__(self, *x, **key):
+        np = self._array
+        if type(x[0]) is dict: x = [x[0][i] for i in self.input]
+        tp = [isinstance(i, numpy.ndarray) for i in x]
+        need = sum(tp) > 0 and numpy is not np
+        if need: x = [np.asarray(i) if b else i for i, b in zip(x, tp)]
+        rst = self.forward(*x, **key)
+        if need: rst = tuple([i.get() for i in rst])
+        return rst[0] if len(rst) == 1 else rst
+
+
+def _tick(np):
+    if np is not B:
+        return time.time()
+    import ctypes as C
+    from . import _capi
+    ev = C.c_void_p()
+    _capi.check(B.lib().plnr_event_create(C.byref(ev)))
+    _capi.check(B.lib().plnr_event_record(B.ctx(), ev))
+    return ev
+
+
+def _tock(np, t0):
+    if np is not B:
+        return time.time() - t0
+    import ctypes as C
+    from . import _capi
+    ev, ms = C.c_void_p(), C.c_float()
+    _capi.check(B.lib().plnr_event_create(C.byref(ev)))
+    _capi.check(B.lib().plnr_event_record(B.ctx(), ev))
+    _capi.check(B.lib().plnr_event_elapsed_ms(t0, ev, C.byref(ms)))
+    B.lib().plnr_event_destroy(t0)
+    B.lib().plnr_event_destroy(ev)
+    return ms.value / 1e3

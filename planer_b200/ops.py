@@ -1,0 +1,161 @@
+"""Destination-passing wrappers over the C ABI (one Python call = one kernel launch).
+
+These are the primitives both the eager operator table (``layer.py``) and the fused plan (``plan.py``)
+are made of.  Every function takes pre-allocated DeviceArrays, mirrors the argument meaning of the
+reference function it replaces, and raises ``PlanerB200Error`` on any failure (no fallback).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from . import backend as B
+from ._capi import (ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ALGO_AUTO, ALGO_TCGEN05, ALGO_DIRECT,
+                    EW_RELU, EW_LEAKY, EW_SIGMOID, EW_ADD, EW_SCALE_SHIFT)
+
+
+def out_size(n_in, pad_lo, pad_hi, k, dil, stride):
+    """planer/util.py:25-26."""
+    return (n_in + pad_lo + pad_hi - (k - 1) * dil - 1 + stride) // stride
+
+
+def conv_out_shape(xshape, kshape, strides, dilations, pads):
+    n, c, h, w = xshape
+    co, _, kh, kw = kshape
+    return (n, co, out_size(h, pads[0], pads[2], kh, dilations[0], strides[0]),
+            out_size(w, pads[1], pads[3], kw, dilations[1], strides[1]))
+
+
+def pool_out_shape(xshape, w, pads, strides):
+    """planer/util.py:84-85."""
+    n, c, h, ww = xshape
+    return (n, c, (h + pads[0] + pads[2] - w[0] + strides[0]) // strides[0],
+            (ww + pads[1] + pads[3] - w[1] + strides[1]) // strides[1])
+
+
+def _epilogue(scale, shift, residual, act, alpha, res_after_act=False):
+    keep = []
+    ep = _capi.Epilogue()
+    ep.scale = scale.ptr if scale is not None else None
+    ep.shift = shift.ptr if shift is not None else None
+    if residual is not None:
+        t = residual.tensor()
+        keep.append(t)
+        ep.residual = C.pointer(t)
+    ep.act, ep.alpha, ep.res_after_act = int(act), float(alpha), int(bool(res_after_act))
+    return ep, keep
+
+
+def pack_weight(K, cin_pad, dtype):
+    """OIHW -> [Cout][kh][kw][cin_pad] in ``dtype`` (one-off per layer)."""
+    co, cg, kh, kw = K.shape
+    out = B.empty((co, kh, kw, cin_pad), dtype)
+    _capi.check(B.lib().plnr_pack_conv_weight(B.ctx(), K.ptr, _capi.dtype_code(K.dtype), out.ptr,
+                                              _capi.dtype_code(dtype), co, cg, kh, kw, cin_pad),
+                'plnr_pack_conv_weight')
+    return out
+
+
+def fold_affine(bias, bn_k, bn_b, c):
+    """(bias, folded-BN K, B) -> fp32 per-channel (scale, shift) of the fused epilogue."""
+    dts = {a.dtype for a in (bias, bn_k, bn_b) if a is not None}
+    if len(dts) > 1:   # mixed precision inits: compute the fold in fp32
+        bias, bn_k, bn_b = [None if a is None else a.astype(np.float32) for a in (bias, bn_k, bn_b)]
+        dts = {np.dtype(np.float32)}
+    dt = dts.pop() if dts else np.dtype(np.float32)
+    scale, shift = B.empty((c,), np.float32), B.empty((c,), np.float32)
+    p = lambda a: a.ptr if a is not None else None
+    _capi.check(B.lib().plnr_fold_affine(B.ctx(), p(bias), p(bn_k), p(bn_b), _capi.dtype_code(dt), scale.ptr,
+                                         shift.ptr, c), 'plnr_fold_affine')
+    return scale, shift
+
+
+def conv2d_into(x, w_packed, y, kh, kw, strides, dilations, pads, groups=1, scale=None, shift=None,
+                residual=None, act=ACT_NONE, alpha=0.0, algo=ALGO_AUTO, res_after_act=False):
+    d = _capi.ConvDesc(_capi.dtype_code(x.dtype), kh, kw, pads[0], pads[1], pads[2], pads[3],
+                       strides[0], strides[1], dilations[0], dilations[1], groups, algo)
+    tx, ty = x.tensor(), y.tensor()
+    ep, keep = _epilogue(scale, shift, residual, act, alpha, res_after_act)
+    _capi.check(B.lib().plnr_conv2d_fwd(B.ctx(), C.byref(d), C.byref(tx), w_packed.ptr, C.byref(ty), C.byref(ep)),
+                'plnr_conv2d_fwd')
+    return y
+
+
+def conv2d_algo(x, y, kh, kw, strides, dilations, pads, groups=1):
+    d = _capi.ConvDesc(_capi.dtype_code(x.dtype), kh, kw, pads[0], pads[1], pads[2], pads[3],
+                       strides[0], strides[1], dilations[0], dilations[1], groups, ALGO_AUTO)
+    tx, ty = x.tensor(), y.tensor()
+    return B.lib().plnr_conv2d_algo(C.byref(d), C.byref(tx), C.byref(ty))
+
+
+def dense_into(x, w, y, scale=None, shift=None, residual=None, act=ACT_NONE, alpha=0.0, algo=ALGO_AUTO,
+               res_after_act=False):
+    m, k = x.shape
+    n = w.shape[0]
+    ep, keep = _epilogue(scale, shift, residual, act, alpha, res_after_act)
+    _capi.check(B.lib().plnr_dense_fwd(B.ctx(), _capi.dtype_code(x.dtype), x.ptr, w.ptr, y.ptr, m, n, k,
+                                       C.byref(ep), algo), 'plnr_dense_fwd')
+    return y
+
+
+def maxpool_into(x, y, w, pads, strides):
+    tx, ty = x.tensor(), y.tensor()
+    _capi.check(B.lib().plnr_maxpool2d(B.ctx(), _capi.dtype_code(x.dtype), C.byref(tx), C.byref(ty), w[0], w[1],
+                                       pads[0], pads[1], strides[0], strides[1]), 'plnr_maxpool2d')
+    return y
+
+
+def upsample_into(x, y, fh, fw):
+    tx, ty = x.tensor(), y.tensor()
+    _capi.check(B.lib().plnr_upsample_nearest(B.ctx(), _capi.dtype_code(x.dtype), C.byref(tx), C.byref(ty), fh, fw),
+                'plnr_upsample_nearest')
+    return y
+
+
+def copy_channels(x, y):
+    tx, ty = x.tensor(), y.tensor()
+    _capi.check(B.lib().plnr_copy_channels(B.ctx(), _capi.dtype_code(x.dtype), C.byref(tx), C.byref(ty)),
+                'plnr_copy_channels')
+    return y
+
+
+def channel_slice(a, c0, c):
+    """View of channels [c0, c0+c) of an nhwc array (zero-copy concat target)."""
+    n, _, h, w = a.shape
+    return B.DeviceArray(a.buf, (n, c, h, w), a.dtype, 'nhwc', ld=a.ld, coff=a.coff + c0, offset=a.offset)
+
+
+def eltwise(op, x, y, p0=None, p1=None, alpha=0.0):
+    """x, y: dense nhwc (ld == C) or flat arrays of equal size; per-channel params index the last (C) axis."""
+    if x.layout == 'nhwc':
+        assert x.ld == x.shape[1] and x.coff == 0, 'eltwise needs dense rows'
+        c = x.shape[1]
+    else:
+        c = x.shape[-1] if x.ndim else 1
+    npix = x.size // max(c, 1)
+    p = lambda a: a.ptr if a is not None else None
+    _capi.check(B.lib().plnr_eltwise(B.ctx(), op, _capi.dtype_code(x.dtype), x.ptr, p(p0), p(p1), y.ptr, npix, c,
+                                     float(alpha)), 'plnr_eltwise')
+    return y
+
+
+def gap_into(x, y):
+    tx = x.tensor()
+    _capi.check(B.lib().plnr_global_avgpool(B.ctx(), _capi.dtype_code(x.dtype), C.byref(tx), y.ptr),
+                'plnr_global_avgpool')
+    return y
+
+
+def nchw_to_nhwc_into(x_flat, y, c_src=None):
+    t = y.tensor()
+    _capi.check(B.lib().plnr_nchw_to_nhwc(B.ctx(), x_flat.ptr, _capi.dtype_code(x_flat.dtype),
+                                          x_flat.shape[1] if c_src is None else c_src, C.byref(t),
+                                          _capi.dtype_code(y.dtype)), 'plnr_nchw_to_nhwc')
+    return y
+
+
+def nhwc_to_nchw_into(x, y_flat):
+    t = x.tensor()
+    _capi.check(B.lib().plnr_nhwc_to_nchw(B.ctx(), C.byref(t), _capi.dtype_code(x.dtype), y_flat.ptr,
+                                          _capi.dtype_code(y_flat.dtype)), 'plnr_nhwc_to_nchw')
+    return y_flat

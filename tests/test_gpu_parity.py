@@ -1,0 +1,205 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against
+  (1) the committed golden fixtures produced by the unmodified reference,
+  (2) the numpy oracle on the same seeded inputs,
+  (3) size-independent properties at BASELINE.json's full sizes (batch independence, linearity,
+      tcgen05 == direct kernel).
+Tolerances are the north star's: range-relative 1e-3 for fp32, 1e-2 for fp16.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import planer_oracle as oracle
+from tests import cases
+from tests.cases import rel_err
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+TOL = {np.dtype('float32'): 1e-3, np.dtype('float16'): 1e-2}
+
+
+@pytest.fixture(scope='module')
+def planer():
+    import planer_b200 as p
+    p.core(p.b200)
+    return p
+
+
+@pytest.fixture(scope='module')
+def ops_gold():
+    return np.load(os.path.join(GOLD, 'ops.npz'))
+
+
+@pytest.fixture(scope='module')
+def graphs_gold():
+    return np.load(os.path.join(GOLD, 'graphs.npz'))
+
+
+def _dev(planer, a):
+    return planer.b200.asarray(a) if isinstance(a, np.ndarray) else a
+
+
+@pytest.mark.parametrize('name', list(cases.OP_CASES))
+def test_op_vs_reference_golden(planer, ops_gold, name):
+    """Every hot-path operator of the eager table vs the reference's output on the same seeded input."""
+    kind, args, kw = cases.make_case(name)
+    dt = np.dtype(args[0].dtype)
+    if name == 'upsample_2x3_f16':
+        dargs = [_dev(planer, args[0]), args[1]]
+    else:
+        dargs = [_dev(planer, a) for a in args]
+    y = planer.layer_map[kind](*dargs, **kw)
+    got = y.get()
+    ref = ops_gold[name]
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert rel_err(got, ref) <= TOL[dt], (name, rel_err(got, ref))
+
+
+@pytest.mark.parametrize('name', list(cases.GRAPH_CASES))
+def test_graph_vs_reference_golden(planer, graphs_gold, name):
+    """Whole graphs through Net (fused plan + CUDA graph) vs the reference Net's outputs."""
+    model, blob, x, half = cases.make_graph_case(name)
+    net = planer.from_model(model, blob, half=half)
+    y = net(x)
+    ys = y if isinstance(y, tuple) else (y,)
+    assert len(ys) == int(graphs_gold[name + '.nout'])
+    tol = 1e-2 if half else 1e-3
+    for i, t in enumerate(ys):
+        assert t.shape == tuple(graphs_gold['%s.shape%d' % (name, i)])
+        ref = graphs_gold['%s.out%d' % (name, i)]
+        scale = float(graphs_gold['%s.absmax%d' % (name, i)])
+        err = float(np.abs(cases.sample(t).astype(np.float64) - ref.astype(np.float64)).max() / scale)
+        assert err <= tol, (name, i, err)
+    # second call replays the captured CUDA graph: must give the same answer
+    y2 = net(x)
+    y2 = y2 if isinstance(y2, tuple) else (y2,)
+    for a, b in zip(ys, y2):
+        assert np.array_equal(a, b)
+
+
+def test_debug_interpreter_matches_plan(planer):
+    """forward(debug=True) (per-layer eager table, the reference's interpreter loop) == fused plan."""
+    model, blob, x, _ = cases.make_graph_case('resnet18_small_f32')
+    net = planer.from_model(model, blob)
+    a = net(x)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()) as buf:
+        b = net(x, debug=True)
+    assert 'conv1 conv' in buf.getvalue()
+    assert rel_err(b, a) < 1e-4
+    assert set(net.timer) >= {'conv', 'batchnorm', 'relu', 'maxpool', 'dense'}
+
+
+CONV_SWEEP = [
+    # n, cin, h, w, cout, k, stride, pad, dil
+    (2, 64, 16, 16, 64, 1, 1, 0, 1), (2, 64, 14, 14, 64, 3, 1, 1, 1), (3, 64, 15, 13, 128, 3, 2, 1, 1),
+    (2, 128, 9, 9, 256, 3, 1, 1, 1), (1, 256, 7, 7, 512, 3, 1, 1, 1), (2, 64, 12, 12, 64, 3, 1, 2, 2),
+    (2, 32, 14, 14, 64, 3, 2, 1, 1), (2, 16, 10, 10, 48, 3, 1, 1, 1), (1, 96, 10, 10, 80, 3, 1, 1, 1),
+    (1, 64, 13, 13, 255, 1, 1, 0, 1), (2, 64, 8, 8, 64, 5, 1, 2, 1), (1, 64, 30, 30, 32, 3, 1, 0, 1),
+]
+
+
+@pytest.mark.parametrize('cfg', CONV_SWEEP)
+@pytest.mark.parametrize('algo', ['tcgen05', 'direct'])
+def test_conv_fp16_kernels_vs_oracle(planer, cfg, algo):
+    """Both conv kernels, forced, with the full fused epilogue, vs the oracle evaluated in fp32."""
+    from planer_b200 import ops, backend as B
+    n, cin, h, w, cout, k, s, p, d = cfg
+    rng = np.random.default_rng(hash(cfg) % (2 ** 31))
+    x = rng.standard_normal((n, cin, h, w)).astype(np.float16)
+    K = (rng.standard_normal((cout, cin, k, k)) * np.sqrt(2.0 / (cin * k * k))).astype(np.float16)
+    bias = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    bk = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bb = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    ref = oracle.conv2d(x.astype(np.float32), K.astype(np.float32), bias, 1, (s, s), (d, d), (p,) * 4)
+    ref = oracle.batchnorm(ref, bk.reshape(1, -1, 1, 1), bb.reshape(1, -1, 1, 1))
+    r = rng.standard_normal(ref.shape).astype(np.float16)
+    ref = oracle.relu(oracle.add(ref, r.astype(np.float32)))
+    xd = B.to_nhwc(B.asarray(x))
+    wp = ops.pack_weight(B.asarray(K), cin, np.float16)
+    y = B.empty(ref.shape, np.float16, 'nhwc')
+    scale, shift = ops.fold_affine(B.asarray(bias), B.asarray(bk), B.asarray(bb), cout)
+    ops.conv2d_into(xd, wp, y, k, k, (s, s), (d, d), (p,) * 4, 1, scale, shift, B.to_nhwc(B.asarray(r)), ops.ACT_RELU,
+                    0.0, ops.ALGO_TCGEN05 if algo == 'tcgen05' else ops.ALGO_DIRECT)
+    B.synchronize()
+    assert rel_err(y.get(), ref) <= 1e-2
+
+
+def test_rejects_what_the_reference_breaks_on(planer):
+    """Asymmetric pads with bottom>top are silently wrong in the reference (App. D Q1): we raise.  Operators
+    outside the hot path raise by name; there is no CPU fallback."""
+    from planer_b200 import _capi
+    x = planer.b200.asarray(np.zeros((1, 8, 8, 8), np.float32))
+    K = planer.b200.asarray(np.zeros((8, 8, 3, 3), np.float32))
+    with pytest.raises(_capi.PlanerB200Error):
+        planer.layer_map['conv'](x, K, None, pads=(0, 0, 1, 1))
+    with pytest.raises(NotImplementedError):
+        planer.layer_map['lstm']
+    with pytest.raises(NotImplementedError):
+        planer.core(np)
+
+
+def test_relu_aliases_like_the_reference(planer):
+    x = planer.b200.asarray(np.array([[-1.0, 2.0, -3.0, 4.0]], np.float32))
+    y = planer.layer_map['relu'](x)
+    assert y is x and np.array_equal(x.get(), [[0.0, 2.0, 0.0, 4.0]])
+
+
+# ---------------------------------------------------------------------------------------------
+# properties at BASELINE.json's full sizes (no oracle run needed)
+# ---------------------------------------------------------------------------------------------
+
+def test_resnet18_fp16_batch128_batch_independence(planer):
+    """Config 3 (ResNet-18 fp16, batch 128): images are independent, so rows of the batch-128 logits must
+    equal the batch-4 logits of the same images (different tile decomposition, same arithmetic)."""
+    model, blob = cases.get_model('resnet18')
+    net = planer.from_model(model, blob, half=True)
+    x = np.random.default_rng(5).standard_normal((128, 3, 224, 224)).astype(np.float16)
+    y = net(x)
+    assert y.shape == (128, 1000) and np.isfinite(y.astype(np.float32)).all()
+    y4 = net(x[60:64].copy())
+    assert rel_err(y[60:64], y4) < 2e-3
+    # and against the reference's fp32 golden for image 0 of the seed-1 input (fp16 vs fp32 oracle: 1e-2 bar)
+    g = np.load(os.path.join(GOLD, 'graphs.npz'))
+    x1 = np.random.default_rng(1).standard_normal((1, 3, 224, 224)).astype(np.float32)
+    xb = np.repeat(x1.astype(np.float16), 128, axis=0)
+    yb = net(xb)
+    ref = g['resnet18_f32_n1.out0']
+    assert rel_err(yb[0], ref) <= 1e-2 and rel_err(yb[127], ref) <= 1e-2
+
+
+def test_big_conv_tcgen05_equals_direct_and_is_linear(planer):
+    """layer1-sized conv at batch 128 (M = 401 408): the tensor-core kernel agrees with the direct kernel, and
+    conv(2x) == 2 conv(x) exactly in fp16 (power-of-two scaling commutes with every rounding)."""
+    from planer_b200 import ops, backend as B
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((128, 64, 56, 56)).astype(np.float16)
+    K = (rng.standard_normal((64, 64, 3, 3)) * np.sqrt(2.0 / 576)).astype(np.float16)
+    xd, wp = B.to_nhwc(B.asarray(x)), ops.pack_weight(B.asarray(K), 64, np.float16)
+    ya, yb, yc = (B.empty((128, 64, 56, 56), np.float16, 'nhwc') for _ in range(3))
+    args = (3, 3, (1, 1), (1, 1), (1, 1, 1, 1), 1)
+    ops.conv2d_into(xd, wp, ya, *args, algo=ops.ALGO_TCGEN05)
+    ops.conv2d_into(xd, wp, yb, *args, algo=ops.ALGO_DIRECT)
+    x2 = B.to_nhwc(B.asarray(x * np.float16(2)))
+    ops.conv2d_into(x2, wp, yc, *args, algo=ops.ALGO_TCGEN05)
+    B.synchronize()
+    a, b, c = ya.get(), yb.get(), yc.get()
+    assert rel_err(a, b) < 2e-3
+    assert np.array_equal(c, a * np.float16(2))
+
+
+def test_yolov3_fp16_batch_runs_and_matches_fp32_golden(planer, graphs_gold):
+    """Config 4 graph (YOLOv3-416) in fp16 at batch 2 vs the reference's fp32 outputs for image 0."""
+    model, blob = cases.get_model('yolov3')
+    net = planer.from_model(model, blob, half=True)
+    x1 = np.random.default_rng(1).standard_normal((1, 3, 416, 416)).astype(np.float32)
+    ys = net(np.repeat(x1.astype(np.float16), 2, axis=0))
+    assert [t.shape for t in ys] == [(2, 255, 13, 13), (2, 255, 26, 26), (2, 255, 52, 52)]
+    for i, t in enumerate(ys):
+        ref = graphs_gold['yolov3_416_f32_n1.out%d' % i]
+        scale = float(graphs_gold['yolov3_416_f32_n1.absmax%d' % i])
+        err = float(np.abs(cases.sample(t[0]).astype(np.float64) - ref.astype(np.float64)).max() / scale)
+        assert err <= 1e-2, (i, err)
+        assert np.array_equal(t[0], t[1])

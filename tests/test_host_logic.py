@@ -1,0 +1,295 @@
+"""CPU tests of the host side: C-ABI surface, flow compiler (fusion / liveness / shapes / FLOPs), Net plumbing,
+model files, multi-process weight broadcast over gloo.  No GPU, no compute through the library."""
+import ctypes
+import io
+import json
+import os
+import re
+import contextlib
+
+import numpy as np
+import pytest
+
+import planer_oracle as oracle
+import planer_b200 as planer
+from planer_b200 import plan as P, zoo, _capi, dist
+from tests import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+@pytest.fixture(scope='module')
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    return _capi.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    """include/planer_b200.h is the contract: every declared function must be exported and bound."""
+    hdr = open(os.path.join(ROOT, 'include', 'planer_b200.h')).read()
+    declared = set(re.findall(r'\b(plnr_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 30
+    raw = ctypes.CDLL(_capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), 'header declares %s but the library does not export it' % name
+    assert declared - {'plnr_last_error'} == set(_capi.PROTOTYPES), 'ctypes binding and header differ'
+    assert lib.plnr_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header():
+    assert ctypes.sizeof(_capi.Tensor) == 32
+    assert ctypes.sizeof(_capi.ConvDesc) == 13 * 4
+    assert ctypes.sizeof(_capi.Epilogue) == 40
+    assert _capi.Epilogue.act.offset == 24 and _capi.Epilogue.res_after_act.offset == 32
+
+
+def test_no_cpu_fallback(lib):
+    """Without a GPU the product path must fail loudly, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(_capi.PlanerB200Error):
+        planer.b200.init()
+    with pytest.raises(NotImplementedError):
+        planer.core(np)
+    with pytest.raises(NotImplementedError):
+        planer.layer_map['softmax']
+    assert planer.core(planer.b200) is planer.b200
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'planer_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert 'planer_oracle' not in src and 'import oracle' not in src, fn
+
+
+# ---------------------------------------------------------------------------------------------
+# flow compiler
+# ---------------------------------------------------------------------------------------------
+
+def test_resnet18_plan_fuses_to_24_launch_steps():
+    model, _ = cases.get_model('resnet18')
+    gp = P.compile_graph(model, {'x': (128, 3, 224, 224)})
+    assert gp.summary() == {'conv': 20, 'maxpool': 1, 'gap': 1, 'flatten': 1, 'dense': 1}
+    # 3.627123 GFLOP conv + 0.001024 dense per image
+    assert gp.flops == 128 * 3628146688
+    fused = {s.name: s for s in gp.steps}
+    assert fused['conv1'].fused == ['conv1', 'bn1', 'relu'] and fused['conv1'].act == 1
+    blk = fused['layer1.0.conv2']
+    assert blk.fused == ['layer1.0.conv2', 'layer1.0.bn2', 'layer1.0.add', 'layer1.0.relu2'] and blk.res is not None
+    # downsample block: the 1x1 conv runs BEFORE conv2, which takes its output as residual
+    names = [s.name for s in gp.steps]
+    assert names.index('layer2.0.downsample.0') < names.index('layer2.0.conv2')
+    assert fused['layer2.0.downsample.0'].act == 0 and fused['layer2.0.conv2'].res is not None
+    assert gp.values[gp.outputs[0]].shape == (128, 1000)
+
+
+def test_yolov3_plan_shapes_and_darknet_shortcut_fusion():
+    model, _ = cases.get_model('yolov3_quarter')
+    consts = {n: np.array([1, 1, 2, 2], np.float32) for n, s, d in model['inits'] if 'scales' in n}
+    gp = P.compile_graph(model, {'x': (2, 3, 96, 96)}, consts)
+    assert gp.summary() == {'conv': 75, 'upsample': 2, 'concat': 2}       # 23 shortcut adds live in conv epilogues
+    assert sum(1 for s in gp.steps if s.res_after) == 23
+    assert [gp.values[o].shape for o in gp.outputs] == [(2, 255, 3, 3), (2, 255, 6, 6), (2, 255, 12, 12)]
+
+
+def test_yolov3_416_flops_match_survey():
+    shp = P.infer_shapes(*[zoo.yolov3(0)[0]], {'x': (1, 3, 416, 416)})
+    total = sum(n['flops'] for n in shp['nodes'])
+    assert abs(total / 1e9 - 65.864) < 0.01           # Darknet's 65.86 BFLOPs
+    assert shp['outputs'] == [(1, 255, 13, 13), (1, 255, 26, 26), (1, 255, 52, 52)]
+
+
+def test_fusion_respects_multiple_consumers_and_outputs():
+    b = zoo._Builder(0)
+    y = b.conv('x', 8, 8, 3)
+    r = b.op('relu', {}, [y])
+    z = b.op('add', {}, [r, y])          # y (== r after the in-place relu) is read twice
+    model, _ = b.finish(['x'], [z, r])
+    gp = P.compile_graph(model, {'x': (1, 8, 8, 8)})
+    # the in-place relu renames y -> r for every later reader (App. D Q4), so the conv output has ONE reader (the
+    # relu) and is folded; the add then reads the relu'd value twice, exactly what the reference computes
+    assert [s.op for s in gp.steps] == ['conv', 'add'] and gp.steps[0].act == 1
+    add = gp.steps[1]
+    assert add.ins[0] == add.ins[1] == gp.steps[0].out
+    # a second consumer of the PRE-activation value blocks the fold (leakyrelu is not in place)
+    b = zoo._Builder(0)
+    y = b.conv('x', 8, 8, 3)
+    r = b.op('leakyrelu', {'alpha': 0.1}, [y])
+    z = b.op('add', {}, [r, y])
+    model, _ = b.finish(['x'], [z])
+    gp = P.compile_graph(model, {'x': (1, 8, 8, 8)})
+    assert [s.op for s in gp.steps] == ['conv', 'leakyrelu', 'add']
+    # a graph output is never folded away
+    b = zoo._Builder(0)
+    y = b.conv('x', 8, 8, 3)
+    r = b.op('leakyrelu', {'alpha': 0.1}, [y])
+    model, _ = b.finish(['x'], [y, r])
+    gp = P.compile_graph(model, {'x': (1, 8, 8, 8)})
+    assert [s.op for s in gp.steps] == ['conv', 'leakyrelu']
+
+
+def test_liveness_reuses_buffers_but_never_outputs():
+    model, _ = cases.get_model('resnet18')
+    gp = P.compile_graph(model, {'x': (8, 3, 224, 224)})
+    P.assign_buffers(gp, 2, lambda v: gp.values[v].shape[1])
+    n_values = len({P._root(gp.values, s.out) for s in gp.steps})
+    assert len(gp.buffer_bytes) < n_values            # reuse happened
+    # no step may write a buffer that one of its own inputs lives in (unless it is the in-place alias)
+    for s in gp.steps:
+        out_b = gp.buffer_of.get(P._root(gp.values, s.out))
+        for r in s.reads():
+            rr = P._root(gp.values, r)
+            if rr != P._root(gp.values, s.out) and rr in gp.buffer_of:
+                assert gp.buffer_of[rr] != out_b, s.name
+
+
+def test_liveness_simulation_no_overlap():
+    """Replay the schedule: a buffer may be rewritten only after the last read of its previous tenant."""
+    model, _ = cases.get_model('yolov3_quarter')
+    consts = {n: np.array([1, 1, 2, 2], np.float32) for n, s, d in model['inits'] if 'scales' in n}
+    gp = P.compile_graph(model, {'x': (1, 3, 64, 64)}, consts)
+    P.assign_buffers(gp, 2, lambda v: gp.values[v].shape[1])
+    root = lambda v: P._root(gp.values, v)
+    last = {}
+    for pos, s in enumerate(gp.steps):
+        for r in s.reads():
+            last[root(r)] = pos
+    tenant = {}
+    for pos, s in enumerate(gp.steps):
+        o = root(s.out)
+        if o in gp.buffer_of:
+            b = gp.buffer_of[o]
+            prev = tenant.get(b)
+            if prev is not None and prev != o:
+                assert last.get(prev, -1) < pos, (s.name, prev, o)
+            tenant[b] = o
+
+
+def test_unknown_operator_raises_by_name():
+    model = {'input': ['x'], 'inits': [], 'layers': [['sm', 'softmax', {}]], 'flow': [['x', ['sm'], 'y']]}
+    with pytest.raises(NotImplementedError, match='softmax'):
+        P.compile_graph(model, {'x': (1, 10)})
+    with pytest.raises(NotImplementedError, match='softmax'):
+        planer.Net().load_json(model['input'], model['inits'], model['layers'], model['flow'])
+
+
+def test_bad_pads_rejected_like_documented():
+    model, _ = zoo.single_conv(8, 8, 3, pad=0)
+    model['layers'][0][2]['pads'] = [0, 0, 1, 1]
+    with pytest.raises(ValueError, match='undefined in the reference'):
+        P.compile_graph(model, {'x': (1, 8, 8, 8)})
+
+
+# ---------------------------------------------------------------------------------------------
+# Net plumbing: our front-end driving the oracle's numpy operator table must be BIT-IDENTICAL to the
+# reference Net (BASELINE config 1 "plumbing + bit-level correctness": IR parsing, blob slicing, flow
+# chaining, liveness).  The table/array module are injected by the test; the package itself has no CPU path.
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('name', ['readme_f32', 'readme_f16', 'resnet18_small_f32', 'yolov3_quarter_f32'])
+def test_net_plumbing_bit_exact_with_injected_numpy_table(name):
+    g = np.load(os.path.join(GOLD, 'graphs.npz'))
+    model, blob, x, half = cases.make_graph_case(name)
+    net = planer.Net(table=oracle.layer_map, array_module=np)
+    net.load_json(model['input'], model['inits'], model['layers'], model['flow'])
+    net.load_weights(blob)
+    if half:
+        net.half()
+    y = net(x.copy())
+    ys = y if isinstance(y, tuple) else (y,)
+    for i, t in enumerate(ys):
+        assert cases.sample(t).tobytes() == g['%s.out%d' % (name, i)].tobytes()
+    assert set(net.timer) >= {'conv'}
+
+
+def test_c1_single_conv_plumbing_bit_exact():
+    """BASELINE config 1 through the whole front-end (zoo IR -> Net -> op table) on numpy."""
+    ops_gold = np.load(os.path.join(GOLD, 'ops.npz'))
+    for name, pad in (('c1_conv_p0', 0), ('c1_conv_p1', 1)):
+        kind, (x, K, B), kw = cases.make_case(name)
+        model, _ = zoo.single_conv(3, 64, 3, 1, pad)
+        blob = np.concatenate([K.reshape(-1).view(np.uint8), B.view(np.uint8)])
+        net = planer.Net(table=oracle.layer_map, array_module=np)
+        net.load_json(model['input'], model['inits'], model['layers'], model['flow'])
+        net.load_weights(blob)
+        assert net(x.copy()).tobytes() == ops_gold[name].tobytes()
+
+
+def test_model_files_roundtrip(tmp_path):
+    """.json+.npy and .pla written by zoo.save_model carry the reference's format (planer/io.py:8-24,286)."""
+    import zipfile
+    model, blob = zoo.readme_net(0)
+    zoo.save_model(str(tmp_path / 'm'), model, blob)
+    zoo.save_model(str(tmp_path / 'p'), model, blob, pla=True)
+    assert np.load(tmp_path / 'm.npy').dtype == np.uint8 and np.load(tmp_path / 'm.npy').ndim == 1
+    body = json.load(open(tmp_path / 'm.json'))
+    assert set(body) == {'input', 'inits', 'layers', 'flow'}
+    with zipfile.ZipFile(tmp_path / 'p.pla') as z:
+        assert sorted(z.namelist()) == ['p.json', 'p.npy']
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        assert planer.read_net(str(tmp_path / 'missing')) is None     # planer/io.py:30-31
+    assert 'not found' in out.getvalue()
+    if os.path.isdir('/root/reference/planer'):
+        # the reference itself can read our files (only in the authoring container)
+        import subprocess, sys
+        code = ("import sys; sys.path.insert(0, '/root/reference'); import planer, numpy as np;"
+                "net = planer.read_net(%r); print(net(np.zeros((1,3,8,8),'float32')).shape)" % str(tmp_path / 'p'))
+        r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True,
+                           env=dict(os.environ, HOME=str(tmp_path), PYTHONDONTWRITEBYTECODE='1'))
+        assert '(1, 128, 8, 8)' in r.stdout, r.stderr[-500:]
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-process path on CPU: gloo, world_size 2
+# ---------------------------------------------------------------------------------------------
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as td
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    td.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        model, blob = zoo.readme_net(0)
+        total = blob.size
+        got = dist.broadcast_host_blob(blob if rank == 0 else None, total)      # only rank 0 holds the bytes
+        lo, hi = dist.shard_batch(5)
+        # each rank runs ITS shard through the (injected numpy) front-end; no collective on the forward path
+        net = planer.Net(table=oracle.layer_map, array_module=np)
+        net.load_json(model['input'], model['inits'], model['layers'], model['flow'])
+        net.load_weights(got)
+        x = np.random.default_rng(1).standard_normal((5, 3, 16, 16)).astype(np.float32)
+        y = net(x[lo:hi].copy())
+        t = dist.max_over_ranks(float(rank + 1))
+        q.put((rank, lo, hi, got.tobytes() == blob.tobytes(), y, t))
+    finally:
+        td.destroy_process_group()
+
+
+def test_gloo_world2_blob_broadcast_and_batch_shard():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda r: r[0])
+    for p in procs: p.join(60)
+    assert [(r[1], r[2]) for r in res] == [(0, 3), (3, 5)]
+    assert all(r[3] for r in res), 'rank did not receive the exact blob bytes'
+    assert all(r[5] == 2.0 for r in res)
+    model, blob = zoo.readme_net(0)
+    x = np.random.default_rng(1).standard_normal((5, 3, 16, 16)).astype(np.float32)
+    full = oracle.build_net(model, blob)(x.copy())
+    assert np.array_equal(np.concatenate([res[0][4], res[1][4]]), full)      # shards concatenate to the full batch
+
+
+def test_shard_batch_covers_everything():
+    for n in (1, 7, 128, 1024):
+        for w in (1, 2, 4, 8):
+            parts = [dist.shard_batch(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
