@@ -147,11 +147,12 @@ def per_kernel_profile(net, x_dev, flops_by_step, reps=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=BATCH, help='images per GPU (the headline config is 128)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--min-warm-sec', type=float, default=1.5, help='keep warming up at least this long (clock sampling)')
     ap.add_argument('--dump', default=None, help='write the per-kernel table to this JSON file')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -187,16 +188,23 @@ def main():
 
     ex = net.executor([shape])
     flops = ex.plan.flops
-    for i in range(warmup):
+    # clocks are sampled from the start of the warm-up to the end of the timed region: the same load throughout.
+    # The warm-up runs at least W steps AND at least ~1.5 s so that nvidia-smi (200 ms period) sees the loaded state.
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    t_w, i = time.perf_counter(), 0
+    while i < warmup or time.perf_counter() - t_w < args.min_warm_sec:
         net.forward(xs[i % N_INPUT_BUFFERS])
+        i += 1
+        if i % 50 == 0:
+            B.synchronize()
     B.synchronize()
+    warmup = i
 
     # ---- timed region: device events on the library stream, barrier + sync on both sides ----
     stream = B.stream()
-    clocks = ClockSampler(local)
     dist.barrier(); torch.cuda.synchronize()
-    if rank == 0:
-        clocks.start()
     l0 = B.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
@@ -240,11 +248,16 @@ def main():
                 'flops_per_step': flops, 'kernel_ms_per_step': conv_ms, 'kernel_share_of_step': conv_ms / all_ms,
                 'whole_step_frac': (flops * steps / (ms_total / 1e3) / 1e12) / pk['tflops_sustained']}
     if args.dump:
-        convs = iter(conv_nodes)
+        by_name = {n.name: n for n in conv_nodes}
+        launched = iter([s for s in ex.plan.steps if s.op not in ('alias',) and not (s.op == 'flatten' and ex.values[s.out].alias_of is not None)])
         for r in table:
+            if r['kind'] == 'to_nchw':
+                continue
+            st = next(launched)
+            r['name'] = '+'.join(st.fused)
             if r['kind'] in ('conv', 'dense'):
-                nd = next(convs)
-                r.update(name=nd.name, gflop=nd.flops / 1e9, tflops=nd.flops / (r['ms'] / 1e3) / 1e12)
+                nd = by_name[st.name]
+                r.update(gflop=nd.flops / 1e9, tflops=nd.flops / (r['ms'] / 1e3) / 1e12)
         with open(args.dump, 'w') as f:
             json.dump({'batch': args.batch, 'table': table}, f, indent=1)
 

@@ -19,6 +19,7 @@
 //
 // K is walked in "units" of kc input channels of one filter tap (kc = 64/32/16 -> 128B/64B/32B swizzle); a
 // pipeline stage holds 64/kc units, i.e. always 64 k-values = one 128-byte row per pixel / per output channel.
+#include <stdlib.h>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -461,6 +462,10 @@ int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tenso
     ctx->igemm_attr_set = true;
   }
   int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
+  if (const char* cap = getenv("PLNR_MAX_CTAS")) {        // experiment knob: restrict the persistent grid
+    int c = atoi(cap);
+    if (c > 0 && c < grid) grid = c;
+  }
   conv_igemm_f16_kernel<<<grid, kThreads, smem_bytes, ctx->stream>>>(mapA, mapB, p);
   return plnr_after_launch(ctx, "conv2d_tcgen05");
 }

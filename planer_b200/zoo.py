@@ -52,10 +52,10 @@ class _Builder:
         attrs = {'group': group, 'strides': [stride, stride], 'dilations': [dil, dil], 'pads': [pad] * 4}
         return self.op('conv', attrs, ins, name=name)
 
-    def bn(self, x, c, name=None):
+    def bn(self, x, c, name=None, gamma_scale=1.0):
         """Random (gamma, beta, mean, var) folded exactly like planer/io.py:76-91."""
         name = name or 'bn_%d' % (self.uid + 1)
-        gamma = self.rng.uniform(0.5, 1.5, c).astype(np.float32)
+        gamma = (self.rng.uniform(0.5, 1.5, c) * gamma_scale).astype(np.float32)
         beta = (self.rng.standard_normal(c) * 0.1).astype(np.float32)
         mean = (self.rng.standard_normal(c) * 0.1).astype(np.float32)
         var = self.rng.uniform(0.5, 1.5, c).astype(np.float32)
@@ -143,9 +143,9 @@ def yolov3(seed=0, num_out=255, width=1.0):
     b = _Builder(seed)
     ch = lambda c: max(8, int(c * width))
 
-    def cbl(x, cin, cout, k, stride=1):
+    def cbl(x, cin, cout, k, stride=1, gamma_scale=1.0):
         y = b.conv(x, cin, cout, k, stride)
-        y = b.bn(y, cout)
+        y = b.bn(y, cout, gamma_scale=gamma_scale)
         return b.op('leakyrelu', {'alpha': 0.1}, [y])
 
     x = cbl('x', 3, ch(32), 3)
@@ -155,8 +155,8 @@ def yolov3(seed=0, num_out=255, width=1.0):
         x = cbl(x, cin, c, 3, 2)
         for _ in range(n_res):
             y = cbl(x, c, c // 2, 1)
-            y = cbl(y, c // 2, c, 3)
-            x = b.op('add', {}, [x, y])
+            y = cbl(y, c // 2, c, 3, gamma_scale=0.3)     # damped residual branch: 23 shortcut adds would
+            x = b.op('add', {}, [x, y])                   # otherwise grow activations past the fp16 range
         cin = c
         routes.append((x, c))
 

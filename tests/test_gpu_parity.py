@@ -172,7 +172,7 @@ def test_resnet18_fp16_batch128_batch_independence(planer):
 
 def test_big_conv_tcgen05_equals_direct_and_is_linear(planer):
     """layer1-sized conv at batch 128 (M = 401 408): the tensor-core kernel agrees with the direct kernel, and
-    conv(2x) == 2 conv(x) exactly in fp16 (power-of-two scaling commutes with every rounding)."""
+    conv(2x) == 2 conv(x) exactly in fp16 (power-of-two scaling commutes with every rounding of normal numbers)."""
     from planer_b200 import ops, backend as B
     rng = np.random.default_rng(11)
     x = rng.standard_normal((128, 64, 56, 56)).astype(np.float16)
@@ -187,7 +187,10 @@ def test_big_conv_tcgen05_equals_direct_and_is_linear(planer):
     B.synchronize()
     a, b, c = ya.get(), yb.get(), yc.get()
     assert rel_err(a, b) < 2e-3
-    assert np.array_equal(c, a * np.float16(2))
+    # exact wherever the fp16 result is a normal number (below 2^-14 the subnormal grid breaks the commutation)
+    normal = np.abs(a) >= np.float16(2.0 ** -13)
+    assert np.array_equal(c[normal], (a * np.float16(2))[normal])
+    assert np.abs(c.astype(np.float32) - 2 * a.astype(np.float32)).max() <= 2.0 ** -22
 
 
 def test_yolov3_fp16_batch_runs_and_matches_fp32_golden(planer, graphs_gold):
