@@ -164,6 +164,10 @@ int plnr_event_elapsed_ms(plnr_event* start, plnr_event* stop, float* ms);   /* 
 int plnr_event_destroy(plnr_event* ev);
 
 /* ---- diagnostics -------------------------------------------------------------------------- */
+/* Debug aid: per-CTA cycle counters of the last tensor-core conv launch, 8 int64 per CTA:
+ * [0] producer wait-for-empty, [1] producer total, [2] MMA wait-for-full, [3] MMA wait-for-accumulator,
+ * [4] MMA total, [5] epilogue wait-for-accumulator, [6] epilogue total.  enable=1 arms it, out (host) may be NULL. */
+int plnr_debug_conv_profile(plnr_ctx* ctx, int enable, int64_t* out, int n);
 /* Which kernel plnr_conv2d_fwd would pick for this problem: PLNR_ALGO_TCGEN05 or PLNR_ALGO_DIRECT. */
 int plnr_conv2d_algo(const plnr_conv_desc* desc, const plnr_tensor* x, const plnr_tensor* y);
 

@@ -71,6 +71,7 @@ PROTOTYPES = {
     'plnr_event_elapsed_ms': [_P, _P, C.POINTER(C.c_float)],
     'plnr_event_destroy': [_P],
     'plnr_conv2d_algo': [C.POINTER(ConvDesc), _TP, _TP],
+    'plnr_debug_conv_profile': [_P, C.c_int, C.POINTER(C.c_int64), C.c_int],
 }
 
 _lib = None

@@ -78,6 +78,20 @@ int plnr_stream_sync(plnr_ctx* ctx) {
   return PLNR_OK;
 }
 
+int plnr_debug_conv_profile(plnr_ctx* ctx, int enable, int64_t* out, int n) {
+  PLNR_REQUIRE(ctx, "plnr_debug_conv_profile: ctx is NULL");
+  if (enable && !ctx->prof) {
+    PLNR_CHECK_CUDA(cudaMalloc(&ctx->prof, sizeof(long long) * 8 * 256));
+    PLNR_CHECK_CUDA(cudaMemset(ctx->prof, 0, sizeof(long long) * 8 * 256));
+  }
+  if (out && ctx->prof) {
+    PLNR_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLNR_CHECK_CUDA(cudaMemcpy(out, ctx->prof, sizeof(long long) * (n < 2048 ? n : 2048), cudaMemcpyDeviceToHost));
+  }
+  if (!enable && ctx->prof) { cudaFree(ctx->prof); ctx->prof = nullptr; }
+  return PLNR_OK;
+}
+
 int plnr_launch_count(plnr_ctx* ctx, int64_t* out) {
   PLNR_REQUIRE(ctx && out, "plnr_launch_count: NULL argument");
   *out = ctx->launches;

@@ -24,6 +24,7 @@ struct plnr_ctx {
   int64_t capture_launches = 0;    // kernels recorded into the graph being captured
   // device-side error word written by kernels that time out on a barrier (debug aid)
   int* dev_error = nullptr;
+  long long* prof = nullptr;       // debug: per-CTA role cycle counters of the last tcgen05 conv launch
   bool igemm_attr_set = false;     // cudaFuncSetAttribute(max dynamic smem) done for this device
   // cache of TMA descriptors keyed by a byte string of their parameters
   std::unordered_map<std::string, CUtensorMap> tmap_cache;

@@ -50,6 +50,7 @@ struct IgemmParams {
   int act; float alpha; int res_after;
   int vec_ok;
   int* err;
+  long long* prof;   // optional [grid][8] cycle counters per role (debug)
 };
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int role) {
@@ -118,72 +119,98 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
-        const int m0 = m_idx * kTileM;
-        const int q0 = m0 % p.OW;
-        const int t1 = m0 / p.OW;
-        const int p0 = t1 % p.OH, img = t1 / p.OH;
-        const int cw = q0 * p.sw - p.pad_l, chh = p0 * p.sh - p.pad_t;   // base input coordinate of the tile's first pixel
-        int r = 0, sx = 0, cc = 0;                                       // filter row / column / channel chunk of the next unit
-        int u = 0;
-        for (int j = 0; j < p.kstages; ++j) {
-          mbar_wait(bar_empty + 8 * s, ph ^ 1, p.err, 0);
-          const int nu = min(p.tps, p.units - u);
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)nu * p.a_unit_bytes + p.b_stage_bytes);
-          const uint32_t a_dst = sA + s * kAStageBytes;
+    // The whole warp walks the loop (converged, so address arithmetic stays on the uniform datapath); one elected
+    // lane issues the TMA instructions.
+    uint32_t s = 0, ph = 0;
+    long long t_wait = 0;
+    const long long t_all0 = clock64();
+    const int tps = p.tps, units = p.units, cchunks = p.cchunks, kc = p.kc, S = p.S, dw = p.dw, dh = p.dh;
+    const uint32_t a_unit_bytes = p.a_unit_bytes, b_stage_bytes = p.b_stage_bytes;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
+      const int m0 = m_idx * kTileM;
+      const int q0 = m0 % p.OW;
+      const int t1 = m0 / p.OW;
+      const int p0 = t1 % p.OH, img = t1 / p.OH;
+      const int cw = q0 * p.sw - p.pad_l, chh = p0 * p.sh - p.pad_t;   // input coordinate of the tile's first pixel
+      const int n_row = n_idx * p.n_tile;
+      int r = 0, sx = 0, cc = 0, u = 0;                                // filter row / column / channel chunk of the next unit
+      for (int j = 0; j < p.kstages; ++j) {
+        const long long tw0 = clock64();
+        mbar_wait(bar_empty + 8 * s, ph ^ 1, p.err, 0);
+        t_wait += clock64() - tw0;
+        const int nu = min(tps, units - u);
+        if (ptx::elect_one()) {
+          const uint32_t full = bar_full + 8 * s;
+          ptx::mbar_arrive_expect_tx(full, (uint32_t)nu * a_unit_bytes + b_stage_bytes);
+          uint32_t a_dst = sA + s * kAStageBytes;
+          int r2 = r, sx2 = sx, cc2 = cc;
           for (int t = 0; t < nu; ++t) {
-            ptx::tma_load_im2col_4d(a_dst + t * p.a_unit_bytes, &mapA, bar_full + 8 * s, cc * p.kc, cw, chh, img,
-                                    (uint16_t)(sx * p.dw), (uint16_t)(r * p.dh));
-            if (++cc == p.cchunks) { cc = 0; if (++sx == p.S) { sx = 0; ++r; } }
+            ptx::tma_load_im2col_4d(a_dst, &mapA, full, cc2 * kc, cw, chh, img, (uint16_t)(sx2 * dw), (uint16_t)(r2 * dh));
+            a_dst += a_unit_bytes;
+            if (++cc2 == cchunks) { cc2 = 0; if (++sx2 == S) { sx2 = 0; ++r2; } }
           }
-          u += nu;
-          ptx::tma_load_2d(sB + s * p.b_stage_bytes, &mapB, bar_full + 8 * s, j * 64, n_idx * p.n_tile);
-          if (++s == stages) { s = 0; ph ^= 1; }
+          ptx::tma_load_2d(sB + s * b_stage_bytes, &mapB, full, j * 64, n_row);
         }
+        __syncwarp();
+        for (int t = 0; t < nu; ++t) { if (++cc == cchunks) { cc = 0; if (++sx == S) { sx = 0; ++r; } } }
+        u += nu;
+        if (++s == stages) { s = 0; ph ^= 1; }
       }
     }
-    __syncwarp();
+    if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 0] = t_wait; p.prof[blockIdx.x * 8 + 1] = clock64() - t_all0; }
   } else if (warp == 1) {
     // ===================================== MMA issuer =========================================
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0, it = 0;
-      const int kper = p.kc >> 4;   // MMAs (K=16) per unit
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t a = it & 1, aph = (it >> 1) & 1;
-        mbar_wait(bar_tempty + 8 * a, aph ^ 1, p.err, 1);   // epilogue has drained this accumulator
+    // Converged warp; one elected lane issues tcgen05.mma / tcgen05.commit.  Descriptors are advanced by adding
+    // to their 14-bit (address >> 4) field: +2 per K=16 step (32 bytes), a constant per stage.
+    uint32_t s = 0, ph = 0, it = 0;
+    long long t_full = 0, t_tempty = 0;
+    const long long t_all0 = clock64();
+    const int kper = p.kc >> 4, tps = p.tps, units = p.units;
+    const uint32_t idesc = p.idesc;
+    const uint64_t adesc0 = ptx::make_smem_desc(sA, p.a_sbo, p.a_layout);
+    const uint64_t bdesc0 = ptx::make_smem_desc(sB, 1024, 2);
+    const uint32_t a_step = kAStageBytes >> 4, b_step = p.b_stage_bytes >> 4;
+    const uint32_t a_unit_skip = (p.a_unit_bytes - (uint32_t)kper * 32u) >> 4;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t a = it & 1, aph = (it >> 1) & 1;
+      const long long te0 = clock64();
+      mbar_wait(bar_tempty + 8 * a, aph ^ 1, p.err, 1);   // epilogue has drained this accumulator
+      t_tempty += clock64() - te0;
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + a * (uint32_t)p.n_tile;
+      int u = 0;
+      for (int j = 0; j < p.kstages; ++j) {
+        const long long tf0 = clock64();
+        mbar_wait(bar_full + 8 * s, ph, p.err, 2);        // TMA bytes have landed
+        t_full += clock64() - tf0;
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + a * (uint32_t)p.n_tile;
-        uint32_t accumulate = 0;
-        int u = 0;
-        for (int j = 0; j < p.kstages; ++j) {
-          mbar_wait(bar_full + 8 * s, ph, p.err, 2);        // TMA bytes have landed
-          ptx::tc_fence_after();
-          const int nu = min(p.tps, p.units - u);
-          const uint32_t a_src = sA + s * kAStageBytes, b_src = sB + s * p.b_stage_bytes;
+        const int nu = min(tps, units - u);
+        if (ptx::elect_one()) {
+          uint64_t da = adesc0 + (uint64_t)(s * a_step), db = bdesc0 + (uint64_t)(s * b_step);
+          uint32_t acc = j > 0 ? 1u : 0u;
           for (int t = 0; t < nu; ++t) {
             for (int k = 0; k < kper; ++k) {
-              const uint64_t da = ptx::make_smem_desc(a_src + t * p.a_unit_bytes + k * 32, p.a_sbo, p.a_layout);
-              const uint64_t db = ptx::make_smem_desc(b_src + (t * p.kc + k * 16) * 2, 1024, 2);
-              ptx::umma_f16(d_tmem, da, db, p.idesc, accumulate);
-              accumulate = 1;
+              ptx::umma_f16(d_tmem, da, db, idesc, acc);
+              acc = 1u; da += 2; db += 2;
             }
+            da += a_unit_skip;
           }
-          u += nu;
-          ptx::umma_commit(bar_empty + 8 * s);              // smem slot reusable once these MMAs retire
-          if (++s == stages) { s = 0; ph ^= 1; }
+          ptx::umma_commit(bar_empty + 8 * s);            // smem slot reusable once these MMAs retire
+          if (j == p.kstages - 1) ptx::umma_commit(bar_tfull + 8 * a);   // accumulator complete -> epilogue
         }
-        ptx::umma_commit(bar_tfull + 8 * a);                // accumulator complete -> epilogue
+        __syncwarp();
+        u += nu;
+        if (++s == stages) { s = 0; ph ^= 1; }
       }
     }
-    __syncwarp();
+    if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 2] = t_full; p.prof[blockIdx.x * 8 + 3] = t_tempty; p.prof[blockIdx.x * 8 + 4] = clock64() - t_all0; }
   } else if (warp >= 4) {
     // ===================================== epilogue ===========================================
     const int ew = warp - 4;                 // == warp % 4: the TMEM lane quarter this warp may read
     const int et = threadIdx.x - 128;        // 0..127
     uint32_t it = 0;
+    long long t_tfull = 0, t_all0 = clock64();
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t a = it & 1, aph = (it >> 1) & 1;
       const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
@@ -198,7 +225,9 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
 
+      const long long tt0 = clock64();
       mbar_wait(bar_tfull + 8 * a, aph, p.err, 3);
+      t_tfull += clock64() - tt0;
       ptx::tc_fence_after();
 
       const int m = m_idx * kTileM + ew * 32 + lane;
@@ -275,7 +304,9 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         }
       }
     }
+    if (p.prof && threadIdx.x == 128) { p.prof[blockIdx.x * 8 + 5] = t_tfull; p.prof[blockIdx.x * 8 + 6] = clock64() - t_all0; }
   }
+
 
   // ---- teardown: everyone is done with TMEM before the allocator warp frees it ----
   ptx::tc_fence_before();
@@ -416,6 +447,7 @@ int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tenso
   }
   p.vec_ok = vec ? 1 : 0;
   p.err = ctx->dev_error;
+  p.prof = ctx->prof;
 
   // ---- activation map: im2col over (C, W, H, N) ----
   CUtensorMap mapA, mapB;
