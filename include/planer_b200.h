@@ -105,6 +105,12 @@ int plnr_memset(plnr_ctx* ctx, void* dst, int value, size_t bytes);
 /* NCHW (dense, x_dtype) -> pixel-major view y (y_dtype); channels [c, y.c) of y are zero-filled
  * (channel padding for the tensor-core path).  Graph entry: planer/net.py:96-98. */
 int plnr_nchw_to_nhwc(plnr_ctx* ctx, const void* x, int x_dtype, int c_src, const plnr_tensor* y, int y_dtype);
+/* First-layer input packing (fp16 out): NCHW x (n,c,h,w; few channels) -> y[n, h2, ow, (ph*kw + sx)*c + ci] =
+ * x[n, ci, stride*h2 + ph, stride*ow + sx - pad_l] (zero outside), so that a kh x kw / stride-s convolution of the
+ * graph input (planer/layer.py:22-26 on the raw image) runs as a (T x 1) stride-1 convolution over y with the
+ * filter taps re-ordered accordingly by the host (planer_b200/executor.py).  y->c >= stride*kw*c, multiple of 8. */
+int plnr_stem_pack(plnr_ctx* ctx, const void* x, int x_dtype, int n, int c, int h, int w, const plnr_tensor* y, int kw,
+                   int stride, int pad_l);
 /* pixel-major view x -> NCHW dense y.  Graph exit: planer/net.py:100. */
 int plnr_nhwc_to_nchw(plnr_ctx* ctx, const plnr_tensor* x, int x_dtype, void* y, int y_dtype);
 /* flat cast, n elements (Net.half, planer/net.py:26-29). */

@@ -51,6 +51,7 @@ PROTOTYPES = {
     'plnr_memcpy_d2h': [_P, _P, _P, C.c_size_t],
     'plnr_memset': [_P, _P, C.c_int, C.c_size_t],
     'plnr_nchw_to_nhwc': [_P, _P, C.c_int, C.c_int, _TP, C.c_int],
+    'plnr_stem_pack': [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _TP, C.c_int, C.c_int, C.c_int],
     'plnr_nhwc_to_nchw': [_P, _TP, C.c_int, _P, C.c_int],
     'plnr_cast': [_P, _P, C.c_int, _P, C.c_int, C.c_int64],
     'plnr_pack_conv_weight': [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],

@@ -68,6 +68,53 @@ __global__ void nhwc_to_nchw_kernel(const Tin* __restrict__ x, Tout* __restrict_
   }
 }
 
+// Stem packing: NCHW input (few channels) -> pixel-major tensor whose "channels" are the horizontal filter taps x
+// vertical stride phases x input channels of one output column, so that a k x k / stride-s convolution becomes a
+// (T x 1) stride-1 convolution with 16/32/64 channels (one TMA row per pixel instead of k*k tiny ones).
+//   y[n, h2, ow, (ph*kw + sx)*C + c] = x[n, c, s*h2 + ph, s*ow + sx - pad_l]      (0 outside the image)
+template <typename Tin>
+__global__ void __launch_bounds__(256) stem_pack_kernel(const Tin* __restrict__ x, __half* __restrict__ y, int N, int C,
+                                                         int H, int W, int H2, int OW, int CP, int kw, int s, int pad_l,
+                                                         int Wp) {
+  // one CTA per packed row (n, h2): stage the s*C source rows in shared memory (coalesced reads), then emit the
+  // OW * CP packed values as 16-byte stores (coalesced writes).  tab[ch] = offset of packed channel ch in `rows`.
+  extern __shared__ __half stem_smem[];
+  __half* rows = stem_smem;                       // [s*C][Wp], column j holds input column j - pad_l
+  int* tab = reinterpret_cast<int*>(stem_smem + ((s * C * Wp + 7) / 8) * 8);
+  const int n = blockIdx.x / H2, h2 = blockIdx.x % H2;
+  const int real = s * kw * C;
+  for (int i = threadIdx.x; i < s * C * Wp; i += blockDim.x) {
+    const int j = i % Wp, rc = i / Wp;
+    const int c = rc % C, ph = rc / C;
+    const int ih = s * h2 + ph, iw = j - pad_l;
+    float v = 0.f;
+    if (ih < H && iw >= 0 && iw < W) v = ld_f(x + (((size_t)n * C + c) * H + ih) * W + iw);
+    rows[i] = __float2half_rn(v);
+  }
+  for (int ch = threadIdx.x; ch < CP; ch += blockDim.x) {
+    int off = -1;
+    if (ch < real) {
+      const int c = ch % C, tap = ch / C;
+      const int sx = tap % kw, ph = tap / kw;
+      off = (ph * C + c) * Wp + sx;
+    }
+    tab[ch] = off;
+  }
+  __syncthreads();
+  const int groups = CP / 8;
+  __half* yrow = y + ((size_t)n * H2 + h2) * OW * CP;
+  for (int i = threadIdx.x; i < OW * groups; i += blockDim.x) {
+    const int g = i % groups, ow = i / groups;
+    Vec<__half, 8> o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int off = tab[g * 8 + j];
+      o.v[j] = off >= 0 ? rows[off + s * ow] : __float2half_rn(0.f);
+    }
+    *reinterpret_cast<Vec<__half, 8>*>(yrow + (size_t)ow * CP + g * 8) = o;
+  }
+}
+
 template <typename Tin, typename Tout>
 __global__ void cast_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -106,10 +153,13 @@ __global__ void fold_affine_kernel(const T* __restrict__ bias, const T* __restri
 // ---------------------------------------------------------------------------------------------
 // maxpool: zero padding + -1e4 floor (planer/util.py:79-95)
 // ---------------------------------------------------------------------------------------------
-template <typename T, int V>
+template <typename T, int V, int KH, int KW>
 __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int xld,
-                               int xcoff, int OH, int OW, int yld, int ycoff, int kh, int kw, int pt, int pl, int sh,
-                               int sw) {
+                               int xcoff, int OH, int OW, int yld, int ycoff, int kh_rt, int kw_rt, int pt, int pl,
+                               int sh, int sw) {
+  // KH/KW > 0: compile-time window, every tap is an unconditional (clamped) 16-byte load so that all KH*KW loads
+  // are in flight together; out-of-image taps contribute 0 (the reference zero-pads), the accumulator starts at -1e4.
+  const int kh = KH > 0 ? KH : kh_rt, kw = KW > 0 ? KW : kw_rt;
   const int CV = C / V;
   const int64_t total = (int64_t)N * OH * OW * CV;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -122,18 +172,36 @@ __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int N
     float m[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) m[k] = -1e4f;
-    for (int r = 0; r < kh; ++r) {
-      int ih = oh * sh + r - pt;
-      for (int s = 0; s < kw; ++s) {
-        int iw = ow * sw + s - pl;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-          const Vec<T, V> v =
-              *reinterpret_cast<const Vec<T, V>*>(x + (((size_t)n * H + ih) * W + iw) * xld + xcoff + cv * V);
+    const T* xb = x + (size_t)n * H * W * xld + xcoff + cv * V;
+    if (KH > 0) {
+      Vec<T, V> v[(KH > 0 ? KH : 1) * (KW > 0 ? KW : 1)];
+      bool ok[(KH > 0 ? KH : 1) * (KW > 0 ? KW : 1)];
 #pragma unroll
-          for (int k = 0; k < V; ++k) m[k] = fmaxf(m[k], ld_f(&v.v[k]));
-        } else {
+      for (int r = 0; r < KH; ++r)
 #pragma unroll
-          for (int k = 0; k < V; ++k) m[k] = fmaxf(m[k], 0.f);  // the reference pads with ZERO, not -inf
+        for (int q = 0; q < KW; ++q) {
+          const int ih = oh * sh + r - pt, iw = ow * sw + q - pl;
+          ok[r * KW + q] = ih >= 0 && ih < H && iw >= 0 && iw < W;
+          const int ihc = min(max(ih, 0), H - 1), iwc = min(max(iw, 0), W - 1);
+          v[r * KW + q] = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)ihc * W + iwc) * xld);
+        }
+#pragma unroll
+      for (int j = 0; j < KH * KW; ++j)
+#pragma unroll
+        for (int k = 0; k < V; ++k) m[k] = fmaxf(m[k], ok[j] ? ld_f(&v[j].v[k]) : 0.f);
+    } else {
+      for (int r = 0; r < kh; ++r) {
+        int ih = oh * sh + r - pt;
+        for (int q = 0; q < kw; ++q) {
+          int iw = ow * sw + q - pl;
+          if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+            const Vec<T, V> v = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)ih * W + iw) * xld);
+#pragma unroll
+            for (int k = 0; k < V; ++k) m[k] = fmaxf(m[k], ld_f(&v.v[k]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < V; ++k) m[k] = fmaxf(m[k], 0.f);  // the reference pads with ZERO, not -inf
+          }
         }
       }
     }
@@ -249,6 +317,26 @@ int plnr_nchw_to_nhwc(plnr_ctx* ctx, const void* x, int x_dtype, int c_src, cons
   return plnr_after_launch(ctx, "nchw_to_nhwc");
 }
 
+int plnr_stem_pack(plnr_ctx* ctx, const void* x, int x_dtype, int n, int c, int h, int w, const plnr_tensor* y, int kw,
+                   int stride, int pad_l) {
+  PLNR_REQUIRE(ctx && x && y && y->ptr, "stem_pack: NULL argument");
+  PLNR_REQUIRE(stride >= 1 && kw >= 1 && c >= 1 && stride * kw * c <= y->c && y->c % 8 == 0 && y->ld == y->c &&
+                   y->coff == 0 && y->n == n, "stem_pack: packed channel count %d cannot hold %d x %d x %d taps",
+               y->c, stride, kw, c);
+  PLNR_REQUIRE(aligned16(y->ptr), "stem_pack: output must be 16-byte aligned");
+  const int Wp = stride * (y->w - 1) + kw;                 // widest source column index + 1 (in padded coordinates)
+  const size_t smem = (size_t)((stride * c * Wp + 7) / 8) * 8 * 2 + (size_t)y->c * 4;
+  PLNR_REQUIRE(smem <= 48 * 1024, "stem_pack: source rows do not fit shared memory (%zu bytes)", smem);
+  const int grid = n * y->h;
+  if (x_dtype == PLNR_F16)
+    stem_pack_kernel<__half><<<grid, 256, smem, ctx->stream>>>((const __half*)x, (__half*)y->ptr, n, c, h, w, y->h, y->w,
+                                                               y->c, kw, stride, pad_l, Wp);
+  else
+    stem_pack_kernel<float><<<grid, 256, smem, ctx->stream>>>((const float*)x, (__half*)y->ptr, n, c, h, w, y->h, y->w,
+                                                              y->c, kw, stride, pad_l, Wp);
+  return plnr_after_launch(ctx, "stem_pack");
+}
+
 int plnr_nhwc_to_nchw(plnr_ctx* ctx, const plnr_tensor* x, int x_dtype, void* y, int y_dtype) {
   PLNR_REQUIRE(ctx && x && x->ptr && y, "nhwc_to_nchw: NULL argument");
   const int HW = x->h * x->w;
@@ -310,20 +398,23 @@ int plnr_maxpool2d(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_te
   PLNR_REQUIRE(x->n == y->n && x->c == y->c, "maxpool2d: batch/channel mismatch");
   PLNR_REQUIRE(kh >= 1 && kw >= 1 && stride_h >= 1 && stride_w >= 1 && pad_t >= 0 && pad_l >= 0, "maxpool2d: bad window");
   int64_t work;
+#define MP_LAUNCH(VV, KH_, KW_)                                                                                         \
+  maxpool_kernel<T, VV, KH_, KW_><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(                    \
+      (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, kh, kw, pad_t, \
+      pad_l, stride_h, stride_w)
   DISPATCH_T(dtype, {
     constexpr int V = VecWidth<T>::value;
     if (view_vec_ok(x, V, sizeof(T)) && view_vec_ok(y, V, sizeof(T))) {
       work = (int64_t)y->n * y->h * y->w * (y->c / V);
-      maxpool_kernel<T, V><<<grid_for(work, ctx->sm_count), kThreads, 0, ctx->stream>>>(
-          (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, kh, kw,
-          pad_t, pad_l, stride_h, stride_w);
+      if (kh == 3 && kw == 3) MP_LAUNCH(V, 3, 3);
+      else if (kh == 2 && kw == 2) MP_LAUNCH(V, 2, 2);
+      else MP_LAUNCH(V, 0, 0);
     } else {
       work = (int64_t)y->n * y->h * y->w * y->c;
-      maxpool_kernel<T, 1><<<grid_for(work, ctx->sm_count), kThreads, 0, ctx->stream>>>(
-          (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, kh, kw,
-          pad_t, pad_l, stride_h, stride_w);
+      MP_LAUNCH(1, 0, 0);
     }
   })
+#undef MP_LAUNCH
   return plnr_after_launch(ctx, "maxpool2d");
 }
 

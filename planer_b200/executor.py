@@ -56,13 +56,31 @@ class Executor:
                     return c
         return _round_up(c, 16)
 
+    def _stem_of(self, vid):
+        """The conv step that can absorb graph input ``vid`` through ``plnr_stem_pack`` (few input channels, fp16):
+        its filter taps along W, its stride phases along H and the input channels become the packed channels."""
+        v = self.values[vid]
+        if self.dtype != np.float16 or len(v.shape) != 4:
+            return None
+        users = [st for st in self.plan.steps if vid in [self._root(r) for r in st.reads()]]
+        if len(users) != 1 or users[0].op != 'conv' or self._root(users[0].ins[0]) != vid or v.is_output:
+            return None
+        st, a = users[0], users[0].attrs
+        kshape = self.values[st.w].shape
+        s = a['strides'][0]
+        if a['group'] != 1 or a['dilations'] != (1, 1) or a['strides'][0] != a['strides'][1] or s not in (1, 2):
+            return None
+        if s * kshape[3] * v.shape[1] > 64 or v.shape[1] % 16 == 0:
+            return None
+        return st
+
     def _get(self, vid):
         return self.arr[self._root(vid)]
 
     def _view(self, vid):
         """DeviceArray of value ``vid`` with ITS logical shape on its root's storage."""
         a, v = self._get(vid), self.values[vid]
-        if a.shape == v.shape:
+        if a.shape == v.shape or self._root(vid) in getattr(self, 'stems', {}):
             return a
         if a.layout == 'nhwc' and len(v.shape) == 2:          # flatten of an (N,C,1,1) map
             return DeviceArray(a.buf, v.shape, a.dtype, 'flat', offset=a.offset)
@@ -89,9 +107,18 @@ class Executor:
             return self.arr[r]
 
         # graph inputs: pixel-major staging filled by an eager transform at every forward
+        self.stems = {}
         for vid in self.input_ids:
             shp = vals[vid].shape
-            if len(shp) == 4:
+            st = self._stem_of(vid)
+            if st is not None:
+                kshape, at = vals[st.w].shape, st.attrs
+                g = ops.stem_geometry(shp[2], shp[3], kshape[2], kshape[3], at['strides'][0], at['pads'])
+                real = at['strides'][0] * kshape[3] * shp[1]
+                cp = 16 if real <= 16 else (32 if real <= 32 else 64)
+                a = B.empty((shp[0], cp, g['h2'], g['ow']), dt, 'nhwc')
+                self.stems[vid] = dict(step=st, geom=g, cp=cp, kw=kshape[3], stride=at['strides'][0], pad_l=at['pads'][1])
+            elif len(shp) == 4:
                 cp = self._input_cpad(vid)
                 a = B.empty((shp[0], cp, shp[2], shp[3]), dt, 'nhwc')
             else:
@@ -134,6 +161,16 @@ class Executor:
             res = self._view(st.res) if st.res is not None else None
             y = alloc(st.out)
             self._keep += [scale, shift]
+            stem = self.stems.get(self._root(st.ins[0])) if op == 'conv' else None
+            if stem is not None:
+                # first layer on the packed input: (T x 1) stride-1 conv, taps re-ordered on the host (tiny, load time)
+                g = stem['geom']
+                w2 = ops.stem_pack_weight(K.get().astype(np.float16), stem['stride'], st.attrs['pads'], stem['cp'])
+                wp = B.asarray(w2)
+                self._keep.append(wp)
+                pads2 = (g['pad_t2'], 0, g['pad_b2'], 0)
+                return lambda: ops.conv2d_into(x, wp, y, g['T'], 1, (1, 1), (1, 1), pads2, 1, scale, shift, res,
+                                               st.act, st.alpha, res_after_act=st.res_after)
             if op == 'conv':
                 a = st.attrs
                 g = a['group']
@@ -201,7 +238,10 @@ class Executor:
                 raise ValueError('input %r: plan compiled for shape %s, got %s' % (self.values[vid].name, shp, x.shape))
             if x.layout != 'flat':
                 x = B.to_flat(x)
-            if len(shp) == 4:
+            if vid in self.stems:
+                sm = self.stems[vid]
+                ops.stem_pack_into(x, a, sm['kw'], sm['stride'], sm['pad_l'])
+            elif len(shp) == 4:
                 ops.nchw_to_nhwc_into(x, a, shp[1])
             else:
                 _capi.check(B.lib().plnr_cast(B.ctx(), x.ptr, _capi.dtype_code(x.dtype), a.ptr,

@@ -154,6 +154,46 @@ def nchw_to_nhwc_into(x_flat, y, c_src=None):
     return y
 
 
+def stem_geometry(h, w, kh, kw, stride, pads):
+    """Geometry of the packed first layer: a kh x kw / stride-s conv of an (h, w) image == a (T x 1) / 1 conv over
+    a packed tensor of H2 rows x OW columns.  Vertical tap r of the original filter satisfies
+    r - pad_top = s*e + ph  (e = packed row offset, ph = stride phase)."""
+    pt, pl, pb, pr = pads
+    oh, ow = out_size(h, pt, pb, kh, 1, stride), out_size(w, pl, pr, kw, 1, stride)
+    e_min, e_max = (-pt) // stride, (kh - 1 - pt) // stride
+    T = e_max - e_min + 1
+    h2 = (h + stride - 1) // stride
+    pad_t2 = -e_min
+    pad_b2 = oh - h2 - pad_t2 + T - 1
+    return dict(oh=oh, ow=ow, T=T, h2=h2, pad_t2=pad_t2, pad_b2=pad_b2, e_min=e_min)
+
+
+def stem_pack_weight(K, stride, pads, cp):
+    """Host-side (tiny, load-time) re-ordering of an OIHW stem filter into the packed [Cout][T][1][cp] layout that
+    matches ``plnr_stem_pack``:  W2[co, e, (ph*kw + sx)*C + c] = K[co, c, s*(e+e_min) + ph + pad_top, sx]."""
+    co, c, kh, kw = K.shape
+    pt = pads[0]
+    e_min, e_max = (-pt) // stride, (kh - 1 - pt) // stride
+    T = e_max - e_min + 1
+    out = np.zeros((co, T, 1, cp), K.dtype)
+    for e in range(T):
+        for ph in range(stride):
+            r = stride * (e + e_min) + ph + pt
+            if 0 <= r < kh:
+                for sx in range(kw):
+                    base = (ph * kw + sx) * c
+                    out[:, e, 0, base:base + c] = K[:, :, r, sx]
+    return out
+
+
+def stem_pack_into(x_flat, y, kw, stride, pad_l):
+    n, c, h, w = x_flat.shape
+    t = y.tensor()
+    _capi.check(B.lib().plnr_stem_pack(B.ctx(), x_flat.ptr, _capi.dtype_code(x_flat.dtype), n, c, h, w, C.byref(t), kw,
+                                       stride, pad_l), 'plnr_stem_pack')
+    return y
+
+
 def nhwc_to_nchw_into(x, y_flat):
     t = x.tensor()
     _capi.check(B.lib().plnr_nhwc_to_nchw(B.ctx(), C.byref(t), _capi.dtype_code(x.dtype), y_flat.ptr,
