@@ -145,6 +145,39 @@ class DeviceArray:
         assert int(np.prod(shape)) == self.size, (shape, self.shape)
         return DeviceArray(self.buf, shape, self.dtype, 'flat', offset=self.offset)
 
+    # -- the handful of numpy idioms the reference's Net.load_weights uses on weights (planer/net.py:83-88):
+    #    data.view(uint8); w.ravel().view(uint8)[:] = data[s:s+n]
+    def ravel(self):
+        assert self.layout == 'flat', 'ravel() of an internal nhwc array is not a view'
+        return DeviceArray(self.buf, (self.size,), self.dtype, 'flat', offset=self.offset)
+
+    def view(self, dtype=None):
+        dtype = np.dtype(dtype)
+        assert self.layout == 'flat'
+        nbytes = self.size * self.dtype.itemsize
+        assert nbytes % dtype.itemsize == 0
+        shape = (nbytes // dtype.itemsize,) if self.ndim <= 1 else self.shape[:-1] + (
+            self.shape[-1] * self.dtype.itemsize // dtype.itemsize,)
+        return DeviceArray(self.buf, shape, dtype, 'flat', offset=self.offset)
+
+    def __getitem__(self, key):
+        if not (self.layout == 'flat' and self.ndim == 1 and isinstance(key, slice) and key.step in (None, 1)):
+            raise NotImplementedError('DeviceArray supports only contiguous 1-D slices (weight-blob views); '
+                                      'operators are replaced one level up, not emulated through numpy indexing')
+        start, stop, _ = key.indices(self.shape[0])
+        return DeviceArray(self.buf, (max(stop - start, 0),), self.dtype, 'flat',
+                           offset=self.offset + start * self.dtype.itemsize)
+
+    def __setitem__(self, key, value):
+        dst = self[key] if not (isinstance(key, slice) and key == slice(None)) else self.ravel() if self.layout == 'flat' else None
+        if dst is None:
+            raise NotImplementedError('DeviceArray assignment supports whole-array / 1-D slice copies only')
+        src = asarray(value) if not isinstance(value, DeviceArray) else to_flat(value)
+        if src.size != dst.size or src.dtype.itemsize != dst.dtype.itemsize:
+            raise ValueError('shape mismatch in device copy: %s <- %s' % (dst.shape, src.shape))
+        with _torch().cuda.stream(stream()):
+            dst._typed().copy_(src._typed().view(_torch_dtype(dst.dtype)), non_blocking=True)
+
     def astype(self, dtype):
         dtype = np.dtype(dtype)
         src = to_flat(self)

@@ -25,6 +25,7 @@ struct plnr_ctx {
   // device-side error word written by kernels that time out on a barrier (debug aid)
   int* dev_error = nullptr;
   long long* prof = nullptr;       // debug: per-CTA role cycle counters of the last tcgen05 conv launch
+  bool shift_attr_set = false;
   bool igemm_attr_set = false;     // cudaFuncSetAttribute(max dynamic smem) done for this device
   // cache of TMA descriptors keyed by a byte string of their parameters
   std::unordered_map<std::string, CUtensorMap> tmap_cache;
@@ -100,3 +101,6 @@ int plnr_conv2d_direct(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor
 int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w,
                         const plnr_tensor* y, const plnr_epilogue* ep);
 bool plnr_conv2d_tcgen05_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y);
+int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w,
+                      const plnr_tensor* y, const plnr_epilogue* ep);
+bool plnr_conv2d_shift_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y);

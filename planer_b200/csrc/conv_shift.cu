@@ -1,0 +1,592 @@
+// Stride-1 fp16 convolution as a "shift GEMM": every input row is loaded into shared memory ONCE per 64-channel chunk
+// and all kh*kw filter taps are fed to tcgen05.mma from row-shifted views of that one buffer.
+//
+// Replaces the same reference code as conv_tcgen05.cu (planer/layer.py:22-26 + planer/util.py:17-44 and the fused
+// batchnorm / add / relu layers) for stride-1 convolutions with Cin % 64 == 0 -- 16 of ResNet-18's 20 convolutions and
+// every 3x3/s1 and 1x1 convolution of YOLOv3.  The im2col kernel re-reads each input pixel kh*kw times through the
+// TMA unit, whose im2col mode sustains only ~46 B/clk per SM (tools/tma_stream_probe.cu): its main loop is bound by
+// that, not by the tensor pipe.  Here:
+//
+//   * the image is viewed as rows of Wv = W + pad_left pixels (left padding materialised by TMA out-of-bounds zero
+//     fill; the right padding of one row IS the left padding of the next) and Hv = H + pad_top rows per image, all
+//     flattened: output position o = (n*Hv + p)*Wv + q needs input position o + r*dil_h*Wv + s*dil_w for tap (r, s);
+//   * a tile is 128 consecutive positions o (x2 for a CTA pair); its A buffer holds positions [o0 - Wv', o0 + 128 +
+//     halo) as whole rows fetched by tiled TMA boxes (64 ch x Wv px, ~80-100 B/clk); positions with p >= OH or
+//     q >= OW are computed and discarded (OH*OW/(Hv*Wv) efficiency: 96.5 % at 56x56, 87 % at 14x14);
+//   * tcgen05 reads a 128B-swizzled K-major operand from ANY 128-byte-aligned start address (the swizzle is a
+//     function of the absolute shared-memory address; tools/swizzle_probe.cu), so tap (r, s) is just the A descriptor
+//     advanced by (r*dil_h*Wv + s*dil_w) rows;
+//   * weights stream through their own ring, one [n_tile x 64] box per (chunk, tap) -- or stay resident in shared
+//     memory for the whole kernel when they fit (Cout = 64 / 128 layers);
+//   * CG = 2 runs a CTA pair per 256 positions with cta_group::2 MMAs (M = 256): half the B bytes per CTA and half
+//     the MMA instructions per output row, which matters because an M=128 MMA costs ~85-100 clk even at N <= 128.
+//
+// Warp roles, TMEM double buffering, the fused epilogue and the watchdog are those of conv_tcgen05.cu.
+#include <stdlib.h>
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 256;
+constexpr uint32_t kEpiBytes = 2 * 2 * 256 * 4;
+constexpr int kMaxA = 4, kMaxB = 40;
+constexpr long long kWatchdogCycles = 4000000000ll;
+
+struct ShiftParams {
+  int N, OH, OW, Hv, Wv, HvWv;
+  int pad_t, pad_l;
+  long long Mv;             // N * Hv * Wv virtual output positions
+  int halo;                 // (R-1)*dil_h*Wv + (S-1)*dil_w
+  int R, S, dh, dw;
+  int C, cchunks;
+  int n_tile, num_m_tiles, num_tiles;
+  int na, nb, b_resident;
+  uint32_t a_buf_bytes, b_stage_bytes, idesc, tmem_cols;
+  __half* y; int yld, ycoff, Cout;
+  const float* scale; const float* shift;
+  const __half* res; int rld, rcoff;
+  int act; float alpha; int res_after;
+  int vec_ok;
+  int* err;
+  long long* prof;
+};
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int role) {
+  if (ptx::mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFF) == 0) {
+      if (*reinterpret_cast<volatile int*>(err) != 0) return;
+      if (clock64() - t0 > kWatchdogCycles) {
+        if (atomicCAS(err, 0, 2) == 0) { err[1] = blockIdx.x; err[2] = role; err[3] = (int)parity; }
+        __threadfence();
+        return;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// tiled 4-D box load (c, w, h, n); CG = 2 reports the bytes to the pair leader's mbarrier
+template <int CG>
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w, int h, int n) {
+  if (CG == 2) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & ptx::kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(n),
+          "l"(ptx::kTmaCacheHintDefault)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
+        : "memory");
+  }
+}
+
+// rows of the A buffer a CTA whose first position is o0 has to load: [v0, v0 + nrows)
+__device__ __forceinline__ void tile_rows(long long o0, int Wv, int halo, long long& v0, int& nrows, int& off) {
+  v0 = o0 / Wv;
+  off = (int)(o0 - v0 * Wv);
+  nrows = (int)((o0 + kTileM - 1 + halo) / Wv - v0) + 1;
+}
+
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                      const ShiftParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t na = (uint32_t)p.na, nb = (uint32_t)p.nb;
+  const uint32_t sA = base;
+  const uint32_t sB = sA + na * p.a_buf_bytes;
+  const uint32_t epi_off = na * p.a_buf_bytes + nb * p.b_stage_bytes;
+  float* epi = reinterpret_cast<float*>(base_ptr + epi_off);
+  const uint32_t sBar = base + epi_off + kEpiBytes;
+  const uint32_t bar_afull = sBar, bar_aempty = sBar + 8 * kMaxA;
+  const uint32_t bar_bfull = sBar + 16 * kMaxA, bar_bempty = bar_bfull + 8 * kMaxB;
+  const uint32_t bar_tfull = bar_bempty + 8 * kMaxB, bar_tempty = bar_tfull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + epi_off + kEpiBytes + 16 * kMaxA + 16 * kMaxB + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nunits = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int Wv = p.Wv, RS = p.R * p.S;
+  const uint32_t row_bytes = (uint32_t)Wv * 128u;       // one virtual row of 64 channels in shared memory
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&mapA);
+    ptx::prefetch_tmap(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (uint32_t i = 0; i < na; ++i) { ptx::mbar_init(bar_afull + 8 * i, 1); ptx::mbar_init(bar_aempty + 8 * i, 1); }
+    for (uint32_t i = 0; i < nb; ++i) { ptx::mbar_init(bar_bfull + 8 * i, 1); ptx::mbar_init(bar_bempty + 8 * i, 1); }
+    for (uint32_t a = 0; a < 2; ++a) { ptx::mbar_init(bar_tfull + 8 * a, 1); ptx::mbar_init(bar_tempty + 8 * a, 128 * CG); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    if (CG == 2) { ptx::tmem_alloc_pair(ptx::smem_u32(tmem_slot), p.tmem_cols); ptx::tmem_relinquish_pair(); }
+    else { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), p.tmem_cols); ptx::tmem_relinquish(); }
+  }
+  ptx::tc_fence_before();
+  if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    uint32_t ab = 0, aph = 0, bs = 0, bph = 0;
+    bool first = true;
+    long long t_wait = 0;
+    const long long t_all0 = clock64();
+    for (int tile = unit; tile < p.num_tiles; tile += nunits) {
+      const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
+      const long long o0 = ((long long)m_idx * CG + rank) * kTileM;
+      long long v0; int nrows, off;
+      tile_rows(o0, Wv, p.halo, v0, nrows, off);
+      uint32_t a_bytes = (uint32_t)nrows * row_bytes;
+      if (CG == 2) {                                     // the leader arms the barrier for both CTAs' rows
+        long long v0p; int nrows_p, off_p;
+        tile_rows(o0 + (leader ? kTileM : -kTileM), Wv, p.halo, v0p, nrows_p, off_p);
+        a_bytes += (uint32_t)nrows_p * row_bytes;
+      }
+      const int n_row = n_idx * p.n_tile + (int)rank * (p.n_tile / CG);
+      // position o0 always lands at row-offset Wv of the buffer, so the A descriptors are tile-independent and
+      // identical in both CTAs of a pair (they share ONE descriptor per MMA)
+      const uint32_t row0_off = (uint32_t)(Wv - off) * 128u;
+      for (int cc = 0; cc < p.cchunks; ++cc) {
+        const long long tw0 = clock64();
+        mbar_wait(bar_aempty + 8 * ab, aph ^ 1, p.err, 0);
+        t_wait += clock64() - tw0;
+        if (ptx::elect_one()) {
+          const uint32_t full = bar_afull + 8 * ab;
+          if (leader) ptx::mbar_arrive_expect_tx(full, a_bytes);
+          uint32_t dst = sA + ab * p.a_buf_bytes + row0_off;
+          long long v = v0;
+          int img = (int)(v / p.Hv), hrow = (int)(v - (long long)img * p.Hv);
+          for (int i = 0; i < nrows; ++i) {
+            tma_load_4d<CG>(dst, &mapA, full, cc * 64, -p.pad_l, hrow - p.pad_t, img);
+            dst += row_bytes;
+            if (++hrow == p.Hv) { hrow = 0; ++img; }
+          }
+        }
+        __syncwarp();
+        if (++ab == na) { ab = 0; aph ^= 1; }
+        if (!p.b_resident || first) {
+          for (int tap = 0; tap < RS; ++tap) {
+            if (!p.b_resident) {
+              const long long tb0 = clock64();
+              mbar_wait(bar_bempty + 8 * bs, bph ^ 1, p.err, 4);
+              t_wait += clock64() - tb0;
+            }
+            if (ptx::elect_one()) {
+              const uint32_t full = bar_bfull + 8 * bs;
+              if (leader) ptx::mbar_arrive_expect_tx(full, (uint32_t)CG * p.b_stage_bytes);
+              if (CG == 2) ptx::tma_load_2d_pair(sB + bs * p.b_stage_bytes, &mapB, full, tap * p.C + cc * 64, n_row);
+              else ptx::tma_load_2d(sB + bs * p.b_stage_bytes, &mapB, full, tap * p.C + cc * 64, n_row);
+            }
+            __syncwarp();
+            if (++bs == nb) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+      first = false;
+    }
+    if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 0] = t_wait; p.prof[blockIdx.x * 8 + 1] = clock64() - t_all0; }
+  } else if (warp == 1 && leader) {
+    // ===================================== MMA issuer =========================================
+    uint32_t ab = 0, aph = 0, bs = 0, bph = 0, it = 0;
+    bool first = true;
+    long long t_full = 0, t_tempty = 0;
+    const long long t_all0 = clock64();
+    const uint32_t idesc = p.idesc;
+    // descriptor of position o0 (row offset Wv) in A buffer 0; +8 per pixel row (128 B >> 4)
+    const uint64_t adesc0 = ptx::make_smem_desc(sA + (uint32_t)Wv * 128u, 1024, 2);
+    const uint64_t bdesc0 = ptx::make_smem_desc(sB, 1024, 2);
+    const uint32_t a_step = p.a_buf_bytes >> 4, b_step = p.b_stage_bytes >> 4;
+    const uint32_t r_step = (uint32_t)(p.dh * Wv) * 8u, s_step = (uint32_t)p.dw * 8u;
+    for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
+      const uint32_t a = it & 1, tph = (it >> 1) & 1;
+      const long long te0 = clock64();
+      mbar_wait(bar_tempty + 8 * a, tph ^ 1, p.err, 1);
+      t_tempty += clock64() - te0;
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + a * (uint32_t)p.n_tile;
+      for (int cc = 0; cc < p.cchunks; ++cc) {
+        const long long tf0 = clock64();
+        mbar_wait(bar_afull + 8 * ab, aph, p.err, 2);
+        t_full += clock64() - tf0;
+        ptx::tc_fence_after();
+        const uint64_t da_chunk = adesc0 + (uint64_t)(ab * a_step);
+        int tap = 0;
+        for (int r = 0; r < p.R; ++r) {
+          for (int sx = 0; sx < p.S; ++sx, ++tap) {
+            if (!p.b_resident || first) {
+              const long long tb0 = clock64();
+              mbar_wait(bar_bfull + 8 * bs, bph, p.err, 5);
+              t_full += clock64() - tb0;
+              ptx::tc_fence_after();
+            }
+            if (ptx::elect_one()) {
+              uint64_t da = da_chunk + (uint64_t)(r * r_step + sx * s_step);
+              uint64_t db = bdesc0 + (uint64_t)(bs * b_step);
+              uint32_t acc = (cc | tap) ? 1u : 0u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (CG == 2) ptx::umma_f16_pair(d_tmem, da, db, idesc, acc);
+                else ptx::umma_f16(d_tmem, da, db, idesc, acc);
+                acc = 1u; da += 2; db += 2;
+              }
+              const bool last_tap = tap == RS - 1;
+              if (CG == 2) {
+                if (!p.b_resident) ptx::umma_commit_pair(bar_bempty + 8 * bs, 3);
+                if (last_tap) ptx::umma_commit_pair(bar_aempty + 8 * ab, 3);
+                if (last_tap && cc == p.cchunks - 1) ptx::umma_commit_pair(bar_tfull + 8 * a, 3);
+              } else {
+                if (!p.b_resident) ptx::umma_commit(bar_bempty + 8 * bs);
+                if (last_tap) ptx::umma_commit(bar_aempty + 8 * ab);
+                if (last_tap && cc == p.cchunks - 1) ptx::umma_commit(bar_tfull + 8 * a);
+              }
+            }
+            __syncwarp();
+            if (++bs == nb) { bs = 0; bph ^= 1; }
+          }
+        }
+        if (++ab == na) { ab = 0; aph ^= 1; }
+      }
+      first = false;
+    }
+    if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 2] = t_full; p.prof[blockIdx.x * 8 + 3] = t_tempty; p.prof[blockIdx.x * 8 + 4] = clock64() - t_all0; }
+  } else if (warp >= 4) {
+    // ===================================== epilogue ===========================================
+    const int ew = warp - 4;
+    const int et = threadIdx.x - 128;
+    uint32_t it = 0;
+    long long t_tfull = 0;
+    const long long t_all0 = clock64();
+    for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
+      const uint32_t a = it & 1, tph = (it >> 1) & 1;
+      const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
+      const int n0 = n_idx * p.n_tile;
+      float* ep_scale = epi + a * 512, *ep_shift = ep_scale + 256;
+      for (int i = et; i < p.n_tile; i += 128) {
+        const int c = n0 + i;
+        float sc = 0.f, sf = 0.f;
+        if (c < p.Cout) { sc = p.scale ? __ldg(p.scale + c) : 1.f; sf = p.shift ? __ldg(p.shift + c) : 0.f; }
+        ep_scale[i] = sc; ep_shift[i] = sf;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      // this thread's virtual position -> output pixel (or nothing, for the padded rim)
+      const long long o = ((long long)m_idx * CG + rank) * kTileM + ew * 32 + lane;
+      bool mvalid = o < p.Mv;
+      long long m = 0;
+      if (mvalid) {
+        const int img = (int)(o / p.HvWv);
+        const int rem = (int)(o - (long long)img * p.HvWv);
+        const int pr = rem / Wv, q = rem - pr * Wv;
+        mvalid = pr < p.OH && q < p.OW;
+        m = ((long long)img * p.OH + pr) * p.OW + q;
+      }
+
+      const long long tt0 = clock64();
+      mbar_wait(bar_tfull + 8 * a, tph, p.err, 3);
+      t_tfull += clock64() - tt0;
+      ptx::tc_fence_after();
+
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + a * (uint32_t)p.n_tile;
+      __half* yrow = p.y + (size_t)(mvalid ? m : 0) * p.yld + p.ycoff;
+      const __half* rrow = p.res ? p.res + (size_t)(mvalid ? m : 0) * p.rld + p.rcoff : nullptr;
+
+      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+        __syncwarp();
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(t_row + c0, v);
+        const int cb = n0 + c0;
+        const bool fast = p.vec_ok && (cb + 32 <= p.Cout);
+        uint4 rv[4];
+        if (fast && rrow && mvalid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rv[q] = *reinterpret_cast<const uint4*>(rrow + cb + q * 8);
+        }
+        ptx::tmem_ld_wait();
+        if (c0 + 32 >= p.n_tile) {
+          ptx::tc_fence_before();
+          if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
+          else ptx::mbar_arrive(bar_tempty + 8 * a);
+        }
+        if (mvalid && fast) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float sc[8], sf[8], o8[8];
+            *reinterpret_cast<float4*>(&sc[0]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8);
+            *reinterpret_cast<float4*>(&sc[4]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8 + 4);
+            *reinterpret_cast<float4*>(&sf[0]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8);
+            *reinterpret_cast<float4*>(&sf[4]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8 + 4);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o8[e] = fmaf(__uint_as_float(v[q * 8 + e]), sc[e], sf[e]);
+            float rf[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) rf[e] = 0.f;
+            if (rrow) {
+              const __half2* rh = reinterpret_cast<const __half2*>(&rv[q]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(rh[e]);
+                rf[2 * e] = f.x; rf[2 * e + 1] = f.y;
+              }
+            }
+            if (!p.res_after) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o8[e] += rf[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o8[e] = plnr_apply_act(o8[e], p.act, p.alpha);
+            if (p.res_after) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o8[e] += rf[e];
+            }
+            uint4 pk;
+            pk.x = pack_half2(o8[0], o8[1]); pk.y = pack_half2(o8[2], o8[3]);
+            pk.z = pack_half2(o8[4], o8[5]); pk.w = pack_half2(o8[6], o8[7]);
+            *reinterpret_cast<uint4*>(yrow + cb + q * 8) = pk;
+          }
+        } else if (mvalid) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int c = cb + e;
+            if (c < p.Cout) {
+              float o1 = fmaf(__uint_as_float(v[e]), ep_scale[c0 + e], ep_shift[c0 + e]);
+              const float rf = rrow ? __half2float(rrow[c]) : 0.f;
+              if (!p.res_after) o1 += rf;
+              o1 = plnr_apply_act(o1, p.act, p.alpha);
+              if (p.res_after) o1 += rf;
+              yrow[c] = __float2half_rn(o1);
+            }
+          }
+        }
+      }
+    }
+    if (p.prof && threadIdx.x == 128) { p.prof[blockIdx.x * 8 + 5] = t_tfull; p.prof[blockIdx.x * 8 + 6] = clock64() - t_all0; }
+  }
+
+  ptx::tc_fence_before();
+  if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    if (CG == 2) ptx::tmem_dealloc_pair(tmem_base, p.tmem_cols);
+    else ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+static int g_driver_version = 0;
+
+static int resolve_driver() {
+  if (g_encode_tiled) return PLNR_OK;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+    plnr_set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+    return PLNR_ERR_DRIVER;
+  }
+  g_encode_tiled = (EncodeTiledFn)fn;
+  cudaDriverGetVersion(&g_driver_version);
+  return PLNR_OK;
+}
+
+static void small_tensor_fixup(CUtensorMap* m, uint64_t tensor_bytes) {
+  if (g_driver_version <= 13010 && tensor_bytes < 131072) reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct ShiftPlan {
+  int cg, n_tile, na, nb, b_resident, rows_max, Wv, Hv, halo;
+  uint32_t a_buf_bytes, b_stage_bytes;
+  size_t smem_bytes;
+  bool ok;
+};
+
+// Shared-memory plan for a problem; ok == false when the shift kernel does not apply / does not fit.
+static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y, int sm_count) {
+  ShiftPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  if (d->dtype != PLNR_F16 || d->groups != 1 || d->stride_h != 1 || d->stride_w != 1) return pl;
+  if (x->c % 64 != 0 || x->ld % 8 != 0 || x->coff % 8 != 0 || (reinterpret_cast<uintptr_t>(x->ptr) & 15)) return pl;
+  if (d->pad_b > d->pad_t || d->pad_r > d->pad_l) return pl;
+  pl.Wv = x->w + d->pad_l;
+  pl.Hv = x->h + d->pad_t;
+  if (pl.Wv > 256 || d->kh * d->kw > kMaxB) return pl;
+  pl.halo = (d->kh - 1) * d->dil_h * pl.Wv + (d->kw - 1) * d->dil_w;
+  pl.rows_max = (pl.Wv - 1 + kTileM - 1 + pl.halo) / pl.Wv + 1;
+  // + one row of slack in front: position o0 sits at row offset Wv whatever its column (see the producer)
+  pl.a_buf_bytes = (uint32_t)round_up((pl.rows_max + 1) * pl.Wv * 128, 1024);
+  const long long Mv = (long long)x->n * pl.Hv * pl.Wv;
+  if (Mv >= (1ll << 31) - 512) return pl;
+  const double eff = (double)y->h * y->w / ((double)pl.Hv * pl.Wv);
+  if (eff < 0.70) return pl;                              // small maps: too many discarded rim positions
+  const int m_tiles_128 = (int)((Mv + kTileM - 1) / kTileM);
+  // Measured on ResNet-18 (profiles/r01_shift_cg.md): a CTA pair is never faster here -- shared-memory traffic is not
+  // the limiter once A is loaded once per chunk, and an MMA costs ~90-100 clk whatever M is when N <= 128 -- so the
+  // single-CTA variant is the default; PLNR_SHIFT_CTA_GROUP=2 selects the pair (kept: it is correct and tested).
+  pl.cg = 1;
+  if (const char* e = getenv("PLNR_SHIFT_CTA_GROUP")) { if (atoi(e) == 2 && m_tiles_128 >= 2) pl.cg = 2; }
+  const int cout_r = round_up(y->c, 32);
+  pl.n_tile = cout_r < 256 ? cout_r : 256;
+  if (const char* e = getenv("PLNR_SHIFT_NTILE")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0 && v < pl.n_tile) pl.n_tile = v; }
+  pl.b_stage_bytes = (uint32_t)(pl.n_tile / pl.cg) * 128;
+  const int kst = d->kh * d->kw * (x->c / 64);
+  const int num_n_tiles = (y->c + pl.n_tile - 1) / pl.n_tile;
+  const size_t fixed = kEpiBytes + 16 * kMaxA + 16 * kMaxB + 64 + 1024;
+  const size_t budget = 232448;
+  // resident weights: all (chunk, tap) boxes stay in shared memory for the whole kernel
+  pl.na = 2;
+  if (num_n_tiles == 1 && kst <= kMaxB &&
+      fixed + 2 * (size_t)pl.a_buf_bytes + (size_t)kst * pl.b_stage_bytes <= budget) {
+    pl.b_resident = 1;
+    pl.nb = kst;
+    if (fixed + 3 * (size_t)pl.a_buf_bytes + (size_t)kst * pl.b_stage_bytes <= budget) pl.na = 3;
+  } else {
+    if (fixed + 2 * (size_t)pl.a_buf_bytes + 3 * (size_t)pl.b_stage_bytes > budget) return pl;
+    size_t left = budget - fixed - 2 * (size_t)pl.a_buf_bytes;
+    pl.nb = (int)(left / pl.b_stage_bytes);
+    if (pl.nb > 12) pl.nb = 12;
+    if (pl.nb >= 8 && fixed + 3 * (size_t)pl.a_buf_bytes + 6 * (size_t)pl.b_stage_bytes <= budget) {
+      pl.na = 3;
+      pl.nb = (int)((budget - fixed - 3 * (size_t)pl.a_buf_bytes) / pl.b_stage_bytes);
+      if (pl.nb > 12) pl.nb = 12;
+    }
+  }
+  pl.smem_bytes = fixed + (size_t)pl.na * pl.a_buf_bytes + (size_t)pl.nb * pl.b_stage_bytes;
+  pl.ok = true;
+  (void)sm_count;
+  return pl;
+}
+
+}  // namespace
+
+bool plnr_conv2d_shift_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y) {
+  if (const char* e = getenv("PLNR_NO_SHIFT")) { if (atoi(e)) return false; }
+  return make_plan(d, x, y, 148).ok;
+}
+
+int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w,
+                      const plnr_tensor* y, const plnr_epilogue* ep) {
+  int rc = resolve_driver();
+  if (rc != PLNR_OK) return rc;
+  const ShiftPlan pl = make_plan(d, x, y, ctx->sm_count);
+  PLNR_REQUIRE(pl.ok, "conv2d(shift): problem not eligible");
+  PLNR_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, "conv2d(shift): packed weights must be 16-byte aligned");
+  const int cg = pl.cg;
+
+  ShiftParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = x->n; p.OH = y->h; p.OW = y->w; p.Hv = pl.Hv; p.Wv = pl.Wv; p.HvWv = pl.Hv * pl.Wv;
+  p.pad_t = d->pad_t; p.pad_l = d->pad_l;
+  p.Mv = (long long)x->n * pl.Hv * pl.Wv;
+  p.halo = pl.halo;
+  p.R = d->kh; p.S = d->kw; p.dh = d->dil_h; p.dw = d->dil_w;
+  p.C = x->c; p.cchunks = x->c / 64;
+  p.n_tile = pl.n_tile;
+  p.num_m_tiles = (int)((p.Mv + kTileM * cg - 1) / (kTileM * cg));
+  const int num_n_tiles = (y->c + p.n_tile - 1) / p.n_tile;
+  p.num_tiles = p.num_m_tiles * num_n_tiles;
+  p.na = pl.na; p.nb = pl.nb; p.b_resident = pl.b_resident;
+  p.a_buf_bytes = pl.a_buf_bytes; p.b_stage_bytes = pl.b_stage_bytes;
+  p.idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)((kTileM * cg) >> 4) << 24);
+  uint32_t cols = 32;
+  while (cols < 2u * p.n_tile) cols <<= 1;
+  p.tmem_cols = cols;
+  p.y = (__half*)y->ptr; p.yld = y->ld; p.ycoff = y->coff; p.Cout = y->c;
+  bool vec = (y->ld % 8 == 0) && (y->coff % 8 == 0) && ((reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0);
+  if (ep) {
+    p.scale = ep->scale; p.shift = ep->shift; p.act = ep->act; p.alpha = ep->alpha; p.res_after = ep->res_after_act;
+    if (ep->residual) {
+      const plnr_tensor* r = ep->residual;
+      p.res = (const __half*)r->ptr; p.rld = r->ld; p.rcoff = r->coff;
+      vec = vec && (r->ld % 8 == 0) && (r->coff % 8 == 0) && ((reinterpret_cast<uintptr_t>(r->ptr) & 15) == 0);
+    }
+  }
+  p.vec_ok = vec ? 1 : 0;
+  p.err = ctx->dev_error;
+  p.prof = ctx->prof;
+
+  CUtensorMap mapA, mapB;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)x->c, (cuuint64_t)x->w, (cuuint64_t)x->h, (cuuint64_t)x->n};
+    const cuuint64_t strides[3] = {(cuuint64_t)x->ld * 2, (cuuint64_t)x->w * x->ld * 2,
+                                   (cuuint64_t)x->h * x->w * x->ld * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)pl.Wv, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    void* gaddr = (void*)((__half*)x->ptr + x->coff);
+    CUresult r = g_encode_tiled(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, gaddr, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      plnr_set_error("cuTensorMapEncodeTiled(A) failed with CUresult %d (C=%d W=%d H=%d N=%d Wv=%d)", (int)r, x->c, x->w,
+                     x->h, x->n, pl.Wv);
+      return PLNR_ERR_DRIVER;
+    }
+    small_tensor_fixup(&mapA, (uint64_t)x->n * x->h * x->w * x->ld * 2);
+  }
+  {
+    const int Ktot = d->kh * d->kw * x->c;
+    const cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)y->c};
+    const cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)(p.n_tile / cg)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      plnr_set_error("cuTensorMapEncodeTiled(B) failed with CUresult %d (K=%d Cout=%d)", (int)r, Ktot, y->c);
+      return PLNR_ERR_DRIVER;
+    }
+    small_tensor_fixup(&mapB, (uint64_t)Ktot * y->c * 2);
+  }
+
+  if (!ctx->shift_attr_set) {
+    PLNR_CHECK_CUDA(cudaFuncSetAttribute(conv_shift_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    PLNR_CHECK_CUDA(cudaFuncSetAttribute(conv_shift_f16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    ctx->shift_attr_set = true;
+  }
+  int units = ctx->sm_count / cg;
+  if (p.num_tiles < units) units = p.num_tiles;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(units * cg));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = pl.smem_bytes;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cg;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<2>, mapA, mapB, p)
+                           : cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<1>, mapA, mapB, p);
+  if (le != cudaSuccess) {
+    plnr_set_error("launch of conv_shift_f16_kernel<%d> failed: %s", cg, cudaGetErrorString(le));
+    return PLNR_ERR_CUDA;
+  }
+  return plnr_after_launch(ctx, "conv2d_shift");
+}

@@ -51,6 +51,7 @@ struct IgemmParams {
   int vec_ok;
   int* err;
   long long* prof;   // optional [grid][8] cycle counters per role (debug)
+  int dbg;           // debug: bit0 = epilogue skips global loads/stores, bit1 = epilogue skips tcgen05.ld too
 };
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int role) {
@@ -74,6 +75,12 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// CG = 1: one CTA per 128-pixel tile (tcgen05 cta_group::1).
+// CG = 2: a CTA PAIR (cluster of 2, one TPC) per 256-pixel tile (cta_group::2): each CTA loads its own 128 A rows and
+//         HALF of the B tile; the leader CTA issues M=256 MMAs that read both CTAs' shared memory and write both CTAs'
+//         TMEM.  Per CTA this halves the B bytes written to and read from shared memory -- the resource that bounds the
+//         1-CTA kernel.
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                       const IgemmParams p) {
@@ -92,6 +99,10 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + epi_off + kEpiBytes + 16 * stages + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // position inside the CTA pair
+  const bool leader = rank == 0;
+  const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // persistent work-unit id
+  const int nunits = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&mapA);
@@ -99,21 +110,21 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (uint32_t i = 0; i < stages; ++i) {
-      ptx::mbar_init(bar_full + 8 * i, 1);    // producer's arrive.expect_tx (+ TMA transaction bytes)
-      ptx::mbar_init(bar_empty + 8 * i, 1);   // tcgen05.commit
+      ptx::mbar_init(bar_full + 8 * i, 1);    // leader's arrive.expect_tx (+ TMA transaction bytes of the whole pair)
+      ptx::mbar_init(bar_empty + 8 * i, 1);   // tcgen05.commit (multicast to both CTAs when CG == 2)
     }
     for (uint32_t a = 0; a < 2; ++a) {
-      ptx::mbar_init(bar_tfull + 8 * a, 1);   // tcgen05.commit after the last k-stage of a tile
-      ptx::mbar_init(bar_tempty + 8 * a, 128);  // every epilogue thread
+      ptx::mbar_init(bar_tfull + 8 * a, 1);          // tcgen05.commit after the last k-stage of a tile
+      ptx::mbar_init(bar_tempty + 8 * a, 128 * CG);  // every epilogue thread of the pair (leader's copy is the live one)
     }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), p.tmem_cols);
-    ptx::tmem_relinquish();
+    if (CG == 2) { ptx::tmem_alloc_pair(ptx::smem_u32(tmem_slot), p.tmem_cols); ptx::tmem_relinquish_pair(); }
+    else { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), p.tmem_cols); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
@@ -126,14 +137,14 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     const long long t_all0 = clock64();
     const int tps = p.tps, units = p.units, cchunks = p.cchunks, kc = p.kc, S = p.S, dw = p.dw, dh = p.dh;
     const uint32_t a_unit_bytes = p.a_unit_bytes, b_stage_bytes = p.b_stage_bytes;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < p.num_tiles; tile += nunits) {
       const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
-      const int m0 = m_idx * kTileM;
+      const int m0 = (m_idx * CG + (int)rank) * kTileM;
       const int q0 = m0 % p.OW;
       const int t1 = m0 / p.OW;
       const int p0 = t1 % p.OH, img = t1 / p.OH;
       const int cw = q0 * p.sw - p.pad_l, chh = p0 * p.sh - p.pad_t;   // input coordinate of the tile's first pixel
-      const int n_row = n_idx * p.n_tile;
+      const int n_row = n_idx * p.n_tile + (int)rank * (p.n_tile / CG);
       int r = 0, sx = 0, cc = 0, u = 0;                                // filter row / column / channel chunk of the next unit
       for (int j = 0; j < p.kstages; ++j) {
         const long long tw0 = clock64();
@@ -142,15 +153,19 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         const int nu = min(tps, units - u);
         if (ptx::elect_one()) {
           const uint32_t full = bar_full + 8 * s;
-          ptx::mbar_arrive_expect_tx(full, (uint32_t)nu * a_unit_bytes + b_stage_bytes);
+          if (leader) ptx::mbar_arrive_expect_tx(full, (uint32_t)CG * ((uint32_t)nu * a_unit_bytes + b_stage_bytes));
           uint32_t a_dst = sA + s * kAStageBytes;
           int r2 = r, sx2 = sx, cc2 = cc;
           for (int t = 0; t < nu; ++t) {
-            ptx::tma_load_im2col_4d(a_dst, &mapA, full, cc2 * kc, cw, chh, img, (uint16_t)(sx2 * dw), (uint16_t)(r2 * dh));
+            if (CG == 2)
+              ptx::tma_load_im2col_4d_pair(a_dst, &mapA, full, cc2 * kc, cw, chh, img, (uint16_t)(sx2 * dw), (uint16_t)(r2 * dh));
+            else
+              ptx::tma_load_im2col_4d(a_dst, &mapA, full, cc2 * kc, cw, chh, img, (uint16_t)(sx2 * dw), (uint16_t)(r2 * dh));
             a_dst += a_unit_bytes;
             if (++cc2 == cchunks) { cc2 = 0; if (++sx2 == S) { sx2 = 0; ++r2; } }
           }
-          ptx::tma_load_2d(sB + s * b_stage_bytes, &mapB, full, j * 64, n_row);
+          if (CG == 2) ptx::tma_load_2d_pair(sB + s * b_stage_bytes, &mapB, full, j * 64, n_row);
+          else ptx::tma_load_2d(sB + s * b_stage_bytes, &mapB, full, j * 64, n_row);
         }
         __syncwarp();
         for (int t = 0; t < nu; ++t) { if (++cc == cchunks) { cc = 0; if (++sx == S) { sx = 0; ++r; } } }
@@ -159,7 +174,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       }
     }
     if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 0] = t_wait; p.prof[blockIdx.x * 8 + 1] = clock64() - t_all0; }
-  } else if (warp == 1) {
+  } else if (warp == 1 && leader) {
     // ===================================== MMA issuer =========================================
     // Converged warp; one elected lane issues tcgen05.mma / tcgen05.commit.  Descriptors are advanced by adding
     // to their 14-bit (address >> 4) field: +2 per K=16 step (32 bytes), a constant per stage.
@@ -172,18 +187,21 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     const uint64_t bdesc0 = ptx::make_smem_desc(sB, 1024, 2);
     const uint32_t a_step = kAStageBytes >> 4, b_step = p.b_stage_bytes >> 4;
     const uint32_t a_unit_skip = (p.a_unit_bytes - (uint32_t)kper * 32u) >> 4;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
       const uint32_t a = it & 1, aph = (it >> 1) & 1;
       const long long te0 = clock64();
-      mbar_wait(bar_tempty + 8 * a, aph ^ 1, p.err, 1);   // epilogue has drained this accumulator
+      mbar_wait(bar_tempty + 8 * a, aph ^ 1, p.err, 1);   // epilogue(s) have drained this accumulator
       t_tempty += clock64() - te0;
+      const bool trace = p.prof && blockIdx.x == 0 && it < 40 && lane == 0;
+      if (trace) { p.prof[1200 + it * 4 + 0] = te0 - t_all0; p.prof[1200 + it * 4 + 1] = clock64() - t_all0; }
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + a * (uint32_t)p.n_tile;
       int u = 0;
       for (int j = 0; j < p.kstages; ++j) {
         const long long tf0 = clock64();
-        mbar_wait(bar_full + 8 * s, ph, p.err, 2);        // TMA bytes have landed
+        mbar_wait(bar_full + 8 * s, ph, p.err, 2);        // TMA bytes (of both CTAs) have landed
         t_full += clock64() - tf0;
+        if (trace && j == 0) p.prof[1200 + it * 4 + 2] = clock64() - t_all0;
         ptx::tc_fence_after();
         const int nu = min(tps, units - u);
         if (ptx::elect_one()) {
@@ -191,18 +209,25 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           uint32_t acc = j > 0 ? 1u : 0u;
           for (int t = 0; t < nu; ++t) {
             for (int k = 0; k < kper; ++k) {
-              ptx::umma_f16(d_tmem, da, db, idesc, acc);
+              if (CG == 2) ptx::umma_f16_pair(d_tmem, da, db, idesc, acc);
+              else ptx::umma_f16(d_tmem, da, db, idesc, acc);
               acc = 1u; da += 2; db += 2;
             }
             da += a_unit_skip;
           }
-          ptx::umma_commit(bar_empty + 8 * s);            // smem slot reusable once these MMAs retire
-          if (j == p.kstages - 1) ptx::umma_commit(bar_tfull + 8 * a);   // accumulator complete -> epilogue
+          if (CG == 2) {
+            ptx::umma_commit_pair(bar_empty + 8 * s, 3);          // both CTAs' slots reusable once these MMAs retire
+            if (j == p.kstages - 1) ptx::umma_commit_pair(bar_tfull + 8 * a, 3);
+          } else {
+            ptx::umma_commit(bar_empty + 8 * s);
+            if (j == p.kstages - 1) ptx::umma_commit(bar_tfull + 8 * a);   // accumulator complete -> epilogue
+          }
         }
         __syncwarp();
         u += nu;
         if (++s == stages) { s = 0; ph ^= 1; }
       }
+      if (trace) p.prof[1200 + it * 4 + 3] = clock64() - t_all0;
     }
     if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 2] = t_full; p.prof[blockIdx.x * 8 + 3] = t_tempty; p.prof[blockIdx.x * 8 + 4] = clock64() - t_all0; }
   } else if (warp >= 4) {
@@ -210,8 +235,9 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     const int ew = warp - 4;                 // == warp % 4: the TMEM lane quarter this warp may read
     const int et = threadIdx.x - 128;        // 0..127
     uint32_t it = 0;
-    long long t_tfull = 0, t_all0 = clock64();
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    long long t_tfull = 0;
+    const long long t_all0 = clock64();
+    for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
       const uint32_t a = it & 1, aph = (it >> 1) & 1;
       const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
       const int n0 = n_idx * p.n_tile;
@@ -230,12 +256,18 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       t_tfull += clock64() - tt0;
       ptx::tc_fence_after();
 
-      const int m = m_idx * kTileM + ew * 32 + lane;
-      const bool mvalid = m < p.M;
+      const int m = (m_idx * CG + (int)rank) * kTileM + ew * 32 + lane;
+      const bool mvalid = m < p.M && !(p.dbg & 1);
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + a * (uint32_t)p.n_tile;
       __half* yrow = p.y + (size_t)(mvalid ? m : 0) * p.yld + p.ycoff;
       const __half* rrow = p.res ? p.res + (size_t)(mvalid ? m : 0) * p.rld + p.rcoff : nullptr;
 
+      if (p.dbg & 2) {                      // debug: release the accumulator without reading it
+        ptx::tc_fence_before();
+        if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
+        else ptx::mbar_arrive(bar_tempty + 8 * a);
+        continue;
+      }
       for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
         __syncwarp();                       // tcgen05.ld is warp-collective: re-converge after the guarded stores
         uint32_t v[32];
@@ -248,9 +280,10 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           for (int q = 0; q < 4; ++q) rv[q] = *reinterpret_cast<const uint4*>(rrow + cb + q * 8);
         }
         ptx::tmem_ld_wait();
-        if (c0 + 32 >= p.n_tile) {          // accumulator fully read: hand it back to the MMA warp
+        if (c0 + 32 >= p.n_tile) {          // accumulator fully read: hand it back to the (leader's) MMA warp
           ptx::tc_fence_before();
-          ptx::mbar_arrive(bar_tempty + 8 * a);
+          if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
+          else ptx::mbar_arrive(bar_tempty + 8 * a);
         }
         if (mvalid && fast) {
 #pragma unroll
@@ -307,13 +340,13 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     if (p.prof && threadIdx.x == 128) { p.prof[blockIdx.x * 8 + 5] = t_tfull; p.prof[blockIdx.x * 8 + 6] = clock64() - t_all0; }
   }
 
-
-  // ---- teardown: everyone is done with TMEM before the allocator warp frees it ----
+  // ---- teardown: everyone (in both CTAs) is done with TMEM before the allocator warps free it ----
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+    if (CG == 2) ptx::tmem_dealloc_pair(tmem_base, p.tmem_cols);
+    else ptx::tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -374,7 +407,8 @@ static int pick_n_tile(int cout, int num_m_tiles, int sm_count) {
     const int n_tiles = (cout + n - 1) / n;
     const long long tiles = (long long)num_m_tiles * n_tiles;
     const long long waves = (tiles + sm_count - 1) / sm_count;
-    const double per_stage = 4.0 * (n / 2.0 > 48.0 ? n / 2.0 : 48.0) + 40.0;
+    // measured cycles per 64-k stage of this kernel (per-tile trace, round 1): the im2col A load alone is ~410
+    const double per_stage = n > 192 ? 650.0 : (n > 128 ? 630.0 : (n > 64 ? 600.0 : 560.0));
     const double cost = (double)waves * per_stage;
     if (cost < best_cost * 0.97) { best_cost = cost; best = n; }
   }
@@ -397,6 +431,8 @@ bool plnr_conv2d_tcgen05_supported(const plnr_conv_desc* d, const plnr_tensor* x
 
 int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w,
                         const plnr_tensor* y, const plnr_epilogue* ep) {
+  // stride-1 convolutions with Cin % 64 == 0 take the shift-GEMM kernel (conv_shift.cu): each input row is loaded once
+  if (plnr_conv2d_shift_supported(d, x, y)) return plnr_conv2d_shift(ctx, d, x, w, y, ep);
   int rc = resolve_driver();
   if (rc != PLNR_OK) return rc;
   PLNR_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, "conv2d(tcgen05): packed weights must be 16-byte aligned");
@@ -412,17 +448,22 @@ int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tenso
   p.units = d->kh * d->kw * p.cchunks;
   p.tps = 64 / p.kc;
   p.kstages = (p.units + p.tps - 1) / p.tps;
-  p.num_m_tiles = (p.M + kTileM - 1) / kTileM;
-  p.n_tile = pick_n_tile(Cout, p.num_m_tiles, ctx->sm_count);
+  const int m_tiles_128 = (p.M + kTileM - 1) / kTileM;
+  // CTA pairs (cta_group::2, 256-pixel tiles) whenever there are at least two pixel tiles; PLNR_CTA_GROUP=1 forces
+  // the single-CTA kernel (A/B comparisons, debugging)
+  int cg = 1;   // measured: the im2col main loop is bound by the im2col TMA rate (46 B/clk), which a pair does not relieve
+  if (const char* e = getenv("PLNR_CTA_GROUP")) { if (atoi(e) == 2 && m_tiles_128 >= 2) cg = 2; }
+  p.num_m_tiles = (p.M + kTileM * cg - 1) / (kTileM * cg);
+  p.n_tile = pick_n_tile(Cout, p.num_m_tiles, ctx->sm_count / cg);
   const int num_n_tiles = (Cout + p.n_tile - 1) / p.n_tile;
   p.num_tiles = p.num_m_tiles * num_n_tiles;
   p.a_unit_bytes = (uint32_t)kTileM * p.kc * 2;
-  p.b_stage_bytes = (uint32_t)p.n_tile * 128;
+  p.b_stage_bytes = (uint32_t)(p.n_tile / cg) * 128;     // per CTA: a pair splits the B tile
   p.a_layout = p.kc == 64 ? 2u : (p.kc == 32 ? 4u : 6u);
   p.a_sbo = 8u * p.kc * 2;
   // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 @4, a/b format F16 (0) @7/@10,
   // both K-major (0) @15/@16, N>>3 @17, M>>4 @24
-  p.idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  p.idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)((kTileM * cg) >> 4) << 24);
   uint32_t cols = 32;
   while (cols < 2u * p.n_tile) cols <<= 1;
   p.tmem_cols = cols;
@@ -448,6 +489,7 @@ int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tenso
   p.vec_ok = vec ? 1 : 0;
   p.err = ctx->dev_error;
   p.prof = ctx->prof;
+  if (const char* e = getenv("PLNR_DEBUG_EPI")) p.dbg = atoi(e);
 
   // ---- activation map: im2col over (C, W, H, N) ----
   CUtensorMap mapA, mapB;
@@ -476,7 +518,7 @@ int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tenso
     const int Ktot = d->kh * d->kw * Cin;
     const cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
     const cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    const cuuint32_t box[2] = {64, (cuuint32_t)p.n_tile};
+    const cuuint32_t box[2] = {64, (cuuint32_t)(p.n_tile / cg)};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode_tiled(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w), dims, strides, box,
                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -490,14 +532,34 @@ int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tenso
   }
 
   if (!ctx->igemm_attr_set) {
-    PLNR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    PLNR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    PLNR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_f16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     ctx->igemm_attr_set = true;
   }
-  int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-  if (const char* cap = getenv("PLNR_MAX_CTAS")) {        // experiment knob: restrict the persistent grid
-    int c = atoi(cap);
-    if (c > 0 && c < grid) grid = c;
+  int units = ctx->sm_count / cg;                          // persistent: one CTA (pair) per SM (pair)
+  if (const char* cap = getenv("PLNR_MAX_CTAS")) {         // experiment knob: restrict the persistent grid
+    int c = atoi(cap) / cg;
+    if (c > 0 && c < units) units = c;
   }
-  conv_igemm_f16_kernel<<<grid, kThreads, smem_bytes, ctx->stream>>>(mapA, mapB, p);
+  if (p.num_tiles < units) units = p.num_tiles;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(units * cg));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cg;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_igemm_f16_kernel<2>, mapA, mapB, p)
+                           : cudaLaunchKernelEx(&cfg, conv_igemm_f16_kernel<1>, mapA, mapB, p);
+  if (le != cudaSuccess) {
+    plnr_set_error("launch of conv_igemm_f16_kernel<%d> failed: %s", cg, cudaGetErrorString(le));
+    return PLNR_ERR_CUDA;
+  }
   return plnr_after_launch(ctx, "conv2d_tcgen05");
 }

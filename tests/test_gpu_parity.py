@@ -141,6 +141,24 @@ def test_rejects_what_the_reference_breaks_on(planer):
         planer.core(np)
 
 
+def test_reference_load_weights_idiom_on_device_arrays(planer):
+    """planer_b200.install(planer) lets the REFERENCE Net run on this backend; its load path uses exactly these
+    statements on backend arrays (planer/net.py:20-21, 83-88).  /root/reference is absent on the GPU box, so the
+    statements are replayed verbatim here."""
+    np_ = planer.b200
+    blob = np.arange(64, dtype=np.float32)
+    data = np_.asarray(blob.view(np.uint8))
+    weights = [np_.zeros((4, 4), dtype='float32'), np_.zeros((48,), dtype='float32')]
+    s, data = 0, data.view(dtype=np_.uint8)
+    for i in range(len(weights)):
+        buf = weights[i].ravel().view(dtype=np_.uint8)
+        buf[:] = data[s:s + buf.size]
+        s += buf.size
+    assert np.array_equal(weights[0].get(), blob[:16].reshape(4, 4))
+    assert np.array_equal(weights[1].get(), blob[16:])
+    assert weights[1].astype('float16').dtype == np.float16
+
+
 def test_relu_aliases_like_the_reference(planer):
     x = planer.b200.asarray(np.array([[-1.0, 2.0, -3.0, 4.0]], np.float32))
     y = planer.layer_map['relu'](x)
