@@ -29,9 +29,10 @@
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;          // warps 0-3: producer / MMA / TMEM / table; warps 4-11: two epilogue groups
 constexpr uint32_t kEpiBytes = 2 * 2 * 256 * 4;
 constexpr int kMaxA = 4, kMaxB = 40;
+constexpr uint32_t kStageBytes = 8 * 2048;        // epilogue transposition stage (per epilogue warp: 32 rows x 64 B)
 constexpr long long kWatchdogCycles = 4000000000ll;
 
 struct ShiftParams {
@@ -117,6 +118,7 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   const uint32_t bar_bfull = sBar + 16 * kMaxA, bar_bempty = bar_bfull + 8 * kMaxB;
   const uint32_t bar_tfull = bar_bempty + 8 * kMaxB, bar_tempty = bar_tfull + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + epi_off + kEpiBytes + 16 * kMaxA + 16 * kMaxB + 32);
+  uint8_t* stage = base_ptr + epi_off + kEpiBytes + 16 * kMaxA + 16 * kMaxB + 64;   // 4 warps x 2 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
@@ -133,7 +135,7 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   if (warp == 1 && lane == 0) {
     for (uint32_t i = 0; i < na; ++i) { ptx::mbar_init(bar_afull + 8 * i, 1); ptx::mbar_init(bar_aempty + 8 * i, 1); }
     for (uint32_t i = 0; i < nb; ++i) { ptx::mbar_init(bar_bfull + 8 * i, 1); ptx::mbar_init(bar_bempty + 8 * i, 1); }
-    for (uint32_t a = 0; a < 2; ++a) { ptx::mbar_init(bar_tfull + 8 * a, 1); ptx::mbar_init(bar_tempty + 8 * a, 128 * CG); }
+    for (uint32_t a = 0; a < 2; ++a) { ptx::mbar_init(bar_tfull + 8 * a, 1); ptx::mbar_init(bar_tempty + 8 * a, 256 * CG); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -271,23 +273,31 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 2] = t_full; p.prof[blockIdx.x * 8 + 3] = t_tempty; p.prof[blockIdx.x * 8 + 4] = clock64() - t_all0; }
   } else if (warp >= 4) {
     // ===================================== epilogue ===========================================
-    const int ew = warp - 4;
-    const int et = threadIdx.x - 128;
-    uint32_t it = 0;
+    const int ew = warp & 3;                 // the TMEM lane quarter this warp may read (warp % 4)
+    const int eg = (warp - 4) >> 2;          // epilogue group: 0 -> first half of the tile's columns, 1 -> second half
+    const int et = threadIdx.x - 128;        // 0..255
+    uint32_t it = 0, ebuf = 0;
+    int staged_n = -1;
     long long t_tfull = 0;
     const long long t_all0 = clock64();
     for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
       const uint32_t a = it & 1, tph = (it >> 1) & 1;
       const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
       const int n0 = n_idx * p.n_tile;
-      float* ep_scale = epi + a * 512, *ep_shift = ep_scale + 256;
-      for (int i = et; i < p.n_tile; i += 128) {
-        const int c = n0 + i;
-        float sc = 0.f, sf = 0.f;
-        if (c < p.Cout) { sc = p.scale ? __ldg(p.scale + c) : 1.f; sf = p.shift ? __ldg(p.shift + c) : 0.f; }
-        ep_scale[i] = sc; ep_shift[i] = sf;
+      // per-channel scale/shift of this tile's channel block: re-staged only when the block changes
+      if (n_idx != staged_n) {
+        staged_n = n_idx;
+        ebuf ^= 1u;
+        float* dsc = epi + ebuf * 512, *dsf = dsc + 256;
+        for (int i = et; i < p.n_tile; i += 256) {
+          const int c = n0 + i;
+          float sc = 0.f, sf = 0.f;
+          if (c < p.Cout) { sc = p.scale ? __ldg(p.scale + c) : 1.f; sf = p.shift ? __ldg(p.shift + c) : 0.f; }
+          dsc[i] = sc; dsf[i] = sf;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float* ep_scale = epi + ebuf * 512, *ep_shift = ep_scale + 256;
 
       // this thread's virtual position -> output pixel (or nothing, for the padded rim)
       const long long o = ((long long)m_idx * CG + rank) * kTileM + ew * 32 + lane;
@@ -310,24 +320,45 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       __half* yrow = p.y + (size_t)(mvalid ? m : 0) * p.yld + p.ycoff;
       const __half* rrow = p.res ? p.res + (size_t)(mvalid ? m : 0) * p.rld + p.rcoff : nullptr;
 
-      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+      // Coalescing: a thread owns one output ROW (32 channels = 64 B per chunk), so direct 16-byte accesses would touch
+      // 32 different 128-byte lines per warp instruction.  Rows are transposed through a per-warp shared-memory stage so
+      // that one instruction moves 8 rows x 64 contiguous bytes.  Lane l serves row 8*i + l/4, 16-byte piece l%4.
+      unsigned long long yptr[4];
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int src = 8 * i + (lane >> 2);
+        yptr[i] = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)yrow, src);
+        vmask |= (__shfl_sync(0xffffffffu, mvalid ? 1u : 0u, src) & 1u) << i;
+      }
+      uint8_t* st_o = stage + (warp - 4) * 2048;
+      const uint32_t my_sw = (uint32_t)((lane >> 1) & 3);
+
+      const int nchunks = p.n_tile >> 5, half = (nchunks + 1) >> 1;
+      const int c_begin = eg * half * 32, c_end = min(nchunks, (eg + 1) * half) * 32;
+      if (c_begin >= c_end) {               // nothing to read for this group (n_tile == 32): release at once
+        ptx::tc_fence_before();
+        if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
+        else ptx::mbar_arrive(bar_tempty + 8 * a);
+      }
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         __syncwarp();
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(t_row + c0, v);
         const int cb = n0 + c0;
         const bool fast = p.vec_ok && (cb + 32 <= p.Cout);
         uint4 rv[4];
-        if (fast && rrow && mvalid) {
+        if (fast && rrow && mvalid) {        // residual: direct row-owner loads, issued before the TMEM wait
 #pragma unroll
           for (int q = 0; q < 4; ++q) rv[q] = *reinterpret_cast<const uint4*>(rrow + cb + q * 8);
         }
         ptx::tmem_ld_wait();
-        if (c0 + 32 >= p.n_tile) {
+        if (c0 + 32 >= c_end) {
           ptx::tc_fence_before();
           if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
           else ptx::mbar_arrive(bar_tempty + 8 * a);
         }
-        if (mvalid && fast) {
+        if (fast) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float sc[8], sf[8], o8[8];
@@ -340,7 +371,7 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             float rf[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) rf[e] = 0.f;
-            if (rrow) {
+            if (rrow && mvalid) {
               const __half2* rh = reinterpret_cast<const __half2*>(&rv[q]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -361,7 +392,14 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             uint4 pk;
             pk.x = pack_half2(o8[0], o8[1]); pk.y = pack_half2(o8[2], o8[3]);
             pk.z = pack_half2(o8[4], o8[5]); pk.w = pack_half2(o8[6], o8[7]);
-            *reinterpret_cast<uint4*>(yrow + cb + q * 8) = pk;
+            *reinterpret_cast<uint4*>(st_o + lane * 64 + (((uint32_t)q ^ my_sw) << 4)) = pk;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = 8 * i + (lane >> 2), piece = lane & 3;
+            const uint4 val = *reinterpret_cast<const uint4*>(st_o + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
+            if ((vmask >> i) & 1u) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(yptr[i]) + cb + piece * 8) = val;
           }
         } else if (mvalid) {
 #pragma unroll
@@ -454,7 +492,7 @@ static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
   pl.b_stage_bytes = (uint32_t)(pl.n_tile / pl.cg) * 128;
   const int kst = d->kh * d->kw * (x->c / 64);
   const int num_n_tiles = (y->c + pl.n_tile - 1) / pl.n_tile;
-  const size_t fixed = kEpiBytes + 16 * kMaxA + 16 * kMaxB + 64 + 1024;
+  const size_t fixed = kEpiBytes + 16 * kMaxA + 16 * kMaxB + 64 + kStageBytes + 1024;
   const size_t budget = 232448;
   // resident weights: all (chunk, tap) boxes stay in shared memory for the whole kernel
   pl.na = 2;

@@ -26,10 +26,11 @@
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;          // warps 0-3: producer / MMA / TMEM / table; warps 4-11: two epilogue groups
 constexpr int kMaxStages = 8;
 constexpr uint32_t kAStageBytes = kTileM * 64 * 2;  // 16 KB: 128 pixels x 64 k x fp16
-constexpr uint32_t kEpiBytes = 2 * 2 * 256 * 4;     // [tile parity][scale|shift][256] fp32
+constexpr uint32_t kEpiBytes = 2 * 2 * 256 * 4;     // [buffer][scale|shift][256] fp32
+constexpr uint32_t kStageBytes = 8 * 2048;          // epilogue transposition stage (per epilogue warp: 32 rows x 64 B)
 constexpr long long kWatchdogCycles = 4000000000ll; // ~2 s: a stuck barrier becomes an error, not a hang
 
 struct IgemmParams {
@@ -97,6 +98,8 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   const uint32_t bar_full = sBar, bar_empty = sBar + 8 * stages;
   const uint32_t bar_tfull = sBar + 16 * stages, bar_tempty = bar_tfull + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + epi_off + kEpiBytes + 16 * stages + 32);
+  uint8_t* stage = base_ptr + epi_off + kEpiBytes + 16 * stages + 64;     // 4 warps x 2 KB epilogue transposition stage
+  uint32_t* utab = reinterpret_cast<uint32_t*>(stage + kStageBytes);      // per k-unit: channel | tap offsets
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // position inside the CTA pair
@@ -115,13 +118,22 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     }
     for (uint32_t a = 0; a < 2; ++a) {
       ptx::mbar_init(bar_tfull + 8 * a, 1);          // tcgen05.commit after the last k-stage of a tile
-      ptx::mbar_init(bar_tempty + 8 * a, 128 * CG);  // every epilogue thread of the pair (leader's copy is the live one)
+      ptx::mbar_init(bar_tempty + 8 * a, 256 * CG);  // every epilogue thread of the pair (leader's copy is the live one)
     }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
     if (CG == 2) { ptx::tmem_alloc_pair(ptx::smem_u32(tmem_slot), p.tmem_cols); ptx::tmem_relinquish_pair(); }
     else { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), p.tmem_cols); ptx::tmem_relinquish(); }
+  }
+  if (warp == 3) {
+    // k-unit table: unit u = (filter tap, channel chunk) -> first channel and the im2col tap offsets, so that the
+    // producer's inner loop is a table read + one TMA instruction
+    for (int u = lane; u < p.units; u += 32) {
+      const int tap = u / p.cchunks, cc = u - tap * p.cchunks;
+      const int r = tap / p.S, sx = tap - r * p.S;
+      utab[u] = (uint32_t)(cc * p.kc) | ((uint32_t)(sx * p.dw) << 16) | ((uint32_t)(r * p.dh) << 24);
+    }
   }
   ptx::tc_fence_before();
   if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
@@ -135,7 +147,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     uint32_t s = 0, ph = 0;
     long long t_wait = 0;
     const long long t_all0 = clock64();
-    const int tps = p.tps, units = p.units, cchunks = p.cchunks, kc = p.kc, S = p.S, dw = p.dw, dh = p.dh;
+    const int tps = p.tps, units = p.units;
     const uint32_t a_unit_bytes = p.a_unit_bytes, b_stage_bytes = p.b_stage_bytes;
     for (int tile = unit; tile < p.num_tiles; tile += nunits) {
       const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
@@ -145,7 +157,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       const int p0 = t1 % p.OH, img = t1 / p.OH;
       const int cw = q0 * p.sw - p.pad_l, chh = p0 * p.sh - p.pad_t;   // input coordinate of the tile's first pixel
       const int n_row = n_idx * p.n_tile + (int)rank * (p.n_tile / CG);
-      int r = 0, sx = 0, cc = 0, u = 0;                                // filter row / column / channel chunk of the next unit
+      int u = 0;
       for (int j = 0; j < p.kstages; ++j) {
         const long long tw0 = clock64();
         mbar_wait(bar_empty + 8 * s, ph ^ 1, p.err, 0);
@@ -155,20 +167,18 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           const uint32_t full = bar_full + 8 * s;
           if (leader) ptx::mbar_arrive_expect_tx(full, (uint32_t)CG * ((uint32_t)nu * a_unit_bytes + b_stage_bytes));
           uint32_t a_dst = sA + s * kAStageBytes;
-          int r2 = r, sx2 = sx, cc2 = cc;
           for (int t = 0; t < nu; ++t) {
+            const uint32_t e = utab[u + t];
             if (CG == 2)
-              ptx::tma_load_im2col_4d_pair(a_dst, &mapA, full, cc2 * kc, cw, chh, img, (uint16_t)(sx2 * dw), (uint16_t)(r2 * dh));
+              ptx::tma_load_im2col_4d_pair(a_dst, &mapA, full, (int)(e & 0xffffu), cw, chh, img, (uint16_t)((e >> 16) & 0xffu), (uint16_t)(e >> 24));
             else
-              ptx::tma_load_im2col_4d(a_dst, &mapA, full, cc2 * kc, cw, chh, img, (uint16_t)(sx2 * dw), (uint16_t)(r2 * dh));
+              ptx::tma_load_im2col_4d(a_dst, &mapA, full, (int)(e & 0xffffu), cw, chh, img, (uint16_t)((e >> 16) & 0xffu), (uint16_t)(e >> 24));
             a_dst += a_unit_bytes;
-            if (++cc2 == cchunks) { cc2 = 0; if (++sx2 == S) { sx2 = 0; ++r2; } }
           }
           if (CG == 2) ptx::tma_load_2d_pair(sB + s * b_stage_bytes, &mapB, full, j * 64, n_row);
           else ptx::tma_load_2d(sB + s * b_stage_bytes, &mapB, full, j * 64, n_row);
         }
         __syncwarp();
-        for (int t = 0; t < nu; ++t) { if (++cc == cchunks) { cc = 0; if (++sx == S) { sx = 0; ++r; } } }
         u += nu;
         if (++s == stages) { s = 0; ph ^= 1; }
       }
@@ -207,6 +217,14 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         if (ptx::elect_one()) {
           uint64_t da = adesc0 + (uint64_t)(s * a_step), db = bdesc0 + (uint64_t)(s * b_step);
           uint32_t acc = j > 0 ? 1u : 0u;
+          if (kper == 4) {                       // Cin % 64 == 0: one unit per stage, four K=16 steps, fully unrolled
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (CG == 2) ptx::umma_f16_pair(d_tmem, da, db, idesc, acc);
+              else ptx::umma_f16(d_tmem, da, db, idesc, acc);
+              acc = 1u; da += 2; db += 2;
+            }
+          } else
           for (int t = 0; t < nu; ++t) {
             for (int k = 0; k < kper; ++k) {
               if (CG == 2) ptx::umma_f16_pair(d_tmem, da, db, idesc, acc);
@@ -232,9 +250,11 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 2] = t_full; p.prof[blockIdx.x * 8 + 3] = t_tempty; p.prof[blockIdx.x * 8 + 4] = clock64() - t_all0; }
   } else if (warp >= 4) {
     // ===================================== epilogue ===========================================
-    const int ew = warp - 4;                 // == warp % 4: the TMEM lane quarter this warp may read
-    const int et = threadIdx.x - 128;        // 0..127
-    uint32_t it = 0;
+    const int ew = warp & 3;                 // the TMEM lane quarter this warp may read (warp % 4)
+    const int eg = (warp - 4) >> 2;          // epilogue group: 0 -> first half of the tile's columns, 1 -> second half
+    const int et = threadIdx.x - 128;        // 0..255
+    uint32_t it = 0, ebuf = 0;
+    int staged_n = -1;
     long long t_tfull = 0;
     const long long t_all0 = clock64();
     for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
@@ -242,14 +262,20 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
       const int n0 = n_idx * p.n_tile;
       // stage this tile's per-channel scale/shift in shared memory (double buffered by tile parity)
-      float* ep_scale = epi + a * 512, *ep_shift = ep_scale + 256;
-      for (int i = et; i < p.n_tile; i += 128) {
-        const int c = n0 + i;
-        float sc = 0.f, sf = 0.f;
-        if (c < p.Cout) { sc = p.scale ? __ldg(p.scale + c) : 1.f; sf = p.shift ? __ldg(p.shift + c) : 0.f; }
-        ep_scale[i] = sc; ep_shift[i] = sf;
+      // per-channel scale/shift of this tile's channel block: re-staged only when the block changes
+      if (n_idx != staged_n) {
+        staged_n = n_idx;
+        ebuf ^= 1u;
+        float* dsc = epi + ebuf * 512, *dsf = dsc + 256;
+        for (int i = et; i < p.n_tile; i += 256) {
+          const int c = n0 + i;
+          float sc = 0.f, sf = 0.f;
+          if (c < p.Cout) { sc = p.scale ? __ldg(p.scale + c) : 1.f; sf = p.shift ? __ldg(p.shift + c) : 0.f; }
+          dsc[i] = sc; dsf[i] = sf;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float* ep_scale = epi + ebuf * 512, *ep_shift = ep_scale + 256;
 
       const long long tt0 = clock64();
       mbar_wait(bar_tfull + 8 * a, aph, p.err, 3);
@@ -268,7 +294,27 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         else ptx::mbar_arrive(bar_tempty + 8 * a);
         continue;
       }
-      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+      // Coalescing: a thread owns one output ROW (32 channels = 64 B per chunk); rows are transposed through a per-warp
+      // shared-memory stage so that one store instruction moves 8 rows x 64 contiguous bytes (see conv_shift.cu).
+      unsigned long long yptr[4];
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int src = 8 * i + (lane >> 2);
+        yptr[i] = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)yrow, src);
+        vmask |= (__shfl_sync(0xffffffffu, mvalid ? 1u : 0u, src) & 1u) << i;
+      }
+      uint8_t* st_o = stage + (warp - 4) * 2048;
+      const uint32_t my_sw = (uint32_t)((lane >> 1) & 3);
+
+      const int nchunks = p.n_tile >> 5, half = (nchunks + 1) >> 1;
+      const int c_begin = eg * half * 32, c_end = min(nchunks, (eg + 1) * half) * 32;
+      if (c_begin >= c_end) {               // nothing to read for this group (n_tile == 32): release at once
+        ptx::tc_fence_before();
+        if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
+        else ptx::mbar_arrive(bar_tempty + 8 * a);
+      }
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         __syncwarp();                       // tcgen05.ld is warp-collective: re-converge after the guarded stores
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(t_row + c0, v);
@@ -280,12 +326,12 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           for (int q = 0; q < 4; ++q) rv[q] = *reinterpret_cast<const uint4*>(rrow + cb + q * 8);
         }
         ptx::tmem_ld_wait();
-        if (c0 + 32 >= p.n_tile) {          // accumulator fully read: hand it back to the (leader's) MMA warp
+        if (c0 + 32 >= c_end) {          // accumulator fully read: hand it back to the (leader's) MMA warp
           ptx::tc_fence_before();
           if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
           else ptx::mbar_arrive(bar_tempty + 8 * a);
         }
-        if (mvalid && fast) {
+        if (fast) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float sc[8], sf[8], o[8];
@@ -298,7 +344,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             float rf[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) rf[e] = 0.f;
-            if (rrow) {
+            if (rrow && mvalid) {
               const __half2* rh = reinterpret_cast<const __half2*>(&rv[q]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -319,7 +365,14 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             uint4 pk;
             pk.x = pack_half2(o[0], o[1]); pk.y = pack_half2(o[2], o[3]);
             pk.z = pack_half2(o[4], o[5]); pk.w = pack_half2(o[6], o[7]);
-            *reinterpret_cast<uint4*>(yrow + cb + q * 8) = pk;
+            *reinterpret_cast<uint4*>(st_o + lane * 64 + (((uint32_t)q ^ my_sw) << 4)) = pk;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = 8 * i + (lane >> 2), piece = lane & 3;
+            const uint4 val = *reinterpret_cast<const uint4*>(st_o + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
+            if ((vmask >> i) & 1u) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(yptr[i]) + cb + piece * 8) = val;
           }
         } else if (mvalid) {
 #pragma unroll
@@ -468,12 +521,14 @@ int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tenso
   while (cols < 2u * p.n_tile) cols <<= 1;
   p.tmem_cols = cols;
   const uint32_t stage_bytes = kAStageBytes + p.b_stage_bytes;
-  const uint32_t budget = 232448u - 1024u - kEpiBytes - 256u;
+  PLNR_REQUIRE(p.units <= 4096, "conv2d(tcgen05): too many k-units (%d)", p.units);
+  const uint32_t utab_bytes = (uint32_t)round_up(p.units * 4, 16);
+  const uint32_t budget = 232448u - 1024u - kEpiBytes - 256u - kStageBytes - utab_bytes;
   int stages = (int)(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   PLNR_REQUIRE(stages >= 2, "conv2d(tcgen05): tile does not fit shared memory");
   p.stages = stages;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + kEpiBytes + 16 * stages + 64 + 1024;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + kEpiBytes + 16 * stages + 64 + kStageBytes + utab_bytes + 1024;
 
   p.y = (__half*)y->ptr; p.yld = y->ld; p.ycoff = y->coff; p.Cout = Cout;
   bool vec = (y->ld % 8 == 0) && (y->coff % 8 == 0) && ((reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0);
