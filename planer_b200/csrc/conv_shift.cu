@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                       const ShiftParams p) {
   extern __shared__ uint8_t smem_raw[];
+  const long long t_entry = clock64();
+  const bool stamp = p.prof && blockIdx.x == 0;      // debug: phase time stamps of CTA 0 at prof[1400..]
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
@@ -146,6 +148,10 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  if (stamp && threadIdx.x == 0) {
+    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.prof[1400] = (long long)gt; p.prof[1401] = clock64() - t_entry;
+  }
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -209,68 +215,80 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 0] = t_wait; p.prof[blockIdx.x * 8 + 1] = clock64() - t_all0; }
   } else if (warp == 1 && leader) {
     // ===================================== MMA issuer =========================================
+    // The single issuing thread paces every tile with N <= 128 unless its instruction stream is short (48 / 64 clk of
+    // tensor-pipe time per MMA at N = 64 / 128): descriptors are 32-bit low words advanced by adds, four K=16 steps go
+    // out in one asm block, resident weights are waited for during the first tile only, and nothing else sits between two taps.
     uint32_t ab = 0, aph = 0, bs = 0, bph = 0, it = 0;
-    bool first = true;
     long long t_full = 0, t_tempty = 0;
     const long long t_all0 = clock64();
     const uint32_t idesc = p.idesc;
+    const uint32_t desc_hi = (uint32_t)(ptx::make_smem_desc(0, 1024, 2) >> 32);
     // descriptor of position o0 (row offset Wv) in A buffer 0; +8 per pixel row (128 B >> 4)
-    const uint64_t adesc0 = ptx::make_smem_desc(sA + (uint32_t)Wv * 128u, 1024, 2);
-    const uint64_t bdesc0 = ptx::make_smem_desc(sB, 1024, 2);
+    const uint32_t a_lo0 = (uint32_t)ptx::make_smem_desc(sA + (uint32_t)Wv * 128u, 1024, 2);
+    const uint32_t b_lo0 = (uint32_t)ptx::make_smem_desc(sB, 1024, 2);
     const uint32_t a_step = p.a_buf_bytes >> 4, b_step = p.b_stage_bytes >> 4;
     const uint32_t r_step = (uint32_t)(p.dh * Wv) * 8u, s_step = (uint32_t)p.dw * 8u;
+    const int R = p.R, S = p.S, cchunks = p.cchunks, n_tile = p.n_tile;
+    const bool resident = p.b_resident != 0;
+    const bool elected = ptx::elect_one();       // the same lane issues every MMA and every commit
     for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
       const uint32_t a = it & 1, tph = (it >> 1) & 1;
       const long long te0 = clock64();
       mbar_wait(bar_tempty + 8 * a, tph ^ 1, p.err, 1);
       t_tempty += clock64() - te0;
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + a * (uint32_t)p.n_tile;
-      for (int cc = 0; cc < p.cchunks; ++cc) {
+      const uint32_t d_tmem = tmem_base + a * (uint32_t)n_tile;
+      uint32_t acc = 0u;
+      uint32_t b_lo = b_lo0;                     // resident: (chunk, tap) boxes in order from the start of sB
+      for (int cc = 0; cc < cchunks; ++cc) {
         const long long tf0 = clock64();
         mbar_wait(bar_afull + 8 * ab, aph, p.err, 2);
         t_full += clock64() - tf0;
+        if (stamp && it == 0 && cc == 0 && lane == 0) p.prof[1402] = clock64() - t_entry;
         ptx::tc_fence_after();
-        const uint64_t da_chunk = adesc0 + (uint64_t)(ab * a_step);
-        int tap = 0;
-        for (int r = 0; r < p.R; ++r) {
-          for (int sx = 0; sx < p.S; ++sx, ++tap) {
-            if (!p.b_resident || first) {
-              const long long tb0 = clock64();
+        uint32_t a_row = a_lo0 + ab * a_step;
+        if (resident) {
+          if (it == 0) {                         // weights are loaded once per CTA, chunk by chunk behind the A rows
+            for (int i = 0; i < R * S; ++i) mbar_wait(bar_bfull + 8 * (uint32_t)(cc * R * S + i), 0, p.err, 5);
+            ptx::tc_fence_after();
+          }
+          for (int r = 0; r < R; ++r, a_row += r_step) {
+            uint32_t a_lo = a_row;
+            for (int sx = 0; sx < S; ++sx, a_lo += s_step, b_lo += b_step) {
+              if (elected) ptx::umma_f16_x4<CG>(d_tmem, a_lo, b_lo, desc_hi, idesc, acc);
+              acc = 1u;
+            }
+          }
+        } else {
+          for (int r = 0; r < R; ++r, a_row += r_step) {
+            uint32_t a_lo = a_row;
+            for (int sx = 0; sx < S; ++sx, a_lo += s_step) {
               mbar_wait(bar_bfull + 8 * bs, bph, p.err, 5);
-              t_full += clock64() - tb0;
               ptx::tc_fence_after();
-            }
-            if (ptx::elect_one()) {
-              uint64_t da = da_chunk + (uint64_t)(r * r_step + sx * s_step);
-              uint64_t db = bdesc0 + (uint64_t)(bs * b_step);
-              uint32_t acc = (cc | tap) ? 1u : 0u;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (CG == 2) ptx::umma_f16_pair(d_tmem, da, db, idesc, acc);
-                else ptx::umma_f16(d_tmem, da, db, idesc, acc);
-                acc = 1u; da += 2; db += 2;
+              if (elected) {
+                ptx::umma_f16_x4<CG>(d_tmem, a_lo, b_lo0 + bs * b_step, desc_hi, idesc, acc);
+                if (CG == 2) ptx::umma_commit_pair(bar_bempty + 8 * bs, 3);
+                else ptx::umma_commit(bar_bempty + 8 * bs);
               }
-              const bool last_tap = tap == RS - 1;
-              if (CG == 2) {
-                if (!p.b_resident) ptx::umma_commit_pair(bar_bempty + 8 * bs, 3);
-                if (last_tap) ptx::umma_commit_pair(bar_aempty + 8 * ab, 3);
-                if (last_tap && cc == p.cchunks - 1) ptx::umma_commit_pair(bar_tfull + 8 * a, 3);
-              } else {
-                if (!p.b_resident) ptx::umma_commit(bar_bempty + 8 * bs);
-                if (last_tap) ptx::umma_commit(bar_aempty + 8 * ab);
-                if (last_tap && cc == p.cchunks - 1) ptx::umma_commit(bar_tfull + 8 * a);
-              }
+              acc = 1u;
+              if (++bs == nb) { bs = 0; bph ^= 1; }
             }
-            __syncwarp();
-            if (++bs == nb) { bs = 0; bph ^= 1; }
+          }
+        }
+        if (elected) {
+          if (CG == 2) {
+            ptx::umma_commit_pair(bar_aempty + 8 * ab, 3);
+            if (cc == cchunks - 1) ptx::umma_commit_pair(bar_tfull + 8 * a, 3);
+          } else {
+            ptx::umma_commit(bar_aempty + 8 * ab);
+            if (cc == cchunks - 1) ptx::umma_commit(bar_tfull + 8 * a);
           }
         }
         if (++ab == na) { ab = 0; aph ^= 1; }
       }
-      first = false;
     }
     if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 2] = t_full; p.prof[blockIdx.x * 8 + 3] = t_tempty; p.prof[blockIdx.x * 8 + 4] = clock64() - t_all0; }
+    if (stamp && lane == 0) p.prof[1403] = clock64() - t_entry;
   } else if (warp >= 4) {
     // ===================================== epilogue ===========================================
     const int ew = warp & 3;                 // the TMEM lane quarter this warp may read (warp % 4)
@@ -311,11 +329,6 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         m = ((long long)img * p.OH + pr) * p.OW + q;
       }
 
-      const long long tt0 = clock64();
-      mbar_wait(bar_tfull + 8 * a, tph, p.err, 3);
-      t_tfull += clock64() - tt0;
-      ptx::tc_fence_after();
-
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + a * (uint32_t)p.n_tile;
       __half* yrow = p.y + (size_t)(mvalid ? m : 0) * p.yld + p.ycoff;
       const __half* rrow = p.res ? p.res + (size_t)(mvalid ? m : 0) * p.rld + p.rcoff : nullptr;
@@ -336,6 +349,20 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 
       const int nchunks = p.n_tile >> 5, half = (nchunks + 1) >> 1;
       const int c_begin = eg * half * 32, c_end = min(nchunks, (eg + 1) * half) * 32;
+      // the residual operand of the first chunk is fetched BEFORE waiting for the accumulator: its DRAM latency
+      // hides behind the tile's MMAs; later chunks are fetched one chunk ahead
+      const bool res_vec = p.vec_ok && rrow && mvalid;
+      uint4 rv[4], rvn[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) rv[q] = rvn[q] = make_uint4(0u, 0u, 0u, 0u);
+      if (res_vec && c_begin < c_end && n0 + c_begin + 32 <= p.Cout) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rv[q] = *reinterpret_cast<const uint4*>(rrow + n0 + c_begin + q * 8);
+      }
+      const long long tt0 = clock64();
+      mbar_wait(bar_tfull + 8 * a, tph, p.err, 3);
+      t_tfull += clock64() - tt0;
+      ptx::tc_fence_after();
       if (c_begin >= c_end) {               // nothing to read for this group (n_tile == 32): release at once
         ptx::tc_fence_before();
         if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
@@ -347,10 +374,9 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         ptx::tmem_ld_32x32b_x32(t_row + c0, v);
         const int cb = n0 + c0;
         const bool fast = p.vec_ok && (cb + 32 <= p.Cout);
-        uint4 rv[4];
-        if (fast && rrow && mvalid) {        // residual: direct row-owner loads, issued before the TMEM wait
+        if (res_vec && c0 + 32 < c_end && cb + 64 <= p.Cout) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) rv[q] = *reinterpret_cast<const uint4*>(rrow + cb + q * 8);
+          for (int q = 0; q < 4; ++q) rvn[q] = *reinterpret_cast<const uint4*>(rrow + cb + 32 + q * 8);
         }
         ptx::tmem_ld_wait();
         if (c0 + 32 >= c_end) {
@@ -401,6 +427,8 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             const uint4 val = *reinterpret_cast<const uint4*>(st_o + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
             if ((vmask >> i) & 1u) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(yptr[i]) + cb + piece * 8) = val;
           }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rv[q] = rvn[q];
         } else if (mvalid) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
@@ -418,14 +446,21 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       }
     }
     if (p.prof && threadIdx.x == 128) { p.prof[blockIdx.x * 8 + 5] = t_tfull; p.prof[blockIdx.x * 8 + 6] = clock64() - t_all0; }
+    if (stamp && threadIdx.x == 128) p.prof[1404] = clock64() - t_entry;
   }
 
   ptx::tc_fence_before();
   if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+  if (stamp && threadIdx.x == 0) p.prof[1405] = clock64() - t_entry;
   if (warp == 2) {
     ptx::tc_fence_after();
     if (CG == 2) ptx::tmem_dealloc_pair(tmem_base, p.tmem_cols);
     else ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+    if (stamp && lane == 0) {
+      p.prof[1406] = clock64() - t_entry;
+      unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      p.prof[1407] = (long long)gt;
+    }
   }
 }
 

@@ -191,59 +191,74 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     uint32_t s = 0, ph = 0, it = 0;
     long long t_full = 0, t_tempty = 0;
     const long long t_all0 = clock64();
-    const int kper = p.kc >> 4, tps = p.tps, units = p.units;
+    const int kper = p.kc >> 4, tps = p.tps, units = p.units, kstages = p.kstages;
     const uint32_t idesc = p.idesc;
     const uint64_t adesc0 = ptx::make_smem_desc(sA, p.a_sbo, p.a_layout);
     const uint64_t bdesc0 = ptx::make_smem_desc(sB, 1024, 2);
+    const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0, desc_hi = (uint32_t)(bdesc0 >> 32);
     const uint32_t a_step = kAStageBytes >> 4, b_step = p.b_stage_bytes >> 4;
     const uint32_t a_unit_skip = (p.a_unit_bytes - (uint32_t)kper * 32u) >> 4;
+    const bool elected = ptx::elect_one();       // the same lane issues every MMA and every commit
+    const bool trace_on = p.prof && blockIdx.x == 0 && lane == 0;
     for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
       const uint32_t a = it & 1, aph = (it >> 1) & 1;
       const long long te0 = clock64();
       mbar_wait(bar_tempty + 8 * a, aph ^ 1, p.err, 1);   // epilogue(s) have drained this accumulator
       t_tempty += clock64() - te0;
-      const bool trace = p.prof && blockIdx.x == 0 && it < 40 && lane == 0;
+      const bool trace = trace_on && it < 40;
       if (trace) { p.prof[1200 + it * 4 + 0] = te0 - t_all0; p.prof[1200 + it * 4 + 1] = clock64() - t_all0; }
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + a * (uint32_t)p.n_tile;
-      int u = 0;
-      for (int j = 0; j < p.kstages; ++j) {
-        const long long tf0 = clock64();
-        mbar_wait(bar_full + 8 * s, ph, p.err, 2);        // TMA bytes (of both CTAs) have landed
-        t_full += clock64() - tf0;
-        if (trace && j == 0) p.prof[1200 + it * 4 + 2] = clock64() - t_all0;
-        ptx::tc_fence_after();
-        const int nu = min(tps, units - u);
-        if (ptx::elect_one()) {
-          uint64_t da = adesc0 + (uint64_t)(s * a_step), db = bdesc0 + (uint64_t)(s * b_step);
-          uint32_t acc = j > 0 ? 1u : 0u;
-          if (kper == 4) {                       // Cin % 64 == 0: one unit per stage, four K=16 steps, fully unrolled
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (CG == 2) ptx::umma_f16_pair(d_tmem, da, db, idesc, acc);
-              else ptx::umma_f16(d_tmem, da, db, idesc, acc);
-              acc = 1u; da += 2; db += 2;
+      if (kper == 4) {
+        // Cin % 64 == 0: one k-unit per stage = four K=16 steps issued from one asm block; the issuing thread's
+        // instruction stream between two stages is a barrier poll, two adds and two commits (see ptx::umma_f16_x4)
+        uint32_t acc = 0u;
+        for (int j = 0; j < kstages; ++j) {
+          mbar_wait(bar_full + 8 * s, ph, p.err, 2);      // TMA bytes (of both CTAs) have landed
+          ptx::tc_fence_after();
+          if (elected) {
+            ptx::umma_f16_x4<CG>(d_tmem, a_lo0 + s * a_step, b_lo0 + s * b_step, desc_hi, idesc, acc);
+            if (CG == 2) {
+              ptx::umma_commit_pair(bar_empty + 8 * s, 3);
+              if (j == kstages - 1) ptx::umma_commit_pair(bar_tfull + 8 * a, 3);
+            } else {
+              ptx::umma_commit(bar_empty + 8 * s);
+              if (j == kstages - 1) ptx::umma_commit(bar_tfull + 8 * a);
             }
-          } else
-          for (int t = 0; t < nu; ++t) {
-            for (int k = 0; k < kper; ++k) {
-              if (CG == 2) ptx::umma_f16_pair(d_tmem, da, db, idesc, acc);
-              else ptx::umma_f16(d_tmem, da, db, idesc, acc);
-              acc = 1u; da += 2; db += 2;
-            }
-            da += a_unit_skip;
           }
-          if (CG == 2) {
-            ptx::umma_commit_pair(bar_empty + 8 * s, 3);          // both CTAs' slots reusable once these MMAs retire
-            if (j == p.kstages - 1) ptx::umma_commit_pair(bar_tfull + 8 * a, 3);
-          } else {
-            ptx::umma_commit(bar_empty + 8 * s);
-            if (j == p.kstages - 1) ptx::umma_commit(bar_tfull + 8 * a);   // accumulator complete -> epilogue
-          }
+          acc = 1u;
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
-        u += nu;
-        if (++s == stages) { s = 0; ph ^= 1; }
+      } else {
+        int u = 0;
+        for (int j = 0; j < kstages; ++j) {
+          const long long tf0 = clock64();
+          mbar_wait(bar_full + 8 * s, ph, p.err, 2);
+          t_full += clock64() - tf0;
+          ptx::tc_fence_after();
+          const int nu = min(tps, units - u);
+          if (elected) {
+            uint64_t da = adesc0 + (uint64_t)(s * a_step), db = bdesc0 + (uint64_t)(s * b_step);
+            uint32_t acc = j > 0 ? 1u : 0u;
+            for (int t = 0; t < nu; ++t) {
+              for (int k = 0; k < kper; ++k) {
+                if (CG == 2) ptx::umma_f16_pair(d_tmem, da, db, idesc, acc);
+                else ptx::umma_f16(d_tmem, da, db, idesc, acc);
+                acc = 1u; da += 2; db += 2;
+              }
+              da += a_unit_skip;
+            }
+            if (CG == 2) {
+              ptx::umma_commit_pair(bar_empty + 8 * s, 3);          // both CTAs' slots reusable once these MMAs retire
+              if (j == kstages - 1) ptx::umma_commit_pair(bar_tfull + 8 * a, 3);
+            } else {
+              ptx::umma_commit(bar_empty + 8 * s);
+              if (j == kstages - 1) ptx::umma_commit(bar_tfull + 8 * a);   // accumulator complete -> epilogue
+            }
+          }
+          u += nu;
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
       }
       if (trace) p.prof[1200 + it * 4 + 3] = clock64() - t_all0;
     }
@@ -277,23 +292,12 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       }
       const float* ep_scale = epi + ebuf * 512, *ep_shift = ep_scale + 256;
 
-      const long long tt0 = clock64();
-      mbar_wait(bar_tfull + 8 * a, aph, p.err, 3);
-      t_tfull += clock64() - tt0;
-      ptx::tc_fence_after();
-
       const int m = (m_idx * CG + (int)rank) * kTileM + ew * 32 + lane;
       const bool mvalid = m < p.M && !(p.dbg & 1);
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + a * (uint32_t)p.n_tile;
       __half* yrow = p.y + (size_t)(mvalid ? m : 0) * p.yld + p.ycoff;
       const __half* rrow = p.res ? p.res + (size_t)(mvalid ? m : 0) * p.rld + p.rcoff : nullptr;
 
-      if (p.dbg & 2) {                      // debug: release the accumulator without reading it
-        ptx::tc_fence_before();
-        if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
-        else ptx::mbar_arrive(bar_tempty + 8 * a);
-        continue;
-      }
       // Coalescing: a thread owns one output ROW (32 channels = 64 B per chunk); rows are transposed through a per-warp
       // shared-memory stage so that one store instruction moves 8 rows x 64 contiguous bytes (see conv_shift.cu).
       unsigned long long yptr[4];
@@ -309,6 +313,20 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 
       const int nchunks = p.n_tile >> 5, half = (nchunks + 1) >> 1;
       const int c_begin = eg * half * 32, c_end = min(nchunks, (eg + 1) * half) * 32;
+      // the residual operand of the first chunk is fetched BEFORE waiting for the accumulator: its DRAM latency
+      // hides behind the tile's MMAs; later chunks are fetched one chunk ahead
+      const bool res_vec = p.vec_ok && rrow && mvalid;
+      uint4 rv[4], rvn[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) rv[q] = rvn[q] = make_uint4(0u, 0u, 0u, 0u);
+      if (res_vec && c_begin < c_end && n0 + c_begin + 32 <= p.Cout) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rv[q] = *reinterpret_cast<const uint4*>(rrow + n0 + c_begin + q * 8);
+      }
+      const long long tt0 = clock64();
+      mbar_wait(bar_tfull + 8 * a, aph, p.err, 3);
+      t_tfull += clock64() - tt0;
+      ptx::tc_fence_after();
       if (c_begin >= c_end) {               // nothing to read for this group (n_tile == 32): release at once
         ptx::tc_fence_before();
         if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
@@ -320,10 +338,9 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         ptx::tmem_ld_32x32b_x32(t_row + c0, v);
         const int cb = n0 + c0;
         const bool fast = p.vec_ok && (cb + 32 <= p.Cout);
-        uint4 rv[4];
-        if (fast && rrow && mvalid) {
+        if (res_vec && c0 + 32 < c_end && cb + 64 <= p.Cout) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) rv[q] = *reinterpret_cast<const uint4*>(rrow + cb + q * 8);
+          for (int q = 0; q < 4; ++q) rvn[q] = *reinterpret_cast<const uint4*>(rrow + cb + 32 + q * 8);
         }
         ptx::tmem_ld_wait();
         if (c0 + 32 >= c_end) {          // accumulator fully read: hand it back to the (leader's) MMA warp
@@ -374,6 +391,8 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             const uint4 val = *reinterpret_cast<const uint4*>(st_o + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
             if ((vmask >> i) & 1u) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(yptr[i]) + cb + piece * 8) = val;
           }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rv[q] = rvn[q];
         } else if (mvalid) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {

@@ -94,6 +94,44 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Four K=16 steps of one 64-wide k panel in ONE asm block.  The descriptors are passed as their low words (start
+// address >> 4, + LBO field) plus a shared high word; the three follow-up MMAs add 2 (= 32 bytes) to the address
+// field.  Keeping the 64-bit descriptor arithmetic out of C++ keeps the issuing thread's instruction stream short:
+// with descriptors rebuilt in C++ per MMA the single issuing thread, not the tensor pipe, paces N <= 128 tiles
+// (tools/mma_rate_probe2.cu: 48 / 64 clk per MMA at N = 64 / 128 when the issue loop is tight, ~100 clk otherwise).
+template <int CG>
+__device__ __forceinline__ void umma_f16_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                            uint32_t idesc, uint32_t accumulate_first) {
+  if (CG == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p, t;\n\t.reg .b64 da, db;\n\t.reg .b32 a1, b1;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
+        "add.u32 a1, %1, 2;\n\tadd.u32 b1, %2, 2;\n\tmov.b64 da, {a1, %3};\n\tmov.b64 db, {b1, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, t;\n\t"
+        "add.u32 a1, %1, 4;\n\tadd.u32 b1, %2, 4;\n\tmov.b64 da, {a1, %3};\n\tmov.b64 db, {b1, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, t;\n\t"
+        "add.u32 a1, %1, 6;\n\tadd.u32 b1, %2, 6;\n\tmov.b64 da, {a1, %3};\n\tmov.b64 db, {b1, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, t;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, t;\n\t.reg .b64 da, db;\n\t.reg .b32 a1, b1;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "add.u32 a1, %1, 2;\n\tadd.u32 b1, %2, 2;\n\tmov.b64 da, {a1, %3};\n\tmov.b64 db, {b1, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, t;\n\t"
+        "add.u32 a1, %1, 4;\n\tadd.u32 b1, %2, 4;\n\tmov.b64 da, {a1, %3};\n\tmov.b64 db, {b1, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, t;\n\t"
+        "add.u32 a1, %1, 6;\n\tadd.u32 b1, %2, 6;\n\tmov.b64 da, {a1, %3};\n\tmov.b64 db, {b1, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, t;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
+        : "memory");
+  }
+}
 // mbarrier arrives once every tcgen05 op previously issued by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
