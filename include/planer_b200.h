@@ -111,6 +111,19 @@ int plnr_nchw_to_nhwc(plnr_ctx* ctx, const void* x, int x_dtype, int c_src, cons
  * filter taps re-ordered accordingly by the host (planer_b200/executor.py).  y->c >= stride*kw*c, multiple of 8. */
 int plnr_stem_pack(plnr_ctx* ctx, const void* x, int x_dtype, int n, int c, int h, int w, const plnr_tensor* y, int kw,
                    int stride, int pad_l);
+/* Fused first layer (fp16): NCHW x (n, 3, h, w) -> kh x kw / stride-2 convolution (planer/layer.py:22-26 +
+ * planer/util.py:17-44) -> *scale + shift (bias / folded BatchNorm, planer/layer.py:125-127) -> ReLU
+ * (planer/layer.py:44-46) -> 3x3 / stride-2 / pad-1 Maxpool (planer/layer.py:71-72 + planer/util.py:79-95; after a
+ * ReLU its zero padding and -1e4 floor are neutral) -> pixel-major y (n, poh, pow, 64), in ONE kernel
+ * (csrc/stem_pool.cu).  w_packed: [64][T][64] fp16 with W[co, e, ph*24 + sx*3 + c] = K[co, c, 2(e + e_min) + ph +
+ * pad_t, sx] (zero elsewhere), e_min and T from plnr_stem_pool_geometry.  plnr_stem_pool_supported returns 1 when
+ * the fused kernel applies; otherwise the caller runs plnr_stem_pack / plnr_conv2d_fwd / plnr_maxpool2d. */
+int plnr_stem_pool_supported(int dtype, int c, int h, int w, int cout, int kh, int kw, int stride, int pad_t, int pad_l,
+                             int pad_b, int pad_r, int act, int pool_k, int pool_stride, int pool_pad);
+int plnr_stem_pool_geometry(int h, int kh, int pad_t, int* e_min, int* taps);
+int plnr_stem_pool_fwd(plnr_ctx* ctx, const void* x, int n, int c, int h, int w, const void* w_packed,
+                       const float* scale, const float* shift, int kh, int kw, int stride, int pad_t, int pad_l,
+                       int pad_b, int pad_r, int act, int pool_k, int pool_stride, int pool_pad, const plnr_tensor* y);
 /* pixel-major view x -> NCHW dense y.  Graph exit: planer/net.py:100. */
 int plnr_nhwc_to_nchw(plnr_ctx* ctx, const plnr_tensor* x, int x_dtype, void* y, int y_dtype);
 /* flat cast, n elements (Net.half, planer/net.py:26-29). */

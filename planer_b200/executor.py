@@ -6,6 +6,8 @@ caller's device array in place) and ONE ``plnr_graph_launch`` that replays every
 output transposes.  Weights are packed ([Cout][kh][kw][Cin]) and bias/BatchNorm folded into fp32
 (scale, shift) vectors once, on the device, when the executor is built.
 """
+import os
+
 import numpy as np
 
 from . import _capi, ops, plan as P
@@ -25,6 +27,7 @@ class Executor:
         self.arr = {}             # root value id -> DeviceArray
         self.launches = []        # closures, in order
         self.kinds = []           # step op per closure (for timers / launch accounting)
+        self.names = []           # fused layer names per closure
         self.graph = None
         self.input_ids = list(gplan.inputs)
         self.in_arrays, self.out_arrays, self.out_flat = [], [], []
@@ -74,6 +77,24 @@ class Executor:
             return None
         return st
 
+    def _fused_stem_of(self, vid):
+        """(conv step, maxpool step) when graph input ``vid`` feeds conv -> (bn) -> relu -> maxpool(3x3/s2/p1) and the
+        fused first-layer kernel (csrc/stem_pool.cu) supports the shapes; else None."""
+        st = self._stem_of(vid)
+        if st is None or st.res is not None or os.environ.get('PLNR_NO_FUSED_STEM') == '1':
+            return None
+        out = self._root(st.out)
+        users = [u for u in self.plan.steps if out in [self._root(r) for r in u.reads()]]
+        if len(users) != 1 or users[0].op != 'maxpool' or self.values[st.out].is_output:
+            return None
+        pool, v, a = users[0], self.values[vid], st.attrs
+        kshape = self.values[st.w].shape
+        if x_dtype_ok(self.dtype) and ops.stem_pool_supported(
+                self.dtype, v.shape[1], v.shape[2], v.shape[3], kshape[0], kshape[2], kshape[3], a['strides'][0],
+                a['pads'], st.act, pool.attrs['w'], pool.attrs['strides'], pool.attrs['pads']):
+            return st, pool
+        return None
+
     def _get(self, vid):
         return self.arr[self._root(vid)]
 
@@ -108,10 +129,15 @@ class Executor:
 
         # graph inputs: pixel-major staging filled by an eager transform at every forward
         self.stems = {}
+        self.fused_stems = {}     # graph input -> dict(conv, pool, run): conv+bn+relu+maxpool in ONE kernel at input time
         for vid in self.input_ids:
             shp = vals[vid].shape
+            fs = self._fused_stem_of(vid)
             st = self._stem_of(vid)
-            if st is not None:
+            if fs is not None:
+                self.fused_stems[vid] = dict(conv=fs[0], pool=fs[1], run=None)
+                a = None                                   # the kernel reads the caller's NCHW array in place
+            elif st is not None:
                 kshape, at = vals[st.w].shape, st.attrs
                 g = ops.stem_geometry(shp[2], shp[3], kshape[2], kshape[3], at['strides'][0], at['pads'])
                 real = at['strides'][0] * kshape[3] * shp[1]
@@ -131,6 +157,7 @@ class Executor:
             if fn is not None:
                 self.launches.append(fn)
                 self.kinds.append(st.op)
+                self.names.append('+'.join(st.fused))
 
         # graph outputs: restore NCHW (planer/net.py:100 hands NCHW arrays back)
         for o in gp.outputs:
@@ -139,6 +166,7 @@ class Executor:
                 flat = B.empty(a.shape, dt)
                 self.launches.append(lambda a=a, flat=flat: ops.nhwc_to_nchw_into(a, flat))
                 self.kinds.append('to_nchw')
+                self.names.append('to_nchw')
                 self.out_flat.append(flat)
             else:
                 self.out_flat.append(a)
@@ -148,7 +176,9 @@ class Executor:
         vals, dt = self.values, self.dtype
         op = st.op
         if op in ('conv', 'dense'):
-            x = self._view(st.ins[0])
+            fused = self.fused_stems.get(self._root(st.ins[0])) if op == 'conv' else None
+            fused = fused if fused is not None and fused['conv'] is st else None
+            x = self._view(st.ins[0]) if fused is None else None
             K = self._weight(st.w)
             co = K.shape[0]
             bias = self._weight(st.bias) if st.bias is not None else None
@@ -159,8 +189,17 @@ class Executor:
                 if bn_k is None:
                     scale = None
             res = self._view(st.res) if st.res is not None else None
-            y = alloc(st.out)
             self._keep += [scale, shift]
+            if fused is not None:
+                a = st.attrs
+                yp = alloc(fused['pool'].out)
+                wp = B.asarray(ops.stem_pool_weight(K.get().astype(np.float16), a['pads'][0]))
+                self._keep.append(wp)
+                kh, kw = K.shape[2], K.shape[3]
+                fused['run'] = lambda xf: ops.stem_pool_into(xf, wp, scale, shift, yp, kh, kw, a['strides'][0], a['pads'],
+                                                            st.act)
+                return None
+            y = alloc(st.out)
             stem = self.stems.get(self._root(st.ins[0])) if op == 'conv' else None
             if stem is not None:
                 # first layer on the packed input: (T x 1) stride-1 conv, taps re-ordered on the host (tiny, load time)
@@ -205,6 +244,8 @@ class Executor:
             self._keep += [k, b]
             return lambda: ops.eltwise(ops.EW_SCALE_SHIFT, _dense(x), y, p0=k, p1=b)
         if op == 'maxpool':
+            if any(f['pool'] is st for f in self.fused_stems.values()):
+                return None                              # computed by the fused first-layer kernel
             x, y, a = self._view(st.ins[0]), alloc(st.out), st.attrs
             return lambda: ops.maxpool_into(x, y, a['w'], a['pads'], a['strides'])
         if op == 'upsample':
@@ -238,7 +279,9 @@ class Executor:
                 raise ValueError('input %r: plan compiled for shape %s, got %s' % (self.values[vid].name, shp, x.shape))
             if x.layout != 'flat':
                 x = B.to_flat(x)
-            if vid in self.stems:
+            if vid in self.fused_stems:
+                self.fused_stems[vid]['run'](x)
+            elif vid in self.stems:
                 sm = self.stems[vid]
                 ops.stem_pack_into(x, a, sm['kw'], sm['stride'], sm['pad_l'])
             elif len(shp) == 4:
@@ -270,6 +313,9 @@ class Executor:
                     rc = lib.plnr_graph_end(ctx, C.byref(g))
                 _capi.check(rc, 'plnr_graph_end')
                 self.graph = g
+                # this forward was already computed by the eager pass; replaying the graph now would read first-layer
+                # outputs (written at input time, outside the graph) that later layers have since recycled
+                return tuple(self.out_flat)
             _capi.check(B.lib().plnr_graph_launch(B.ctx(), self.graph), 'plnr_graph_launch')
         return tuple(self.out_flat)
 
@@ -277,6 +323,10 @@ class Executor:
         if self.graph is not None:
             B.lib().plnr_graph_destroy(self.graph)
             self.graph = None
+
+
+def x_dtype_ok(dt):
+    return np.dtype(dt) == np.float16
 
 
 def _dense(a):

@@ -194,6 +194,40 @@ def stem_pack_into(x_flat, y, kw, stride, pad_l):
     return y
 
 
+def stem_pool_supported(dtype, c, h, w, cout, kh, kw, stride, pads, act, pool_w, pool_strides, pool_pads):
+    """True when the fused first-layer kernel (conv + scale/shift + ReLU + 3x3/s2/p1 maxpool) applies."""
+    if tuple(pool_w) != (3, 3) or tuple(pool_strides) != (2, 2) or tuple(pool_pads) != (1, 1, 1, 1):
+        return False
+    return bool(B.lib().plnr_stem_pool_supported(_capi.dtype_code(dtype), c, h, w, cout, kh, kw, stride, pads[0], pads[1],
+                                                 pads[2], pads[3], act, 3, 2, 1))
+
+
+def stem_pool_weight(K, pad_t):
+    """Host-side (tiny, load-time) re-ordering of an OIHW stride-2 first-layer filter into the [Cout][T][64] K-major
+    layout of ``plnr_stem_pool_fwd``: W[co, e, ph*24 + sx*3 + c] = K[co, c, 2(e + e_min) + ph + pad_t, sx]."""
+    co, c, kh, kw = K.shape
+    e_min, taps = C.c_int(), C.c_int()
+    _capi.check(B.lib().plnr_stem_pool_geometry(0, kh, pad_t, C.byref(e_min), C.byref(taps)), 'plnr_stem_pool_geometry')
+    out = np.zeros((co, taps.value, 64), np.float16)
+    for e in range(taps.value):
+        for ph in range(2):
+            r = 2 * (e + e_min.value) + ph + pad_t
+            if 0 <= r < kh:
+                for sx in range(kw):
+                    out[:, e, ph * 24 + sx * 3:ph * 24 + sx * 3 + c] = K[:, :, r, sx]
+    return out
+
+
+def stem_pool_into(x_flat, w_packed, scale, shift, y, kh, kw, stride, pads, act=ACT_RELU):
+    n, c, h, w = x_flat.shape
+    t = y.tensor()
+    p = lambda a: a.ptr if a is not None else None
+    _capi.check(B.lib().plnr_stem_pool_fwd(B.ctx(), x_flat.ptr, n, c, h, w, w_packed.ptr, p(scale), p(shift), kh, kw,
+                                           stride, pads[0], pads[1], pads[2], pads[3], act, 3, 2, 1, C.byref(t)),
+                'plnr_stem_pool_fwd')
+    return y
+
+
 def nhwc_to_nchw_into(x, y_flat):
     t = x.tensor()
     _capi.check(B.lib().plnr_nhwc_to_nchw(B.ctx(), C.byref(t), _capi.dtype_code(x.dtype), y_flat.ptr,

@@ -80,6 +80,18 @@ def single_conv(cin=3, cout=64, k=3, stride=1, pad=0, dil=1, group=1, bias=True,
     return b.finish(['x'], [y])
 
 
+def stem_net(cout=64, k=7, pad=3, bias=False, bn=True, seed=0):
+    """The first four layers of a ResNet: conv k x k / s2 -> (batchnorm) -> relu -> maxpool 3/s2/p1.  The pattern the
+    fused first-layer kernel (csrc/stem_pool.cu) absorbs."""
+    b = _Builder(seed)
+    x = b.conv('x', 3, cout, k, 2, pad, bias=bias, name='conv1')
+    if bn:
+        x = b.bn(x, cout, 'bn1')
+    x = b.op('relu', {}, [x], name='relu')
+    x = b.op('maxpool', {'w': [3, 3], 'pads': [1, 1, 1, 1], 'strides': [2, 2]}, [x], name='maxpool')
+    return b.finish(['x'], [x])
+
+
 def readme_net(seed=0):
     """The README's CustomNet in the real IR: conv+relu chained in one flow,
     maxpool(2), upsample(x2, nearest), concat(axis=1)+sigmoid chained, return."""

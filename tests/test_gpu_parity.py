@@ -127,6 +127,42 @@ def test_conv_fp16_kernels_vs_oracle(planer, cfg, algo):
     assert rel_err(y.get(), ref) <= 1e-2
 
 
+STEM_SWEEP = [
+    # n, h, w, k, pad, bias, bn
+    (2, 224, 224, 7, 3, False, True),      # the ResNet stem itself
+    (3, 64, 64, 7, 3, True, True),         # small maps: bands shorter than the image, bias folded with BN
+    (1, 40, 56, 7, 3, False, False),       # non-square, no BN (scale == NULL)
+    (2, 96, 80, 5, 2, True, False),        # 5x5: three packed-row taps
+    (2, 30, 32, 3, 1, False, True),        # 3x3: two taps, odd conv height (15 rows)
+    (5, 18, 16, 7, 3, False, True),        # tiny: one band per image, pooled height 5
+]
+
+
+@pytest.mark.parametrize('cfg', STEM_SWEEP)
+def test_fused_stem_conv_bn_relu_maxpool_vs_oracle(planer, cfg):
+    """conv(s2) -> bn -> relu -> maxpool(3,2,1) runs as ONE kernel (plnr_stem_pool_fwd) and must equal the oracle's
+    four-layer chain; the same graph with the fusion disabled must give the same numbers."""
+    from planer_b200 import zoo
+    n, h, w, k, pad, bias, bn = cfg
+    model, blob = zoo.stem_net(64, k, pad, bias, bn, seed=k + h)
+    x = np.random.default_rng(h * w + n).standard_normal((n, 3, h, w)).astype(np.float16)
+    ref = oracle.build_net(model, blob)(x.astype(np.float32))
+    net = planer.from_model(model, blob, half=True)
+    y = net(x)
+    ex = net.executor([x.shape])
+    assert len(ex.fused_stems) == 1, 'fused first-layer kernel not selected'
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) <= 1e-2
+    os.environ['PLNR_NO_FUSED_STEM'] = '1'
+    try:
+        net2 = planer.from_model(model, blob, half=True)
+        y2 = net2(x)
+        assert len(net2.executor([x.shape]).fused_stems) == 0
+    finally:
+        del os.environ['PLNR_NO_FUSED_STEM']
+    assert rel_err(y, y2.astype(np.float32)) <= 2e-3
+
+
 def test_rejects_what_the_reference_breaks_on(planer):
     """Asymmetric pads with bottom>top are silently wrong in the reference (App. D Q1): we raise.  Operators
     outside the hot path raise by name; there is no CPU fallback."""
