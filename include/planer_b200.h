@@ -169,6 +169,11 @@ int plnr_eltwise(plnr_ctx* ctx, int op, int dtype, const void* x, const void* p0
 /* Global average pool (n, hw, c) -> (n, c), fp32 accumulate (planer/layer.py:77-78). */
 int plnr_global_avgpool(plnr_ctx* ctx, int dtype, const plnr_tensor* x, void* y);
 
+/* GlobalAveragePool -> Flatten -> Dense fused (planer/layer.py:77-78, :59, :15-18): y[n, o] = act((mean_hw x[n, :, :] . w[o, :]) *
+ * scale[o] + shift[o]); w is the reference's (out, in) matrix in dtype `dtype`; y is (n, out_features) of the same dtype. */
+int plnr_gap_dense_fwd(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const void* w, const float* scale,
+                       const float* shift, void* y, int out_features, int act, float alpha);
+
 /* ---- CUDA-graph capture of a planned forward (replaces the Python interpreter loop of
  *      planer/net.py:43-70 by one replayable launch) ------------------------------------- */
 int plnr_graph_begin(plnr_ctx* ctx);

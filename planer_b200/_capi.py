@@ -66,6 +66,7 @@ PROTOTYPES = {
     'plnr_copy_channels': [_P, C.c_int, _TP, _TP],
     'plnr_eltwise': [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_float],
     'plnr_global_avgpool': [_P, C.c_int, _TP, _P],
+    'plnr_gap_dense_fwd': [_P, C.c_int, _TP, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float],
     'plnr_graph_begin': [_P],
     'plnr_graph_end': [_P, C.POINTER(_P)],
     'plnr_graph_launch': [_P, _P],

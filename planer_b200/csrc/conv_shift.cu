@@ -35,7 +35,25 @@ constexpr int kMaxA = 4, kMaxB = 40;
 constexpr uint32_t kStageBytes = 8 * 2048;        // epilogue transposition stage (per epilogue warp: 32 rows x 64 B)
 constexpr long long kWatchdogCycles = 4000000000ll;
 
+// exact floor(n / d) for n < 2^31 by multiply-high:  q = umulhi(n, mul) >> shr   (mul = ceil(2^(31+s) / d), 2^s >= d)
+struct FastDiv { uint32_t mul, shr, d; };
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f; f.d = d;
+  if (d <= 1) { f.mul = 0; f.shr = 0; return f; }          // d == 1 handled in fast_div
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  f.mul = (uint32_t)((((unsigned long long)1 << (31 + s)) + d - 1) / d);
+  f.shr = s - 1;
+  return f;
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) {
+  return f.d <= 1 ? n : (__umulhi(n, f.mul) >> f.shr);
+}
+
+template <bool B> struct RelUTag { static constexpr bool value = B; };
+
 struct ShiftParams {
+  FastDiv div_hvwv, div_wv, div_mt;     // / (Hv*Wv), / Wv, / num_m_tiles
   int N, OH, OW, Hv, Wv, HvWv;
   int pad_t, pad_l;
   long long Mv;             // N * Hv * Wv virtual output positions
@@ -291,6 +309,11 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     if (stamp && lane == 0) p.prof[1403] = clock64() - t_entry;
   } else if (warp >= 4) {
     // ===================================== epilogue ===========================================
+    // A thread owns one accumulator ROW (TMEM lane) and 32 channels per chunk; rows are transposed through a per-warp
+    // shared-memory stage so that every global access of the warp moves 8 rows x 64 contiguous bytes: lane l serves
+    // row 8i + l/4, 16-byte piece l%4 (i = 0..3).  The residual operand is read in that same coalesced pattern and
+    // added AFTER the transposition (the reference rounds to fp16 between batchnorm, add and relu as well:
+    // planer/layer.py:125-127, :93-95, :44-46), so its loads need no row-owner gather and are issued one tile ahead.
     const int ew = warp & 3;                 // the TMEM lane quarter this warp may read (warp % 4)
     const int eg = (warp - 4) >> 2;          // epilogue group: 0 -> first half of the tile's columns, 1 -> second half
     const int et = threadIdx.x - 128;        // 0..255
@@ -298,9 +321,51 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     int staged_n = -1;
     long long t_tfull = 0;
     const long long t_all0 = clock64();
+    const int nchunks = p.n_tile >> 5, half = (nchunks + 1) >> 1;
+    const int c_begin = eg * half * 32, c_end = min(nchunks, (eg + 1) * half) * 32;
+    const bool has_res = p.res != nullptr;
+    const uint32_t HvWv = (uint32_t)p.HvWv, uWv = (uint32_t)Wv, uMv = (uint32_t)p.Mv;
+    uint8_t* st_o = stage + (warp - 4) * 2048;
+    const uint32_t my_sw = (uint32_t)((lane >> 1) & 3);
+    const int piece = lane & 3;
+
+    // geometry of a tile for this thread: its own row (scalar tail path) and the four rows it serves in the coalesced
+    // pattern; pixel index -1 = padded rim / beyond the tensor (computed and discarded)
+    struct Geo { int own; int row[4]; };
+    auto tile_geo = [&](int tile_) {
+      Geo g;
+      const uint32_t m_idx_ = (uint32_t)tile_ - fast_div((uint32_t)tile_, p.div_mt) * (uint32_t)p.num_m_tiles;
+      const uint32_t o = (m_idx_ * CG + rank) * kTileM + (uint32_t)(ew * 32 + lane);
+      g.own = -1;
+      if (o < uMv) {
+        const uint32_t img = fast_div(o, p.div_hvwv), rem = o - img * HvWv;
+        const uint32_t pr = fast_div(rem, p.div_wv), q = rem - pr * uWv;
+        if (pr < (uint32_t)p.OH && q < (uint32_t)p.OW) g.own = (int)((img * (uint32_t)p.OH + pr) * (uint32_t)p.OW + q);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) g.row[i] = __shfl_sync(0xffffffffu, g.own, 8 * i + (lane >> 2));
+      return g;
+    };
+    // residual pieces of a tile's FIRST chunk, fetched one tile ahead: by the time an epilogue warp reaches a tile its
+    // accumulator is usually complete, and a load issued then would expose the DRAM latency once per tile
+    uint4 rvp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rvp[i] = make_uint4(0u, 0u, 0u, 0u);
+    auto fetch_res = [&](const Geo& g, int cb, uint4 (&dst)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (g.row[i] >= 0)
+          dst[i] = *reinterpret_cast<const uint4*>(p.res + (size_t)g.row[i] * p.rld + p.rcoff + cb + piece * 8);
+    };
+    Geo gn = tile_geo(unit < p.num_tiles ? unit : 0);
+    if (has_res && p.vec_ok && c_begin < c_end && unit < p.num_tiles) {
+      const int cb = (int)fast_div((uint32_t)unit, p.div_mt) * p.n_tile + c_begin;
+      if (cb + 32 <= p.Cout) fetch_res(gn, cb, rvp);
+    }
+
     for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
       const uint32_t a = it & 1, tph = (it >> 1) & 1;
-      const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
+      const int n_idx = (int)fast_div((uint32_t)tile, p.div_mt);
       const int n0 = n_idx * p.n_tile;
       // per-channel scale/shift of this tile's channel block: re-staged only when the block changes
       if (n_idx != staged_n) {
@@ -317,52 +382,25 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       }
       const float* ep_scale = epi + ebuf * 512, *ep_shift = ep_scale + 256;
 
-      // this thread's virtual position -> output pixel (or nothing, for the padded rim)
-      const long long o = ((long long)m_idx * CG + rank) * kTileM + ew * 32 + lane;
-      bool mvalid = o < p.Mv;
-      long long m = 0;
-      if (mvalid) {
-        const int img = (int)(o / p.HvWv);
-        const int rem = (int)(o - (long long)img * p.HvWv);
-        const int pr = rem / Wv, q = rem - pr * Wv;
-        mvalid = pr < p.OH && q < p.OW;
-        m = ((long long)img * p.OH + pr) * p.OW + q;
-      }
-
-      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + a * (uint32_t)p.n_tile;
-      __half* yrow = p.y + (size_t)(mvalid ? m : 0) * p.yld + p.ycoff;
-      const __half* rrow = p.res ? p.res + (size_t)(mvalid ? m : 0) * p.rld + p.rcoff : nullptr;
-
-      // Coalescing: a thread owns one output ROW (32 channels = 64 B per chunk), so direct 16-byte accesses would touch
-      // 32 different 128-byte lines per warp instruction.  Rows are transposed through a per-warp shared-memory stage so
-      // that one instruction moves 8 rows x 64 contiguous bytes.  Lane l serves row 8*i + l/4, 16-byte piece l%4.
-      unsigned long long yptr[4];
-      uint32_t vmask = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int src = 8 * i + (lane >> 2);
-        yptr[i] = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)yrow, src);
-        vmask |= (__shfl_sync(0xffffffffu, mvalid ? 1u : 0u, src) & 1u) << i;
-      }
-      uint8_t* st_o = stage + (warp - 4) * 2048;
-      const uint32_t my_sw = (uint32_t)((lane >> 1) & 3);
-
-      const int nchunks = p.n_tile >> 5, half = (nchunks + 1) >> 1;
-      const int c_begin = eg * half * 32, c_end = min(nchunks, (eg + 1) * half) * 32;
-      // the residual operand of the first chunk is fetched BEFORE waiting for the accumulator: its DRAM latency
-      // hides behind the tile's MMAs; later chunks are fetched one chunk ahead
-      const bool res_vec = p.vec_ok && rrow && mvalid;
+      const Geo g = gn;
       uint4 rv[4], rvn[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) rv[q] = rvn[q] = make_uint4(0u, 0u, 0u, 0u);
-      if (res_vec && c_begin < c_end && n0 + c_begin + 32 <= p.Cout) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) rv[q] = *reinterpret_cast<const uint4*>(rrow + n0 + c_begin + q * 8);
+      for (int i = 0; i < 4; ++i) { rv[i] = rvp[i]; rvn[i] = make_uint4(0u, 0u, 0u, 0u); }
+      // next tile: geometry + residual of its first chunk (in flight during this whole epilogue)
+      const int tile_n = tile + nunits;
+      if (tile_n < p.num_tiles) {
+        gn = tile_geo(tile_n);
+        if (has_res && p.vec_ok && c_begin < c_end) {
+          const int cb = (int)fast_div((uint32_t)tile_n, p.div_mt) * p.n_tile + c_begin;
+          if (cb + 32 <= p.Cout) fetch_res(gn, cb, rvp);
+        }
       }
+
       const long long tt0 = clock64();
       mbar_wait(bar_tfull + 8 * a, tph, p.err, 3);
       t_tfull += clock64() - tt0;
       ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + a * (uint32_t)p.n_tile;
       if (c_begin >= c_end) {               // nothing to read for this group (n_tile == 32): release at once
         ptx::tc_fence_before();
         if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
@@ -374,10 +412,7 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         ptx::tmem_ld_32x32b_x32(t_row + c0, v);
         const int cb = n0 + c0;
         const bool fast = p.vec_ok && (cb + 32 <= p.Cout);
-        if (res_vec && c0 + 32 < c_end && cb + 64 <= p.Cout) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) rvn[q] = *reinterpret_cast<const uint4*>(rrow + cb + 32 + q * 8);
-        }
+        if (has_res && p.vec_ok && c0 + 32 < c_end && cb + 64 <= p.Cout) fetch_res(g, cb + 32, rvn);   // one chunk ahead
         ptx::tmem_ld_wait();
         if (c0 + 32 >= c_end) {
           ptx::tc_fence_before();
@@ -385,51 +420,63 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           else ptx::mbar_arrive(bar_tempty + 8 * a);
         }
         if (fast) {
+          // The math of a chunk is compiled twice, once with the activation fixed to ReLU: with the generic runtime
+          // switch this block is ~900 dependent instructions per chunk and the epilogue, not the tensor pipe, paces
+          // Cout = 64 layers.  With a residual the activation (or the add, for the Darknet shortcut x + act(..))
+          // happens after the transposition, in packed fp16 -- the reference rounds to fp16 between batchnorm, add
+          // and relu too, and fp16 + fp16 rounded once is exactly what HADD2 computes.
+          auto chunk_math = [&](auto relu_tag) {
+            constexpr bool kRelu = decltype(relu_tag)::value;
+            const bool act_first = !has_res || p.res_after;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float sc[8], sf[8], o8[8];
-            *reinterpret_cast<float4*>(&sc[0]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8);
-            *reinterpret_cast<float4*>(&sc[4]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8 + 4);
-            *reinterpret_cast<float4*>(&sf[0]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8);
-            *reinterpret_cast<float4*>(&sf[4]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8 + 4);
+            for (int q = 0; q < 4; ++q) {
+              float sc[8], sf[8], o8[8];
+              *reinterpret_cast<float4*>(&sc[0]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8);
+              *reinterpret_cast<float4*>(&sc[4]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8 + 4);
+              *reinterpret_cast<float4*>(&sf[0]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8);
+              *reinterpret_cast<float4*>(&sf[4]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8 + 4);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o8[e] = fmaf(__uint_as_float(v[q * 8 + e]), sc[e], sf[e]);
-            float rf[8];
+              for (int e = 0; e < 8; ++e) {
+                o8[e] = fmaf(__uint_as_float(v[q * 8 + e]), sc[e], sf[e]);
+                if (act_first) o8[e] = kRelu ? fmaxf(o8[e], 0.f) : plnr_apply_act(o8[e], p.act, p.alpha);
+              }
+              uint4 pk;
+              pk.x = pack_half2(o8[0], o8[1]); pk.y = pack_half2(o8[2], o8[3]);
+              pk.z = pack_half2(o8[4], o8[5]); pk.w = pack_half2(o8[6], o8[7]);
+              *reinterpret_cast<uint4*>(st_o + lane * 64 + (((uint32_t)q ^ my_sw) << 4)) = pk;
+            }
+            __syncwarp();
 #pragma unroll
-            for (int e = 0; e < 8; ++e) rf[e] = 0.f;
-            if (rrow && mvalid) {
-              const __half2* rh = reinterpret_cast<const __half2*>(&rv[q]);
+            for (int i = 0; i < 4; ++i) {
+              const int row = 8 * i + (lane >> 2);
+              uint4 val = *reinterpret_cast<const uint4*>(st_o + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
+              if (g.row[i] >= 0) {
+                if (has_res) {
+                  __half2* vh = reinterpret_cast<__half2*>(&val);
+                  const __half2* rh = reinterpret_cast<const __half2*>(&rv[i]);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(rh[e]);
-                rf[2 * e] = f.x; rf[2 * e + 1] = f.y;
+                  for (int e = 0; e < 4; ++e) {
+                    __half2 x = __hadd2(vh[e], rh[e]);
+                    if (!p.res_after) {
+                      if (kRelu) x = __hmax2(x, __float2half2_rn(0.f));
+                      else {
+                        const float2 f = __half22float2(x);
+                        x = __floats2half2_rn(plnr_apply_act(f.x, p.act, p.alpha), plnr_apply_act(f.y, p.act, p.alpha));
+                      }
+                    }
+                    vh[e] = x;
+                  }
+                }
+                *reinterpret_cast<uint4*>(p.y + (size_t)g.row[i] * p.yld + p.ycoff + cb + piece * 8) = val;
               }
             }
-            if (!p.res_after) {
+          };
+          if (p.act == PLNR_ACT_RELU) chunk_math(RelUTag<true>{}); else chunk_math(RelUTag<false>{});
 #pragma unroll
-              for (int e = 0; e < 8; ++e) o8[e] += rf[e];
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o8[e] = plnr_apply_act(o8[e], p.act, p.alpha);
-            if (p.res_after) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o8[e] += rf[e];
-            }
-            uint4 pk;
-            pk.x = pack_half2(o8[0], o8[1]); pk.y = pack_half2(o8[2], o8[3]);
-            pk.z = pack_half2(o8[4], o8[5]); pk.w = pack_half2(o8[6], o8[7]);
-            *reinterpret_cast<uint4*>(st_o + lane * 64 + (((uint32_t)q ^ my_sw) << 4)) = pk;
-          }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = 8 * i + (lane >> 2), piece = lane & 3;
-            const uint4 val = *reinterpret_cast<const uint4*>(st_o + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
-            if ((vmask >> i) & 1u) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(yptr[i]) + cb + piece * 8) = val;
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) rv[q] = rvn[q];
-        } else if (mvalid) {
+          for (int i = 0; i < 4; ++i) rv[i] = rvn[i];
+        } else if (g.own >= 0) {
+          __half* yrow = p.y + (size_t)g.own * p.yld + p.ycoff;
+          const __half* rrow = has_res ? p.res + (size_t)g.own * p.rld + p.rcoff : nullptr;
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const int c = cb + e;
@@ -581,6 +628,9 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
   p.num_m_tiles = (int)((p.Mv + kTileM * cg - 1) / (kTileM * cg));
   const int num_n_tiles = (y->c + p.n_tile - 1) / p.n_tile;
   p.num_tiles = p.num_m_tiles * num_n_tiles;
+  p.div_hvwv = make_fastdiv((uint32_t)p.HvWv);
+  p.div_wv = make_fastdiv((uint32_t)p.Wv);
+  p.div_mt = make_fastdiv((uint32_t)p.num_m_tiles);
   p.na = pl.na; p.nb = pl.nb; p.b_resident = pl.b_resident;
   p.a_buf_bytes = pl.a_buf_bytes; p.b_stage_bytes = pl.b_stage_bytes;
   p.idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)((kTileM * cg) >> 4) << 24);

@@ -288,6 +288,93 @@ __global__ void gap_kernel(const T* __restrict__ x, T* __restrict__ y, int N, in
   *reinterpret_cast<Vec<T, V>*>(y + (size_t)n * C + cv * V) = o;
 }
 
+
+// GlobalAveragePool -> Flatten -> Dense in one launch (planer/layer.py:77-78, :59, :15-18).  A CTA takes IMGS images and a
+// slice of the output features: (1) the pooled vectors (fp32) of its images go to shared memory, every thread summing HW
+// rows of one 16-byte channel group; (2) each warp walks output features of the slice, one 16-byte weight load per lane
+// and 32 lanes per weight row, IMGS dot products at a time, then a shuffle reduction and the fused scale/shift/activation.
+// The tail of a network is ~65 MFLOP on 6 MB of input: launch latency, not bandwidth -- one small kernel instead of a
+// pooling launch and a tensor-core GEMM launch with its TMEM/TMA set-up.
+template <typename T, int V, int IMGS>
+__global__ void __launch_bounds__(512) gap_dense_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                         const float* __restrict__ scale, const float* __restrict__ shift,
+                                                         T* __restrict__ y, int N, int HW, int C, int xld, int xcoff,
+                                                         int OUT, int och, int act, float alpha) {
+  extern __shared__ float pooled[];                 // [IMGS][C]
+  const int n0 = blockIdx.x * IMGS, o0 = blockIdx.y * och;
+  const int CV = C / V;
+  const float inv = 1.f / (float)HW;
+  constexpr int PB = 16;                            // pixel rows fetched per batch: PB independent 16-byte loads in flight
+  for (int idx = threadIdx.x; idx < IMGS * CV; idx += blockDim.x) {
+    const int img = idx / CV, cv = idx - img * CV;
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    if (n0 + img < N) {
+      const T* xp = x + (size_t)(n0 + img) * HW * xld + xcoff + cv * V;
+      for (int p0 = 0; p0 < HW; p0 += PB) {
+        Vec<T, V> v[PB];
+#pragma unroll
+        for (int j = 0; j < PB; ++j)
+          if (p0 + j < HW) v[j] = *reinterpret_cast<const Vec<T, V>*>(xp + (size_t)(p0 + j) * xld);
+#pragma unroll
+        for (int j = 0; j < PB; ++j)
+          if (p0 + j < HW) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] += ld_f(&v[j].v[k]);
+          }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) pooled[img * C + cv * V + k] = acc[k] * inv;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int o_end = min(o0 + och, OUT);
+  constexpr int OPW = 4;                            // output features per warp step: OPW weight rows in flight
+  for (int ob = o0 + warp * OPW; ob < o_end; ob += nwarps * OPW) {
+    float acc[OPW][IMGS];
+#pragma unroll
+    for (int j = 0; j < OPW; ++j)
+#pragma unroll
+      for (int i = 0; i < IMGS; ++i) acc[j][i] = 0.f;
+    for (int cv = lane; cv < CV; cv += 32) {
+      Vec<T, V> wv[OPW];
+#pragma unroll
+      for (int j = 0; j < OPW; ++j)
+        wv[j] = *reinterpret_cast<const Vec<T, V>*>(w + (size_t)min(ob + j, OUT - 1) * C + cv * V);
+#pragma unroll
+      for (int i = 0; i < IMGS; ++i) {
+        // 16-byte shared-memory reads: scalar reads at this 4*V-byte lane stride would be V-way bank conflicts
+        float pf[V];
+#pragma unroll
+        for (int k = 0; k < V; k += 4)
+          *reinterpret_cast<float4*>(&pf[k]) = *reinterpret_cast<const float4*>(pooled + i * C + cv * V + k);
+#pragma unroll
+        for (int j = 0; j < OPW; ++j)
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[j][i] = fmaf(ld_f(&wv[j].v[k]), pf[k], acc[j][i]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < OPW; ++j) {
+#pragma unroll
+      for (int i = 0; i < IMGS; ++i) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) acc[j][i] += __shfl_xor_sync(0xffffffffu, acc[j][i], d);
+      }
+      const int o = ob + j;
+      if (o < o_end && lane < IMGS && n0 + lane < N) {
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < IMGS; ++i) v = lane == i ? acc[j][i] : v;
+        v = fmaf(v, scale ? scale[o] : 1.f, shift ? shift[o] : 0.f);
+        st_f(y + (size_t)(n0 + lane) * OUT + o, plnr_apply_act(v, act, alpha));
+      }
+    }
+  }
+}
+
 static inline bool view_vec_ok(const plnr_tensor* t, int V, size_t esz) {
   return t->c % V == 0 && t->ld % V == 0 && t->coff % V == 0 && aligned16(t->ptr) && (V * esz == 16);
 }
@@ -492,6 +579,35 @@ int plnr_global_avgpool(plnr_ctx* ctx, int dtype, const plnr_tensor* x, void* y)
     }
   })
   return plnr_after_launch(ctx, "global_avgpool");
+}
+
+int plnr_gap_dense_fwd(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const void* w, const float* scale,
+                       const float* shift, void* y, int out_features, int act, float alpha) {
+  PLNR_REQUIRE(ctx && x && x->ptr && w && y, "gap_dense: NULL argument");
+  const int HW = x->h * x->w;
+  constexpr int IMGS = 8;
+  DISPATCH_T(dtype, {
+    constexpr int V = VecWidth<T>::value;
+    PLNR_REQUIRE(view_vec_ok(x, V, sizeof(T)) && aligned16(w) && x->c % V == 0,
+                 "gap_dense: channels (%d) must be a multiple of %d and pointers 16-byte aligned", x->c, V);
+    const size_t smem = (size_t)IMGS * x->c * sizeof(float);
+    PLNR_REQUIRE(smem <= 96 * 1024, "gap_dense: %d channels do not fit the pooled-vector stage", x->c);
+    // enough CTAs to fill the GPU: images in groups of 8, output features in slices
+    const int gx = (x->n + IMGS - 1) / IMGS;
+    int gy = (ctx->sm_count + gx - 1) / gx;          // ~one CTA per SM; every slice re-reads its images' pixels (L2)
+    if (gy < 1) gy = 1;
+    if (gy > 6) gy = 6;
+    int och = (out_features + gy - 1) / gy;
+    if (och < 64) och = 64;
+    gy = (out_features + och - 1) / och;
+    if (smem > 48 * 1024) {
+      PLNR_CHECK_CUDA(cudaFuncSetAttribute(gap_dense_kernel<T, V, IMGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           96 * 1024));
+    }
+    gap_dense_kernel<T, V, IMGS><<<dim3(gx, gy), 512, smem, ctx->stream>>>(
+        (const T*)x->ptr, (const T*)w, scale, shift, (T*)y, x->n, HW, x->c, x->ld, x->coff, out_features, och, act, alpha);
+  })
+  return plnr_after_launch(ctx, "gap_dense");
 }
 
 }  // extern "C"

@@ -95,6 +95,26 @@ class Executor:
             return st, pool
         return None
 
+    def _gap_dense_tail(self, gap):
+        """The dense step of a  gap -> flatten -> dense  tail (each value used once, none a graph output), or None."""
+        if os.environ.get('PLNR_NO_GAP_DENSE') == '1' or len(self.values[gap.ins[0]].shape) != 4:
+            return None
+        cur, steps, chain = gap, self.plan.steps, []
+        for want in ('flatten', 'dense'):
+            if self.values[cur.out].is_output:
+                return None
+            users = [u for u in steps if cur.out in u.reads() and u is not cur]
+            if len(users) != 1 or users[0].op != want:
+                return None
+            cur = users[0]
+            chain.append(cur)
+        if cur.res is not None or self._root(cur.ins[0]) != self._root(gap.out):
+            return None
+        c = self.values[gap.ins[0]].shape[1]
+        if c % (16 // self.dtype.itemsize) != 0 or c * 8 * 4 > 96 * 1024:
+            return None
+        return chain
+
     def _get(self, vid):
         return self.arr[self._root(vid)]
 
@@ -129,6 +149,7 @@ class Executor:
 
         # graph inputs: pixel-major staging filled by an eager transform at every forward
         self.stems = {}
+        self.fused_dense = set()
         self.fused_stems = {}     # graph input -> dict(conv, pool, run): conv+bn+relu+maxpool in ONE kernel at input time
         for vid in self.input_ids:
             shp = vals[vid].shape
@@ -157,7 +178,8 @@ class Executor:
             if fn is not None:
                 self.launches.append(fn)
                 self.kinds.append(st.op)
-                self.names.append('+'.join(st.fused))
+                self.names.append(getattr(self, 'names_override', None) or '+'.join(st.fused))
+                self.names_override = None
 
         # graph outputs: restore NCHW (planer/net.py:100 hands NCHW arrays back)
         for o in gp.outputs:
@@ -175,6 +197,8 @@ class Executor:
     def _make(self, st, alloc):
         vals, dt = self.values, self.dtype
         op = st.op
+        if id(st) in self.fused_dense:
+            return None                                  # computed by the gap step's fused kernel
         if op in ('conv', 'dense'):
             fused = self.fused_stems.get(self._root(st.ins[0])) if op == 'conv' else None
             fused = fused if fused is not None and fused['conv'] is st else None
@@ -260,6 +284,25 @@ class Executor:
                     ops.copy_channels(x, v)
             return run
         if op == 'gap':
+            tail = self._gap_dense_tail(st)
+            if tail is not None:
+                # gap -> flatten -> dense: ONE small kernel instead of a pooling launch + a tensor-core GEMM launch
+                fl, dn = tail
+                x = self._view(st.ins[0])
+                K = self._weight(dn.w)
+                bias = self._weight(dn.bias) if dn.bias is not None else None
+                bn_k, bn_b = (self._weight(dn.bn[0]), self._weight(dn.bn[1])) if dn.bn else (None, None)
+                scale = shift = None
+                if bias is not None or bn_k is not None:
+                    scale, shift = ops.fold_affine(bias, bn_k, bn_b, K.shape[0])
+                    if bn_k is None:
+                        scale = None
+                Kc = K.astype(dt)
+                y = alloc(dn.out)
+                self._keep += [scale, shift, Kc]
+                self.fused_dense |= {id(fl), id(dn)}
+                self.names_override = '+'.join(st.fused + dn.fused)
+                return lambda: ops.gap_dense_into(x, Kc, y, scale, shift, dn.act, dn.alpha)
             x, y = self._view(st.ins[0]), alloc(st.out)
             return lambda: ops.gap_into(x, y)
         if op == 'flatten':

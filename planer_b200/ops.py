@@ -146,6 +146,15 @@ def gap_into(x, y):
     return y
 
 
+def gap_dense_into(x, w, y, scale=None, shift=None, act=ACT_NONE, alpha=0.0):
+    """GlobalAveragePool -> Flatten -> Dense in one launch: x nhwc (n, c, h, w), w (out, c), y flat (n, out)."""
+    tx = x.tensor()
+    p = lambda a: a.ptr if a is not None else None
+    _capi.check(B.lib().plnr_gap_dense_fwd(B.ctx(), _capi.dtype_code(x.dtype), C.byref(tx), w.ptr, p(scale), p(shift), y.ptr,
+                                           w.shape[0], act, float(alpha)), 'plnr_gap_dense_fwd')
+    return y
+
+
 def nchw_to_nhwc_into(x_flat, y, c_src=None):
     t = y.tensor()
     _capi.check(B.lib().plnr_nchw_to_nhwc(B.ctx(), x_flat.ptr, _capi.dtype_code(x_flat.dtype),
