@@ -115,12 +115,13 @@ int plnr_stem_pack(plnr_ctx* ctx, const void* x, int x_dtype, int n, int c, int 
  * planer/util.py:17-44) -> *scale + shift (bias / folded BatchNorm, planer/layer.py:125-127) -> ReLU
  * (planer/layer.py:44-46) -> 3x3 / stride-2 / pad-1 Maxpool (planer/layer.py:71-72 + planer/util.py:79-95; after a
  * ReLU its zero padding and -1e4 floor are neutral) -> pixel-major y (n, poh, pow, 64), in ONE kernel
- * (csrc/stem_pool.cu).  w_packed: [64][T][64] fp16 with W[co, e, ph*24 + sx*3 + c] = K[co, c, 2(e + e_min) + ph +
- * pad_t, sx] (zero elsewhere), e_min and T from plnr_stem_pool_geometry.  plnr_stem_pool_supported returns 1 when
- * the fused kernel applies; otherwise the caller runs plnr_stem_pack / plnr_conv2d_fwd / plnr_maxpool2d. */
+ * (csrc/stem_pool.cu).  w_packed: [64][T][64] fp16 with W[co, e, (ph*3 + c)*8 + sx + col_shift] =
+ * K[co, c, 2(e + e_min) + ph + pad_t, sx] (zero elsewhere); e_min, T and col_shift from plnr_stem_pool_geometry.
+ * plnr_stem_pool_supported returns 1 when the fused kernel applies; otherwise the caller runs plnr_stem_pack /
+ * plnr_conv2d_fwd / plnr_maxpool2d. */
 int plnr_stem_pool_supported(int dtype, int c, int h, int w, int cout, int kh, int kw, int stride, int pad_t, int pad_l,
                              int pad_b, int pad_r, int act, int pool_k, int pool_stride, int pool_pad);
-int plnr_stem_pool_geometry(int h, int kh, int pad_t, int* e_min, int* taps);
+int plnr_stem_pool_geometry(int kh, int pad_t, int pad_l, int* e_min, int* taps, int* col_shift);
 int plnr_stem_pool_fwd(plnr_ctx* ctx, const void* x, int n, int c, int h, int w, const void* w_packed,
                        const float* scale, const float* shift, int kh, int kw, int stride, int pad_t, int pad_l,
                        int pad_b, int pad_r, int act, int pool_k, int pool_stride, int pool_pad, const plnr_tensor* y);

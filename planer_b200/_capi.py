@@ -53,7 +53,7 @@ PROTOTYPES = {
     'plnr_nchw_to_nhwc': [_P, _P, C.c_int, C.c_int, _TP, C.c_int],
     'plnr_stem_pack': [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _TP, C.c_int, C.c_int, C.c_int],
     'plnr_stem_pool_supported': [C.c_int] * 16,
-    'plnr_stem_pool_geometry': [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    'plnr_stem_pool_geometry': [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
     'plnr_stem_pool_fwd': [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P] + [C.c_int] * 11 + [_TP],
     'plnr_nhwc_to_nchw': [_P, _TP, C.c_int, _P, C.c_int],
     'plnr_cast': [_P, _P, C.c_int, _P, C.c_int, C.c_int64],

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <unordered_map>
 #include <string>
@@ -70,6 +71,15 @@ static inline int plnr_after_launch(plnr_ctx* ctx, const char* what) {
   if (ctx->capturing) ctx->capture_launches++;
   else ctx->launches++;
   return PLNR_OK;
+}
+
+// PLNR_PDL=1 launches the tensor-core conv kernels with programmatic dependent launch (set-up overlapping the previous
+// kernel's tail).  Measured on ResNet-18 batch 128: no gain (every CTA needs the whole SM's shared memory, so a dependent
+// CTA cannot start before its predecessor on that SM exits) -- off by default, kept as an experiment switch.
+static inline bool plnr_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PLNR_PDL"); v = (e && atoi(e)) ? 1 : 0; }
+  return v == 1;
 }
 
 static inline size_t plnr_dtype_size(int dt) { return dt == PLNR_F16 ? 2 : 4; }

@@ -139,6 +139,10 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // programmatic dependent launch: let the next kernel of the stream start its own set-up, then wait until every
+  // kernel before this one has completed and flushed its results (no-ops when launched without the attribute)
+  ptx::grid_launch_dependents();
+  ptx::grid_dependency_wait();
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -622,13 +626,17 @@ int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tenso
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)cg;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // Programmatic dependent launch: this grid may start while the previous kernel of the stream drains; everything it
+  // does before griddepcontrol.wait (barrier init, TMEM allocation, tensor-map prefetch) overlaps that kernel's tail.
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = plnr_pdl_enabled() ? 2 : 1;
   cudaError_t le = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_igemm_f16_kernel<2>, mapA, mapB, p)
                            : cudaLaunchKernelEx(&cfg, conv_igemm_f16_kernel<1>, mapA, mapB, p);
   if (le != cudaSuccess) {

@@ -217,7 +217,7 @@ class Executor:
             if fused is not None:
                 a = st.attrs
                 yp = alloc(fused['pool'].out)
-                wp = B.asarray(ops.stem_pool_weight(K.get().astype(np.float16), a['pads'][0]))
+                wp = B.asarray(ops.stem_pool_weight(K.get().astype(np.float16), a['pads'][0], a['pads'][1]))
                 self._keep.append(wp)
                 kh, kw = K.shape[2], K.shape[3]
                 fused['run'] = lambda xf: ops.stem_pool_into(xf, wp, scale, shift, yp, kh, kw, a['strides'][0], a['pads'],

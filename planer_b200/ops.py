@@ -211,19 +211,21 @@ def stem_pool_supported(dtype, c, h, w, cout, kh, kw, stride, pads, act, pool_w,
                                                  pads[2], pads[3], act, 3, 2, 1))
 
 
-def stem_pool_weight(K, pad_t):
+def stem_pool_weight(K, pad_t, pad_l):
     """Host-side (tiny, load-time) re-ordering of an OIHW stride-2 first-layer filter into the [Cout][T][64] K-major
-    layout of ``plnr_stem_pool_fwd``: W[co, e, ph*24 + sx*3 + c] = K[co, c, 2(e + e_min) + ph + pad_t, sx]."""
+    layout of ``plnr_stem_pool_fwd``: W[co, e, (ph*3 + c)*8 + sx + col_shift] = K[co, c, 2(e + e_min) + ph + pad_t, sx]."""
     co, c, kh, kw = K.shape
-    e_min, taps = C.c_int(), C.c_int()
-    _capi.check(B.lib().plnr_stem_pool_geometry(0, kh, pad_t, C.byref(e_min), C.byref(taps)), 'plnr_stem_pool_geometry')
+    e_min, taps, shift = C.c_int(), C.c_int(), C.c_int()
+    _capi.check(B.lib().plnr_stem_pool_geometry(kh, pad_t, pad_l, C.byref(e_min), C.byref(taps), C.byref(shift)),
+                'plnr_stem_pool_geometry')
     out = np.zeros((co, taps.value, 64), np.float16)
     for e in range(taps.value):
         for ph in range(2):
             r = 2 * (e + e_min.value) + ph + pad_t
             if 0 <= r < kh:
-                for sx in range(kw):
-                    out[:, e, ph * 24 + sx * 3:ph * 24 + sx * 3 + c] = K[:, :, r, sx]
+                for ci in range(c):
+                    k0 = (ph * 3 + ci) * 8 + shift.value
+                    out[:, e, k0:k0 + kw] = K[:, ci, r, :]
     return out
 
 
