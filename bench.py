@@ -239,16 +239,26 @@ def main():
         return
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), timed live per launch ----
     table = per_kernel_profile(net, xs[0], None)
-    conv_ms = sum(r['ms'] for r in table if r['kind'] in ('conv', 'dense'))
+    conv_ms = sum(r['ms'] for r in table if r['kind'] in ('conv', 'dense', 'gap'))
     all_ms = sum(r['ms'] for r in table)
     conv_nodes = [n for n in ex.plan.nodes if n.kind in ('conv', 'dense')]
     pk = peaks()
     achieved = flops / (conv_ms / 1e3) / 1e12
-    roofline = {'bound': 'tensor', 'kernel': 'tcgen05 conv kernels: stem_pool + conv_shift_f16 + conv_igemm_f16 (%d conv/dense layers per step)' % len(conv_nodes),
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, 'profiles', 'r01_step_traffic.json')
+    if os.path.exists(tpath) and args.batch == BATCH:
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = sum(int((k['dram_read_mb'] + k['dram_write_mb']) * 1e6) for k in tj['kernels'])
+        traffic_src = 'dram__bytes_read.sum + dram__bytes_write.sum summed over the same launches of one step, ncu --set full (profiles/r01_step_full.md)'
+    roofline = {'bound': 'tensor',
+                'kernel': 'tcgen05 conv kernels of one step: stem_pool + conv_shift_f16 + conv_igemm_f16 + gap_dense (%d conv/dense layers)' % len(conv_nodes),
                 'achieved': achieved, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved / pk['tflops_sustained'], 'traffic': None,
+                'frac': achieved / pk['tflops_sustained'], 'traffic': traffic, 'traffic_source': traffic_src,
                 'peak_source': pk['source'] + ', sustained figure (kernel timed inside a long step)',
+                'frac_of_burst_peak': achieved / pk['tflops_burst'],
                 'flops_per_step': flops, 'kernel_ms_per_step': conv_ms, 'kernel_share_of_step': conv_ms / all_ms,
+                'algorithmic_bytes_per_step': int(args.batch * 9.34e6 + 23.4e6),
                 'whole_step_frac': (flops * steps / (ms_total / 1e3) / 1e12) / pk['tflops_sustained']}
     if args.dump:
         by_name = {n.name: n for n in conv_nodes}

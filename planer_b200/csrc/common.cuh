@@ -105,6 +105,23 @@ __device__ __forceinline__ float plnr_apply_act(float v, int act, float alpha) {
   return v;
 }
 
+// exact floor(n / d) for n < 2^31 by multiply-high:  q = umulhi(n, mul) >> shr   (mul = ceil(2^(31+s) / d), 2^s >= d)
+struct FastDiv { uint32_t mul, shr, d; };
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f; f.d = d;
+  if (d <= 1) { f.mul = 0; f.shr = 0; return f; }          // d == 1 handled in fast_div
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  f.mul = (uint32_t)((((unsigned long long)1 << (31 + s)) + d - 1) / d);
+  f.shr = s - 1;
+  return f;
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) {
+  return f.d <= 1 ? n : (__umulhi(n, f.mul) >> f.shr);
+}
+
+template <bool B> struct RelUTag { static constexpr bool value = B; };   // compile-time "activation is ReLU" switch
+
 // internal entry points implemented in the other translation units
 int plnr_conv2d_direct(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w,
                        const plnr_tensor* y, const plnr_epilogue* ep);

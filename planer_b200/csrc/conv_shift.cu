@@ -35,23 +35,6 @@ constexpr int kMaxA = 4, kMaxB = 40;
 constexpr uint32_t kStageBytes = 8 * 2048;        // epilogue transposition stage (per epilogue warp: 32 rows x 64 B)
 constexpr long long kWatchdogCycles = 4000000000ll;
 
-// exact floor(n / d) for n < 2^31 by multiply-high:  q = umulhi(n, mul) >> shr   (mul = ceil(2^(31+s) / d), 2^s >= d)
-struct FastDiv { uint32_t mul, shr, d; };
-static inline FastDiv make_fastdiv(uint32_t d) {
-  FastDiv f; f.d = d;
-  if (d <= 1) { f.mul = 0; f.shr = 0; return f; }          // d == 1 handled in fast_div
-  uint32_t s = 0;
-  while ((1ull << s) < d) ++s;
-  f.mul = (uint32_t)((((unsigned long long)1 << (31 + s)) + d - 1) / d);
-  f.shr = s - 1;
-  return f;
-}
-__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) {
-  return f.d <= 1 ? n : (__umulhi(n, f.mul) >> f.shr);
-}
-
-template <bool B> struct RelUTag { static constexpr bool value = B; };
-
 struct ShiftParams {
   FastDiv div_hvwv, div_wv, div_mt;     // / (Hv*Wv), / Wv, / num_m_tiles
   int N, OH, OW, Hv, Wv, HvWv;

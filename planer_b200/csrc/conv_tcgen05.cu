@@ -34,6 +34,7 @@ constexpr uint32_t kStageBytes = 8 * 2048;          // epilogue transposition st
 constexpr long long kWatchdogCycles = 4000000000ll; // ~2 s: a stuck barrier becomes an error, not a hang
 
 struct IgemmParams {
+  FastDiv div_mt;   // / num_m_tiles
   int M, OW, OH;
   int pad_t, pad_l, sh, sw, dh, dw;
   int S;          // filter width
@@ -269,6 +270,11 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 2] = t_full; p.prof[blockIdx.x * 8 + 3] = t_tempty; p.prof[blockIdx.x * 8 + 4] = clock64() - t_all0; }
   } else if (warp >= 4) {
     // ===================================== epilogue ===========================================
+    // A thread owns one accumulator ROW (TMEM lane) and 32 channels per chunk; rows are transposed through a per-warp
+    // shared-memory stage so that every global access of the warp moves 8 rows x 64 contiguous bytes: lane l serves
+    // row 8i + l/4, 16-byte piece l%4 (i = 0..3).  The residual operand is read in that same coalesced pattern and
+    // added AFTER the transposition (the reference rounds to fp16 between batchnorm, add and relu as well:
+    // planer/layer.py:125-127, :93-95, :44-46), so its loads need no row-owner gather and are issued one tile ahead.
     const int ew = warp & 3;                 // the TMEM lane quarter this warp may read (warp % 4)
     const int eg = (warp - 4) >> 2;          // epilogue group: 0 -> first half of the tile's columns, 1 -> second half
     const int et = threadIdx.x - 128;        // 0..255
@@ -276,11 +282,47 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     int staged_n = -1;
     long long t_tfull = 0;
     const long long t_all0 = clock64();
+    const int nchunks = p.n_tile >> 5, half = (nchunks + 1) >> 1;
+    const int c_begin = eg * half * 32, c_end = min(nchunks, (eg + 1) * half) * 32;
+    const bool has_res = p.res != nullptr;
+    const uint32_t uM = (uint32_t)p.M;
+    uint8_t* st_o = stage + (warp - 4) * 2048;
+    const uint32_t my_sw = (uint32_t)((lane >> 1) & 3);
+    const int piece = lane & 3;
+
+    // geometry of a tile for this thread: its own row (scalar tail path) and the four rows it serves in the coalesced
+    // pattern; pixel index -1 = beyond the tensor
+    struct Geo { int own; int row[4]; };
+    auto tile_geo = [&](int tile_) {
+      Geo g;
+      const uint32_t m_idx_ = (uint32_t)tile_ - fast_div((uint32_t)tile_, p.div_mt) * (uint32_t)p.num_m_tiles;
+      const uint32_t o = (m_idx_ * CG + rank) * kTileM + (uint32_t)(ew * 32 + lane);
+      g.own = o < uM ? (int)o : -1;          // output pixel index == GEMM row (no padded rim in the im2col kernel)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) g.row[i] = __shfl_sync(0xffffffffu, g.own, 8 * i + (lane >> 2));
+      return g;
+    };
+    // residual pieces of a tile's FIRST chunk, fetched one tile ahead: by the time an epilogue warp reaches a tile its
+    // accumulator is usually complete, and a load issued then would expose the DRAM latency once per tile
+    uint4 rvp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rvp[i] = make_uint4(0u, 0u, 0u, 0u);
+    auto fetch_res = [&](const Geo& g, int cb, uint4 (&dst)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (g.row[i] >= 0)
+          dst[i] = *reinterpret_cast<const uint4*>(p.res + (size_t)g.row[i] * p.rld + p.rcoff + cb + piece * 8);
+    };
+    Geo gn = tile_geo(unit < p.num_tiles ? unit : 0);
+    if (has_res && p.vec_ok && c_begin < c_end && unit < p.num_tiles) {
+      const int cb = (int)fast_div((uint32_t)unit, p.div_mt) * p.n_tile + c_begin;
+      if (cb + 32 <= p.Cout) fetch_res(gn, cb, rvp);
+    }
+
     for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
-      const uint32_t a = it & 1, aph = (it >> 1) & 1;
-      const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
+      const uint32_t a = it & 1, tph = (it >> 1) & 1;
+      const int n_idx = (int)fast_div((uint32_t)tile, p.div_mt);
       const int n0 = n_idx * p.n_tile;
-      // stage this tile's per-channel scale/shift in shared memory (double buffered by tile parity)
       // per-channel scale/shift of this tile's channel block: re-staged only when the block changes
       if (n_idx != staged_n) {
         staged_n = n_idx;
@@ -296,118 +338,111 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       }
       const float* ep_scale = epi + ebuf * 512, *ep_shift = ep_scale + 256;
 
-      const int m = (m_idx * CG + (int)rank) * kTileM + ew * 32 + lane;
-      const bool mvalid = m < p.M && !(p.dbg & 1);
-      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + a * (uint32_t)p.n_tile;
-      __half* yrow = p.y + (size_t)(mvalid ? m : 0) * p.yld + p.ycoff;
-      const __half* rrow = p.res ? p.res + (size_t)(mvalid ? m : 0) * p.rld + p.rcoff : nullptr;
-
-      // Coalescing: a thread owns one output ROW (32 channels = 64 B per chunk); rows are transposed through a per-warp
-      // shared-memory stage so that one store instruction moves 8 rows x 64 contiguous bytes (see conv_shift.cu).
-      unsigned long long yptr[4];
-      uint32_t vmask = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int src = 8 * i + (lane >> 2);
-        yptr[i] = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)yrow, src);
-        vmask |= (__shfl_sync(0xffffffffu, mvalid ? 1u : 0u, src) & 1u) << i;
-      }
-      uint8_t* st_o = stage + (warp - 4) * 2048;
-      const uint32_t my_sw = (uint32_t)((lane >> 1) & 3);
-
-      const int nchunks = p.n_tile >> 5, half = (nchunks + 1) >> 1;
-      const int c_begin = eg * half * 32, c_end = min(nchunks, (eg + 1) * half) * 32;
-      // the residual operand of the first chunk is fetched BEFORE waiting for the accumulator: its DRAM latency
-      // hides behind the tile's MMAs; later chunks are fetched one chunk ahead
-      const bool res_vec = p.vec_ok && rrow && mvalid;
+      const Geo g = gn;
       uint4 rv[4], rvn[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) rv[q] = rvn[q] = make_uint4(0u, 0u, 0u, 0u);
-      if (res_vec && c_begin < c_end && n0 + c_begin + 32 <= p.Cout) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) rv[q] = *reinterpret_cast<const uint4*>(rrow + n0 + c_begin + q * 8);
+      for (int i = 0; i < 4; ++i) { rv[i] = rvp[i]; rvn[i] = make_uint4(0u, 0u, 0u, 0u); }
+      // next tile: geometry + residual of its first chunk (in flight during this whole epilogue)
+      const int tile_n = tile + nunits;
+      if (tile_n < p.num_tiles) {
+        gn = tile_geo(tile_n);
+        if (has_res && p.vec_ok && c_begin < c_end) {
+          const int cb = (int)fast_div((uint32_t)tile_n, p.div_mt) * p.n_tile + c_begin;
+          if (cb + 32 <= p.Cout) fetch_res(gn, cb, rvp);
+        }
       }
+
       const long long tt0 = clock64();
-      mbar_wait(bar_tfull + 8 * a, aph, p.err, 3);
+      mbar_wait(bar_tfull + 8 * a, tph, p.err, 3);
       t_tfull += clock64() - tt0;
       ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + a * (uint32_t)p.n_tile;
       if (c_begin >= c_end) {               // nothing to read for this group (n_tile == 32): release at once
         ptx::tc_fence_before();
         if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
         else ptx::mbar_arrive(bar_tempty + 8 * a);
       }
       for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-        __syncwarp();                       // tcgen05.ld is warp-collective: re-converge after the guarded stores
+        __syncwarp();
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(t_row + c0, v);
         const int cb = n0 + c0;
         const bool fast = p.vec_ok && (cb + 32 <= p.Cout);
-        if (res_vec && c0 + 32 < c_end && cb + 64 <= p.Cout) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) rvn[q] = *reinterpret_cast<const uint4*>(rrow + cb + 32 + q * 8);
-        }
+        if (has_res && p.vec_ok && c0 + 32 < c_end && cb + 64 <= p.Cout) fetch_res(g, cb + 32, rvn);   // one chunk ahead
         ptx::tmem_ld_wait();
-        if (c0 + 32 >= c_end) {          // accumulator fully read: hand it back to the (leader's) MMA warp
+        if (c0 + 32 >= c_end) {
           ptx::tc_fence_before();
           if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
           else ptx::mbar_arrive(bar_tempty + 8 * a);
         }
         if (fast) {
+          // The math of a chunk is compiled twice, once with the activation fixed to ReLU: with the generic runtime
+          // switch this block is ~900 dependent instructions per chunk and the epilogue, not the tensor pipe, paces
+          // Cout = 64 layers.  With a residual the activation (or the add, for the Darknet shortcut x + act(..))
+          // happens after the transposition, in packed fp16 -- the reference rounds to fp16 between batchnorm, add
+          // and relu too, and fp16 + fp16 rounded once is exactly what HADD2 computes.
+          auto chunk_math = [&](auto relu_tag) {
+            constexpr bool kRelu = decltype(relu_tag)::value;
+            const bool act_first = !has_res || p.res_after;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float sc[8], sf[8], o[8];
-            *reinterpret_cast<float4*>(&sc[0]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8);
-            *reinterpret_cast<float4*>(&sc[4]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8 + 4);
-            *reinterpret_cast<float4*>(&sf[0]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8);
-            *reinterpret_cast<float4*>(&sf[4]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8 + 4);
+            for (int q = 0; q < 4; ++q) {
+              float sc[8], sf[8], o8[8];
+              *reinterpret_cast<float4*>(&sc[0]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8);
+              *reinterpret_cast<float4*>(&sc[4]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8 + 4);
+              *reinterpret_cast<float4*>(&sf[0]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8);
+              *reinterpret_cast<float4*>(&sf[4]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8 + 4);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = fmaf(__uint_as_float(v[q * 8 + e]), sc[e], sf[e]);
-            float rf[8];
+              for (int e = 0; e < 8; ++e) {
+                o8[e] = fmaf(__uint_as_float(v[q * 8 + e]), sc[e], sf[e]);
+                if (act_first) o8[e] = kRelu ? fmaxf(o8[e], 0.f) : plnr_apply_act(o8[e], p.act, p.alpha);
+              }
+              uint4 pk;
+              pk.x = pack_half2(o8[0], o8[1]); pk.y = pack_half2(o8[2], o8[3]);
+              pk.z = pack_half2(o8[4], o8[5]); pk.w = pack_half2(o8[6], o8[7]);
+              *reinterpret_cast<uint4*>(st_o + lane * 64 + (((uint32_t)q ^ my_sw) << 4)) = pk;
+            }
+            __syncwarp();
 #pragma unroll
-            for (int e = 0; e < 8; ++e) rf[e] = 0.f;
-            if (rrow && mvalid) {
-              const __half2* rh = reinterpret_cast<const __half2*>(&rv[q]);
+            for (int i = 0; i < 4; ++i) {
+              const int row = 8 * i + (lane >> 2);
+              uint4 val = *reinterpret_cast<const uint4*>(st_o + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
+              if (g.row[i] >= 0) {
+                if (has_res) {
+                  __half2* vh = reinterpret_cast<__half2*>(&val);
+                  const __half2* rh = reinterpret_cast<const __half2*>(&rv[i]);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(rh[e]);
-                rf[2 * e] = f.x; rf[2 * e + 1] = f.y;
+                  for (int e = 0; e < 4; ++e) {
+                    __half2 x = __hadd2(vh[e], rh[e]);
+                    if (!p.res_after) {
+                      if (kRelu) x = __hmax2(x, __float2half2_rn(0.f));
+                      else {
+                        const float2 f = __half22float2(x);
+                        x = __floats2half2_rn(plnr_apply_act(f.x, p.act, p.alpha), plnr_apply_act(f.y, p.act, p.alpha));
+                      }
+                    }
+                    vh[e] = x;
+                  }
+                }
+                *reinterpret_cast<uint4*>(p.y + (size_t)g.row[i] * p.yld + p.ycoff + cb + piece * 8) = val;
               }
             }
-            if (!p.res_after) {
+          };
+          if (p.act == PLNR_ACT_RELU) chunk_math(RelUTag<true>{}); else chunk_math(RelUTag<false>{});
 #pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] += rf[e];
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = plnr_apply_act(o[e], p.act, p.alpha);
-            if (p.res_after) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] += rf[e];
-            }
-            uint4 pk;
-            pk.x = pack_half2(o[0], o[1]); pk.y = pack_half2(o[2], o[3]);
-            pk.z = pack_half2(o[4], o[5]); pk.w = pack_half2(o[6], o[7]);
-            *reinterpret_cast<uint4*>(st_o + lane * 64 + (((uint32_t)q ^ my_sw) << 4)) = pk;
-          }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = 8 * i + (lane >> 2), piece = lane & 3;
-            const uint4 val = *reinterpret_cast<const uint4*>(st_o + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
-            if ((vmask >> i) & 1u) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(yptr[i]) + cb + piece * 8) = val;
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) rv[q] = rvn[q];
-        } else if (mvalid) {
+          for (int i = 0; i < 4; ++i) rv[i] = rvn[i];
+        } else if (g.own >= 0) {
+          __half* yrow = p.y + (size_t)g.own * p.yld + p.ycoff;
+          const __half* rrow = has_res ? p.res + (size_t)g.own * p.rld + p.rcoff : nullptr;
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const int c = cb + e;
             if (c < p.Cout) {
-              float o = fmaf(__uint_as_float(v[e]), ep_scale[c0 + e], ep_shift[c0 + e]);
+              float o1 = fmaf(__uint_as_float(v[e]), ep_scale[c0 + e], ep_shift[c0 + e]);
               const float rf = rrow ? __half2float(rrow[c]) : 0.f;
-              if (!p.res_after) o += rf;
-              o = plnr_apply_act(o, p.act, p.alpha);
-              if (p.res_after) o += rf;
-              yrow[c] = __float2half_rn(o);
+              if (!p.res_after) o1 += rf;
+              o1 = plnr_apply_act(o1, p.act, p.alpha);
+              if (p.res_after) o1 += rf;
+              yrow[c] = __float2half_rn(o1);
             }
           }
         }
@@ -533,6 +568,7 @@ int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tenso
   p.n_tile = pick_n_tile(Cout, p.num_m_tiles, ctx->sm_count / cg);
   const int num_n_tiles = (Cout + p.n_tile - 1) / p.n_tile;
   p.num_tiles = p.num_m_tiles * num_n_tiles;
+  p.div_mt = make_fastdiv((uint32_t)p.num_m_tiles);
   p.a_unit_bytes = (uint32_t)kTileM * p.kc * 2;
   p.b_stage_bytes = (uint32_t)(p.n_tile / cg) * 128;     // per CTA: a pair splits the B tile
   p.a_layout = p.kc == 64 ? 2u : (p.kc == 32 ? 4u : 6u);

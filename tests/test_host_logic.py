@@ -170,6 +170,77 @@ def test_liveness_simulation_no_overlap():
             tenant[b] = o
 
 
+def _emulate_stem_contraction(x, W2, kh, kw, pad_t, pad_l, e_min, taps):
+    """numpy restatement of what csrc/stem_pool.cu contracts: packed rows t = input rows (2t, 2t+1), operand
+    A_t[ow, (ph*3 + c)*8 + j] = x[c, 2t + ph, 2ow + j - P] (P = pad_l rounded up to even), conv row h =
+    sum_e A_{h + e + e_min} @ W2[:, e, :].T  -- the index algebra of the kernel, without the GPU."""
+    n, c, H, W = x.shape
+    P = pad_l + (pad_l & 1)
+    OH = (H + 2 * pad_t - kh) // 2 + 1
+    OW = (W + 2 * pad_l - kw) // 2 + 1
+    xp = np.zeros((n, c, H + 64, W + 64), np.float32)          # generous zero frame: index (row + 32, col + 32)
+    xp[:, :, 32:32 + H, 32:32 + W] = x
+    out = np.zeros((n, W2.shape[0], OH, OW), np.float32)
+    for h in range(OH):
+        for e in range(taps):
+            t = h + e + e_min
+            A = np.zeros((n, OW, 64), np.float32)
+            for ph in range(2):
+                for ci in range(c):
+                    for j in range(8):
+                        cols = 2 * np.arange(OW) + j - P + 32
+                        A[:, :, (ph * 3 + ci) * 8 + j] = xp[:, ci, 2 * t + ph + 32, cols]
+            out[:, :, h, :] += np.einsum('nwk,ok->now', A, W2[:, e, :].astype(np.float32))
+    return out
+
+
+@pytest.mark.parametrize('k,pad', [(7, 3), (5, 2), (3, 1), (6, 2), (4, 1)])
+def test_stem_pool_weight_packing_reproduces_the_convolution(lib, k, pad):
+    """The fused first-layer kernel's filter layout (ops.stem_pool_weight) and its packed-row algebra, emulated in
+    numpy, must equal the oracle convolution (planer/util.py:17-44) -- this pins e_min / taps / column shift on the CPU."""
+    from planer_b200 import ops
+    rng = np.random.default_rng(k)
+    x = rng.standard_normal((2, 3, 20, 24)).astype(np.float32)
+    K = rng.standard_normal((64, 3, k, k)).astype(np.float32)
+    e_min, taps, shift = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.plnr_stem_pool_geometry(k, pad, pad, ctypes.byref(e_min), ctypes.byref(taps), ctypes.byref(shift)) == 0
+    assert shift.value == pad % 2 and 1 <= taps.value <= 4
+    W2 = ops.stem_pool_weight(K, pad, pad).astype(np.float32)
+    assert W2.shape == (64, taps.value, 64)
+    got = _emulate_stem_contraction(x, W2, k, k, pad, pad, e_min.value, taps.value)
+    ref = oracle.conv2d(x, K, None, 1, (2, 2), (1, 1), (pad,) * 4)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 2e-3 * np.abs(ref).max()      # W2 is stored in fp16
+
+
+def test_stem_pool_supported_truth_table(lib):
+    names = ('dtype', 'c', 'h', 'w', 'cout', 'kh', 'kw', 'stride', 'pad_t', 'pad_l', 'pad_b', 'pad_r', 'act', 'pool_k',
+             'pool_stride', 'pool_pad')
+    base = dict(dtype=_capi.F16, c=3, h=224, w=224, cout=64, kh=7, kw=7, stride=2, pad_t=3, pad_l=3, pad_b=3, pad_r=3,
+                act=_capi.ACT_RELU, pool_k=3, pool_stride=2, pool_pad=1)
+    f = lambda **kw: lib.plnr_stem_pool_supported(*[{**base, **kw}[n] for n in names])
+    assert f() == 1                                   # the ResNet stem
+    assert f(h=64, w=64) == 1
+    assert f(dtype=_capi.F32) == 0                    # fp32 runs the generic path
+    assert f(act=_capi.ACT_NONE) == 0                 # only a ReLU makes the pooling pad neutral
+    assert f(cout=32) == 0 and f(c=4) == 0 and f(stride=1) == 0
+    assert f(pool_k=2) == 0 and f(pool_pad=0) == 0
+    assert f(w=228) == 0                              # rows must be 16-byte multiples
+    assert f(h=512, w=512) == 0                       # conv row wider than one 128-row MMA tile
+    assert f(kh=9, kw=9, pad_t=4, pad_l=4, pad_b=4, pad_r=4) == 0
+
+
+def test_resnet18_executor_patterns_are_planned():
+    """The graph patterns the executor hands to single kernels exist in the compiled plan: input -> conv(relu) ->
+    maxpool(3,2,1) with one consumer each, and gap -> flatten -> dense at the tail."""
+    model, _ = zoo.resnet18(0)
+    plan = P.compile_graph(model, {'x': (4, 3, 224, 224)})
+    ops_ = [s.op for s in plan.steps]
+    assert ops_[0] == 'conv' and ops_[1] == 'maxpool' and plan.steps[0].act == _capi.ACT_RELU
+    assert plan.steps[1].attrs['w'] in ([3, 3], (3, 3)) and tuple(plan.steps[1].attrs['pads']) == (1, 1, 1, 1)
+    assert ops_[-3:] == ['gap', 'flatten', 'dense'] or ops_[-4:-1] == ['gap', 'flatten', 'dense']
+
+
 def test_unknown_operator_raises_by_name():
     model = {'input': ['x'], 'inits': [], 'layers': [['sm', 'softmax', {}]], 'flow': [['x', ['sm'], 'y']]}
     with pytest.raises(NotImplementedError, match='softmax'):
