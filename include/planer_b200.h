@@ -148,6 +148,16 @@ int plnr_fold_affine(plnr_ctx* ctx, const void* bias, const void* bn_k, const vo
  * the direct CUDA-core kernel (fp32 accumulate in both). */
 int plnr_conv2d_fwd(plnr_ctx* ctx, const plnr_conv_desc* desc, const plnr_tensor* x, const void* w_packed,
                     const plnr_tensor* y, const plnr_epilogue* ep);
+/* Conv2d + fused 1x1 shortcut convolution: y = act((conv(x, W) + conv1x1_stride(x2, W2)) * scale + shift).  Replaces the
+ * tail of a down-sampling residual block -- Conv2d -> BatchNorm on the main path, Conv2d(1x1, stride) -> BatchNorm on
+ * the shortcut, Add, ReLU (planer/layer.py:22-26, :125-127, :93-95, :44-46) -- by ONE launch: the shortcut's k-chunks
+ * accumulate into the same tensor-memory tile.  w_cat: [Cout][kh*kw*Cin + C2] = plnr_pack_conv_weight(W) with
+ * W2[co, c2] * (scale2[co] / scale[co]) appended along K (the caller folds the two BatchNorm scales; shift = shift +
+ * shift2).  x2: (n, C2, h2, w2) with ceil(h2 / stride2) == y.h; needs the fp16 stride-1 tensor-core path. */
+int plnr_conv2d_shortcut_supported(const plnr_conv_desc* desc, const plnr_tensor* x, const plnr_tensor* x2, int stride2,
+                                   const plnr_tensor* y);
+int plnr_conv2d_shortcut_fwd(plnr_ctx* ctx, const plnr_conv_desc* desc, const plnr_tensor* x, const void* w_cat,
+                             const plnr_tensor* x2, int stride2, const plnr_tensor* y, const plnr_epilogue* ep);
 /* Dense forward  y[M,N] = x[M,K] @ w[N,K]^T (+ epilogue).  Replaces planer/layer.py:15-18 (Dense);
  * w is the reference's (out,in) matrix as stored.  Runs as a 1x1 convolution over M pixels. */
 int plnr_dense_fwd(plnr_ctx* ctx, int dtype, const void* x, const void* w, void* y, int m, int n, int k,

@@ -60,6 +60,8 @@ PROTOTYPES = {
     'plnr_pack_conv_weight': [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
     'plnr_fold_affine': [_P, _P, _P, _P, C.c_int, _P, _P, C.c_int],
     'plnr_conv2d_fwd': [_P, C.POINTER(ConvDesc), _TP, _P, _TP, C.POINTER(Epilogue)],
+    'plnr_conv2d_shortcut_supported': [C.POINTER(ConvDesc), _TP, _TP, C.c_int, _TP],
+    'plnr_conv2d_shortcut_fwd': [_P, C.POINTER(ConvDesc), _TP, _P, _TP, C.c_int, _TP, C.POINTER(Epilogue)],
     'plnr_dense_fwd': [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(Epilogue), C.c_int],
     'plnr_maxpool2d': [_P, C.c_int, _TP, _TP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
     'plnr_upsample_nearest': [_P, C.c_int, _TP, _TP, C.c_int, C.c_int],

@@ -270,6 +270,24 @@ int plnr_conv2d_fwd(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x
   return plnr_conv2d_direct(ctx, d, x, w, y, ep);
 }
 
+int plnr_conv2d_shortcut_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* x2, int stride2,
+                                   const plnr_tensor* y) {
+  if (!d || !x || !x2 || !y) return 0;
+  if (d->dtype != PLNR_F16 || d->groups != 1 || d->algo == PLNR_ALGO_DIRECT) return 0;
+  return plnr_conv2d_shift_shortcut_supported(d, x, x2, stride2, y) ? 1 : 0;
+}
+
+int plnr_conv2d_shortcut_fwd(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w_cat,
+                             const plnr_tensor* x2, int stride2, const plnr_tensor* y, const plnr_epilogue* ep) {
+  PLNR_REQUIRE(ctx && x2 && x2->ptr, "conv2d_shortcut: NULL argument");
+  int rc = validate_conv(d, x, w_cat, y);
+  if (rc != PLNR_OK) return rc;
+  PLNR_REQUIRE(!(ep && ep->residual), "conv2d_shortcut: the shortcut replaces the residual operand");
+  PLNR_REQUIRE(plnr_conv2d_shortcut_supported(d, x, x2, stride2, y), "conv2d_shortcut: problem not eligible "
+               "(needs the fp16 stride-1 shift kernel, shortcut channels %% 64 == 0, stride 1 or 2, matching output size)");
+  return plnr_conv2d_shift(ctx, d, x, w_cat, y, ep, x2, stride2);
+}
+
 int plnr_dense_fwd(plnr_ctx* ctx, int dtype, const void* x, const void* w, void* y, int m, int n, int k,
                    const plnr_epilogue* ep, int algo) {
   PLNR_REQUIRE(ctx && x && w && y, "dense: NULL argument");

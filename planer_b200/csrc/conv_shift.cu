@@ -43,6 +43,8 @@ struct ShiftParams {
   int halo;                 // (R-1)*dil_h*Wv + (S-1)*dil_w
   int R, S, dh, dw;
   int C, cchunks;
+  int c2chunks, s2;         // fused 1x1 shortcut convolution: extra 64-channel chunks read from a second tensor at stride s2
+  uint32_t ctr;             // descriptor offset of the un-shifted (centre) view: (pad_t * dil_h * Wv + pad_l * dil_w) * 8
   int n_tile, num_m_tiles, num_tiles;
   int na, nb, b_resident;
   uint32_t a_buf_bytes, b_stage_bytes, idesc, tmem_cols;
@@ -104,7 +106,7 @@ __device__ __forceinline__ void tile_rows(long long o0, int Wv, int halo, long l
 template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                      const ShiftParams p) {
+                      const __grid_constant__ CUtensorMap mapA2, const ShiftParams p) {
   extern __shared__ uint8_t smem_raw[];
   const long long t_entry = clock64();
   const bool stamp = p.prof && blockIdx.x == 0;      // debug: phase time stamps of CTA 0 at prof[1400..]
@@ -134,6 +136,7 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&mapA);
     ptx::prefetch_tmap(&mapB);
+    if (p.c2chunks) ptx::prefetch_tmap(&mapA2);
   }
   if (warp == 1 && lane == 0) {
     for (uint32_t i = 0; i < na; ++i) { ptx::mbar_init(bar_afull + 8 * i, 1); ptx::mbar_init(bar_aempty + 8 * i, 1); }
@@ -179,7 +182,10 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       // position o0 always lands at row-offset Wv of the buffer, so the A descriptors are tile-independent and
       // identical in both CTAs of a pair (they share ONE descriptor per MMA)
       const uint32_t row0_off = (uint32_t)(Wv - off) * 128u;
-      for (int cc = 0; cc < p.cchunks; ++cc) {
+      // chunks [0, cchunks): 64 input channels of the convolution, RS taps each; chunks [cchunks, +c2chunks): 64
+      // channels of the fused 1x1 shortcut, read from the second tensor at stride s2 into the same row layout, ONE tap
+      for (int cc = 0; cc < p.cchunks + p.c2chunks; ++cc) {
+        const bool sc = cc >= p.cchunks;
         const long long tw0 = clock64();
         mbar_wait(bar_aempty + 8 * ab, aph ^ 1, p.err, 0);
         t_wait += clock64() - tw0;
@@ -189,8 +195,10 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           uint32_t dst = sA + ab * p.a_buf_bytes + row0_off;
           long long v = v0;
           int img = (int)(v / p.Hv), hrow = (int)(v - (long long)img * p.Hv);
+          const CUtensorMap* mA = sc ? &mapA2 : &mapA;
+          const int cs = sc ? p.s2 : 1, c0 = (sc ? cc - p.cchunks : cc) * 64;
           for (int i = 0; i < nrows; ++i) {
-            tma_load_4d<CG>(dst, &mapA, full, cc * 64, -p.pad_l, hrow - p.pad_t, img);
+            tma_load_4d<CG>(dst, mA, full, c0, -p.pad_l * cs, (hrow - p.pad_t) * cs, img);
             dst += row_bytes;
             if (++hrow == p.Hv) { hrow = 0; ++img; }
           }
@@ -198,7 +206,9 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         __syncwarp();
         if (++ab == na) { ab = 0; aph ^= 1; }
         if (!p.b_resident || first) {
-          for (int tap = 0; tap < RS; ++tap) {
+          const int ntaps = sc ? 1 : RS;
+          const int kbase = sc ? RS * p.C + (cc - p.cchunks) * 64 : cc * 64;
+          for (int tap = 0; tap < ntaps; ++tap) {
             if (!p.b_resident) {
               const long long tb0 = clock64();
               mbar_wait(bar_bempty + 8 * bs, bph ^ 1, p.err, 4);
@@ -207,8 +217,8 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             if (ptx::elect_one()) {
               const uint32_t full = bar_bfull + 8 * bs;
               if (leader) ptx::mbar_arrive_expect_tx(full, (uint32_t)CG * p.b_stage_bytes);
-              if (CG == 2) ptx::tma_load_2d_pair(sB + bs * p.b_stage_bytes, &mapB, full, tap * p.C + cc * 64, n_row);
-              else ptx::tma_load_2d(sB + bs * p.b_stage_bytes, &mapB, full, tap * p.C + cc * 64, n_row);
+              if (CG == 2) ptx::tma_load_2d_pair(sB + bs * p.b_stage_bytes, &mapB, full, tap * p.C + kbase, n_row);
+              else ptx::tma_load_2d(sB + bs * p.b_stage_bytes, &mapB, full, tap * p.C + kbase, n_row);
             }
             __syncwarp();
             if (++bs == nb) { bs = 0; bph ^= 1; }
@@ -245,14 +255,31 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       const uint32_t d_tmem = tmem_base + a * (uint32_t)n_tile;
       uint32_t acc = 0u;
       uint32_t b_lo = b_lo0;                     // resident: (chunk, tap) boxes in order from the start of sB
-      for (int cc = 0; cc < cchunks; ++cc) {
+      const int nchunks_all = cchunks + p.c2chunks;
+      for (int cc = 0; cc < nchunks_all; ++cc) {
+        const bool sc = cc >= cchunks;           // chunk of the fused 1x1 shortcut: one tap, the un-shifted view
         const long long tf0 = clock64();
         mbar_wait(bar_afull + 8 * ab, aph, p.err, 2);
         t_full += clock64() - tf0;
         if (stamp && it == 0 && cc == 0 && lane == 0) p.prof[1402] = clock64() - t_entry;
         ptx::tc_fence_after();
         uint32_t a_row = a_lo0 + ab * a_step;
-        if (resident) {
+        if (sc) {
+          const uint32_t bi = resident ? (uint32_t)(cchunks * R * S + (cc - cchunks)) : bs;
+          if (!resident || it == 0) {
+            mbar_wait(bar_bfull + 8 * bi, resident ? 0u : bph, p.err, 5);
+            ptx::tc_fence_after();
+          }
+          if (elected) {
+            ptx::umma_f16_x4<CG>(d_tmem, a_row + p.ctr, b_lo0 + bi * b_step, desc_hi, idesc, acc);
+            if (!resident) {
+              if (CG == 2) ptx::umma_commit_pair(bar_bempty + 8 * bs, 3);
+              else ptx::umma_commit(bar_bempty + 8 * bs);
+            }
+          }
+          acc = 1u;
+          if (!resident) { if (++bs == nb) { bs = 0; bph ^= 1; } }
+        } else if (resident) {
           if (it == 0) {                         // weights are loaded once per CTA, chunk by chunk behind the A rows
             for (int i = 0; i < R * S; ++i) mbar_wait(bar_bfull + 8 * (uint32_t)(cc * R * S + i), 0, p.err, 5);
             ptx::tc_fence_after();
@@ -283,10 +310,10 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         if (elected) {
           if (CG == 2) {
             ptx::umma_commit_pair(bar_aempty + 8 * ab, 3);
-            if (cc == cchunks - 1) ptx::umma_commit_pair(bar_tfull + 8 * a, 3);
+            if (cc == nchunks_all - 1) ptx::umma_commit_pair(bar_tfull + 8 * a, 3);
           } else {
             ptx::umma_commit(bar_aempty + 8 * ab);
-            if (cc == cchunks - 1) ptx::umma_commit(bar_tfull + 8 * a);
+            if (cc == nchunks_all - 1) ptx::umma_commit(bar_tfull + 8 * a);
           }
         }
         if (++ab == na) { ab = 0; aph ^= 1; }
@@ -532,7 +559,8 @@ struct ShiftPlan {
 };
 
 // Shared-memory plan for a problem; ok == false when the shift kernel does not apply / does not fit.
-static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y, int sm_count) {
+static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y, int sm_count,
+                           int c2 = 0) {
   ShiftPlan pl;
   memset(&pl, 0, sizeof(pl));
   if (d->dtype != PLNR_F16 || d->groups != 1 || d->stride_h != 1 || d->stride_w != 1) return pl;
@@ -559,7 +587,7 @@ static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
   pl.n_tile = cout_r < 256 ? cout_r : 256;
   if (const char* e = getenv("PLNR_SHIFT_NTILE")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0 && v < pl.n_tile) pl.n_tile = v; }
   pl.b_stage_bytes = (uint32_t)(pl.n_tile / pl.cg) * 128;
-  const int kst = d->kh * d->kw * (x->c / 64);
+  const int kst = d->kh * d->kw * (x->c / 64) + c2 / 64;    // weight boxes per tile: (chunk, tap) + shortcut chunks
   const int num_n_tiles = (y->c + pl.n_tile - 1) / pl.n_tile;
   const size_t fixed = kEpiBytes + 16 * kMaxA + 16 * kMaxB + 64 + kStageBytes + 1024;
   const size_t budget = 232448;
@@ -594,11 +622,24 @@ bool plnr_conv2d_shift_supported(const plnr_conv_desc* d, const plnr_tensor* x, 
   return make_plan(d, x, y, 148).ok;
 }
 
+// The fused shortcut: x2 is the block input, (n, c2, >= (y.h-1)*s2+1, >= (y.w-1)*s2+1); its 1x1 / stride-s2 convolution is
+// accumulated into the same TMEM tile as extra k-chunks (weights appended to the packed filter along K).
+bool plnr_conv2d_shift_shortcut_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* x2, int s2,
+                                          const plnr_tensor* y) {
+  if (!plnr_conv2d_shift_supported(d, x, y)) return false;
+  if (!x2 || x2->c % 64 != 0 || x2->ld % 8 != 0 || x2->coff % 8 != 0 || (reinterpret_cast<uintptr_t>(x2->ptr) & 15)) return false;
+  if (s2 < 1 || s2 > 2 || x2->n != x->n) return false;
+  if ((x2->h + s2 - 1) / s2 != y->h || (x2->w + s2 - 1) / s2 != y->w) return false;
+  const ShiftPlan pl = make_plan(d, x, y, 148, x2->c);
+  return pl.ok && pl.Wv * s2 <= 256;
+}
+
 int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w,
-                      const plnr_tensor* y, const plnr_epilogue* ep) {
+                      const plnr_tensor* y, const plnr_epilogue* ep, const plnr_tensor* x2, int s2) {
   int rc = resolve_driver();
   if (rc != PLNR_OK) return rc;
-  const ShiftPlan pl = make_plan(d, x, y, ctx->sm_count);
+  const int c2 = x2 ? x2->c : 0;
+  const ShiftPlan pl = make_plan(d, x, y, ctx->sm_count, c2);
   PLNR_REQUIRE(pl.ok, "conv2d(shift): problem not eligible");
   PLNR_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, "conv2d(shift): packed weights must be 16-byte aligned");
   const int cg = pl.cg;
@@ -611,6 +652,8 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
   p.halo = pl.halo;
   p.R = d->kh; p.S = d->kw; p.dh = d->dil_h; p.dw = d->dil_w;
   p.C = x->c; p.cchunks = x->c / 64;
+  p.c2chunks = c2 / 64; p.s2 = x2 ? s2 : 1;
+  p.ctr = (uint32_t)(d->pad_t * pl.Wv + d->pad_l) * 8u;      // the view whose tap reads input pixel (p, q) itself
   p.n_tile = pl.n_tile;
   p.num_m_tiles = (int)((p.Mv + kTileM * cg - 1) / (kTileM * cg));
   const int num_n_tiles = (y->c + p.n_tile - 1) / p.n_tile;
@@ -657,7 +700,7 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
     small_tensor_fixup(&mapA, (uint64_t)x->n * x->h * x->w * x->ld * 2);
   }
   {
-    const int Ktot = d->kh * d->kw * x->c;
+    const int Ktot = d->kh * d->kw * x->c + c2;
     const cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)y->c};
     const cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
     const cuuint32_t box[2] = {64, (cuuint32_t)(p.n_tile / cg)};
@@ -670,6 +713,26 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
       return PLNR_ERR_DRIVER;
     }
     small_tensor_fixup(&mapB, (uint64_t)Ktot * y->c * 2);
+  }
+
+  CUtensorMap mapA2 = mapA;
+  if (x2) {
+    // x2 sampled at stride s2 in W (element stride) and H (row coordinate): one box = Wv positions of one virtual row
+    const cuuint64_t dims[4] = {(cuuint64_t)x2->c, (cuuint64_t)x2->w, (cuuint64_t)x2->h, (cuuint64_t)x2->n};
+    const cuuint64_t strides[3] = {(cuuint64_t)x2->ld * 2, (cuuint64_t)x2->w * x2->ld * 2,
+                                   (cuuint64_t)x2->h * x2->w * x2->ld * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)(pl.Wv * s2), 1, 1};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)s2, 1, 1};
+    void* gaddr = (void*)((__half*)x2->ptr + x2->coff);
+    CUresult r = g_encode_tiled(&mapA2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, gaddr, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      plnr_set_error("cuTensorMapEncodeTiled(shortcut) failed with CUresult %d (C=%d W=%d H=%d N=%d Wv=%d s=%d)", (int)r,
+                     x2->c, x2->w, x2->h, x2->n, pl.Wv, s2);
+      return PLNR_ERR_DRIVER;
+    }
+    small_tensor_fixup(&mapA2, (uint64_t)x2->n * x2->h * x2->w * x2->ld * 2);
   }
 
   if (!ctx->shift_attr_set) {
@@ -696,8 +759,8 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = plnr_pdl_enabled() ? 2 : 1;
-  cudaError_t le = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<2>, mapA, mapB, p)
-                           : cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<1>, mapA, mapB, p);
+  cudaError_t le = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<2>, mapA, mapB, mapA2, p)
+                           : cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<1>, mapA, mapB, mapA2, p);
   if (le != cudaSuccess) {
     plnr_set_error("launch of conv_shift_f16_kernel<%d> failed: %s", cg, cudaGetErrorString(le));
     return PLNR_ERR_CUDA;

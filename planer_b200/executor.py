@@ -95,6 +95,36 @@ class Executor:
             return st, pool
         return None
 
+    @staticmethod
+    def _affine_host(bias, bn_k, bn_b, co):
+        """(scale, shift) of a conv epilogue on the host, fp32: y = acc * scale + shift  (planer/layer.py:26, :125-127)."""
+        k = np.ones(co, np.float32) if bn_k is None else bn_k.get().astype(np.float32).reshape(-1)
+        b = np.zeros(co, np.float32) if bn_b is None else bn_b.get().astype(np.float32).reshape(-1)
+        bi = np.zeros(co, np.float32) if bias is None else bias.get().astype(np.float32).reshape(-1)
+        return k, bi * k + b
+
+    def _step_affine(self, st, co):
+        bias = self._weight(st.bias) if st.bias is not None else None
+        bn_k, bn_b = (self._weight(st.bn[0]), self._weight(st.bn[1])) if st.bn else (None, None)
+        return self._affine_host(bias, bn_k, bn_b, co)
+
+    def _shortcut_eligible(self, main, short):
+        """Can ``short`` (1x1 conv on the shortcut branch) be accumulated inside ``main``'s kernel?  Shapes must suit the
+        shift kernel, and folding the two BatchNorm scales into the shortcut's fp16 weights must be benign."""
+        vals, a = self.values, main.attrs
+        xs, x2s, ys = vals[main.ins[0]].shape, vals[short.ins[0]].shape, vals[main.out].shape
+        if len(xs) != 4 or len(x2s) != 4 or a['group'] != 1 or vals[short.ins[0]].kind == 'input':
+            return False
+        kshape = vals[main.w].shape
+        if not ops.conv2d_shortcut_supported(self.dtype, xs, x2s, short.attrs['strides'][0], ys, kshape[2], kshape[3],
+                                             a['strides'], a['dilations'], a['pads']):
+            return False
+        s_main, _ = self._step_affine(main, kshape[0])
+        s_short, _ = self._step_affine(short, kshape[0])
+        if np.any(np.abs(s_main) < 1e-3 * max(np.abs(s_main).max(), 1e-30)):
+            return False
+        return bool(np.abs(s_short / s_main).max() <= 64.0)
+
     def _gap_dense_tail(self, gap):
         """The dense step of a  gap -> flatten -> dense  tail (each value used once, none a graph output), or None."""
         if os.environ.get('PLNR_NO_GAP_DENSE') == '1' or len(self.values[gap.ins[0]].shape) != 4:
@@ -132,6 +162,8 @@ class Executor:
 
     def _build(self):
         gp, vals, dt = self.plan, self.values, self.dtype
+        if dt == np.float16 and os.environ.get('PLNR_NO_SHORTCUT_FUSION') != '1':
+            P.absorb_shortcuts(gp, self._shortcut_eligible)
         P.assign_buffers(gp, dt.itemsize, self._storage_c)
         pool = [None] * len(gp.buffer_bytes)
 
@@ -224,6 +256,23 @@ class Executor:
                                                             st.act)
                 return None
             y = alloc(st.out)
+            if op == 'conv' and st.shortcut is not None:
+                # conv + bn + add(bn_d(conv1x1_d(x2))) + act in ONE launch: the shortcut's weights, scaled by the ratio of
+                # the two BatchNorm scales, are appended to the packed filter along K; the shifts add up
+                x2_vid, s2, sh = st.shortcut
+                x2 = self._view(x2_vid)
+                a = st.attrs
+                Kd = self._weight(sh.w).get().astype(np.float32)[:, :, 0, 0]
+                s_main, t_main = self._step_affine(st, co)
+                s_short, t_short = self._step_affine(sh, co)
+                w2 = (Kd * (s_short / s_main)[:, None]).astype(np.float16)
+                wp = ops.pack_weight(K, x.shape[1], dt).get().reshape(co, -1)
+                wcat = B.asarray(np.ascontiguousarray(np.concatenate([wp, w2], axis=1)))
+                scale_c, shift_c = B.asarray(s_main.astype(np.float32)), B.asarray((t_main + t_short).astype(np.float32))
+                self._keep += [wcat, scale_c, shift_c]
+                kh, kw = K.shape[2], K.shape[3]
+                return lambda: ops.conv2d_shortcut_into(x, wcat, x2, s2, y, kh, kw, a['strides'], a['dilations'], a['pads'],
+                                                        scale_c, shift_c, st.act, st.alpha)
             stem = self.stems.get(self._root(st.ins[0])) if op == 'conv' else None
             if stem is not None:
                 # first layer on the packed input: (T x 1) stride-1 conv, taps re-ordered on the host (tiny, load time)

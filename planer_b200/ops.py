@@ -81,6 +81,28 @@ def conv2d_into(x, w_packed, y, kh, kw, strides, dilations, pads, groups=1, scal
     return y
 
 
+def conv2d_shortcut_supported(dtype, xshape, x2shape, stride2, yshape, kh, kw, strides, dilations, pads):
+    """True when conv(x) + conv1x1_stride2(x2) can run as ONE launch (plnr_conv2d_shortcut_fwd); shapes are logical
+    (N, C, H, W) of dense pixel-major tensors."""
+    d = _capi.ConvDesc(_capi.dtype_code(dtype), kh, kw, pads[0], pads[1], pads[2], pads[3],
+                       strides[0], strides[1], dilations[0], dilations[1], 1, ALGO_AUTO)
+    mk = lambda shp: _capi.Tensor(256, shp[0], shp[2], shp[3], shp[1], shp[1], 0)     # dummy aligned pointer
+    tx, tx2, ty = mk(xshape), mk(x2shape), mk(yshape)
+    return bool(B.lib().plnr_conv2d_shortcut_supported(C.byref(d), C.byref(tx), C.byref(tx2), stride2, C.byref(ty)))
+
+
+def conv2d_shortcut_into(x, w_cat, x2, stride2, y, kh, kw, strides, dilations, pads, scale=None, shift=None,
+                         act=ACT_NONE, alpha=0.0):
+    """y = act((conv(x, W) + conv1x1(x2, W2, stride2)) * scale + shift); w_cat = packed W with W2 appended along K."""
+    d = _capi.ConvDesc(_capi.dtype_code(x.dtype), kh, kw, pads[0], pads[1], pads[2], pads[3],
+                       strides[0], strides[1], dilations[0], dilations[1], 1, ALGO_AUTO)
+    tx, tx2, ty = x.tensor(), x2.tensor(), y.tensor()
+    ep, keep = _epilogue(scale, shift, None, act, alpha, False)
+    _capi.check(B.lib().plnr_conv2d_shortcut_fwd(B.ctx(), C.byref(d), C.byref(tx), w_cat.ptr, C.byref(tx2), stride2,
+                                                 C.byref(ty), C.byref(ep)), 'plnr_conv2d_shortcut_fwd')
+    return y
+
+
 def conv2d_algo(x, y, kh, kw, strides, dilations, pads, groups=1):
     d = _capi.ConvDesc(_capi.dtype_code(x.dtype), kh, kw, pads[0], pads[1], pads[2], pads[3],
                        strides[0], strides[1], dilations[0], dilations[1], groups, ALGO_AUTO)

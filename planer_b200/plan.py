@@ -175,15 +175,17 @@ def infer_shapes(model, input_shapes, host_consts=None):
 class Step:
     """One kernel launch (or a zero-cost alias) of the compiled forward."""
     __slots__ = ('op', 'name', 'ins', 'out', 'attrs', 'w', 'bias', 'bn', 'res', 'act', 'alpha', 'fused', 'inplace',
-                 'res_after')
+                 'res_after', 'shortcut')
 
     def __init__(self, op, name, ins, out, attrs=None):
         self.op, self.name, self.ins, self.out, self.attrs = op, name, list(ins), out, dict(attrs or {})
         self.w = self.bias = self.bn = self.res = None
         self.act, self.alpha, self.fused, self.inplace, self.res_after = 0, 0.0, [name], False, False
+        self.shortcut = None      # (input value id, stride, absorbed 1x1 conv Step): see absorb_shortcuts
 
     def reads(self):
-        return [i for i in self.ins + [self.res] if i is not None]
+        extra = [self.shortcut[0]] if self.shortcut else []
+        return [i for i in self.ins + [self.res] + extra if i is not None]
 
 
 class GraphPlan:
@@ -302,6 +304,42 @@ def fuse(values, nodes, outputs):
         else:                                                       # pragma: no cover
             raise NotImplementedError(k)
     return steps
+
+
+def absorb_shortcuts(plan, eligible):
+    """Down-sampling residual blocks: ``conv2 -> bn -> add(., bn_d(conv1x1_d(x))) -> relu``.  When ``eligible(main, short)``
+    agrees, the 1x1 shortcut convolution ``short`` (no activation, no residual, result used only as ``main``'s residual)
+    is removed from the step list and ``main`` reads the block input itself (``main.shortcut``): one launch instead of
+    two, the shortcut's k-chunks accumulate into the same tile (plnr_conv2d_shortcut_fwd)."""
+    values, steps = plan.values, plan.steps
+    producer = {st.out: st for st in steps}
+    n_reads = {}
+    for st in steps:
+        for r in st.reads():
+            n_reads[r] = n_reads.get(r, 0) + 1
+    drop = set()
+    for st in steps:
+        if st.op != 'conv' or st.res is None or st.res_after or st.shortcut:
+            continue
+        sh = producer.get(st.res)
+        if sh is None or sh.op != 'conv' or sh.res is not None or sh.act != 0 or n_reads.get(sh.out, 0) != 1:
+            continue
+        if values[sh.out].is_output or id(sh) in drop:
+            continue
+        a = sh.attrs
+        if tuple(values[sh.w].shape[2:]) != (1, 1) or a['group'] != 1 or tuple(a['pads']) != (0, 0, 0, 0):
+            continue
+        if a['strides'][0] != a['strides'][1] or tuple(a['dilations']) != (1, 1):
+            continue
+        if not eligible(st, sh):
+            continue
+        st.shortcut = (sh.ins[0], int(a['strides'][0]), sh)
+        st.res = None
+        st.fused = list(st.fused) + ['(' + '+'.join(sh.fused) + ')']
+        drop.add(id(sh))
+    if drop:
+        plan.steps = [st for st in steps if id(st) not in drop]
+    return len(drop)
 
 
 def _root(values, vid):

@@ -92,6 +92,24 @@ def stem_net(cout=64, k=7, pad=3, bias=False, bn=True, seed=0):
     return b.finish(['x'], [x])
 
 
+def down_block(cin=64, cout=128, stride=2, seed=0):
+    """conv3x3+relu, then one down-sampling BasicBlock: conv3x3/s -> bn -> relu -> conv3x3 -> bn, shortcut conv1x1/s -> bn,
+    add, relu.  The pattern whose shortcut convolution the executor folds into the second conv's launch."""
+    b = _Builder(seed)
+    x = b.conv('x', cin, cin, 3, 1, 1, name='pre')
+    x = b.op('relu', {}, [x], name='pre_relu')
+    y = b.conv(x, cin, cout, 3, stride, 1, name='conv1')
+    y = b.bn(y, cout, 'bn1')
+    y = b.op('relu', {}, [y], name='relu1')
+    y = b.conv(y, cout, cout, 3, 1, 1, name='conv2')
+    y = b.bn(y, cout, 'bn2')
+    idt = b.conv(x, cin, cout, 1, stride, 0, name='downsample.0')
+    idt = b.bn(idt, cout, 'downsample.1')
+    y = b.op('add', {}, [y, idt], name='add')
+    y = b.op('relu', {}, [y], name='relu2')
+    return b.finish(['x'], [y])
+
+
 def readme_net(seed=0):
     """The README's CustomNet in the real IR: conv+relu chained in one flow,
     maxpool(2), upsample(x2, nearest), concat(axis=1)+sigmoid chained, return."""

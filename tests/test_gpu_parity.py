@@ -163,6 +163,30 @@ def test_fused_stem_conv_bn_relu_maxpool_vs_oracle(planer, cfg):
     assert rel_err(y, y2.astype(np.float32)) <= 2e-3
 
 
+@pytest.mark.parametrize('cfg', [(2, 64, 128, 2, 28), (3, 64, 64, 1, 14), (2, 128, 256, 2, 14), (1, 256, 512, 2, 14)])
+def test_shortcut_conv_folded_into_the_block_conv(planer, cfg):
+    """conv2+bn2+add(bn_d(conv1x1_d(x)))+relu as ONE launch (plnr_conv2d_shortcut_fwd) vs the oracle and vs the same
+    graph with the shortcut convolution launched separately."""
+    from planer_b200 import zoo
+    n, cin, cout, stride, hw = cfg
+    model, blob = zoo.down_block(cin, cout, stride, seed=cin + hw)
+    x = np.random.default_rng(hw).standard_normal((n, cin, hw, hw)).astype(np.float16)
+    ref = oracle.build_net(model, blob)(x.astype(np.float32))
+    net = planer.from_model(model, blob, half=True)
+    y = net(x)
+    ex = net.executor([x.shape])
+    assert sum(1 for st in ex.plan.steps if st.shortcut) == 1, 'shortcut convolution not absorbed'
+    assert y.shape == ref.shape and rel_err(y, ref) <= 1e-2
+    os.environ['PLNR_NO_SHORTCUT_FUSION'] = '1'
+    try:
+        net2 = planer.from_model(model, blob, half=True)
+        y2 = net2(x)
+        assert sum(1 for st in net2.executor([x.shape]).plan.steps if st.shortcut) == 0
+    finally:
+        del os.environ['PLNR_NO_SHORTCUT_FUSION']
+    assert rel_err(y, y2.astype(np.float32)) <= 3e-3
+
+
 def test_rejects_what_the_reference_breaks_on(planer):
     """Asymmetric pads with bottom>top are silently wrong in the reference (App. D Q1): we raise.  Operators
     outside the hot path raise by name; there is no CPU fallback."""
