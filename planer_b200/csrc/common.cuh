@@ -130,6 +130,10 @@ int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tenso
 bool plnr_conv2d_tcgen05_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y);
 int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w,
                       const plnr_tensor* y, const plnr_epilogue* ep, const plnr_tensor* x2 = nullptr, int s2 = 1);
+int plnr_conv2d_stack(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w, const plnr_tensor* y,
+                      const plnr_epilogue* ep, const plnr_tensor* x2, int s2);
+bool plnr_conv2d_stack_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y, const plnr_epilogue* ep,
+                                 const plnr_tensor* x2, int s2);
 bool plnr_conv2d_shift_shortcut_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* x2, int s2,
                                           const plnr_tensor* y);
 bool plnr_conv2d_shift_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y);

@@ -636,6 +636,8 @@ bool plnr_conv2d_shift_shortcut_supported(const plnr_conv_desc* d, const plnr_te
 
 int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w,
                       const plnr_tensor* y, const plnr_epilogue* ep, const plnr_tensor* x2, int s2) {
+  // 3-wide filters over 64-channel output blocks whose taps fit in shared memory: the stacked variant (conv_stack.cu)
+  if (plnr_conv2d_stack_supported(d, x, y, ep, x2, s2)) return plnr_conv2d_stack(ctx, d, x, w, y, ep, x2, s2);
   int rc = resolve_driver();
   if (rc != PLNR_OK) return rc;
   const int c2 = x2 ? x2->c : 0;

@@ -98,6 +98,9 @@ CONV_SWEEP = [
     (2, 128, 9, 9, 256, 3, 1, 1, 1), (1, 256, 7, 7, 512, 3, 1, 1, 1), (2, 64, 12, 12, 64, 3, 1, 2, 2),
     (2, 32, 14, 14, 64, 3, 2, 1, 1), (2, 16, 10, 10, 48, 3, 1, 1, 1), (1, 96, 10, 10, 80, 3, 1, 1, 1),
     (1, 64, 13, 13, 255, 1, 1, 0, 1), (2, 64, 8, 8, 64, 5, 1, 2, 1), (1, 64, 30, 30, 32, 3, 1, 0, 1),
+    # 3-wide filters over 64-channel output blocks (also the shapes of the opt-in stacked kernel, conv_stack.cu)
+    (4, 64, 56, 56, 64, 3, 1, 1, 1), (2, 128, 28, 28, 128, 3, 1, 1, 1), (3, 64, 20, 24, 192, 3, 1, 1, 1),
+    (2, 64, 17, 19, 64, 3, 1, 0, 1), (5, 64, 9, 11, 64, 3, 1, 1, 1),
 ]
 
 
@@ -125,6 +128,33 @@ def test_conv_fp16_kernels_vs_oracle(planer, cfg, algo):
                     0.0, ops.ALGO_TCGEN05 if algo == 'tcgen05' else ops.ALGO_DIRECT)
     B.synchronize()
     assert rel_err(y.get(), ref) <= 1e-2
+
+
+@pytest.mark.parametrize('cfg', [(4, 64, 56, 56, 64, True), (2, 128, 28, 28, 128, False), (3, 64, 20, 24, 192, True)])
+def test_stacked_conv_kernel_equals_shift_kernel(planer, cfg):
+    """conv_stack.cu (horizontal taps stacked into N, lane-shifted epilogue) vs conv_shift.cu on the same problem: the two
+    tensor-core formulations must agree to fp16 rounding of the same fp32 sums."""
+    from planer_b200 import ops, backend as B
+    n, cin, h, w, cout, with_res = cfg
+    rng = np.random.default_rng(cin + h + cout)
+    x = B.to_nhwc(B.asarray(rng.standard_normal((n, cin, h, w)).astype(np.float16)))
+    K = B.asarray((rng.standard_normal((cout, cin, 3, 3)) * np.sqrt(2.0 / (cin * 9))).astype(np.float16))
+    wp = ops.pack_weight(K, cin, np.float16)
+    scale, shift = ops.fold_affine(B.asarray((rng.standard_normal(cout) * 0.1).astype(np.float32)),
+                                   B.asarray(rng.uniform(0.5, 1.5, cout).astype(np.float32)),
+                                   B.asarray((rng.standard_normal(cout) * 0.1).astype(np.float32)), cout)
+    r = B.to_nhwc(B.asarray(rng.standard_normal((n, cout, h, w)).astype(np.float16))) if with_res else None
+    outs = []
+    for stack in ('1', '0'):
+        os.environ['PLNR_STACK'] = stack            # opt-in experiment kernel (see conv_stack.cu)
+        try:
+            y = B.empty((n, cout, h, w), np.float16, 'nhwc')
+            ops.conv2d_into(x, wp, y, 3, 3, (1, 1), (1, 1), (1, 1, 1, 1), 1, scale, shift, r, ops.ACT_RELU, 0.0, ops.ALGO_TCGEN05)
+            B.synchronize()
+            outs.append(y.get().astype(np.float32))
+        finally:
+            del os.environ['PLNR_STACK']
+    assert rel_err(outs[0], outs[1]) <= 2e-3
 
 
 STEM_SWEEP = [
