@@ -215,18 +215,21 @@ __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int N
 template <typename T, int V>
 __global__ void upsample_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int xld,
                                 int xcoff, int yld, int ycoff, int fh, int fw) {
-  const int CV = C / V, OH = H * fh, OW = W * fw;
-  const int64_t total = (int64_t)N * OH * OW * CV;
+  // one thread per INPUT vector: a single 16-byte load feeds the fh x fw stores of its replicas (the output side is
+  // fh*fw times larger: the kernel is store-bound, so nothing is read twice)
+  const int CV = C / V, OW = W * fw;
+  const int64_t total = (int64_t)N * H * W * CV;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int cv = (int)(i % CV);
     int64_t t = i / CV;
-    int ow = (int)(t % OW);
-    t /= OW;
-    int oh = (int)(t % OH);
-    int n = (int)(t / OH);
-    const Vec<T, V> v =
-        *reinterpret_cast<const Vec<T, V>*>(x + (((size_t)n * H + oh / fh) * W + ow / fw) * xld + xcoff + cv * V);
-    *reinterpret_cast<Vec<T, V>*>(y + (((size_t)n * OH + oh) * OW + ow) * yld + ycoff + cv * V) = v;
+    int iw = (int)(t % W);
+    t /= W;
+    int ih = (int)(t % H);
+    int n = (int)(t / H);
+    const Vec<T, V> v = *reinterpret_cast<const Vec<T, V>*>(x + (((size_t)n * H + ih) * W + iw) * xld + xcoff + cv * V);
+    T* yb = y + (((size_t)n * H * fh + (size_t)ih * fh) * OW + (size_t)iw * fw) * yld + ycoff + cv * V;
+    for (int r = 0; r < fh; ++r)
+      for (int q = 0; q < fw; ++q) *reinterpret_cast<Vec<T, V>*>(yb + ((size_t)r * OW + q) * yld) = v;
   }
 }
 
@@ -241,6 +244,17 @@ __global__ void copy_channels_kernel(const T* __restrict__ x, T* __restrict__ y,
     *reinterpret_cast<Vec<T, V>*>(y + p * yld + ycoff + cv * V) =
         *reinterpret_cast<const Vec<T, V>*>(x + p * xld + xcoff + cv * V);
   }
+}
+
+// sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5 on fp16 pairs: ONE MUFU op per two elements (tanh.approx.f16x2, abs. error
+// 2^-11) instead of ex2 + rcp per element -- with expf the fp16 sigmoid kernel is MUFU-bound at 66 % of the HBM rate
+__device__ __forceinline__ uint32_t sigmoid_h2(uint32_t v) {
+  const __half2 half = __float2half2_rn(0.5f);
+  __half2 h = __hmul2(*reinterpret_cast<__half2*>(&v), half);
+  uint32_t t, hu = *reinterpret_cast<uint32_t*>(&h);
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(hu));
+  __half2 r = __hfma2(*reinterpret_cast<__half2*>(&t), half, half);
+  return *reinterpret_cast<uint32_t*>(&r);
 }
 
 template <typename T, int V>
@@ -258,6 +272,11 @@ __global__ void eltwise_kernel(int op, const T* __restrict__ x, const T* __restr
       int c = (int)((i * V) % C);
 #pragma unroll
       for (int k = 0; k < V; ++k) st_f(&o.v[k], ld_f(&a.v[k]) * ld_f(p0 + c + k) + ld_f(p1 + c + k));
+    } else if (op == PLNR_EW_SIGMOID && sizeof(T) == 2 && V == 8) {
+      const uint4 in = *reinterpret_cast<const uint4*>(&a);
+      uint4 out;
+      out.x = sigmoid_h2(in.x); out.y = sigmoid_h2(in.y); out.z = sigmoid_h2(in.z); out.w = sigmoid_h2(in.w);
+      *reinterpret_cast<uint4*>(&o) = out;
     } else {
       int act = op == PLNR_EW_RELU ? PLNR_ACT_RELU : (op == PLNR_EW_LEAKY ? PLNR_ACT_LEAKY : PLNR_ACT_SIGMOID);
 #pragma unroll
@@ -513,11 +532,11 @@ int plnr_upsample_nearest(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const 
   DISPATCH_T(dtype, {
     constexpr int V = VecWidth<T>::value;
     if (view_vec_ok(x, V, sizeof(T)) && view_vec_ok(y, V, sizeof(T))) {
-      work = (int64_t)y->n * y->h * y->w * (y->c / V);
+      work = (int64_t)x->n * x->h * x->w * (x->c / V);
       upsample_kernel<T, V><<<grid_for(work, ctx->sm_count), kThreads, 0, ctx->stream>>>(
           (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->ld, y->coff, fh, fw);
     } else {
-      work = (int64_t)y->n * y->h * y->w * y->c;
+      work = (int64_t)x->n * x->h * x->w * x->c;
       upsample_kernel<T, 1><<<grid_for(work, ctx->sm_count), kThreads, 0, ctx->stream>>>(
           (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->ld, y->coff, fh, fw);
     }
