@@ -212,6 +212,91 @@ __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int N
   }
 }
 
+
+// 3x3 / stride-2 max pooling, register blocked: a thread owns TWO adjacent output columns and a strip of RB output
+// rows of one 16-byte channel group.  Every input row of the strip is loaded once (5 columns serve both outputs) and its
+// two horizontal 3-maxima are folded into the running vertical maxima, the row shared by two consecutive outputs being
+// used for both: 5.6 sixteen-byte loads per output instead of 9 (the generic kernel is load-issue bound, not DRAM
+// bound).  Semantics are the reference's (planer/util.py:79-95): taps outside the image contribute 0, floor -1e4.
+template <typename T, int V> struct VMax;
+template <int V> struct VMax<float, V> {
+  static __device__ __forceinline__ Vec<float, V> max2(const Vec<float, V>& a, const Vec<float, V>& b) {
+    Vec<float, V> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k) o.v[k] = fmaxf(a.v[k], b.v[k]);
+    return o;
+  }
+  static __device__ __forceinline__ Vec<float, V> splat(float f) {
+    Vec<float, V> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k) o.v[k] = f;
+    return o;
+  }
+};
+template <int V> struct VMax<__half, V> {
+  static __device__ __forceinline__ Vec<__half, V> max2(const Vec<__half, V>& a, const Vec<__half, V>& b) {
+    Vec<__half, V> o;
+    const __half2* pa = reinterpret_cast<const __half2*>(&a); const __half2* pb = reinterpret_cast<const __half2*>(&b);
+    __half2* po = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int k = 0; k < V / 2; ++k) po[k] = __hmax2(pa[k], pb[k]);
+    return o;
+  }
+  static __device__ __forceinline__ Vec<__half, V> splat(float f) {
+    Vec<__half, V> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k) o.v[k] = __float2half_rn(f);
+    return o;
+  }
+};
+
+template <typename T, int V, int RB>
+__global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int xld,
+                                    int xcoff, int OH, int OW, int yld, int ycoff, int pt, int pl) {
+  using VM = VMax<T, V>;
+  const int CV = C / V, OWP = (OW + 1) / 2, OHS = (OH + RB - 1) / RB;
+  const int64_t total = (int64_t)N * OHS * OWP * CV;
+  const Vec<T, V> zero = VM::splat(0.f), floor_v = VM::splat(-1e4f);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    int64_t t = i / CV;
+    const int owp = (int)(t % OWP); t /= OWP;
+    const int ohs = (int)(t % OHS);
+    const int n = (int)(t / OHS);
+    const int ow0 = 2 * owp, oh0 = ohs * RB;
+    const int nout = min(RB, OH - oh0);
+    const T* xb = x + (size_t)n * H * W * xld + xcoff + cv * V;
+    T* yb = y + (size_t)n * OH * OW * yld + ycoff + cv * V;
+    const int iw0 = 2 * ow0 - pl;                       // five input columns iw0 .. iw0 + 4
+    bool cok[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) cok[q] = iw0 + q >= 0 && iw0 + q < W;
+    Vec<T, V> m0 = floor_v, m1 = floor_v;
+    for (int r = 0; r <= 2 * nout; ++r) {               // input rows of the strip: 2*oh0 - pt + r
+      const int ih = 2 * oh0 - pt + r;
+      Vec<T, V> h0 = zero, h1 = zero;                   // a row outside the image contributes 0 through every tap
+      if (ih >= 0 && ih < H) {
+        Vec<T, V> c[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const int iwc = min(max(iw0 + q, 0), W - 1);
+          c[q] = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)ih * W + iwc) * xld);
+          if (!cok[q]) c[q] = zero;
+        }
+        h0 = VM::max2(VM::max2(c[0], c[1]), c[2]);
+        h1 = VM::max2(VM::max2(c[2], c[3]), c[4]);
+      }
+      m0 = VM::max2(m0, h0); m1 = VM::max2(m1, h1);
+      if (r >= 2 && (r & 1) == 0) {                     // third row of output oh0 + r/2 - 1: emit, restart with this row
+        const int oh = oh0 + (r >> 1) - 1;
+        *reinterpret_cast<Vec<T, V>*>(yb + ((size_t)oh * OW + ow0) * yld) = m0;
+        if (ow0 + 1 < OW) *reinterpret_cast<Vec<T, V>*>(yb + ((size_t)oh * OW + ow0 + 1) * yld) = m1;
+        m0 = VM::max2(floor_v, h0); m1 = VM::max2(floor_v, h1);
+      }
+    }
+  }
+}
+
 template <typename T, int V>
 __global__ void upsample_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int xld,
                                 int xcoff, int yld, int ycoff, int fh, int fw) {
@@ -512,7 +597,12 @@ int plnr_maxpool2d(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_te
     constexpr int V = VecWidth<T>::value;
     if (view_vec_ok(x, V, sizeof(T)) && view_vec_ok(y, V, sizeof(T))) {
       work = (int64_t)y->n * y->h * y->w * (y->c / V);
-      if (kh == 3 && kw == 3) MP_LAUNCH(V, 3, 3);
+      if (kh == 3 && kw == 3 && stride_h == 2 && stride_w == 2) {
+        constexpr int RB = 4;
+        const int64_t w2 = (int64_t)y->n * ((y->h + RB - 1) / RB) * ((y->w + 1) / 2) * (y->c / V);
+        maxpool3x3s2_kernel<T, V, RB><<<grid_for(w2, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
+            (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, pad_t, pad_l);
+      } else if (kh == 3 && kw == 3) MP_LAUNCH(V, 3, 3);
       else if (kh == 2 && kw == 2) MP_LAUNCH(V, 2, 2);
       else MP_LAUNCH(V, 0, 0);
     } else {
