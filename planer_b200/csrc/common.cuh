@@ -120,7 +120,7 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) {
   return f.d <= 1 ? n : (__umulhi(n, f.mul) >> f.shr);
 }
 
-template <bool B> struct RelUTag { static constexpr bool value = B; };   // compile-time "activation is ReLU" switch
+template <int A> struct ActTag { static constexpr int value = A; };   // compile-time activation switch of the conv epilogues
 
 // internal entry points implemented in the other translation units
 int plnr_conv2d_direct(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w,

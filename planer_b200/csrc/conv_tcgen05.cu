@@ -381,8 +381,9 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           // Cout = 64 layers.  With a residual the activation (or the add, for the Darknet shortcut x + act(..))
           // happens after the transposition, in packed fp16 -- the reference rounds to fp16 between batchnorm, add
           // and relu too, and fp16 + fp16 rounded once is exactly what HADD2 computes.
-          auto chunk_math = [&](auto relu_tag) {
-            constexpr bool kRelu = decltype(relu_tag)::value;
+          auto chunk_math = [&](auto act_tag) {
+            constexpr int kAct = decltype(act_tag)::value;      // 1 = ReLU, 2 = LeakyReLU (0 <= alpha <= 1), 0 = generic
+            constexpr bool kRelu = kAct == 1;
             const bool act_first = !has_res || p.res_after;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -394,7 +395,9 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 o8[e] = fmaf(__uint_as_float(v[q * 8 + e]), sc[e], sf[e]);
-                if (act_first) o8[e] = kRelu ? fmaxf(o8[e], 0.f) : plnr_apply_act(o8[e], p.act, p.alpha);
+                if (act_first)
+                  o8[e] = kRelu ? fmaxf(o8[e], 0.f)
+                                : (kAct == 2 ? fmaxf(o8[e], o8[e] * p.alpha) : plnr_apply_act(o8[e], p.act, p.alpha));
               }
               uint4 pk;
               pk.x = pack_half2(o8[0], o8[1]); pk.y = pack_half2(o8[2], o8[3]);
@@ -427,7 +430,9 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
               }
             }
           };
-          if (p.act == PLNR_ACT_RELU) chunk_math(RelUTag<true>{}); else chunk_math(RelUTag<false>{});
+          if (p.act == PLNR_ACT_RELU) chunk_math(ActTag<1>{});
+          else if (p.act == PLNR_ACT_LEAKY && p.alpha >= 0.f && p.alpha <= 1.f) chunk_math(ActTag<2>{});
+          else chunk_math(ActTag<0>{});
 #pragma unroll
           for (int i = 0; i < 4; ++i) rv[i] = rvn[i];
         } else if (g.own >= 0) {
