@@ -245,6 +245,26 @@ def asarray(a, dtype=None, pinned=False):
     return out
 
 
+def asarray_async(a):
+    """Host -> device on a separate COPY stream.  Returns (DeviceArray, event): work on the library stream that reads
+    the array must first ``stream().wait_event(event)``.  Lets the upload of one chunk of a batch overlap the forward
+    of the previous chunk (Net.__call__, planer/net.py:94-101 is one blocking asarray)."""
+    torch = _torch()
+    init()
+    if _state.get('copy_stream') is None:
+        _state['copy_stream'] = torch.cuda.Stream(device=device())
+    cs = _state['copy_stream']
+    a = np.ascontiguousarray(a)
+    out = empty(a.shape, a.dtype)
+    cs.wait_stream(stream())                    # the allocation above was made on the library stream
+    host = torch.from_numpy(a.reshape(-1).view(np.uint8))
+    with torch.cuda.stream(cs):
+        out.buf[:a.nbytes].copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cs)
+    return out, ev
+
+
 def asnumpy(a):
     return a.get() if isinstance(a, DeviceArray) else np.asarray(a)
 

@@ -32,10 +32,10 @@ constexpr int kTileM = 128;
 constexpr int kS = 3;                          // horizontal taps stacked into N
 constexpr int kNT = 64;                        // output channels per tile
 constexpr int kTilePos = kTileM - 1;           // outputs per tile: the last lane has no right-hand neighbour
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;                  // warps 0-3: producer / MMA / TMEM / params; warps 4-19: epilogue
 constexpr int kMaxA = 4, kMaxB = 40;
-constexpr uint32_t kStageBytes = 8 * 2048;     // epilogue transposition stage (per epilogue warp: 32 rows x 64 B)
-constexpr uint32_t kXBytes = 2 * 2 * 5 * 32 * 4;       // [group][tile parity][quarter + 1][32 ch] fp32 boundary exchange
+constexpr uint32_t kStageBytes = 16 * 1024;    // epilogue transposition stage (per epilogue warp: 32 rows x 32 B)
+constexpr uint32_t kXBytes = 4 * 2 * 5 * 16 * 4;       // [channel group][tile parity][quarter + 1][16 ch] fp32 boundary exchange
 constexpr uint32_t kBBox = kNT * 128;          // one (chunk, tap) weight box
 constexpr long long kWatchdogCycles = 4000000000ll;
 
@@ -125,7 +125,7 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   if (warp == 1 && lane == 0) {
     for (uint32_t i = 0; i < na; ++i) { ptx::mbar_init(bar_afull + 8 * i, 1); ptx::mbar_init(bar_aempty + 8 * i, 1); }
     for (uint32_t i = 0; i < nb; ++i) ptx::mbar_init(bar_bfull + 8 * i, 1);
-    for (uint32_t a = 0; a < 2; ++a) { ptx::mbar_init(bar_tfull + 8 * a, 1); ptx::mbar_init(bar_tempty + 8 * a, 256); }
+    for (uint32_t a = 0; a < 2; ++a) { ptx::mbar_init(bar_tfull + 8 * a, 1); ptx::mbar_init(bar_tempty + 8 * a, 512); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 256); ptx::tmem_relinquish(); }
@@ -252,22 +252,24 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     }
     if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 2] = t_full; p.prof[blockIdx.x * 8 + 3] = t_tempty; p.prof[blockIdx.x * 8 + 4] = clock64() - t_all0; }
   } else if (warp >= 4) {
-    // ===================================== epilogue ===========================================
+    // ===================================== epilogue (16 warps) =================================
+    // The epilogue of this kernel is a chain of dependent instructions (TMEM loads, shuffles, the boundary exchange):
+    // spread over SIXTEEN warps -- four TMEM lane quarters x four 16-channel groups -- each warp's chain is half as long
+    // as with eight, and the SM's issue slots (mostly idle in these kernels) absorb the extra warps.
     const int ew = warp & 3;                 // TMEM lane quarter
-    const int eg = (warp - 4) >> 2;          // channel half of the 64-channel block
+    const int cg4 = (warp - 4) >> 2;         // 16-channel group of the 64-channel block (0..3)
     const int L = ew * 32 + lane;            // lane of the tile = position o0 + L
     const bool has_res = p.res != nullptr;
     const uint32_t HvWv = (uint32_t)p.HvWv, uWv = (uint32_t)Wv, uMv = (uint32_t)p.Mv;
-    uint8_t* st_o = stage + (warp - 4) * 2048;
-    const uint32_t my_sw = (uint32_t)((lane >> 1) & 3);
-    const int piece = lane & 3;
-    const float* ep_scale = ss + eg * 32, *ep_shift = ss + kNT + eg * 32;
-    const int cb = n0 + eg * 32;             // first output channel of this warp
+    uint8_t* st_o = stage + (warp - 4) * 1024;                 // per warp: 32 rows x 32 B
+    const int piece = lane & 1;                                // 16-byte half of a row's 32 B
+    const float* ep_scale = ss + cg4 * 16, *ep_shift = ss + kNT + cg4 * 16;
+    const int cb = n0 + cg4 * 16;            // first output channel of this warp
     uint32_t it = 0;
     long long t_tfull = 0, t_bar = 0;
     const long long t_all0 = clock64();
 
-    struct Geo { int own; int row[4]; };
+    struct Geo { int own; int row[2]; };     // own position's pixel, and the two rows this lane serves in the coalesced pattern
     auto tile_geo = [&](int m_idx_) {
       Geo g;
       const uint32_t o = (uint32_t)m_idx_ * kTilePos + (uint32_t)L;
@@ -278,15 +280,14 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         if (pr < (uint32_t)p.OH && q < (uint32_t)p.OW) g.own = (int)((img * (uint32_t)p.OH + pr) * (uint32_t)p.OW + q);
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) g.row[i] = __shfl_sync(0xffffffffu, g.own, 8 * i + (lane >> 2));
+      for (int i = 0; i < 2; ++i) g.row[i] = __shfl_sync(0xffffffffu, g.own, 16 * i + (lane >> 1));
       return g;
     };
-    uint4 rvp[4];
+    uint4 rvp[2];
+    rvp[0] = rvp[1] = make_uint4(0u, 0u, 0u, 0u);
+    auto fetch_res = [&](const Geo& g, uint4 (&dst)[2]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) rvp[i] = make_uint4(0u, 0u, 0u, 0u);
-    auto fetch_res = [&](const Geo& g, uint4 (&dst)[4]) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 2; ++i)
         if (g.row[i] >= 0)
           dst[i] = *reinterpret_cast<const uint4*>(p.res + (size_t)g.row[i] * p.rld + p.rcoff + cb + piece * 8);
     };
@@ -296,9 +297,8 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     for (int m_idx = m_first; m_idx < p.num_m_tiles; m_idx += m_step, ++it) {
       const uint32_t a = it & 1, tph = (it >> 1) & 1;
       const Geo g = gn;
-      uint4 rv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) rv[i] = rvp[i];
+      uint4 rv[2];
+      rv[0] = rvp[0]; rv[1] = rvp[1];
       if (m_idx + m_step < p.num_m_tiles) {           // next tile: geometry + residual, in flight during this epilogue
         gn = tile_geo(m_idx + m_step);
         if (has_res) fetch_res(gn, rvp);
@@ -307,73 +307,64 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       mbar_wait(bar_tfull + 8 * a, tph, p.err, 3);
       t_tfull += clock64() - tt0;
       ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + a * (uint32_t)(2 * kNT) + (uint32_t)(eg * 32);
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + a * (uint32_t)(2 * kNT) + (uint32_t)(cg4 * 16);
 
-      // ---- pass A: lane 0 of every quarter publishes what the previous quarter's last lane needs: its D[., 64 + c] values
-      float* xq = xch + (((eg * 2 + (it & 1)) * 5 + ew)) * 32;
-      {
-        uint32_t t1[32];
-        ptx::tmem_ld_32x32b_x32(t_row + kNT, t1);
-        ptx::tmem_ld_wait();
-        if (lane == 0) {
+      uint32_t d0[16], d1[16];
+      ptx::tmem_ld_32x32b_x16(t_row, d0);
+      ptx::tmem_ld_32x32b_x16(t_row + kNT, d1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar_tempty + 8 * a);             // accumulator fully read: hand it back to the MMA warp
+
+      // lane 0 of every quarter publishes what the previous quarter's last lane needs: its D[., 64 + c] values
+      float* xq = xch + (((cg4 * 2 + (it & 1)) * 5 + ew)) * 16;
+      if (lane == 0) {
 #pragma unroll
-          for (int k = 0; k < 32; k += 4)
-            *reinterpret_cast<float4*>(xq + k) = make_float4(__uint_as_float(t1[k]), __uint_as_float(t1[k + 1]),
-                                                             __uint_as_float(t1[k + 2]), __uint_as_float(t1[k + 3]));
-        }
+        for (int k = 0; k < 16; k += 4)
+          *reinterpret_cast<float4*>(xq + k) = make_float4(__uint_as_float(d1[k]), __uint_as_float(d1[k + 1]),
+                                                           __uint_as_float(d1[k + 2]), __uint_as_float(d1[k + 3]));
       }
-      // one barrier per tile and channel half (the exchange is double buffered by tile parity)
+      float o16[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        o16[k] = __uint_as_float(d0[k]) + __shfl_down_sync(0xffffffffu, __uint_as_float(d1[k]), 1);
+      // one barrier per tile and channel group (the exchange is double buffered by tile parity)
       const long long tb0 = clock64();
-      if (eg == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + cg4) : "memory");
       t_bar += clock64() - tb0;
-      const float* xn = xq + 32;              // the NEXT quarter's vector (slot 4 is never written: the tile's last lane is discarded)
+      if (lane == 31) {                       // the lane whose neighbour lives in the next quarter: ONE divergent block
+        const float* xn = xq + 16;            // slot 4 is never written: the tile's last lane is discarded
+        float xv[16];
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) *reinterpret_cast<float4*>(&xv[k]) = *reinterpret_cast<const float4*>(xn + k);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) o16[k] = __uint_as_float(d0[k]) + xv[k];
+      }
 
-      // ---- pass B: two halves of 16 channels: out = D[l, c] + D[l + 1, 64 + c], affine, activation, transposition
       const bool act_first = !has_res || p.res_after;
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t d0[16], d1[16];
-        ptx::tmem_ld_32x32b_x16(t_row + 16 * hf, d0);
-        ptx::tmem_ld_32x32b_x16(t_row + kNT + 16 * hf, d1);
-        ptx::tmem_ld_wait();
-        if (hf == 1) {                        // accumulator fully read: hand it back to the MMA warp
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(bar_tempty + 8 * a);
+      for (int q = 0; q < 2; ++q) {
+        float sc[8], sf[8], o8[8];
+        *reinterpret_cast<float4*>(&sc[0]) = *reinterpret_cast<const float4*>(ep_scale + q * 8);
+        *reinterpret_cast<float4*>(&sc[4]) = *reinterpret_cast<const float4*>(ep_scale + q * 8 + 4);
+        *reinterpret_cast<float4*>(&sf[0]) = *reinterpret_cast<const float4*>(ep_shift + q * 8);
+        *reinterpret_cast<float4*>(&sf[4]) = *reinterpret_cast<const float4*>(ep_shift + q * 8 + 4);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          o8[e] = fmaf(o16[q * 8 + e], sc[e], sf[e]);
+          if (act_first) o8[e] = p.act == PLNR_ACT_RELU ? fmaxf(o8[e], 0.f) : plnr_apply_act(o8[e], p.act, p.alpha);
         }
-        float o16[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          o16[k] = __uint_as_float(d0[k]) + __shfl_down_sync(0xffffffffu, __uint_as_float(d1[k]), 1);
-        if (lane == 31) {                     // the lane whose neighbour lives in the next quarter: ONE divergent block
-          float xv[16];
-#pragma unroll
-          for (int k = 0; k < 16; k += 4) *reinterpret_cast<float4*>(&xv[k]) = *reinterpret_cast<const float4*>(xn + 16 * hf + k);
-#pragma unroll
-          for (int k = 0; k < 16; ++k) o16[k] = __uint_as_float(d0[k]) + xv[k];
-        }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          float sc[8], sf[8], o8[8];
-          *reinterpret_cast<float4*>(&sc[0]) = *reinterpret_cast<const float4*>(ep_scale + 16 * hf + q * 8);
-          *reinterpret_cast<float4*>(&sc[4]) = *reinterpret_cast<const float4*>(ep_scale + 16 * hf + q * 8 + 4);
-          *reinterpret_cast<float4*>(&sf[0]) = *reinterpret_cast<const float4*>(ep_shift + 16 * hf + q * 8);
-          *reinterpret_cast<float4*>(&sf[4]) = *reinterpret_cast<const float4*>(ep_shift + 16 * hf + q * 8 + 4);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            o8[e] = fmaf(o16[q * 8 + e], sc[e], sf[e]);
-            if (act_first) o8[e] = p.act == PLNR_ACT_RELU ? fmaxf(o8[e], 0.f) : plnr_apply_act(o8[e], p.act, p.alpha);
-          }
-          uint4 pk;
-          pk.x = pack_half2(o8[0], o8[1]); pk.y = pack_half2(o8[2], o8[3]);
-          pk.z = pack_half2(o8[4], o8[5]); pk.w = pack_half2(o8[6], o8[7]);
-          *reinterpret_cast<uint4*>(st_o + lane * 64 + (((uint32_t)(2 * hf + q) ^ my_sw) << 4)) = pk;
-        }
+        uint4 pk;
+        pk.x = pack_half2(o8[0], o8[1]); pk.y = pack_half2(o8[2], o8[3]);
+        pk.z = pack_half2(o8[4], o8[5]); pk.w = pack_half2(o8[6], o8[7]);
+        // row `lane` of the warp's stage: 32 B = two 16-byte pieces, piece index swizzled by a row bit (bank spread)
+        *reinterpret_cast<uint4*>(st_o + lane * 32 + (((uint32_t)q ^ ((uint32_t)(lane >> 2) & 1u)) << 4)) = pk;
       }
       __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = 8 * i + (lane >> 2);
-        uint4 val = *reinterpret_cast<const uint4*>(st_o + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
+      for (int i = 0; i < 2; ++i) {
+        const int row = 16 * i + (lane >> 1);
+        uint4 val = *reinterpret_cast<const uint4*>(st_o + row * 32 + ((((uint32_t)piece) ^ ((uint32_t)(row >> 2) & 1u)) << 4));
         if (g.row[i] >= 0) {
           if (has_res) {
             __half2* vh = reinterpret_cast<__half2*>(&val);
