@@ -5,6 +5,7 @@
     net = planer.read_net('resnet18')         # .json + .npy / .pla, planer/io.py:8-34
     net.half()                                # planer/net.py:26-29
     y = net(x)                                # numpy NCHW in, numpy out, planer/net.py:94-101
+    for y in net.map(batches): ...            # the same call, pipelined over a stream of host batches (net.py)
 
 ``core(obj)`` accepts the B200 backend module (``planer_b200.b200``); there is NO CPU path in this package:
 passing numpy raises.  ``install(planer)`` plugs the same kernels into the reference package's operator
@@ -40,6 +41,9 @@ def asnumpy(arr, **key): return b200.asnumpy(arr)
 
 
 def asarray(arr, **key): return b200.asarray(arr, **key)
+
+
+def pinned_empty(shape, dtype='float32'): return b200.pinned_empty(shape, dtype)
 
 
 def install(planer):

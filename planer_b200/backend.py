@@ -245,15 +245,30 @@ def asarray(a, dtype=None, pinned=False):
     return out
 
 
+def copy_stream():
+    """The stream host<->device copies of pipelined calls run on (Net.map, chunked Net.__call__)."""
+    init()
+    if _state.get('copy_stream') is None:
+        _state['copy_stream'] = _torch().cuda.Stream(device=device())
+    return _state['copy_stream']
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """Page-locked host array (numpy view of a pinned torch buffer): uploads from it run at the full PCIe rate and
+    asynchronously; a pageable numpy array is staged by the driver at a fraction of that."""
+    torch = _torch()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    return torch.empty(max(n, 1), dtype=torch.uint8).pin_memory().numpy()[:n].view(dtype).reshape(shape)
+
+
 def asarray_async(a):
     """Host -> device on a separate COPY stream.  Returns (DeviceArray, event): work on the library stream that reads
     the array must first ``stream().wait_event(event)``.  Lets the upload of one chunk of a batch overlap the forward
     of the previous chunk (Net.__call__, planer/net.py:94-101 is one blocking asarray)."""
     torch = _torch()
     init()
-    if _state.get('copy_stream') is None:
-        _state['copy_stream'] = torch.cuda.Stream(device=device())
-    cs = _state['copy_stream']
+    cs = copy_stream()
     a = np.ascontiguousarray(a)
     out = empty(a.shape, a.dtype)
     cs.wait_stream(stream())                    # the allocation above was made on the library stream

@@ -314,3 +314,39 @@ def test_yolov3_fp16_batch_runs_and_matches_fp32_golden(planer, graphs_gold):
         err = float(np.abs(cases.sample(t[0]).astype(np.float64) - ref.astype(np.float64)).max() / scale)
         assert err <= 1e-2, (i, err)
         assert np.array_equal(t[0], t[1])
+
+
+def test_map_pipelined_stream_equals_blocking_calls(planer):
+    """``Net.map`` (upload / forward / download of consecutive batches overlapped) returns, in order, bit-for-bit
+    what the blocking ``net(x)`` returns for each batch -- pinned and pageable inputs, a shape change mid-stream
+    and a ragged last batch; the chunked upload inside ``net(x)`` equals the one-piece call."""
+    model, blob = cases.get_model('resnet18')
+    net = planer.from_model(model, blob, half=True)
+    rng = np.random.default_rng(21)
+    batches = []
+    for i, n in enumerate((64, 64, 64, 64, 8, 8, 64, 3)):
+        x = rng.standard_normal((n, 3, 224, 224)).astype(np.float16)
+        if i % 2 == 0:
+            p = planer.pinned_empty(x.shape, x.dtype)
+            p[...] = x
+            x = p
+        batches.append(x)
+    want = [net(x) for x in batches]
+    for depth in (1, 2, 3):
+        got = list(net.map(iter(batches), depth=depth))
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert g.shape == w.shape and np.array_equal(g, w)
+    # chunked blocking call (two halves on the copy stream) == one upload
+    x = batches[0]
+    os.environ['PLNR_E2E_CHUNKS'] = '1'
+    try:
+        one = net(x)
+    finally:
+        del os.environ['PLNR_E2E_CHUNKS']
+    assert np.array_equal(net(x), one)
+    # results do not alias the pinned ring: a later call must not change an earlier result
+    first = net(x).copy()
+    keep = net(x)
+    net(batches[1])
+    assert np.array_equal(keep, first)
