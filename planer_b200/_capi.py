@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libplaner_b200.so')
+# PLNR_LIB: another build of the same library (A/B timing of two kernel versions on one box); never a different backend
+LIB_PATH = os.environ.get('PLNR_LIB') or os.path.join(HERE, 'libplaner_b200.so')
 
 F32, F16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3

@@ -30,9 +30,9 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kThreads = 384;          // warps 0-3: producer / MMA / TMEM / table; warps 4-11: two epilogue groups
-constexpr uint32_t kEpiBytes = 2 * 2 * 256 * 4;
+constexpr uint32_t kEpiBytes = 2 * 2 * 256 * 4 + 2 * 2 * 256 * 2;   // fp32 + fp16 copies of scale | shift, double buffered
 constexpr int kMaxA = 4, kMaxB = 40;
-constexpr uint32_t kStageBytes = 8 * 2048;        // epilogue transposition stage (per epilogue warp: 32 rows x 64 B)
+constexpr uint32_t kStageBytes = 8 * 1024;        // epilogue transposition stage (per epilogue warp: 32 rows x 32 B = 16 channels)
 constexpr long long kWatchdogCycles = 4000000000ll;
 
 struct ShiftParams {
@@ -324,8 +324,9 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   } else if (warp >= 4) {
     // ===================================== epilogue ===========================================
     // A thread owns one accumulator ROW (TMEM lane) and 32 channels per chunk; rows are transposed through a per-warp
-    // shared-memory stage so that every global access of the warp moves 8 rows x 64 contiguous bytes: lane l serves
-    // row 8i + l/4, 16-byte piece l%4 (i = 0..3).  The residual operand is read in that same coalesced pattern and
+    // shared-memory stage, 16 channels (32 B per row) at a time -- 1 KB per warp, which is what lets the weights of the
+    // 128-channel layers stay resident next to the A buffers -- so that every global access of the warp moves 16 rows x
+    // 32 contiguous bytes: lane l serves row 16i + l/2, 16-byte piece l%2 (i = 0, 1), twice per 32-channel chunk.  The residual operand is read in that same coalesced pattern and
     // added AFTER the transposition (the reference rounds to fp16 between batchnorm, add and relu as well:
     // planer/layer.py:125-127, :93-95, :44-46), so its loads need no row-owner gather and are issued one tile ahead.
     const int ew = warp & 3;                 // the TMEM lane quarter this warp may read (warp % 4)
@@ -339,13 +340,13 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     const int c_begin = eg * half * 32, c_end = min(nchunks, (eg + 1) * half) * 32;
     const bool has_res = p.res != nullptr;
     const uint32_t HvWv = (uint32_t)p.HvWv, uWv = (uint32_t)Wv, uMv = (uint32_t)p.Mv;
-    uint8_t* st_o = stage + (warp - 4) * 2048;
-    const uint32_t my_sw = (uint32_t)((lane >> 1) & 3);
-    const int piece = lane & 3;
+    uint8_t* st_o = stage + (warp - 4) * 1024;
+    const uint32_t my_sw = (uint32_t)((lane >> 2) & 1);
+    const int piece = lane & 1;
 
     // geometry of a tile for this thread: its own row (scalar tail path) and the four rows it serves in the coalesced
     // pattern; pixel index -1 = padded rim / beyond the tensor (computed and discarded)
-    struct Geo { int own; int row[4]; };
+    struct Geo { int own; int row[2]; };
     auto tile_geo = [&](int tile_) {
       Geo g;
       const uint32_t m_idx_ = (uint32_t)tile_ - fast_div((uint32_t)tile_, p.div_mt) * (uint32_t)p.num_m_tiles;
@@ -357,7 +358,7 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         if (pr < (uint32_t)p.OH && q < (uint32_t)p.OW) g.own = (int)((img * (uint32_t)p.OH + pr) * (uint32_t)p.OW + q);
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) g.row[i] = __shfl_sync(0xffffffffu, g.own, 8 * i + (lane >> 2));
+      for (int i = 0; i < 2; ++i) g.row[i] = __shfl_sync(0xffffffffu, g.own, 16 * i + (lane >> 1));
       return g;
     };
     // residual pieces of a tile's FIRST chunk, fetched one tile ahead: by the time an epilogue warp reaches a tile its
@@ -365,11 +366,13 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     uint4 rvp[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) rvp[i] = make_uint4(0u, 0u, 0u, 0u);
-    auto fetch_res = [&](const Geo& g, int cb, uint4 (&dst)[4]) {
+    auto fetch_res = [&](const Geo& g, int cb, uint4 (&dst)[4]) {      // [16-channel half h][row i] -> dst[2h + i]
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (g.row[i] >= 0)
-          dst[i] = *reinterpret_cast<const uint4*>(p.res + (size_t)g.row[i] * p.rld + p.rcoff + cb + piece * 8);
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          if (g.row[i] >= 0)
+            dst[2 * h + i] = *reinterpret_cast<const uint4*>(p.res + (size_t)g.row[i] * p.rld + p.rcoff + cb + h * 16 + piece * 8);
     };
     Geo gn = tile_geo(unit < p.num_tiles ? unit : 0);
     if (has_res && p.vec_ok && c_begin < c_end && unit < p.num_tiles) {
@@ -386,15 +389,18 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         staged_n = n_idx;
         ebuf ^= 1u;
         float* dsc = epi + ebuf * 512, *dsf = dsc + 256;
+        __half* hsc = reinterpret_cast<__half*>(epi + 1024) + ebuf * 512, *hsf = hsc + 256;
         for (int i = et; i < p.n_tile; i += 256) {
           const int c = n0 + i;
           float sc = 0.f, sf = 0.f;
           if (c < p.Cout) { sc = p.scale ? __ldg(p.scale + c) : 1.f; sf = p.shift ? __ldg(p.shift + c) : 0.f; }
           dsc[i] = sc; dsf[i] = sf;
+          hsc[i] = __float2half_rn(sc); hsf[i] = __float2half_rn(sf);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       const float* ep_scale = epi + ebuf * 512, *ep_shift = ep_scale + 256;
+      const __half* ep_hscale = reinterpret_cast<const __half*>(epi + 1024) + ebuf * 512, *ep_hshift = ep_hscale + 256;
 
       const Geo g = gn;
       uint4 rv[4], rvn[4];
@@ -439,53 +445,64 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           // Cout = 64 layers.  With a residual the activation (or the add, for the Darknet shortcut x + act(..))
           // happens after the transposition, in packed fp16 -- the reference rounds to fp16 between batchnorm, add
           // and relu too, and fp16 + fp16 rounded once is exactly what HADD2 computes.
+          // The accumulator is rounded to fp16 FIRST (the reference's conv output is an fp16 array: planer/layer.py:22-26
+          // on fp16 inputs), transposed, and batchnorm / bias, add and the activation run on the transposed pieces in
+          // packed fp16 -- x*K+B as one HFMA2 (the reference: two fp16 roundings, planer/layer.py:125-127).  After the
+          // transposition a lane owns the SAME 8 channels in each of its four rows, so scale/shift are two 16-byte
+          // loads per chunk instead of sixteen broadcast loads per row, and the math is 4 HFMA2 per row instead of
+          // 8 FFMA + 8 FMNMX: the shared-memory pipe these loads shared with the MMA operand reads is what bounds the
+          // Cout = 64 / 128 layers (profiles/r01_smem_budget.md).
           auto chunk_math = [&](auto act_tag) {
             constexpr int kAct = decltype(act_tag)::value;      // 1 = ReLU, 2 = LeakyReLU (0 <= alpha <= 1), 0 = generic
-            constexpr bool kRelu = kAct == 1;
             const bool act_first = !has_res || p.res_after;
+            const __half2 zero2 = __float2half2_rn(0.f), alpha2 = __float2half2_rn(p.alpha);
+            auto act2 = [&](__half2 x) {
+              if (kAct == 1) return __hmax2(x, zero2);
+              if (kAct == 2) return __hmax2(x, __hmul2(x, alpha2));
+              const float2 f = __half22float2(x);
+              return __floats2half2_rn(plnr_apply_act(f.x, p.act, p.alpha), plnr_apply_act(f.y, p.act, p.alpha));
+            };
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float sc[8], sf[8], o8[8];
-              *reinterpret_cast<float4*>(&sc[0]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8);
-              *reinterpret_cast<float4*>(&sc[4]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8 + 4);
-              *reinterpret_cast<float4*>(&sf[0]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8);
-              *reinterpret_cast<float4*>(&sf[4]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8 + 4);
+            for (int h = 0; h < 2; ++h) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                o8[e] = fmaf(__uint_as_float(v[q * 8 + e]), sc[e], sf[e]);
-                if (act_first)
-                  o8[e] = kRelu ? fmaxf(o8[e], 0.f)
-                                : (kAct == 2 ? fmaxf(o8[e], o8[e] * p.alpha) : plnr_apply_act(o8[e], p.act, p.alpha));
+              for (int q = 2 * h; q < 2 * h + 2; ++q) {
+                uint4 pk;
+                pk.x = pack_half2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+                pk.y = pack_half2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+                pk.z = pack_half2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+                pk.w = pack_half2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+                *reinterpret_cast<uint4*>(st_o + lane * 32 + ((((uint32_t)q & 1u) ^ my_sw) << 4)) = pk;
               }
-              uint4 pk;
-              pk.x = pack_half2(o8[0], o8[1]); pk.y = pack_half2(o8[2], o8[3]);
-              pk.z = pack_half2(o8[4], o8[5]); pk.w = pack_half2(o8[6], o8[7]);
-              *reinterpret_cast<uint4*>(st_o + lane * 64 + (((uint32_t)q ^ my_sw) << 4)) = pk;
-            }
-            __syncwarp();
+              const uint4 sc4 = *reinterpret_cast<const uint4*>(ep_hscale + c0 + h * 16 + piece * 8);
+              const uint4 sf4 = *reinterpret_cast<const uint4*>(ep_hshift + c0 + h * 16 + piece * 8);
+              const __half2* sch = reinterpret_cast<const __half2*>(&sc4);
+              const __half2* sfh = reinterpret_cast<const __half2*>(&sf4);
+              __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int row = 8 * i + (lane >> 2);
-              uint4 val = *reinterpret_cast<const uint4*>(st_o + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
-              if (g.row[i] >= 0) {
-                if (has_res) {
+              for (int i = 0; i < 2; ++i) {
+                const int row = 16 * i + (lane >> 1);
+                uint4 val = *reinterpret_cast<const uint4*>(st_o + row * 32 + ((((uint32_t)piece) ^ ((uint32_t)(row >> 2) & 1u)) << 4));
+                if (g.row[i] >= 0) {
                   __half2* vh = reinterpret_cast<__half2*>(&val);
-                  const __half2* rh = reinterpret_cast<const __half2*>(&rv[i]);
+                  const __half2* rh = reinterpret_cast<const __half2*>(&rv[2 * h + i]);
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    __half2 x = __hadd2(vh[e], rh[e]);
-                    if (!p.res_after) {
-                      if (kRelu) x = __hmax2(x, __float2half2_rn(0.f));
-                      else {
-                        const float2 f = __half22float2(x);
-                        x = __floats2half2_rn(plnr_apply_act(f.x, p.act, p.alpha), plnr_apply_act(f.y, p.act, p.alpha));
-                      }
+                    __half2 x;
+                    if (kAct == 1 && act_first) x = __hfma2_relu(vh[e], sch[e], sfh[e]);
+                    else {
+                      x = __hfma2(vh[e], sch[e], sfh[e]);
+                      if (act_first) x = act2(x);
+                    }
+                    if (has_res) {
+                      x = __hadd2(x, rh[e]);
+                      if (!p.res_after) x = act2(x);
                     }
                     vh[e] = x;
                   }
+                  *reinterpret_cast<uint4*>(p.y + (size_t)g.row[i] * p.yld + p.ycoff + cb + h * 16 + piece * 8) = val;
                 }
-                *reinterpret_cast<uint4*>(p.y + (size_t)g.row[i] * p.yld + p.ycoff + cb + piece * 8) = val;
               }
+              __syncwarp();                    // the 1 KB stage is rewritten by the next half / chunk
             }
           };
           if (p.act == PLNR_ACT_RELU) chunk_math(ActTag<1>{});
@@ -583,11 +600,15 @@ static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
   const double eff = (double)y->h * y->w / ((double)pl.Hv * pl.Wv);
   if (eff < 0.70) return pl;                              // small maps: too many discarded rim positions
   const int m_tiles_128 = (int)((Mv + kTileM - 1) / kTileM);
-  // Measured on ResNet-18 (profiles/r01_shift_cg.md): a CTA pair is never faster here -- shared-memory traffic is not
-  // the limiter once A is loaded once per chunk, and an MMA costs ~90-100 clk whatever M is when N <= 128 -- so the
-  // single-CTA variant is the default; PLNR_SHIFT_CTA_GROUP=2 selects the pair (kept: it is correct and tested).
+  // A CTA pair (cta_group::2: M = 256, each CTA supplies half of the B rows) is chosen when it is what makes the WEIGHTS
+  // RESIDENT: a 128 -> 128 channel 3x3 filter is 288 KB -- too much for one CTA, whose shared-memory pipe then carries
+  // 32*N B of streamed-weight TMA writes per MMA on top of the operand reads -- but 144 KB per CTA of a pair fits next to
+  // the A buffers (measured, 128 -> 128 @14x14 x512: 50.1 -> 35.7 us, profiles/r01_cg2_resident.md).  With streamed
+  // weights the pair was never faster (profiles/r01_shift_cg.md).  PLNR_SHIFT_CTA_GROUP=1|2 forces either.
   pl.cg = 1;
-  if (const char* e = getenv("PLNR_SHIFT_CTA_GROUP")) { if (atoi(e) == 2 && m_tiles_128 >= 2) pl.cg = 2; }
+  int forced = 0;
+  if (const char* e = getenv("PLNR_SHIFT_CTA_GROUP")) forced = atoi(e);
+  if (forced == 2 && m_tiles_128 >= 2) pl.cg = 2;
   const int cout_r = round_up(y->c, 32);
   pl.n_tile = cout_r < 256 ? cout_r : 256;
   if (const char* e = getenv("PLNR_SHIFT_NTILE")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0 && v < pl.n_tile) pl.n_tile = v; }
@@ -598,11 +619,18 @@ static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
   const size_t budget = 232448;
   // resident weights: all (chunk, tap) boxes stay in shared memory for the whole kernel
   pl.na = 2;
-  if (num_n_tiles == 1 && kst <= kMaxB &&
-      fixed + 2 * (size_t)pl.a_buf_bytes + (size_t)kst * pl.b_stage_bytes <= budget) {
+  auto resident_fits = [&](int cg_, int na_) {
+    return num_n_tiles == 1 && kst <= kMaxB &&
+           fixed + (size_t)na_ * pl.a_buf_bytes + (size_t)kst * (size_t)(pl.n_tile / cg_) * 128 <= budget;
+  };
+  if (forced == 0 && !resident_fits(1, 2) && m_tiles_128 >= 2 && pl.n_tile % 32 == 0 && resident_fits(2, 2)) {
+    pl.cg = 2;
+    pl.b_stage_bytes = (uint32_t)(pl.n_tile / 2) * 128;
+  }
+  if (resident_fits(pl.cg, 2)) {
     pl.b_resident = 1;
     pl.nb = kst;
-    if (fixed + 3 * (size_t)pl.a_buf_bytes + (size_t)kst * pl.b_stage_bytes <= budget) pl.na = 3;
+    if (resident_fits(pl.cg, 3)) pl.na = 3;
   } else {
     if (fixed + 2 * (size_t)pl.a_buf_bytes + 3 * (size_t)pl.b_stage_bytes > budget) return pl;
     size_t left = budget - fixed - 2 * (size_t)pl.a_buf_bytes;

@@ -29,7 +29,7 @@ constexpr int kTileM = 128;
 constexpr int kThreads = 384;          // warps 0-3: producer / MMA / TMEM / table; warps 4-11: two epilogue groups
 constexpr int kMaxStages = 8;
 constexpr uint32_t kAStageBytes = kTileM * 64 * 2;  // 16 KB: 128 pixels x 64 k x fp16
-constexpr uint32_t kEpiBytes = 2 * 2 * 256 * 4;     // [buffer][scale|shift][256] fp32
+constexpr uint32_t kEpiBytes = 2 * 2 * 256 * 4 + 2 * 2 * 256 * 2;     // [buffer][scale|shift][256] fp32, then the same in fp16
 constexpr uint32_t kStageBytes = 8 * 2048;          // epilogue transposition stage (per epilogue warp: 32 rows x 64 B)
 constexpr long long kWatchdogCycles = 4000000000ll; // ~2 s: a stuck barrier becomes an error, not a hang
 
@@ -328,15 +328,18 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         staged_n = n_idx;
         ebuf ^= 1u;
         float* dsc = epi + ebuf * 512, *dsf = dsc + 256;
+        __half* hsc = reinterpret_cast<__half*>(epi + 1024) + ebuf * 512, *hsf = hsc + 256;
         for (int i = et; i < p.n_tile; i += 256) {
           const int c = n0 + i;
           float sc = 0.f, sf = 0.f;
           if (c < p.Cout) { sc = p.scale ? __ldg(p.scale + c) : 1.f; sf = p.shift ? __ldg(p.shift + c) : 0.f; }
           dsc[i] = sc; dsf[i] = sf;
+          hsc[i] = __float2half_rn(sc); hsf[i] = __float2half_rn(sf);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       const float* ep_scale = epi + ebuf * 512, *ep_shift = ep_scale + 256;
+      const __half* ep_hscale = reinterpret_cast<const __half*>(epi + 1024) + ebuf * 512, *ep_hshift = ep_hscale + 256;
 
       const Geo g = gn;
       uint4 rv[4], rvn[4];
@@ -381,50 +384,57 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           // Cout = 64 layers.  With a residual the activation (or the add, for the Darknet shortcut x + act(..))
           // happens after the transposition, in packed fp16 -- the reference rounds to fp16 between batchnorm, add
           // and relu too, and fp16 + fp16 rounded once is exactly what HADD2 computes.
+          // The accumulator is rounded to fp16 FIRST (the reference's conv output is an fp16 array: planer/layer.py:22-26
+          // on fp16 inputs), transposed, and batchnorm / bias, add and the activation run on the transposed pieces in
+          // packed fp16 -- x*K+B as one HFMA2 (the reference: two fp16 roundings, planer/layer.py:125-127).  After the
+          // transposition a lane owns the SAME 8 channels in each of its four rows, so scale/shift are two 16-byte
+          // loads per chunk instead of sixteen broadcast loads per row, and the math is 4 HFMA2 per row instead of
+          // 8 FFMA + 8 FMNMX: the shared-memory pipe these loads shared with the MMA operand reads is what bounds the
+          // Cout = 64 / 128 layers (profiles/r01_smem_budget.md).
           auto chunk_math = [&](auto act_tag) {
             constexpr int kAct = decltype(act_tag)::value;      // 1 = ReLU, 2 = LeakyReLU (0 <= alpha <= 1), 0 = generic
-            constexpr bool kRelu = kAct == 1;
             const bool act_first = !has_res || p.res_after;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              float sc[8], sf[8], o8[8];
-              *reinterpret_cast<float4*>(&sc[0]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8);
-              *reinterpret_cast<float4*>(&sc[4]) = *reinterpret_cast<const float4*>(ep_scale + c0 + q * 8 + 4);
-              *reinterpret_cast<float4*>(&sf[0]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8);
-              *reinterpret_cast<float4*>(&sf[4]) = *reinterpret_cast<const float4*>(ep_shift + c0 + q * 8 + 4);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                o8[e] = fmaf(__uint_as_float(v[q * 8 + e]), sc[e], sf[e]);
-                if (act_first)
-                  o8[e] = kRelu ? fmaxf(o8[e], 0.f)
-                                : (kAct == 2 ? fmaxf(o8[e], o8[e] * p.alpha) : plnr_apply_act(o8[e], p.act, p.alpha));
-              }
               uint4 pk;
-              pk.x = pack_half2(o8[0], o8[1]); pk.y = pack_half2(o8[2], o8[3]);
-              pk.z = pack_half2(o8[4], o8[5]); pk.w = pack_half2(o8[6], o8[7]);
+              pk.x = pack_half2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+              pk.y = pack_half2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+              pk.z = pack_half2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+              pk.w = pack_half2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
               *reinterpret_cast<uint4*>(st_o + lane * 64 + (((uint32_t)q ^ my_sw) << 4)) = pk;
             }
+            const uint4 sc4 = *reinterpret_cast<const uint4*>(ep_hscale + c0 + piece * 8);
+            const uint4 sf4 = *reinterpret_cast<const uint4*>(ep_hshift + c0 + piece * 8);
+            const __half2* sch = reinterpret_cast<const __half2*>(&sc4);
+            const __half2* sfh = reinterpret_cast<const __half2*>(&sf4);
+            const __half2 zero2 = __float2half2_rn(0.f), alpha2 = __float2half2_rn(p.alpha);
+            auto act2 = [&](__half2 x) {
+              if (kAct == 1) return __hmax2(x, zero2);
+              if (kAct == 2) return __hmax2(x, __hmul2(x, alpha2));
+              const float2 f = __half22float2(x);
+              return __floats2half2_rn(plnr_apply_act(f.x, p.act, p.alpha), plnr_apply_act(f.y, p.act, p.alpha));
+            };
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int row = 8 * i + (lane >> 2);
               uint4 val = *reinterpret_cast<const uint4*>(st_o + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
               if (g.row[i] >= 0) {
-                if (has_res) {
-                  __half2* vh = reinterpret_cast<__half2*>(&val);
-                  const __half2* rh = reinterpret_cast<const __half2*>(&rv[i]);
+                __half2* vh = reinterpret_cast<__half2*>(&val);
+                const __half2* rh = reinterpret_cast<const __half2*>(&rv[i]);
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    __half2 x = __hadd2(vh[e], rh[e]);
-                    if (!p.res_after) {
-                      if (kRelu) x = __hmax2(x, __float2half2_rn(0.f));
-                      else {
-                        const float2 f = __half22float2(x);
-                        x = __floats2half2_rn(plnr_apply_act(f.x, p.act, p.alpha), plnr_apply_act(f.y, p.act, p.alpha));
-                      }
-                    }
-                    vh[e] = x;
+                for (int e = 0; e < 4; ++e) {
+                  __half2 x;
+                  if (kAct == 1 && act_first) x = __hfma2_relu(vh[e], sch[e], sfh[e]);
+                  else {
+                    x = __hfma2(vh[e], sch[e], sfh[e]);
+                    if (act_first) x = act2(x);
                   }
+                  if (has_res) {
+                    x = __hadd2(x, rh[e]);
+                    if (!p.res_after) x = act2(x);
+                  }
+                  vh[e] = x;
                 }
                 *reinterpret_cast<uint4*>(p.y + (size_t)g.row[i] * p.yld + p.ycoff + cb + piece * 8) = val;
               }

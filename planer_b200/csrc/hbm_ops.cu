@@ -394,12 +394,14 @@ __global__ void gap_kernel(const T* __restrict__ x, T* __restrict__ y, int N, in
 
 
 // GlobalAveragePool -> Flatten -> Dense in one launch (planer/layer.py:77-78, :59, :15-18).  A CTA takes IMGS images and a
-// slice of the output features: (1) the pooled vectors (fp32) of its images go to shared memory, every thread summing HW
-// rows of one 16-byte channel group; (2) each warp walks output features of the slice, one 16-byte weight load per lane
-// and 32 lanes per weight row, IMGS dot products at a time, then a shuffle reduction and the fused scale/shift/activation.
-// The tail of a network is ~65 MFLOP on 6 MB of input: launch latency, not bandwidth -- one small kernel instead of a
-// pooling launch and a tensor-core GEMM launch with its TMEM/TMA set-up.
-template <typename T, int V, int IMGS>
+// slice of the output features: (1) the pooled vectors (fp32) of its images go to shared memory: SPLIT adjacent lanes
+// share one 16-byte channel group of one image and sum interleaved pixel rows, with all PB row loads of a lane in flight
+// at once; (2) each warp walks output features of the slice, OPW weight rows x two 16-byte pieces per lane in flight,
+// IMGS dot products at a time, then a shuffle reduction and the fused scale/shift/activation.
+// The tail of a network is ~65 MFLOP on 6 MB of input: neither FLOPs nor bandwidth but the NUMBER OF DEPENDENT LOAD
+// ROUNDS bounds it (ncu: the first version spent its time in long-scoreboard stalls behind 4 pixel rounds + 6 weight
+// rounds per CTA, 23 us) -- here 1-2 + 2 rounds.
+template <typename T, int V, int IMGS, int SPLIT, int PB, int OPW>
 __global__ void __launch_bounds__(512) gap_dense_kernel(const T* __restrict__ x, const T* __restrict__ w,
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          T* __restrict__ y, int N, int HW, int C, int xld, int xcoff,
@@ -408,56 +410,73 @@ __global__ void __launch_bounds__(512) gap_dense_kernel(const T* __restrict__ x,
   const int n0 = blockIdx.x * IMGS, o0 = blockIdx.y * och;
   const int CV = C / V;
   const float inv = 1.f / (float)HW;
-  constexpr int PB = 16;                            // pixel rows fetched per batch: PB independent 16-byte loads in flight
-  for (int idx = threadIdx.x; idx < IMGS * CV; idx += blockDim.x) {
-    const int img = idx / CV, cv = idx - img * CV;
+  const int items = IMGS * CV * SPLIT;
+  for (int idx = threadIdx.x; idx < ((items + 31) & ~31); idx += blockDim.x) {      // whole warps: shuffles below
+    const int item = idx / SPLIT, part = idx - item * SPLIT;
+    const int img = item / CV, cv = item - img * CV;
     float acc[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) acc[k] = 0.f;
-    if (n0 + img < N) {
+    if (idx < items && n0 + img < N) {
       const T* xp = x + (size_t)(n0 + img) * HW * xld + xcoff + cv * V;
-      for (int p0 = 0; p0 < HW; p0 += PB) {
+      for (int p0 = part; p0 < HW; p0 += PB * SPLIT) {
         Vec<T, V> v[PB];
 #pragma unroll
         for (int j = 0; j < PB; ++j)
-          if (p0 + j < HW) v[j] = *reinterpret_cast<const Vec<T, V>*>(xp + (size_t)(p0 + j) * xld);
+          if (p0 + j * SPLIT < HW) v[j] = *reinterpret_cast<const Vec<T, V>*>(xp + (size_t)(p0 + j * SPLIT) * xld);
 #pragma unroll
         for (int j = 0; j < PB; ++j)
-          if (p0 + j < HW) {
+          if (p0 + j * SPLIT < HW) {
 #pragma unroll
             for (int k = 0; k < V; ++k) acc[k] += ld_f(&v[j].v[k]);
           }
       }
     }
+    // the SPLIT partial sums sit in adjacent lanes (SPLIT divides 32 and the loop bound is a multiple of SPLIT)
 #pragma unroll
-    for (int k = 0; k < V; ++k) pooled[img * C + cv * V + k] = acc[k] * inv;
+    for (int d = 1; d < SPLIT; d <<= 1) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
+    }
+    if (part == 0 && idx < items) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) pooled[img * C + cv * V + k] = acc[k] * inv;
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int o_end = min(o0 + och, OUT);
-  constexpr int OPW = 4;                            // output features per warp step: OPW weight rows in flight
   for (int ob = o0 + warp * OPW; ob < o_end; ob += nwarps * OPW) {
     float acc[OPW][IMGS];
 #pragma unroll
     for (int j = 0; j < OPW; ++j)
 #pragma unroll
       for (int i = 0; i < IMGS; ++i) acc[j][i] = 0.f;
-    for (int cv = lane; cv < CV; cv += 32) {
-      Vec<T, V> wv[OPW];
+    for (int cv0 = lane; cv0 < CV; cv0 += 64) {
+      Vec<T, V> wv[2][OPW];
 #pragma unroll
-      for (int j = 0; j < OPW; ++j)
-        wv[j] = *reinterpret_cast<const Vec<T, V>*>(w + (size_t)min(ob + j, OUT - 1) * C + cv * V);
-#pragma unroll
-      for (int i = 0; i < IMGS; ++i) {
-        // 16-byte shared-memory reads: scalar reads at this 4*V-byte lane stride would be V-way bank conflicts
-        float pf[V];
-#pragma unroll
-        for (int k = 0; k < V; k += 4)
-          *reinterpret_cast<float4*>(&pf[k]) = *reinterpret_cast<const float4*>(pooled + i * C + cv * V + k);
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int j = 0; j < OPW; ++j)
+          if (cv0 + 32 * u < CV)
+            wv[u][j] = *reinterpret_cast<const Vec<T, V>*>(w + (size_t)min(ob + j, OUT - 1) * C + (cv0 + 32 * u) * V);
 #pragma unroll
-          for (int k = 0; k < V; ++k) acc[j][i] = fmaf(ld_f(&wv[j].v[k]), pf[k], acc[j][i]);
+      for (int u = 0; u < 2; ++u) {
+        const int cv = cv0 + 32 * u;
+        if (cv < CV) {
+#pragma unroll
+          for (int i = 0; i < IMGS; ++i) {
+            // 16-byte shared-memory reads: scalar reads at this 4*V-byte lane stride would be V-way bank conflicts
+            float pf[V];
+#pragma unroll
+            for (int k = 0; k < V; k += 4)
+              *reinterpret_cast<float4*>(&pf[k]) = *reinterpret_cast<const float4*>(pooled + i * C + cv * V + k);
+#pragma unroll
+            for (int j = 0; j < OPW; ++j)
+#pragma unroll
+              for (int k = 0; k < V; ++k) acc[j][i] = fmaf(ld_f(&wv[u][j].v[k]), pf[k], acc[j][i]);
+          }
+        }
       }
     }
 #pragma unroll
@@ -694,26 +713,28 @@ int plnr_gap_dense_fwd(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const voi
                        const float* shift, void* y, int out_features, int act, float alpha) {
   PLNR_REQUIRE(ctx && x && x->ptr && w && y, "gap_dense: NULL argument");
   const int HW = x->h * x->w;
-  constexpr int IMGS = 8;
+  constexpr int IMGS = 4, SPLIT = 2, PB = 13, OPW = 8;
   DISPATCH_T(dtype, {
     constexpr int V = VecWidth<T>::value;
     PLNR_REQUIRE(view_vec_ok(x, V, sizeof(T)) && aligned16(w) && x->c % V == 0,
                  "gap_dense: channels (%d) must be a multiple of %d and pointers 16-byte aligned", x->c, V);
     const size_t smem = (size_t)IMGS * x->c * sizeof(float);
     PLNR_REQUIRE(smem <= 96 * 1024, "gap_dense: %d channels do not fit the pooled-vector stage", x->c);
-    // enough CTAs to fill the GPU: images in groups of 8, output features in slices
+    // ~one CTA per SM: images in groups of IMGS, output features in slices.  Every slice re-reads its images' pixels and
+    // every image group re-reads the weights (both from L2): 32 x 4 for ResNet-18 at batch 128 keeps the two about equal.
     const int gx = (x->n + IMGS - 1) / IMGS;
-    int gy = (ctx->sm_count + gx - 1) / gx;          // ~one CTA per SM; every slice re-reads its images' pixels (L2)
+    int gy = ctx->sm_count / gx;                     // never more CTAs than SMs: a CTA fills an SM's register file
     if (gy < 1) gy = 1;
-    if (gy > 6) gy = 6;
+    if (gy > 8) gy = 8;
     int och = (out_features + gy - 1) / gy;
+    och = (och + OPW - 1) / OPW * OPW;
     if (och < 64) och = 64;
     gy = (out_features + och - 1) / och;
+    auto kern = gap_dense_kernel<T, V, IMGS, SPLIT, PB, OPW>;
     if (smem > 48 * 1024) {
-      PLNR_CHECK_CUDA(cudaFuncSetAttribute(gap_dense_kernel<T, V, IMGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           96 * 1024));
+      PLNR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     }
-    gap_dense_kernel<T, V, IMGS><<<dim3(gx, gy), 512, smem, ctx->stream>>>(
+    kern<<<dim3(gx, gy), 512, smem, ctx->stream>>>(
         (const T*)x->ptr, (const T*)w, scale, shift, (T*)y, x->n, HW, x->c, x->ld, x->coff, out_features, och, act, alpha);
   })
   return plnr_after_launch(ctx, "gap_dense");

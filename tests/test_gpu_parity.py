@@ -350,3 +350,57 @@ def test_map_pipelined_stream_equals_blocking_calls(planer):
     keep = net(x)
     net(batches[1])
     assert np.array_equal(keep, first)
+
+
+@pytest.mark.parametrize('cfg', [(5, 24, 3, 3, 37, np.float16), (9, 512, 7, 7, 1000, np.float16),
+                                 (3, 8, 1, 5, 3, np.float16), (6, 20, 4, 4, 70, np.float32)])
+def test_gap_dense_tail_kernel_vs_oracle(planer, cfg):
+    """gap -> flatten -> dense in one launch (planer/layer.py:77-78, :59, :15-18) on ragged sizes: image groups and
+    feature slices that do not divide, channel counts below one warp of 16-byte pieces."""
+    from planer_b200 import ops, backend as B
+    n, c, h, w, out, dt = cfg
+    rng = np.random.default_rng(31)
+    x = rng.standard_normal((n, c, h, w)).astype(dt)
+    K = (rng.standard_normal((out, c)) * 0.2).astype(dt)
+    bias = rng.standard_normal(out).astype(dt)
+    ref = oracle.dense(oracle.flatten(oracle.gap(x.copy())), K, bias)
+    xd = B.to_nhwc(B.asarray(x))
+    y = B.empty((n, out), dt)
+    shift = B.asarray(bias.astype(np.float32))
+    ops.gap_dense_into(xd, B.asarray(K), y, None, shift)
+    B.synchronize()
+    assert rel_err(y.get(), ref) <= TOL[np.dtype(dt)]
+
+
+@pytest.mark.parametrize('cfg', [(2, 128, 28, 28, 128, True), (8, 128, 14, 14, 128, False), (4, 64, 56, 56, 64, True),
+                                 (3, 64, 20, 24, 192, False), (1, 256, 14, 14, 256, True)])
+def test_shift_conv_cta_pair_equals_single_cta(planer, cfg):
+    """conv_shift.cu as a CTA pair (cta_group::2, M = 256; chosen automatically when it makes the weights resident, e.g.
+    128 -> 128 channels) vs the single-CTA variant: same k order, same epilogue -> bit-identical outputs, including the
+    ragged last pair of tiles and the residual path."""
+    from planer_b200 import ops, backend as B
+    n, cin, h, w, cout, with_res = cfg
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((n, cin, h, w)).astype(np.float16)
+    K = (rng.standard_normal((cout, cin, 3, 3)) * np.sqrt(2.0 / (cin * 9))).astype(np.float16)
+    bk = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bb = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    xd, wp = B.to_nhwc(B.asarray(x)), ops.pack_weight(B.asarray(K), cin, np.float16)
+    scale, shift = ops.fold_affine(None, B.asarray(bk), B.asarray(bb), cout)
+    r = B.to_nhwc(B.asarray(rng.standard_normal((n, cout, h, w)).astype(np.float16))) if with_res else None
+    outs = {}
+    for cg in ('1', '2'):
+        os.environ['PLNR_SHIFT_CTA_GROUP'] = cg
+        try:
+            y = B.empty((n, cout, h, w), np.float16, 'nhwc')
+            ops.conv2d_into(xd, wp, y, 3, 3, (1, 1), (1, 1), (1, 1, 1, 1), 1, scale, shift, r, ops.ACT_RELU, 0.0, ops.ALGO_TCGEN05)
+            B.synchronize()
+            outs[cg] = y.get()
+        finally:
+            del os.environ['PLNR_SHIFT_CTA_GROUP']
+    assert np.array_equal(outs['1'], outs['2'])
+    ref = oracle.conv2d(x.astype(np.float32), K.astype(np.float32), None, 1, (1, 1), (1, 1), (1, 1, 1, 1))
+    ref = oracle.batchnorm(ref, bk.reshape(1, -1, 1, 1), bb.reshape(1, -1, 1, 1))
+    if with_res:
+        ref = oracle.add(ref, r.get().astype(np.float32))
+    assert rel_err(outs['2'], oracle.relu(ref)) <= 1e-2
