@@ -30,7 +30,7 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kThreads = 384;          // warps 0-3: producer / MMA / TMEM / table; warps 4-11: two epilogue groups
-constexpr uint32_t kEpiBytes = 2 * 2 * 256 * 4 + 2 * 2 * 256 * 2;   // fp32 + fp16 copies of scale | shift, double buffered
+constexpr uint32_t kEpiBytes = 2 * 2 * 256 * 2;   // [buffer][scale | shift][256] fp16 (the epilogue math is packed fp16)
 constexpr int kMaxA = 4, kMaxB = 40;
 constexpr uint32_t kStageBytes = 8 * 1024;        // epilogue transposition stage (per epilogue warp: 32 rows x 32 B = 16 channels)
 constexpr long long kWatchdogCycles = 4000000000ll;
@@ -388,19 +388,16 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       if (n_idx != staged_n) {
         staged_n = n_idx;
         ebuf ^= 1u;
-        float* dsc = epi + ebuf * 512, *dsf = dsc + 256;
-        __half* hsc = reinterpret_cast<__half*>(epi + 1024) + ebuf * 512, *hsf = hsc + 256;
+        __half* hsc = reinterpret_cast<__half*>(epi) + ebuf * 512, *hsf = hsc + 256;
         for (int i = et; i < p.n_tile; i += 256) {
           const int c = n0 + i;
           float sc = 0.f, sf = 0.f;
           if (c < p.Cout) { sc = p.scale ? __ldg(p.scale + c) : 1.f; sf = p.shift ? __ldg(p.shift + c) : 0.f; }
-          dsc[i] = sc; dsf[i] = sf;
           hsc[i] = __float2half_rn(sc); hsf[i] = __float2half_rn(sf);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      const float* ep_scale = epi + ebuf * 512, *ep_shift = ep_scale + 256;
-      const __half* ep_hscale = reinterpret_cast<const __half*>(epi + 1024) + ebuf * 512, *ep_hshift = ep_hscale + 256;
+      const __half* ep_hscale = reinterpret_cast<const __half*>(epi) + ebuf * 512, *ep_hshift = ep_hscale + 256;
 
       const Geo g = gn;
       uint4 rv[4], rvn[4];
@@ -517,7 +514,8 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           for (int e = 0; e < 32; ++e) {
             const int c = cb + e;
             if (c < p.Cout) {
-              float o1 = fmaf(__uint_as_float(v[e]), ep_scale[c0 + e], ep_shift[c0 + e]);
+              float o1 = fmaf(__half2float(__float2half_rn(__uint_as_float(v[e]))), __half2float(ep_hscale[c0 + e]),
+                              __half2float(ep_hshift[c0 + e]));
               const float rf = rrow ? __half2float(rrow[c]) : 0.f;
               if (!p.res_after) o1 += rf;
               o1 = plnr_apply_act(o1, p.act, p.alpha);
@@ -593,8 +591,14 @@ static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
   if (pl.Wv > 256 || d->kh * d->kw > kMaxB) return pl;
   pl.halo = (d->kh - 1) * d->dil_h * pl.Wv + (d->kw - 1) * d->dil_w;
   pl.rows_max = (pl.Wv - 1 + kTileM - 1 + pl.halo) / pl.Wv + 1;
-  // + one row of slack in front: position o0 sits at row offset Wv whatever its column (see the producer)
-  pl.a_buf_bytes = (uint32_t)round_up((pl.rows_max + 1) * pl.Wv * 128, 1024);
+  // position o0 sits at row offset Wv whatever its column `off` (see the producer): the rows of a tile start at
+  // Wv - off and there are floor((off + 127 + halo) / Wv) + 1 of them -- the buffer is sized for the worst `off`
+  int need = 0;
+  for (int off = 0; off < pl.Wv; ++off) {
+    const int end = pl.Wv - off + ((off + kTileM - 1 + pl.halo) / pl.Wv + 1) * pl.Wv;
+    if (end > need) need = end;
+  }
+  pl.a_buf_bytes = (uint32_t)round_up(need * 128, 1024);
   const long long Mv = (long long)x->n * pl.Hv * pl.Wv;
   if (Mv >= (1ll << 31) - 512) return pl;
   const double eff = (double)y->h * y->w / ((double)pl.Hv * pl.Wv);

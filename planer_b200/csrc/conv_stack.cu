@@ -6,20 +6,20 @@
 //
 // Why.  With SS-mode tcgen05.mma every K=16 step reads its A rows (128 x 32 B = 4 KB) and its B rows (N x 32 B) from
 // shared memory, which delivers 128 B/clk: an N = 64 step costs 48 clk of shared-memory time for 32 clk of tensor time
-// (tools/mma_rate_probe2.cu), and conv_shift.cu issues kh*kw of them per 64 input channels.  Here two of the three
-// HORIZONTAL taps share one A read: with o = flattened virtual position (conv_shift.cu), output o needs input
-// o + r*Wv + s, so per vertical tap r and K=16 step
-//     D[p, 0:64]   += X[p + r*Wv]     * W[r, 0]  \  one N = 128 MMA (taps s = 0, 1 stacked along N)
-//     D[p, 64:128] += X[p + r*Wv]     * W[r, 1]  /
-//     D[p, 0:64]   += X[p + r*Wv + 2] * W[r, 2]     one N = 64 MMA on the view shifted by two positions
-//     out[o, co]    = D[o, co] + D[o + 1, 64 + co]   the s = 1 shift moves to the epilogue
-// i.e. 14 KB of operand reads per (r, K=16 step) instead of 18 KB, and two MMA instructions instead of three.  (Stacking
-// all three taps, N = 192, cuts the reads to 10 KB but needs two lane shifts and a 3-vector exchange per warp boundary:
-// measured, its epilogue -- ~700 instructions per tile and warp -- was slower than the MMAs it saved.)  The price is an
-// epilogue that adds two accumulator column blocks across LANES: one in-warp shuffle per value, plus a one-vector
-// exchange through shared memory at the three warp boundaries of a tile; a tile yields 127 outputs (tiles advance by
-// 127 positions).  Output-channel blocks are PINNED to CTAs (CTA c serves block c % NT) so that each CTA keeps only its
-// own block's taps resident.
+// (tools/mma_rate_probe2.cu) -- in the running kernel ~82 clk, the A-row TMA writes and the epilogue's staging share the
+// same pipe -- and conv_shift.cu issues kh*kw of them per 64 input channels.  Here the three HORIZONTAL taps share one A
+// read: with o = flattened virtual position (conv_shift.cu), output o needs input o + r*Wv + s, so per vertical tap r and
+// K=16 step ONE N = 192 MMA (96 clk of tensor time, 80 clk of operand reads: tensor-bound)
+//     D[p,   0: 64] += X[p + r*Wv] * W[r, 0]
+//     D[p,  64:128] += X[p + r*Wv] * W[r, 1]
+//     D[p, 128:192] += X[p + r*Wv] * W[r, 2]
+//     out[o, co]     = D[o, co] + D[o + 1, 64 + co] + D[o + 2, 128 + co]      the s shifts move to the epilogue
+// i.e. 10 KB of operand reads per (r, K=16 step) instead of 18 KB and one MMA instruction instead of three.  The price is
+// an epilogue that adds three accumulator column blocks across LANES: two in-warp shuffles per value, plus a three-vector
+// exchange through shared memory at the three warp boundaries of a tile; a tile yields 126 outputs (tiles advance by 126
+// positions).  Sixteen epilogue warps (four TMEM lane quarters x four 16-channel groups) each run ONE short chain per
+// tile; batchnorm / add / activation happen after the transposition in packed fp16 like conv_shift.cu.  Output-channel
+// blocks are PINNED to CTAs (CTA c serves block c % NT) so that each CTA keeps only its own block's taps resident.
 //
 // Warp roles, barriers, the fused epilogue math and the optional fused 1x1 shortcut are those of conv_shift.cu.
 #include <stdlib.h>
@@ -31,11 +31,11 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kS = 3;                          // horizontal taps stacked into N
 constexpr int kNT = 64;                        // output channels per tile
-constexpr int kTilePos = kTileM - 1;           // outputs per tile: the last lane has no right-hand neighbour
+constexpr int kTilePos = kTileM - 2;           // outputs per tile: the last two lanes have no right-hand neighbours
 constexpr int kThreads = 640;                  // warps 0-3: producer / MMA / TMEM / params; warps 4-19: epilogue
 constexpr int kMaxA = 4, kMaxB = 40;
 constexpr uint32_t kStageBytes = 16 * 1024;    // epilogue transposition stage (per epilogue warp: 32 rows x 32 B)
-constexpr uint32_t kXBytes = 4 * 2 * 5 * 16 * 4;       // [channel group][tile parity][quarter + 1][16 ch] fp32 boundary exchange
+constexpr uint32_t kXBytes = 4 * 2 * 5 * 48 * 4;       // [channel group][tile parity][quarter + 1][3 vectors][16 ch] fp32 boundary exchange
 constexpr uint32_t kBBox = kNT * 128;          // one (chunk, tap) weight box
 constexpr long long kWatchdogCycles = 4000000000ll;
 
@@ -87,6 +87,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+template <int kAct>      // 1 = ReLU, 2 = LeakyReLU with 0 <= alpha <= 1, 0 = any (runtime switch)
 __global__ void __launch_bounds__(kThreads, 1)
 conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                       const __grid_constant__ CUtensorMap mapA2, const StackParams p) {
@@ -107,7 +108,7 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + off_ss + 512 + 16 * kMaxA + 8 * kMaxB + 32);
   uint8_t* stage = base_ptr + off_stage;
   float* xch = reinterpret_cast<float*>(base_ptr + off_x);
-  float* ss = reinterpret_cast<float*>(base_ptr + off_ss);
+  __half* ssh = reinterpret_cast<__half*>(base_ptr + off_ss);       // scale[64] | shift[64] in fp16
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Wv = p.Wv;
@@ -128,12 +129,12 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     for (uint32_t a = 0; a < 2; ++a) { ptx::mbar_init(bar_tfull + 8 * a, 1); ptx::mbar_init(bar_tempty + 8 * a, 512); }
     ptx::fence_mbar_init();
   }
-  if (warp == 2) { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 256); ptx::tmem_relinquish(); }
+  if (warp == 2) { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish(); }
   if (warp == 3) {
     for (int i = lane; i < kNT; i += 32) {
       const int c = n0 + i;
-      ss[i] = p.scale ? __ldg(p.scale + c) : 1.f;
-      ss[kNT + i] = p.shift ? __ldg(p.shift + c) : 0.f;
+      ssh[i] = __float2half_rn(p.scale ? __ldg(p.scale + c) : 1.f);
+      ssh[kNT + i] = __float2half_rn(p.shift ? __ldg(p.shift + c) : 0.f);
     }
   }
   ptx::tc_fence_before();
@@ -193,7 +194,7 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   } else if (warp == 1) {
     // ===================================== MMA issuer =========================================
     uint32_t ab = 0, aph = 0, it = 0;
-    const uint32_t idesc_pair = (1u << 4) | ((uint32_t)((2 * kNT) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint32_t idesc_tri = (1u << 4) | ((uint32_t)((kS * kNT) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const uint32_t idesc_one = (1u << 4) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const uint32_t desc_hi = (uint32_t)(ptx::make_smem_desc(0, 1024, 2) >> 32);
     const uint32_t a_lo0 = (uint32_t)ptx::make_smem_desc(sA + (uint32_t)Wv * 128u, 1024, 2);
@@ -210,7 +211,7 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       mbar_wait(bar_tempty + 8 * a, tph ^ 1, p.err, 1);
       t_tempty += clock64() - te0;
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + a * (uint32_t)(2 * kNT);
+      const uint32_t d_tmem = tmem_base + a * (uint32_t)(kS * kNT);
       uint32_t acc = 0u, bi = 0;
       for (int cc = 0; cc < nall; ++cc) {
         const bool sc = cc >= cchunks;
@@ -225,14 +226,9 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           ptx::tc_fence_after();
         }
         if (!sc) {
-          // per vertical tap: taps s = 0, 1 as ONE N = 128 group (their weight boxes are consecutive in sB), tap s = 2 as an
-          // N = 64 group on the view shifted by two positions, accumulating into the first column block
+          // per vertical tap: the three horizontal taps as ONE N = 192 group (their weight boxes are consecutive in sB)
           for (int r = 0; r < R; ++r, bi += kS) {
-            if (elected) {
-              const uint32_t a_r = a_row + (uint32_t)r * r_step;
-              ptx::umma_f16_x4<1>(d_tmem, a_r, b_lo0 + bi * b_step, desc_hi, idesc_pair, acc);
-              ptx::umma_f16_x4<1>(d_tmem, a_r + 2u * 8u, b_lo0 + (bi + 2) * b_step, desc_hi, idesc_one, 1u);
-            }
+            if (elected) ptx::umma_f16_x4<1>(d_tmem, a_row + (uint32_t)r * r_step, b_lo0 + bi * b_step, desc_hi, idesc_tri, acc);
             acc = 1u;
           }
         } else {
@@ -263,11 +259,16 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     const uint32_t HvWv = (uint32_t)p.HvWv, uWv = (uint32_t)Wv, uMv = (uint32_t)p.Mv;
     uint8_t* st_o = stage + (warp - 4) * 1024;                 // per warp: 32 rows x 32 B
     const int piece = lane & 1;                                // 16-byte half of a row's 32 B
-    const float* ep_scale = ss + cg4 * 16, *ep_shift = ss + kNT + cg4 * 16;
+    const __half* ep_hscale = ssh + cg4 * 16 + piece * 8, *ep_hshift = ssh + kNT + cg4 * 16 + piece * 8;
     const int cb = n0 + cg4 * 16;            // first output channel of this warp
     uint32_t it = 0;
-    long long t_tfull = 0, t_bar = 0;
     const long long t_all0 = clock64();
+    // stage addresses: a lane writes its own row (two 16-byte pieces, swizzled by a row bit) and reads rows lane/2, 16 + lane/2
+    uint8_t* st_w0 = st_o + lane * 32 + ((lane >> 2) & 1) * 16;     // piece 0 of its row
+    uint8_t* st_w1 = st_o + lane * 32 + (((lane >> 2) & 1) ^ 1) * 16;   // piece 1
+    const int rrow = lane >> 1;
+    const uint8_t* st_r = st_o + rrow * 32 + ((piece ^ ((rrow >> 2) & 1)) << 4);
+    const int ycol = p.ycoff + cb + piece * 8;
 
     struct Geo { int own; int row[2]; };     // own position's pixel, and the two rows this lane serves in the coalesced pattern
     auto tile_geo = [&](int m_idx_) {
@@ -293,7 +294,27 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     };
     Geo gn = tile_geo(m_first < p.num_m_tiles ? m_first : 0);
     if (has_res && m_first < p.num_m_tiles) fetch_res(gn, rvp);
-
+    // this lane's 8 channels are the same in every tile: scale / shift live in registers as packed fp16
+    const uint4 sc4 = *reinterpret_cast<const uint4*>(ep_hscale);
+    const uint4 sf4 = *reinterpret_cast<const uint4*>(ep_hshift);
+    const __half2* sch = reinterpret_cast<const __half2*>(&sc4);
+    const __half2* sfh = reinterpret_cast<const __half2*>(&sf4);
+    const __half2 zero2 = __float2half2_rn(0.f), alpha2 = __float2half2_rn(p.alpha);
+    auto act2 = [&](__half2 x) {
+      if (kAct == 1) return __hmax2(x, zero2);
+      if (kAct == 2) return __hmax2(x, __hmul2(x, alpha2));
+      const float2 f = __half22float2(x);
+      return __floats2half2_rn(plnr_apply_act(f.x, p.act, p.alpha), plnr_apply_act(f.y, p.act, p.alpha));
+    };
+    const bool act_first = !has_res || p.res_after;
+    const bool add_then_act = has_res && !p.res_after;
+    const uint32_t bar_id = 2u + (uint32_t)cg4;
+    const bool is30 = lane == 30, is31 = lane == 31;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(cg4 * 16);
+    float* xq0 = xch + (cg4 * 10 + ew) * 48;
+    // The loop body is the instruction budget of this kernel: 16 warps x (instructions per tile) / 4 schedulers must stay
+    // below the ~1150 clk the MMAs of a tile take, so everything per tile is straight-line and the activation is a
+    // template parameter (the first version, ~800 instructions per warp and tile, was issue-bound at 3300 clk per tile).
     for (int m_idx = m_first; m_idx < p.num_m_tiles; m_idx += m_step, ++it) {
       const uint32_t a = it & 1, tph = (it >> 1) & 1;
       const Geo g = gn;
@@ -303,90 +324,85 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         gn = tile_geo(m_idx + m_step);
         if (has_res) fetch_res(gn, rvp);
       }
-      const long long tt0 = clock64();
       mbar_wait(bar_tfull + 8 * a, tph, p.err, 3);
-      t_tfull += clock64() - tt0;
       ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + a * (uint32_t)(2 * kNT) + (uint32_t)(cg4 * 16);
+      const uint32_t t_row = t_lane + a * (uint32_t)(kS * kNT);
 
-      uint32_t d0[16], d1[16];
+      uint32_t d0[16], d1[16], d2[16];
       ptx::tmem_ld_32x32b_x16(t_row, d0);
       ptx::tmem_ld_32x32b_x16(t_row + kNT, d1);
+      ptx::tmem_ld_32x32b_x16(t_row + 2 * kNT, d2);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar_tempty + 8 * a);             // accumulator fully read: hand it back to the MMA warp
 
-      // lane 0 of every quarter publishes what the previous quarter's last lane needs: its D[., 64 + c] values
-      float* xq = xch + (((cg4 * 2 + (it & 1)) * 5 + ew)) * 16;
-      if (lane == 0) {
+      // lanes 0 and 1 of every quarter publish what the previous quarter's last two lanes need:
+      //   vector 0 = D1 of lane 0, vector 1 = D2 of lane 0, vector 2 = D2 of lane 1   (double buffered by tile parity)
+      float* xq = xq0 + a * (5 * 48);
+      if (lane < 2) {
+        float* xd2 = xq + 16 + 16 * lane;
 #pragma unroll
-        for (int k = 0; k < 16; k += 4)
-          *reinterpret_cast<float4*>(xq + k) = make_float4(__uint_as_float(d1[k]), __uint_as_float(d1[k + 1]),
-                                                           __uint_as_float(d1[k + 2]), __uint_as_float(d1[k + 3]));
+        for (int k = 0; k < 16; k += 4) {
+          if (lane == 0) *reinterpret_cast<uint4*>(xq + k) = make_uint4(d1[k], d1[k + 1], d1[k + 2], d1[k + 3]);
+          *reinterpret_cast<uint4*>(xd2 + k) = make_uint4(d2[k], d2[k + 1], d2[k + 2], d2[k + 3]);
+        }
       }
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      // in-warp neighbours by shuffle; lanes 30 / 31 take theirs from the next quarter's slot (slot 4 is never written:
+      // the last two lanes of a tile are discarded).  Predicated loads, no divergent block.
+      const float* xn = xq + 48;
+      const float* x2p = xn + (is31 ? 32 : 16);
       float o16[16];
 #pragma unroll
-      for (int k = 0; k < 16; ++k)
-        o16[k] = __uint_as_float(d0[k]) + __shfl_down_sync(0xffffffffu, __uint_as_float(d1[k]), 1);
-      // one barrier per tile and channel group (the exchange is double buffered by tile parity)
-      const long long tb0 = clock64();
-      asm volatile("bar.sync %0, 128;" ::"r"(2 + cg4) : "memory");
-      t_bar += clock64() - tb0;
-      if (lane == 31) {                       // the lane whose neighbour lives in the next quarter: ONE divergent block
-        const float* xn = xq + 16;            // slot 4 is never written: the tile's last lane is discarded
-        float xv[16];
+      for (int k = 0; k < 16; k += 4) {
+        float s1[4], s2[4];
 #pragma unroll
-        for (int k = 0; k < 16; k += 4) *reinterpret_cast<float4*>(&xv[k]) = *reinterpret_cast<const float4*>(xn + k);
+        for (int j = 0; j < 4; ++j) {
+          s1[j] = __shfl_down_sync(0xffffffffu, __uint_as_float(d1[k + j]), 1);
+          s2[j] = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[k + j]), 2);
+        }
+        if (is31) *reinterpret_cast<float4*>(s1) = *reinterpret_cast<const float4*>(xn + k);
+        if (is30 | is31) *reinterpret_cast<float4*>(s2) = *reinterpret_cast<const float4*>(x2p + k);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) o16[k] = __uint_as_float(d0[k]) + xv[k];
+        for (int j = 0; j < 4; ++j) o16[k + j] = __uint_as_float(d0[k + j]) + s1[j] + s2[j];
       }
 
-      const bool act_first = !has_res || p.res_after;
+      // fp16-round the conv output (the reference's conv returns an fp16 array), transpose 32 rows x 32 B through the
+      // warp's stage, then batchnorm (one HFMA2), residual add and activation on the transposed pieces in packed fp16
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        float sc[8], sf[8], o8[8];
-        *reinterpret_cast<float4*>(&sc[0]) = *reinterpret_cast<const float4*>(ep_scale + q * 8);
-        *reinterpret_cast<float4*>(&sc[4]) = *reinterpret_cast<const float4*>(ep_scale + q * 8 + 4);
-        *reinterpret_cast<float4*>(&sf[0]) = *reinterpret_cast<const float4*>(ep_shift + q * 8);
-        *reinterpret_cast<float4*>(&sf[4]) = *reinterpret_cast<const float4*>(ep_shift + q * 8 + 4);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          o8[e] = fmaf(o16[q * 8 + e], sc[e], sf[e]);
-          if (act_first) o8[e] = p.act == PLNR_ACT_RELU ? fmaxf(o8[e], 0.f) : plnr_apply_act(o8[e], p.act, p.alpha);
-        }
         uint4 pk;
-        pk.x = pack_half2(o8[0], o8[1]); pk.y = pack_half2(o8[2], o8[3]);
-        pk.z = pack_half2(o8[4], o8[5]); pk.w = pack_half2(o8[6], o8[7]);
+        pk.x = pack_half2(o16[q * 8 + 0], o16[q * 8 + 1]); pk.y = pack_half2(o16[q * 8 + 2], o16[q * 8 + 3]);
+        pk.z = pack_half2(o16[q * 8 + 4], o16[q * 8 + 5]); pk.w = pack_half2(o16[q * 8 + 6], o16[q * 8 + 7]);
         // row `lane` of the warp's stage: 32 B = two 16-byte pieces, piece index swizzled by a row bit (bank spread)
-        *reinterpret_cast<uint4*>(st_o + lane * 32 + (((uint32_t)q ^ ((uint32_t)(lane >> 2) & 1u)) << 4)) = pk;
+        *reinterpret_cast<uint4*>(q == 0 ? st_w0 : st_w1) = pk;
       }
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int row = 16 * i + (lane >> 1);
-        uint4 val = *reinterpret_cast<const uint4*>(st_o + row * 32 + ((((uint32_t)piece) ^ ((uint32_t)(row >> 2) & 1u)) << 4));
+        uint4 val = *reinterpret_cast<const uint4*>(st_r + i * 512);
         if (g.row[i] >= 0) {
-          if (has_res) {
-            __half2* vh = reinterpret_cast<__half2*>(&val);
-            const __half2* rh = reinterpret_cast<const __half2*>(&rv[i]);
+          __half2* vh = reinterpret_cast<__half2*>(&val);
+          const __half2* rh = reinterpret_cast<const __half2*>(&rv[i]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __half2 x = __hadd2(vh[e], rh[e]);
-              if (!p.res_after) {
-                if (p.act == PLNR_ACT_RELU) x = __hmax2(x, __float2half2_rn(0.f));
-                else {
-                  const float2 f = __half22float2(x);
-                  x = __floats2half2_rn(plnr_apply_act(f.x, p.act, p.alpha), plnr_apply_act(f.y, p.act, p.alpha));
-                }
-              }
-              vh[e] = x;
+          for (int e = 0; e < 4; ++e) {
+            __half2 x;
+            if (kAct == 1) {
+              x = act_first ? __hfma2_relu(vh[e], sch[e], sfh[e]) : __hfma2(vh[e], sch[e], sfh[e]);
+            } else {
+              x = __hfma2(vh[e], sch[e], sfh[e]);
+              if (act_first) x = act2(x);
             }
+            if (has_res) x = __hadd2(x, rh[e]);
+            if (add_then_act) x = act2(x);
+            vh[e] = x;
           }
-          *reinterpret_cast<uint4*>(p.y + (size_t)g.row[i] * p.yld + p.ycoff + cb + piece * 8) = val;
+          *reinterpret_cast<uint4*>(p.y + (size_t)g.row[i] * p.yld + ycol) = val;
         }
       }
       __syncwarp();                          // the transposition stage is rewritten by the next tile
     }
+    long long t_tfull = 0, t_bar = 0;
     if (p.prof && threadIdx.x == 128) { p.prof[blockIdx.x * 8 + 5] = t_tfull; p.prof[blockIdx.x * 8 + 6] = clock64() - t_all0; p.prof[blockIdx.x * 8 + 7] = t_bar; }
   }
 
@@ -394,7 +410,7 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 256);
+    ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -434,11 +450,9 @@ struct StackPlan {
 static StackPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y, int sm_count, int c2) {
   StackPlan pl;
   memset(&pl, 0, sizeof(pl));
-  // Measured on ResNet-18 layer1 (128 x 64 x 56 x 56, B200): 54 us against 46 us for conv_shift.cu -- the lane-shifting
-  // epilogue (3450 clk per tile, instruction-latency bound) costs more than the operand traffic it saves -- so this
-  // kernel is an opt-in experiment (PLNR_STACK=1), kept correct by the parity tests.
+  // PLNR_STACK=0 falls back to conv_shift.cu (A/B timing; both are covered by the parity tests)
   const char* on = getenv("PLNR_STACK");
-  if (!on || !atoi(on)) return pl;
+  if (on && !atoi(on)) return pl;
   if (d->dtype != PLNR_F16 || d->groups != 1 || d->stride_h != 1 || d->stride_w != 1) return pl;
   if (d->kw != kS || d->dil_w != 1 || d->kh < 1 || d->kh > 5) return pl;
   if (x->c % 64 != 0 || x->ld % 8 != 0 || x->coff % 8 != 0 || (reinterpret_cast<uintptr_t>(x->ptr) & 15)) return pl;
@@ -450,8 +464,13 @@ static StackPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
   pl.Hv = x->h + d->pad_t;
   if (pl.Wv > 256) return pl;
   pl.halo = (d->kh - 1) * d->dil_h * pl.Wv + (kS - 1);
-  const int rows_max = (pl.Wv - 1 + kTileM - 1 + pl.halo) / pl.Wv + 1;
-  pl.a_buf_bytes = (uint32_t)round_up((rows_max + 1) * pl.Wv * 128, 1024);
+  // position o0 sits at row offset Wv whatever its column `off`: rows start at Wv - off, floor((off + 127 + halo) / Wv) + 1 of them
+  int need = 0;
+  for (int off = 0; off < pl.Wv; ++off) {
+    const int end = pl.Wv - off + ((off + kTileM - 1 + pl.halo) / pl.Wv + 1) * pl.Wv;
+    if (end > need) need = end;
+  }
+  pl.a_buf_bytes = (uint32_t)round_up(need * 128, 1024);
   const long long Mv = (long long)x->n * pl.Hv * pl.Wv;
   if (Mv >= (1ll << 31) - 512) return pl;
   const double eff = (double)y->h * y->w / ((double)pl.Hv * pl.Wv);
@@ -550,14 +569,16 @@ int plnr_conv2d_stack(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
     small_tensor_fixup(&mapA2, (uint64_t)x2->n * x2->h * x2->w * x2->ld * 2);
   }
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    PLNR_CHECK_CUDA(cudaFuncSetAttribute(conv_stack_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
+  const int kact = p.act == PLNR_ACT_RELU ? 1 : (p.act == PLNR_ACT_LEAKY && p.alpha >= 0.f && p.alpha <= 1.f ? 2 : 0);
+  auto kern = kact == 1 ? conv_stack_f16_kernel<1> : (kact == 2 ? conv_stack_f16_kernel<2> : conv_stack_f16_kernel<0>);
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[kact]) {
+    PLNR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set[kact] = true;
   }
   int per_block = ctx->sm_count / pl.NT;                        // every output-channel block gets the same number of CTAs
   if (per_block > pl.num_m_tiles) per_block = pl.num_m_tiles;
   int grid = per_block * pl.NT;
-  conv_stack_f16_kernel<<<grid, kThreads, pl.smem_bytes, ctx->stream>>>(mapA, mapB, mapA2, p);
+  kern<<<grid, kThreads, pl.smem_bytes, ctx->stream>>>(mapA, mapB, mapA2, p);
   return plnr_after_launch(ctx, "conv2d_stack");
 }
