@@ -31,7 +31,6 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kS = 3;                          // horizontal taps stacked into N
 constexpr int kNT = 64;                        // output channels per tile
-constexpr int kTilePos = kTileM - 2;           // outputs per tile: the last two lanes have no right-hand neighbours
 constexpr int kThreads = 640;                  // warps 0-3: producer / MMA / TMEM / params; warps 4-19: epilogue
 constexpr int kMaxA = 4, kMaxB = 40;
 constexpr uint32_t kStageBytes = 16 * 1024;    // epilogue transposition stage (per epilogue warp: 32 rows x 32 B)
@@ -87,11 +86,18 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
-template <int kAct>      // 1 = ReLU, 2 = LeakyReLU with 0 <= alpha <= 1, 0 = any (runtime switch)
+// kAct : 1 = ReLU, 2 = LeakyReLU with 0 <= alpha <= 1, 0 = any (runtime switch)
+// kTaps: horizontal taps stacked into ONE MMA.  3: N = 192, out[o] = D0[o] + D1[o+1] + D2[o+2], 126 outputs per tile.
+//        2: taps 0, 1 as an N = 128 MMA and tap 2 as an N = 64 MMA on the view shifted by two positions, accumulating into
+//        D0: out[o] = D0[o] + D1[o+1], 127 outputs per tile -- half the epilogue's shuffles for 14 instead of 10 KB of
+//        operand reads; chosen for 64-input-channel layers, whose tiles have too few MMAs to hide the longer epilogue.
+template <int kAct, int kTaps>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                       const __grid_constant__ CUtensorMap mapA2, const StackParams p) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int kTilePos = kTileM - (kTaps - 1);     // outputs per tile: the last kTaps-1 lanes lack right-hand neighbours
+  constexpr uint32_t kAccCols = (uint32_t)(kTaps * kNT);
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
@@ -194,7 +200,7 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   } else if (warp == 1) {
     // ===================================== MMA issuer =========================================
     uint32_t ab = 0, aph = 0, it = 0;
-    const uint32_t idesc_tri = (1u << 4) | ((uint32_t)((kS * kNT) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint32_t idesc_tri = (1u << 4) | ((uint32_t)(kAccCols >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);   // N = 192 or 128
     const uint32_t idesc_one = (1u << 4) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const uint32_t desc_hi = (uint32_t)(ptx::make_smem_desc(0, 1024, 2) >> 32);
     const uint32_t a_lo0 = (uint32_t)ptx::make_smem_desc(sA + (uint32_t)Wv * 128u, 1024, 2);
@@ -211,7 +217,7 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       mbar_wait(bar_tempty + 8 * a, tph ^ 1, p.err, 1);
       t_tempty += clock64() - te0;
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + a * (uint32_t)(kS * kNT);
+      const uint32_t d_tmem = tmem_base + a * kAccCols;
       uint32_t acc = 0u, bi = 0;
       for (int cc = 0; cc < nall; ++cc) {
         const bool sc = cc >= cchunks;
@@ -228,7 +234,11 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         if (!sc) {
           // per vertical tap: the three horizontal taps as ONE N = 192 group (their weight boxes are consecutive in sB)
           for (int r = 0; r < R; ++r, bi += kS) {
-            if (elected) ptx::umma_f16_x4<1>(d_tmem, a_row + (uint32_t)r * r_step, b_lo0 + bi * b_step, desc_hi, idesc_tri, acc);
+            if (elected) {
+              const uint32_t a_r = a_row + (uint32_t)r * r_step;
+              ptx::umma_f16_x4<1>(d_tmem, a_r, b_lo0 + bi * b_step, desc_hi, idesc_tri, acc);
+              if (kTaps == 2) ptx::umma_f16_x4<1>(d_tmem, a_r + 2u * 8u, b_lo0 + (bi + 2) * b_step, desc_hi, idesc_one, 1u);
+            }
             acc = 1u;
           }
         } else {
@@ -326,12 +336,12 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       }
       mbar_wait(bar_tfull + 8 * a, tph, p.err, 3);
       ptx::tc_fence_after();
-      const uint32_t t_row = t_lane + a * (uint32_t)(kS * kNT);
+      const uint32_t t_row = t_lane + a * kAccCols;
 
       uint32_t d0[16], d1[16], d2[16];
       ptx::tmem_ld_32x32b_x16(t_row, d0);
       ptx::tmem_ld_32x32b_x16(t_row + kNT, d1);
-      ptx::tmem_ld_32x32b_x16(t_row + 2 * kNT, d2);
+      if (kTaps == 3) ptx::tmem_ld_32x32b_x16(t_row + 2 * kNT, d2);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar_tempty + 8 * a);             // accumulator fully read: hand it back to the MMA warp
@@ -339,17 +349,17 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       // lanes 0 and 1 of every quarter publish what the previous quarter's last two lanes need:
       //   vector 0 = D1 of lane 0, vector 1 = D2 of lane 0, vector 2 = D2 of lane 1   (double buffered by tile parity)
       float* xq = xq0 + a * (5 * 48);
-      if (lane < 2) {
+      if (lane < kTaps - 1) {
         float* xd2 = xq + 16 + 16 * lane;
 #pragma unroll
         for (int k = 0; k < 16; k += 4) {
           if (lane == 0) *reinterpret_cast<uint4*>(xq + k) = make_uint4(d1[k], d1[k + 1], d1[k + 2], d1[k + 3]);
-          *reinterpret_cast<uint4*>(xd2 + k) = make_uint4(d2[k], d2[k + 1], d2[k + 2], d2[k + 3]);
+          if (kTaps == 3) *reinterpret_cast<uint4*>(xd2 + k) = make_uint4(d2[k], d2[k + 1], d2[k + 2], d2[k + 3]);
         }
       }
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       // in-warp neighbours by shuffle; lanes 30 / 31 take theirs from the next quarter's slot (slot 4 is never written:
-      // the last two lanes of a tile are discarded).  Predicated loads, no divergent block.
+      // the last lanes of a tile are discarded).  Predicated loads, no divergent block.
       const float* xn = xq + 48;
       const float* x2p = xn + (is31 ? 32 : 16);
       float o16[16];
@@ -359,12 +369,13 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           s1[j] = __shfl_down_sync(0xffffffffu, __uint_as_float(d1[k + j]), 1);
-          s2[j] = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[k + j]), 2);
+          s2[j] = kTaps == 3 ? __shfl_down_sync(0xffffffffu, __uint_as_float(d2[k + j]), 2) : 0.f;
         }
         if (is31) *reinterpret_cast<float4*>(s1) = *reinterpret_cast<const float4*>(xn + k);
-        if (is30 | is31) *reinterpret_cast<float4*>(s2) = *reinterpret_cast<const float4*>(x2p + k);
+        if (kTaps == 3 && (is30 | is31)) *reinterpret_cast<float4*>(s2) = *reinterpret_cast<const float4*>(x2p + k);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o16[k + j] = __uint_as_float(d0[k + j]) + s1[j] + s2[j];
+        for (int j = 0; j < 4; ++j)
+          o16[k + j] = kTaps == 3 ? __uint_as_float(d0[k + j]) + s1[j] + s2[j] : __uint_as_float(d0[k + j]) + s1[j];
       }
 
       // fp16-round the conv output (the reference's conv returns an fp16 array), transpose 32 rows x 32 B through the
@@ -442,7 +453,7 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct StackPlan {
   bool ok;
-  int Wv, Hv, halo, na, nb, NT, num_m_tiles;
+  int Wv, Hv, halo, na, nb, NT, num_m_tiles, taps;
   uint32_t a_buf_bytes;
   size_t smem_bytes;
 };
@@ -475,7 +486,11 @@ static StackPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
   if (Mv >= (1ll << 31) - 512) return pl;
   const double eff = (double)y->h * y->w / ((double)pl.Hv * pl.Wv);
   if (eff < 0.70) return pl;
-  pl.num_m_tiles = (int)((Mv + kTilePos - 1) / kTilePos);
+  // 64 input channels = ONE k-chunk per tile: 12 MMAs cannot hide the two-shift epilogue (measured: layer1, epilogue-bound)
+  pl.taps = x->c == 64 ? 2 : 3;
+  if (const char* e = getenv("PLNR_STACK_TAPS")) { int v = atoi(e); if (v == 2 || v == 3) pl.taps = v; }
+  const int tile_pos = kTileM - (pl.taps - 1);
+  pl.num_m_tiles = (int)((Mv + tile_pos - 1) / tile_pos);
   pl.nb = d->kh * kS * (x->c / 64) + c2 / 64;
   if (pl.nb > kMaxB) return pl;
   const size_t fixed = kStageBytes + kXBytes + 512 + 16 * kMaxA + 8 * kMaxB + 64 + 1024;
@@ -570,11 +585,15 @@ int plnr_conv2d_stack(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
   }
 
   const int kact = p.act == PLNR_ACT_RELU ? 1 : (p.act == PLNR_ACT_LEAKY && p.alpha >= 0.f && p.alpha <= 1.f ? 2 : 0);
-  auto kern = kact == 1 ? conv_stack_f16_kernel<1> : (kact == 2 ? conv_stack_f16_kernel<2> : conv_stack_f16_kernel<0>);
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[kact]) {
+  typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const StackParams);
+  static const KernFn kerns[2][3] = {
+      {conv_stack_f16_kernel<0, 2>, conv_stack_f16_kernel<1, 2>, conv_stack_f16_kernel<2, 2>},
+      {conv_stack_f16_kernel<0, 3>, conv_stack_f16_kernel<1, 3>, conv_stack_f16_kernel<2, 3>}};
+  KernFn kern = kerns[pl.taps - 2][kact];
+  static bool attr_set[2][3] = {{false, false, false}, {false, false, false}};
+  if (!attr_set[pl.taps - 2][kact]) {
     PLNR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set[kact] = true;
+    attr_set[pl.taps - 2][kact] = true;
   }
   int per_block = ctx->sm_count / pl.NT;                        // every output-channel block gets the same number of CTAs
   if (per_block > pl.num_m_tiles) per_block = pl.num_m_tiles;

@@ -145,15 +145,17 @@ def test_stacked_conv_kernel_equals_shift_kernel(planer, cfg):
                                    B.asarray((rng.standard_normal(cout) * 0.1).astype(np.float32)), cout)
     r = B.to_nhwc(B.asarray(rng.standard_normal((n, cout, h, w)).astype(np.float16))) if with_res else None
     outs = []
-    for stack in ('1', '0'):
-        os.environ['PLNR_STACK'] = stack            # opt-in experiment kernel (see conv_stack.cu)
+    for stack, taps in (('1', '2'), ('1', '3'), ('0', '3')):
+        os.environ['PLNR_STACK'] = stack            # '0' = conv_shift.cu
+        os.environ['PLNR_STACK_TAPS'] = taps        # horizontal taps stacked into one MMA (conv_stack.cu)
         try:
             y = B.empty((n, cout, h, w), np.float16, 'nhwc')
             ops.conv2d_into(x, wp, y, 3, 3, (1, 1), (1, 1), (1, 1, 1, 1), 1, scale, shift, r, ops.ACT_RELU, 0.0, ops.ALGO_TCGEN05)
             B.synchronize()
             outs.append(y.get().astype(np.float32))
         finally:
-            del os.environ['PLNR_STACK']
+            del os.environ['PLNR_STACK'], os.environ['PLNR_STACK_TAPS']
+    assert rel_err(outs[1], outs[2]) <= 2e-3
     assert rel_err(outs[0], outs[1]) <= 2e-3
 
 
