@@ -167,6 +167,16 @@ int plnr_dense_fwd(plnr_ctx* ctx, int dtype, const void* x, const void* w, void*
 /* Maxpool with the reference's semantics: ZERO padding and a -1e4 floor (planer/util.py:79-95). */
 int plnr_maxpool2d(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y,
                    int kh, int kw, int pad_t, int pad_l, int stride_h, int stride_w);
+/* AveragePool with the reference's semantics: ZERO padding, divisor kh*kw whatever the window covers
+ * (planer/layer.py:74-75 -> planer/util.py:97-100). */
+int plnr_avgpool2d(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y,
+                   int kh, int kw, int pad_t, int pad_l, int stride_h, int stride_w);
+/* The two data movements of ConvTranspose2d (planer/layer.py:28-34), which then runs plnr_conv2d_fwd at stride 1:
+ * zero_stuff: y[n, lo_h + i*stride_h, lo_w + j*stride_w, :] = x[n, i, j, :], zero elsewhere (planer/layer.py:32-33);
+ * flip_weight: K (ci, co, kh, kw) -> K' (co, ci, kh, kw) = K.transpose(1,0,2,3)[:, :, ::-1, ::-1] (planer/layer.py:34). */
+int plnr_zero_stuff(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y, int lo_h, int lo_w,
+                    int stride_h, int stride_w);
+int plnr_flip_weight(plnr_ctx* ctx, int dtype, const void* w, void* out, int ci, int co, int kh, int kw);
 /* Integer-factor nearest upsample, zero pixel shift (planer/util.py:184-192 with the default mode
  * strings of planer/util.py:212). */
 int plnr_upsample_nearest(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y, int fh, int fw);

@@ -44,8 +44,11 @@ def ref_net(model, blob, half=False):
 def op_cases():
     """Seeded per-op cases; shared with tests/cases.py via the same generator function."""
     from tests.cases import OP_CASES, make_case
-    out = {}
+    path = os.path.join(OUT, 'ops.npz')
+    out = dict(np.load(path)) if INCREMENTAL and os.path.exists(path) else {}
     for name in OP_CASES:
+        if name in out:
+            continue
         kind, args, kw = make_case(name)
         fn = L.layer_map[kind]
         planer.util.clear_buf()   # quirk Q6: the global im2col scratch keeps its dtype between calls
@@ -59,9 +62,13 @@ def op_cases():
 
 def graph_cases():
     from tests.cases import GRAPH_CASES, make_graph_case, sample
-    out = {}
+    path = os.path.join(OUT, 'graphs.npz')
+    out = dict(np.load(path)) if INCREMENTAL and os.path.exists(path) else {}
     for name in GRAPH_CASES:
+        if name + '.nout' in out:
+            continue
         model, blob, x, half = make_graph_case(name)
+        planer.util.clear_buf()   # quirk Q6: a scratch buffer left by an earlier fp16 conv would make this graph's im2col fp16
         net = ref_net(model, blob, half)
         y = net(x.copy())
         ys = y if isinstance(y, tuple) else (y,)
@@ -76,6 +83,9 @@ def graph_cases():
         print(name, [t.shape for t in ys], flush=True)
     np.savez_compressed(os.path.join(OUT, 'graphs.npz'), **out)
 
+
+# ``--add``: keep the fixtures already in the .npz files and run the reference only for cases that are not there yet
+INCREMENTAL = '--add' in sys.argv
 
 if __name__ == '__main__':
     op_cases()

@@ -90,6 +90,22 @@ def conv2d(x, K, B=None, group=1, strides=(1, 1), dilations=(1, 1), pads=(0, 0, 
     return out
 
 
+def convtranspose2d(x, K, B=None, strides=(2, 2), dilations=(1, 1), pads=(0, 0, 0, 0), output_padding=(0, 0), group=1):
+    """Transposed convolution = zero-stuffing + ``conv2d`` with the filter transposed (in <-> out) and flipped.
+
+    reference: planer/layer.py:28-34 (ConvTranspose2d).  K is (C_in, C_out, kh, kw); the stuffed buffer has
+    ``(k-1)*d - pad`` zeros in front, ``(k-1)*d - pad + output_padding`` behind and ``stride-1`` zeros between pixels
+    (layer.py:30-33); the convolution runs at stride 1 without padding (layer.py:34).
+    """
+    n, c, h, w = x.shape
+    (s1, s2), (d1, d2), (kh, kw) = strides, dilations, K.shape[2:]
+    low_h, high_h = (kh - 1) * d1 - pads[0], (kh - 1) * d1 - pads[2] + output_padding[0]
+    low_w, high_w = (kw - 1) * d2 - pads[1], (kw - 1) * d2 - pads[3] + output_padding[1]
+    buf = np.zeros((n, c, (h - 1) * s1 + low_h + high_h + 1, (w - 1) * s2 + low_w + high_w + 1), dtype=x.dtype)
+    buf[:, :, low_h:buf.shape[2] - high_h:s1, low_w:buf.shape[3] - high_w:s2] = x
+    return conv2d(buf, K.transpose(1, 0, 2, 3)[:, :, ::-1, ::-1], B, group, (1, 1), dilations)
+
+
 def dense(x, K, B, shp=None):
     """``x @ K.T + B`` with K stored (out, in).  reference: planer/layer.py:15-18 (Dense)."""
     y = np.matmul(x, K.T)
@@ -280,7 +296,7 @@ layer_map = {
     'conv': conv2d, 'dense': dense, 'matmul': matmul, 'relu': relu, 'leakyrelu': leakyrelu,
     'sigmoid': sigmoid, 'add': add, 'batchnorm': batchnorm, 'flatten': flatten, 'gap': gap,
     'concat': concat, 'maxpool': maxpool, 'averagepool': avgpool, 'upsample': upsample,
-    'return': ret,
+    'convtranspose': convtranspose2d, 'return': ret,
 }
 """Hot-path subset of planer/layer.py:262-281 (layer_map)."""
 

@@ -393,6 +393,86 @@ __global__ void gap_kernel(const T* __restrict__ x, T* __restrict__ y, int N, in
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// averagepool: zero padding, the divisor is ALWAYS kh*kw (planer/util.py:97-100: pool(np.add) then rst /= c[0]*c[1])
+// ---------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void avgpool_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int xld,
+                               int xcoff, int OH, int OW, int yld, int ycoff, int kh, int kw, int pt, int pl, int sh, int sw) {
+  const int CV = C / V;
+  const int64_t total = (int64_t)N * OH * OW * CV;
+  const float inv = 1.f / (float)(kh * kw);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    int64_t t = i / CV;
+    int ow = (int)(t % OW);
+    t /= OW;
+    int oh = (int)(t % OH);
+    int n = (int)(t / OH);
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    const T* xb = x + (size_t)n * H * W * xld + xcoff + cv * V;
+    for (int r = 0; r < kh; ++r) {
+      const int ih = oh * sh + r - pt;
+      if (ih < 0 || ih >= H) continue;
+      for (int q = 0; q < kw; ++q) {
+        const int iw = ow * sw + q - pl;
+        if (iw < 0 || iw >= W) continue;
+        const Vec<T, V> v = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)ih * W + iw) * xld);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += ld_f(&v.v[k]);
+      }
+    }
+    Vec<T, V> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k) st_f(&o.v[k], acc[k] * inv);
+    *reinterpret_cast<Vec<T, V>*>(y + (((size_t)n * OH + oh) * OW + ow) * yld + ycoff + cv * V) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ConvTranspose2d (planer/layer.py:28-34) = zero-stuffing + an ordinary stride-1 convolution with the filter transposed
+// (in <-> out channels) and flipped in both spatial axes.  zero_stuff: y[n, lo_h + i*sh, lo_w + j*sw, :] = x[n, i, j, :],
+// zero elsewhere (one pass: every output pixel is written once).  flip_weight: K (ci, co, kh, kw) -> (co, ci, kh, kw)
+// with K'[o, i, r, s] = K[i, o, kh-1-r, kw-1-s], done once when the executor is built.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void zero_stuff_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int xld, int xcoff,
+                                  int OH, int OW, int yld, int ycoff, int lo_h, int lo_w, int sh, int sw) {
+  const int CV = C / V;
+  const int64_t total = (int64_t)N * OH * OW * CV;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    int64_t t = i / CV;
+    int ow = (int)(t % OW);
+    t /= OW;
+    int oh = (int)(t % OH);
+    int n = (int)(t / OH);
+    Vec<T, V> v;
+#pragma unroll
+    for (int k = 0; k < V; ++k) st_f(&v.v[k], 0.f);
+    const int a = oh - lo_h, b = ow - lo_w;
+    if (a >= 0 && b >= 0 && a % sh == 0 && b % sw == 0 && a / sh < H && b / sw < W)
+      v = *reinterpret_cast<const Vec<T, V>*>(x + (((size_t)n * H + a / sh) * W + b / sw) * xld + xcoff + cv * V);
+    *reinterpret_cast<Vec<T, V>*>(y + (((size_t)n * OH + oh) * OW + ow) * yld + ycoff + cv * V) = v;
+  }
+}
+
+template <typename T>
+__global__ void flip_weight_kernel(const T* __restrict__ w, T* __restrict__ out, int ci, int co, int kh, int kw) {
+  const int64_t total = (int64_t)ci * co * kh * kw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int s = (int)(i % kw);
+    int64_t t = i / kw;
+    int r = (int)(t % kh);
+    t /= kh;
+    int c = (int)(t % ci);
+    int o = (int)(t / ci);
+    out[i] = w[(((size_t)c * co + o) * kh + (kh - 1 - r)) * kw + (kw - 1 - s)];
+  }
+}
+
 // GlobalAveragePool -> Flatten -> Dense in one launch (planer/layer.py:77-78, :59, :15-18).  A CTA takes IMGS images and a
 // slice of the output features: (1) the pooled vectors (fp32) of its images go to shared memory: SPLIT adjacent lanes
 // share one 16-byte channel group of one image and sum interleaved pixel rows, with all PB row loads of a lane in flight
@@ -633,6 +713,59 @@ int plnr_maxpool2d(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_te
   return plnr_after_launch(ctx, "maxpool2d");
 }
 
+int plnr_avgpool2d(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y, int kh, int kw, int pad_t,
+                   int pad_l, int stride_h, int stride_w) {
+  PLNR_REQUIRE(ctx && x && y && x->ptr && y->ptr, "avgpool2d: NULL argument");
+  PLNR_REQUIRE(x->n == y->n && x->c == y->c, "avgpool2d: batch/channel mismatch");
+  PLNR_REQUIRE(kh >= 1 && kw >= 1 && stride_h >= 1 && stride_w >= 1 && pad_t >= 0 && pad_l >= 0, "avgpool2d: bad window");
+  DISPATCH_T(dtype, {
+    constexpr int V = VecWidth<T>::value;
+    if (view_vec_ok(x, V, sizeof(T)) && view_vec_ok(y, V, sizeof(T))) {
+      const int64_t work = (int64_t)y->n * y->h * y->w * (y->c / V);
+      avgpool_kernel<T, V><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
+          (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, kh, kw, pad_t,
+          pad_l, stride_h, stride_w);
+    } else {
+      const int64_t work = (int64_t)y->n * y->h * y->w * y->c;
+      avgpool_kernel<T, 1><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
+          (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, kh, kw, pad_t,
+          pad_l, stride_h, stride_w);
+    }
+  })
+  return plnr_after_launch(ctx, "avgpool2d");
+}
+
+int plnr_zero_stuff(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y, int lo_h, int lo_w, int stride_h,
+                    int stride_w) {
+  PLNR_REQUIRE(ctx && x && y && x->ptr && y->ptr, "zero_stuff: NULL argument");
+  PLNR_REQUIRE(x->n == y->n && x->c == y->c && stride_h >= 1 && stride_w >= 1, "zero_stuff: shape mismatch");
+  PLNR_REQUIRE(lo_h >= 0 && lo_w >= 0 && lo_h + (x->h - 1) * stride_h < y->h && lo_w + (x->w - 1) * stride_w < y->w,
+               "zero_stuff: the stuffed input does not fit the output (negative crop is not supported)");
+  DISPATCH_T(dtype, {
+    constexpr int V = VecWidth<T>::value;
+    if (view_vec_ok(x, V, sizeof(T)) && view_vec_ok(y, V, sizeof(T))) {
+      const int64_t work = (int64_t)y->n * y->h * y->w * (y->c / V);
+      zero_stuff_kernel<T, V><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
+          (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, lo_h, lo_w,
+          stride_h, stride_w);
+    } else {
+      const int64_t work = (int64_t)y->n * y->h * y->w * y->c;
+      zero_stuff_kernel<T, 1><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
+          (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, lo_h, lo_w,
+          stride_h, stride_w);
+    }
+  })
+  return plnr_after_launch(ctx, "zero_stuff");
+}
+
+int plnr_flip_weight(plnr_ctx* ctx, int dtype, const void* w, void* out, int ci, int co, int kh, int kw) {
+  PLNR_REQUIRE(ctx && w && out && ci >= 1 && co >= 1 && kh >= 1 && kw >= 1, "flip_weight: bad argument");
+  const int64_t work = (int64_t)ci * co * kh * kw;
+  DISPATCH_T(dtype, flip_weight_kernel<T><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
+                        (const T*)w, (T*)out, ci, co, kh, kw);)
+  return plnr_after_launch(ctx, "flip_weight");
+}
+
 int plnr_upsample_nearest(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y, int fh, int fw) {
   PLNR_REQUIRE(ctx && x && y && x->ptr && y->ptr, "upsample_nearest: NULL argument");
   PLNR_REQUIRE(fh >= 1 && fw >= 1 && y->h == x->h * fh && y->w == x->w * fw && y->n == x->n && y->c == x->c,
@@ -713,7 +846,7 @@ int plnr_gap_dense_fwd(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const voi
                        const float* shift, void* y, int out_features, int act, float alpha) {
   PLNR_REQUIRE(ctx && x && x->ptr && w && y, "gap_dense: NULL argument");
   const int HW = x->h * x->w;
-  constexpr int IMGS = 4, SPLIT = 2, PB = 13, OPW = 8;
+  constexpr int IMGS = 4, SPLIT = 2, PB = 13, OPW = 4;    // OPW = 8 spills in the fp16 instantiation (ptxas -v)
   DISPATCH_T(dtype, {
     constexpr int V = VecWidth<T>::value;
     PLNR_REQUIRE(view_vec_ok(x, V, sizeof(T)) && aligned16(w) && x->c % V == 0,

@@ -236,6 +236,9 @@ class Executor:
             fused = fused if fused is not None and fused['conv'] is st else None
             x = self._view(st.ins[0]) if fused is None else None
             K = self._weight(st.w)
+            if op == 'conv' and st.attrs.get('flip'):
+                K = ops.flip_weight(K)                   # convtranspose: (C_in, C_out, kh, kw) -> flipped (C_out, C_in, kh, kw)
+                self._keep.append(K)
             co = K.shape[0]
             bias = self._weight(st.bias) if st.bias is not None else None
             bn_k, bn_b = (self._weight(st.bn[0]), self._weight(st.bn[1])) if st.bn else (None, None)
@@ -324,6 +327,12 @@ class Executor:
         if op == 'upsample':
             x, y, a = self._view(st.ins[0]), alloc(st.out), st.attrs
             return lambda: ops.upsample_into(x, y, a['fh'], a['fw'])
+        if op == 'averagepool':
+            x, y, a = self._view(st.ins[0]), alloc(st.out), st.attrs
+            return lambda: ops.avgpool_into(x, y, a['w'], a['pads'], a['strides'])
+        if op == 'zero_stuff':
+            x, y, a = self._view(st.ins[0]), alloc(st.out), st.attrs
+            return lambda: ops.zero_stuff_into(x, y, a['lo_h'], a['lo_w'], a['strides'])
         if op == 'concat':
             xs, y = [self._view(i) for i in st.ins], alloc(st.out)
             offs = np.cumsum([0] + [x.shape[1] for x in xs]).tolist()

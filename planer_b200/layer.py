@@ -165,6 +165,46 @@ def Maxpool(x, w=(2, 2), pads=(0, 0, 0, 0), strides=(2, 2)):
     return ops.maxpool_into(x, y, w, pads, strides)
 
 
+def AveragePool(x, w=(2, 2), pads=(0, 0, 0, 0), strides=(2, 2)):
+    """planer/layer.py:74-75 -> planer/util.py:97-100 (zero padding, divisor kh*kw)."""
+    if pads[2] > pads[0] or pads[3] > pads[1]:
+        raise ValueError('AveragePool: bottom/right padding larger than top/left is undefined in the reference '
+                         '(planer/util.py:4-10)')
+    x = _as_nhwc(x)
+    y = B.empty(ops.pool_out_shape(x.shape, w, pads, strides), x.dtype, 'nhwc')
+    return ops.avgpool_into(x, y, w, pads, strides)
+
+
+_flip_cache = {}
+
+
+def _flipped(K):
+    key = (K.ptr, K.shape, str(K.dtype))
+    if key not in _flip_cache:
+        if len(_flip_cache) > 1024: _flip_cache.clear()
+        _flip_cache[key] = (ops.flip_weight(K), K)
+    return _flip_cache[key][0]
+
+
+def ConvTranspose2d(x, K, B_=None, strides=(2, 2), dilations=(1, 1), pads=(0, 0, 0, 0), output_padding=(0, 0), group=1):
+    """planer/layer.py:28-34: zero-stuff the input, then an ordinary stride-1 convolution with the filter transposed and
+    flipped -- the same tensor-core conv kernels.  K is (C_in, C_out, kh, kw)."""
+    if group != 1:
+        raise NotImplementedError('ConvTranspose2d with group > 1: the reference transposes the whole filter '
+                                  '(planer/layer.py:34), which is only meaningful for group == 1')
+    dt = _compute_dtype(x, K)
+    xin = _as_nhwc(x, dt)
+    low_h, low_w, sh_, sw_ = ops.convtranspose_geometry(xin.shape, K.shape, strides, dilations, pads, output_padding)
+    c = xin.shape[1]
+    cpad = _round_up(c, 16) if dt == np.float16 and c % 16 else c
+    buf = B.empty((xin.shape[0], cpad, sh_, sw_), dt, 'nhwc')
+    if cpad != c:                                   # padded channels must be zero for the conv
+        xin = B.to_nhwc(B.to_flat(xin), dt, cpad)
+    ops.zero_stuff_into(xin, buf, low_h, low_w, strides)
+    stuffed = DeviceArray(buf.buf, (xin.shape[0], c, sh_, sw_), dt, 'nhwc', ld=cpad, offset=buf.offset) if cpad != c else buf
+    return Conv2d(stuffed, _flipped(K), B_, 1, (1, 1), dilations, (0, 0, 0, 0))
+
+
 def upsample_factors(k):
     """planer/layer.py:80-82: last two ONNX scales, truncated to int."""
     k = k.get() if isinstance(k, DeviceArray) else np.asarray(k)
@@ -225,5 +265,7 @@ layer_map = _HotPathOnly({
     'dense': Dense, 'conv': Conv2d, 'relu': ReLU, 'leakyrelu': LeakyReLU, 'batchnorm': BatchNorm,
     'flatten': Flatten, 'sigmoid': Sigmoid, 'maxpool': Maxpool, 'upsample': UpSample,
     'concat': Concatenate, 'add': Add, 'gap': GlobalAveragePool, 'identity': Identity, 'return': Return,
+    # SURVEY 8f rank 2 (the callers either side of the path): same kernels, same parity bar
+    'averagepool': AveragePool, 'convtranspose': ConvTranspose2d,
 })
 """Hot-path subset of planer/layer.py:262-281."""

@@ -127,6 +127,41 @@ def maxpool_into(x, y, w, pads, strides):
     return y
 
 
+def avgpool_into(x, y, w, pads, strides):
+    tx, ty = x.tensor(), y.tensor()
+    _capi.check(B.lib().plnr_avgpool2d(B.ctx(), _capi.dtype_code(x.dtype), C.byref(tx), C.byref(ty), w[0], w[1],
+                                       pads[0], pads[1], strides[0], strides[1]), 'plnr_avgpool2d')
+    return y
+
+
+def convtranspose_geometry(x_shape, k_shape, strides, dilations, pads, output_padding):
+    """planer/layer.py:29-32: (low_h, low_w, stuffed H, stuffed W) of the zero-stuffed buffer the stride-1 conv then reads."""
+    n, c, h, w = x_shape
+    kh, kw = k_shape[2:]
+    low_h, high_h = (kh - 1) * dilations[0] - pads[0], (kh - 1) * dilations[0] - pads[2] + output_padding[0]
+    low_w, high_w = (kw - 1) * dilations[1] - pads[1], (kw - 1) * dilations[1] - pads[3] + output_padding[1]
+    if min(low_h, high_h, low_w, high_w) < 0:
+        raise NotImplementedError('ConvTranspose2d: pads larger than (k-1)*dilation crop the stuffed input (the reference\'s '
+                                  'negative slice bounds, planer/layer.py:32-33); not supported')
+    return low_h, low_w, (h - 1) * strides[0] + low_h + high_h + 1, (w - 1) * strides[1] + low_w + high_w + 1
+
+
+def zero_stuff_into(x, y, low_h, low_w, strides):
+    tx, ty = x.tensor(), y.tensor()
+    _capi.check(B.lib().plnr_zero_stuff(B.ctx(), _capi.dtype_code(x.dtype), C.byref(tx), C.byref(ty), low_h, low_w,
+                                        strides[0], strides[1]), 'plnr_zero_stuff')
+    return y
+
+
+def flip_weight(K):
+    """K (ci, co, kh, kw) -> K.transpose(1,0,2,3)[:, :, ::-1, ::-1] as a new flat device array (planer/layer.py:34)."""
+    ci, co, kh, kw = K.shape
+    src = B.to_flat(K)
+    out = B.empty((co, ci, kh, kw), K.dtype)
+    _capi.check(B.lib().plnr_flip_weight(B.ctx(), _capi.dtype_code(K.dtype), src.ptr, out.ptr, ci, co, kh, kw), 'plnr_flip_weight')
+    return out
+
+
 def upsample_into(x, y, fh, fw):
     tx, ty = x.tensor(), y.tensor()
     _capi.check(B.lib().plnr_upsample_nearest(B.ctx(), _capi.dtype_code(x.dtype), C.byref(tx), C.byref(ty), fh, fw),

@@ -18,7 +18,8 @@ into kernel launches and a CUDA graph.  Operators outside the hot path raise Not
 import numpy as np
 
 HOT_OPS = ('conv', 'dense', 'relu', 'leakyrelu', 'sigmoid', 'add', 'batchnorm', 'flatten', 'gap', 'concat',
-           'maxpool', 'upsample', 'identity', 'return')
+           'maxpool', 'upsample', 'identity', 'return',
+           'averagepool', 'convtranspose')          # the same kernels either side of the path
 ACTS = {'relu': 1, 'leakyrelu': 2, 'sigmoid': 3}
 
 
@@ -79,6 +80,20 @@ def flatten(model, input_shapes):
                 continue
             if not isinstance(y, str):
                 raise NotImplementedError('multi-output layer %r is not on the B200 hot path' % lname)
+            if kind == 'convtranspose':
+                # planer/layer.py:28-34: zero-stuffing, then an ordinary stride-1 conv with the flipped, transposed filter
+                if (attrs.get('group', 1) or 1) != 1:
+                    raise NotImplementedError('convtranspose %r: group > 1 is not supported' % lname)
+                mid = new(None, 'act', y + '.stuffed')
+                mid.producer = len(nodes)
+                nodes.append(Node(lname + '.stuff', 'zero_stuff', dict(attrs), [ins[0], ins[1]], [mid.id]))
+                conv_attrs = {'group': 1, 'strides': (1, 1), 'dilations': tuple(attrs.get('dilations') or (1, 1)),
+                              'pads': (0, 0, 0, 0), 'flip': True}
+                out = new(None, 'act', y)
+                out.producer = len(nodes)
+                nodes.append(Node(lname, 'conv', conv_attrs, [mid.id] + ins[1:], [out.id]))
+                cur[y] = out.id
+                continue
             out = new(None, 'act', y)
             out.producer = len(nodes)
             nodes.append(Node(lname, kind, dict(attrs), ins, [out.id]))
@@ -103,6 +118,8 @@ def infer(values, nodes, host_consts=None):
         k, a = nd.kind, nd.attrs
         if k == 'conv':
             (n, c, h, w), (co, cg, kh, kw) = sh[0], sh[1]
+            if a.get('flip'):
+                co, cg = cg, co                      # convtranspose filter is stored (C_in, C_out, kh, kw)
             g = a.get('group', 1) or 1
             st = a.get('strides') or (1, 1)
             dl = a.get('dilations') or (1, 1)
@@ -115,7 +132,7 @@ def infer(values, nodes, host_consts=None):
                                  '(planer/util.py:4-10, SURVEY App. D Q1)' % (nd.name, list(pd)))
             out = (n, co, oh, ow)
             nd.flops = 2 * n * co * cg * kh * kw * oh * ow
-            nd.attrs = dict(group=g, strides=tuple(st), dilations=tuple(dl), pads=tuple(pd))
+            nd.attrs = dict(group=g, strides=tuple(st), dilations=tuple(dl), pads=tuple(pd), flip=bool(a.get('flip')))
         elif k == 'dense':
             (m, kk), (nn, k2) = sh[0], sh[1]
             if kk != k2:
@@ -129,7 +146,19 @@ def infer(values, nodes, host_consts=None):
                 raise NotImplementedError('add %r: broadcasting (%s + %s) is outside the B200 hot path'
                                           % (nd.name, sh[0], sh[1]))
             out = sh[0]
-        elif k == 'maxpool':
+        elif k == 'zero_stuff':
+            (n, c, h, w), (ci, co, kh, kw) = sh[0], sh[1]
+            if c != ci:
+                raise ValueError('convtranspose %r: input has %d channels, weight expects %d' % (nd.name, c, ci))
+            st, dl = a.get('strides') or (2, 2), a.get('dilations') or (1, 1)
+            pd, op_ = a.get('pads') or (0, 0, 0, 0), a.get('output_padding') or (0, 0)
+            lo_h, hi_h = (kh - 1) * dl[0] - pd[0], (kh - 1) * dl[0] - pd[2] + op_[0]
+            lo_w, hi_w = (kw - 1) * dl[1] - pd[1], (kw - 1) * dl[1] - pd[3] + op_[1]
+            if min(lo_h, hi_h, lo_w, hi_w) < 0:
+                raise NotImplementedError('convtranspose %r: pads larger than (k-1)*dilation are not supported' % nd.name)
+            out = (n, c, (h - 1) * st[0] + lo_h + hi_h + 1, (w - 1) * st[1] + lo_w + hi_w + 1)
+            nd.attrs = dict(lo_h=lo_h, lo_w=lo_w, strides=tuple(st))
+        elif k in ('maxpool', 'averagepool'):
             n, c, h, w = sh[0]
             kw_, pd, st = a.get('w', (2, 2)), a.get('pads', (0, 0, 0, 0)), a.get('strides', (2, 2))
             out = (n, c, (h + pd[0] + pd[2] - kw_[0] + st[0]) // st[0], (w + pd[1] + pd[3] - kw_[1] + st[1]) // st[1])
@@ -291,8 +320,8 @@ def fuse(values, nodes, outputs):
         elif k == 'batchnorm':
             st = emit(Step('scale_shift', nd.name, [x], out))
             st.bn = (nd.ins[1], nd.ins[2])
-        elif k == 'maxpool':
-            emit(Step('maxpool', nd.name, [x], out, nd.attrs))
+        elif k in ('maxpool', 'averagepool', 'zero_stuff'):
+            emit(Step(k, nd.name, [x], out, nd.attrs))
         elif k == 'upsample':
             emit(Step('upsample', nd.name, [x], out, nd.attrs))
         elif k == 'concat':

@@ -110,6 +110,31 @@ def down_block(cin=64, cout=128, stride=2, seed=0):
     return b.finish(['x'], [y])
 
 
+def decoder_net(seed=0, width=32):
+    """A small encoder-decoder of the kind the reference's README demos run (U-Net / GAN style, readme.md:105-108), in the
+    real IR: conv+bn+relu -> averagepool(2) -> conv+relu -> convtranspose(4, s2, p1)+bias -> relu -> concat with the skip ->
+    convtranspose(3, s1, p1) -> sigmoid.  Covers the two SURVEY 8f rank-2 operators (planer/layer.py:28-34, :74-75)."""
+    b = _Builder(seed)
+    w = width
+    x = b.conv('x', 3, w, 3, name='enc1')
+    x = b.bn(x, w, name='enc1.bn')
+    e1 = b.op('relu', {}, [x], name='enc1.relu')
+    x = b.op('averagepool', {'w': [2, 2], 'pads': [0, 0, 0, 0], 'strides': [2, 2]}, [e1], name='pool')
+    x = b.conv(x, w, 2 * w, 3, name='enc2', bias=True)
+    x = b.op('relu', {}, [x], name='enc2.relu')
+    kt = (b.rng.standard_normal((2 * w, w, 4, 4)) * np.sqrt(2.0 / (2 * w * 4))).astype(np.float32)
+    ins = [x, b.init('up.weight', kt), b.init('up.bias', (b.rng.standard_normal(w) * 0.1).astype(np.float32))]
+    x = b.op('convtranspose', {'strides': [2, 2], 'dilations': [1, 1], 'pads': [1, 1, 1, 1], 'output_padding': [0, 0],
+                               'group': 1}, ins, name='up')
+    x = b.op('relu', {}, [x], name='up.relu')
+    x = b.op('concat', {'axis': 1}, [e1, x], name='cat')
+    ko = (b.rng.standard_normal((2 * w, 3, 3, 3)) * np.sqrt(2.0 / (2 * w * 9))).astype(np.float32)
+    x = b.op('convtranspose', {'strides': [1, 1], 'dilations': [1, 1], 'pads': [1, 1, 1, 1], 'output_padding': [0, 0],
+                               'group': 1}, [x, b.init('out.weight', ko)], name='out')
+    y = b.op('sigmoid', {}, [x], name='out.sigmoid')
+    return b.finish(['x'], [y])
+
+
 def readme_net(seed=0):
     """The README's CustomNet in the real IR: conv+relu chained in one flow,
     maxpool(2), upsample(x2, nearest), concat(axis=1)+sigmoid chained, return."""

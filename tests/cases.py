@@ -24,6 +24,16 @@ def _conv(name, xs, ks, bias=True, dtype='float32', **kw):
     return 'conv', args, kw
 
 
+def _convt(name, xs, ks, bias=True, dtype='float32', **kw):
+    """ConvTranspose2d case: K is (C_in, C_out, kh, kw) (planer/layer.py:28-34)."""
+    rng = _rng(name)
+    fan = ks[0] * ks[2] * ks[3]
+    args = [_x(rng, xs, dtype), (rng.standard_normal(ks) * np.sqrt(2.0 / fan)).astype(dtype)]
+    if bias:
+        args.append((rng.standard_normal(ks[1]) * 0.1).astype(dtype))
+    return 'convtranspose', args, kw
+
+
 # name -> builder;  every builder returns (op kind, positional args, attrs)
 OP_CASES = {
     # BASELINE config 1: README Conv2d(3, 64, 3, 1) on 1x3x32x32, both paddings
@@ -76,6 +86,18 @@ OP_CASES = {
     'gap': lambda n: ('gap', [_x(_rng(n), (2, 16, 7, 7), 'float32')], {}),
     'gap_f16': lambda n: ('gap', [_x(_rng(n), (2, 16, 7, 7), 'float16')], {}),
     'flatten': lambda n: ('flatten', [_x(_rng(n), (2, 16, 1, 1), 'float32')], {}),
+    # AveragePool (zero padding, divisor always kh*kw) and ConvTranspose2d (planer/layer.py:28-34, :74-75)
+    'averagepool_k2s2': lambda n: ('averagepool', [_x(_rng(n), (2, 8, 9, 11), 'float32')], {}),
+    'averagepool_k3s2p1': lambda n: ('averagepool', [_x(_rng(n), (2, 8, 13, 15), 'float32') + 1.0],
+                                     {'w': (3, 3), 'pads': (1, 1, 1, 1), 'strides': (2, 2)}),
+    'averagepool_k3s1p1_f16': lambda n: ('averagepool', [_x(_rng(n), (2, 16, 12, 12), 'float16')],
+                                         {'w': (3, 3), 'pads': (1, 1, 1, 1), 'strides': (1, 1)}),
+    'convtranspose_k4s2p1': lambda n: _convt(n, (2, 16, 7, 9), (16, 8, 4, 4), strides=(2, 2), pads=(1, 1, 1, 1)),
+    'convtranspose_k3s2_outpad': lambda n: _convt(n, (1, 8, 6, 6), (8, 12, 3, 3), strides=(2, 2), pads=(1, 1, 1, 1),
+                                                   output_padding=(1, 1)),
+    'convtranspose_k2s2_nobias': lambda n: _convt(n, (2, 8, 5, 5), (8, 4, 2, 2), bias=False, strides=(2, 2)),
+    'convtranspose_k3s1p1_d2': lambda n: _convt(n, (1, 4, 9, 9), (4, 6, 3, 3), strides=(1, 1), dilations=(2, 2), pads=(2, 2, 2, 2)),
+    'convtranspose_64_f16': lambda n: _convt(n, (2, 64, 7, 7), (64, 64, 4, 4), dtype='float16', strides=(2, 2), pads=(1, 1, 1, 1)),
 }
 
 
@@ -91,6 +113,7 @@ BUILDERS = {
     'resnet18': lambda: zoo.resnet18(0),
     'yolov3_quarter': lambda: zoo.yolov3(0, width=0.25),
     'yolov3': lambda: zoo.yolov3(0),
+    'decoder': lambda: zoo.decoder_net(0),
 }
 GRAPH_CASES = {
     'readme_f32': ('readme', (2, 3, 32, 32), False),
@@ -101,6 +124,8 @@ GRAPH_CASES = {
     'resnet18_small_f32': ('resnet18', (3, 3, 64, 64), False),
     'yolov3_quarter_f32': ('yolov3_quarter', (2, 3, 96, 96), False),
     'yolov3_416_f32_n1': ('yolov3', (1, 3, 416, 416), False),     # BASELINE config 4 graph
+    'decoder_f32': ('decoder', (2, 3, 32, 40), False),            # averagepool + convtranspose in a graph
+    'decoder_f16': ('decoder', (2, 3, 32, 40), True),
 }
 
 _model_cache = {}

@@ -364,3 +364,22 @@ def test_shard_batch_covers_everything():
             parts = [dist.shard_batch(n, r, w) for r in range(w)]
             assert parts[0][0] == 0 and parts[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+
+
+def test_decoder_plan_expands_convtranspose_into_zero_stuff_plus_conv():
+    """ConvTranspose2d (planer/layer.py:28-34) compiles to a zero-stuffing step + an ordinary stride-1
+    conv step (flipped filter) whose epilogue still absorbs bias / relu / sigmoid; AveragePool is one HBM step."""
+    model, _ = cases.get_model('decoder')
+    gp = P.compile_graph(model, {'x': (2, 3, 32, 40)})
+    assert gp.summary() == {'conv': 4, 'averagepool': 1, 'zero_stuff': 2, 'concat': 1}
+    steps = {s.name: s for s in gp.steps}
+    up, out = steps['up'], steps['out']
+    assert up.attrs['flip'] and up.attrs['strides'] == (1, 1) and up.attrs['pads'] == (0, 0, 0, 0)
+    assert up.fused == ['up', 'up.relu'] and up.act == 1 and up.bias is not None
+    assert out.fused == ['out', 'out.sigmoid'] and out.act == 3
+    st = steps['up.stuff']
+    assert st.attrs == {'lo_h': 2, 'lo_w': 2, 'strides': (2, 2)}
+    shp = {s.name: gp.values[s.out].shape for s in gp.steps}
+    assert shp['up.stuff'] == (2, 64, 35, 43) and shp['up'] == (2, 32, 32, 40) and shp['out'] == (2, 3, 32, 40)
+    # 2 * N * Cout * Cin * kh * kw * OH * OW of the stride-1 conv over the stuffed buffer (what the kernels execute)
+    assert [n.flops for n in gp.nodes if n.name == 'up'] == [2 * 2 * 32 * 64 * 16 * 32 * 40]
