@@ -267,14 +267,16 @@ def main():
     pk = peaks()
     achieved = flops / (conv_ms / 1e3) / 1e12
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, 'profiles', 'r01_step_traffic.json')
-    if os.path.exists(tpath) and args.batch == BATCH:
-        with open(tpath) as f:
+    # newest committed ncu --set full capture of one step (tools/gpu_profile.sh + tools/ncu_step_summary.py)
+    cands = sorted(f for f in os.listdir(os.path.join(ROOT, 'profiles')) if f.endswith('_step_traffic.json'))
+    if cands and args.batch == BATCH:
+        with open(os.path.join(ROOT, 'profiles', cands[-1])) as f:
             tj = json.load(f)
         traffic = sum(int((k['dram_read_mb'] + k['dram_write_mb']) * 1e6) for k in tj['kernels'])
-        traffic_src = 'dram__bytes_read.sum + dram__bytes_write.sum summed over the same launches of one step, ncu --set full (profiles/r01_step_full.md)'
+        traffic_src = ('dram__bytes_read.sum + dram__bytes_write.sum summed over the same launches of one step, ncu --set full '
+                       '(profiles/%s)' % cands[-1].replace('_traffic.json', '_full.md'))
     roofline = {'bound': 'tensor',
-                'kernel': 'tcgen05 conv kernels of one step: stem_pool + conv_shift_f16 + conv_igemm_f16 + gap_dense (%d conv/dense layers)' % len(conv_nodes),
+                'kernel': 'tcgen05 conv kernels of one step: stem_pool + conv_stack_f16 + conv_shift_f16 + conv_igemm_f16 + gap_dense (%d conv/dense layers)' % len(conv_nodes),
                 'achieved': achieved, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved / pk['tflops_sustained'], 'traffic': traffic, 'traffic_source': traffic_src,
                 'peak_source': pk['source'] + ', sustained figure (kernel timed inside a long step)',
