@@ -44,7 +44,9 @@ enum {
   PLNR_EW_LEAKY = 1,       /* y = x * ((x>0)*(1-a) + a)          planer/layer.py:48-51  */
   PLNR_EW_SIGMOID = 2,     /* y = 1 / (1 + exp(-x))              planer/layer.py:61-64  */
   PLNR_EW_ADD = 3,         /* y = x + x2                         planer/layer.py:93-95  */
-  PLNR_EW_SCALE_SHIFT = 4  /* y = x * K[c] + B[c]  (folded BN)   planer/layer.py:125-127 */
+  PLNR_EW_SCALE_SHIFT = 4, /* y = x * K[c] + B[c]  (folded BN)   planer/layer.py:125-127 */
+  PLNR_EW_CLIP = 5,        /* y = max(min(x, b), a)              planer/layer.py:247-251 (plnr_unary2) */
+  PLNR_EW_HARDSIGMOID = 6  /* y = max(min(x*a + b, 1), 0)        planer/layer.py:66-69   (plnr_unary2) */
 };
 
 typedef struct plnr_ctx plnr_ctx;
@@ -187,6 +189,12 @@ int plnr_copy_channels(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const pln
  * p0/p1: second operand (ADD: x2) or per-channel K/B of dtype `dtype` (SCALE_SHIFT). */
 int plnr_eltwise(plnr_ctx* ctx, int op, int dtype, const void* x, const void* p0, const void* p1, void* y,
                  int64_t npix, int c, float alpha);
+/* Unary operators with two scalar parameters on `n` contiguous elements: PLNR_EW_CLIP (a = min, b = max),
+ * PLNR_EW_HARDSIGMOID (a = alpha, b = beta). */
+int plnr_unary2(plnr_ctx* ctx, int op, int dtype, const void* x, void* y, int64_t n, float a, float b);
+/* Softmax over the last, contiguous axis of a dense (rows, c) array (planer/layer.py:141-146): the channel axis of
+ * pixel-major activations, or the class axis of 2-D logits. */
+int plnr_softmax(plnr_ctx* ctx, int dtype, const void* x, void* y, int64_t rows, int c);
 /* Global average pool (n, hw, c) -> (n, c), fp32 accumulate (planer/layer.py:77-78). */
 int plnr_global_avgpool(plnr_ctx* ctx, int dtype, const plnr_tensor* x, void* y);
 

@@ -147,6 +147,29 @@ def sigmoid(x):
     return np.divide(1, t, out=t)
 
 
+def hardsigmoid(x, alpha=0.2, beta=0.5):
+    """reference: planer/layer.py:66-69 (HardSigmoid): x*alpha, += beta, minimum 1, maximum 0 (each rounded in x's dtype)."""
+    x = x * alpha
+    x += beta
+    x = np.minimum(x, 1, out=x)
+    return np.maximum(x, 0, out=x)
+
+
+def clip(x, min=0, max=1):
+    """reference: planer/layer.py:247-251 (Clip, numpy branch): np.minimum(x, max) then np.maximum(x, min), in place."""
+    x = np.minimum(x, max, out=x)
+    return np.maximum(x, min, out=x)
+
+
+def softmax(x, axis=-1):
+    """reference: planer/layer.py:141-146 (Softmax, numpy branch): y = x - max; e = exp(y); y -= log(sum e); exp(y)."""
+    y = x - np.max(x, axis=axis, keepdims=True)
+    ey = np.exp(y)
+    eX = np.sum(ey, axis=axis, keepdims=True)
+    y -= np.log(eX, out=eX)
+    return np.exp(y, out=y)
+
+
 def add(x1, x2):
     """reference: planer/layer.py:93-95 (Add)."""
     return x1 + x2
@@ -296,7 +319,7 @@ layer_map = {
     'conv': conv2d, 'dense': dense, 'matmul': matmul, 'relu': relu, 'leakyrelu': leakyrelu,
     'sigmoid': sigmoid, 'add': add, 'batchnorm': batchnorm, 'flatten': flatten, 'gap': gap,
     'concat': concat, 'maxpool': maxpool, 'averagepool': avgpool, 'upsample': upsample,
-    'convtranspose': convtranspose2d, 'return': ret,
+    'convtranspose': convtranspose2d, 'hardsigmoid': hardsigmoid, 'clip': clip, 'softmax': softmax, 'return': ret,
 }
 """Hot-path subset of planer/layer.py:262-281 (layer_map)."""
 

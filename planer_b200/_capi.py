@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get('PLNR_LIB') or os.path.join(HERE, 'libplaner_b200.so')
 F32, F16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
 ALGO_AUTO, ALGO_TCGEN05, ALGO_DIRECT = 0, 1, 2
-EW_RELU, EW_LEAKY, EW_SIGMOID, EW_ADD, EW_SCALE_SHIFT = 0, 1, 2, 3, 4
+EW_RELU, EW_LEAKY, EW_SIGMOID, EW_ADD, EW_SCALE_SHIFT, EW_CLIP, EW_HARDSIGMOID = 0, 1, 2, 3, 4, 5, 6
 
 
 class Tensor(C.Structure):
@@ -71,6 +71,8 @@ PROTOTYPES = {
     'plnr_upsample_nearest': [_P, C.c_int, _TP, _TP, C.c_int, C.c_int],
     'plnr_copy_channels': [_P, C.c_int, _TP, _TP],
     'plnr_eltwise': [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_float],
+    'plnr_unary2': [_P, C.c_int, C.c_int, _P, _P, C.c_int64, C.c_float, C.c_float],
+    'plnr_softmax': [_P, C.c_int, _P, _P, C.c_int64, C.c_int],
     'plnr_global_avgpool': [_P, C.c_int, _TP, _P],
     'plnr_gap_dense_fwd': [_P, C.c_int, _TP, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float],
     'plnr_graph_begin': [_P],

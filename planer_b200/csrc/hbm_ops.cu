@@ -371,6 +371,43 @@ __global__ void eltwise_kernel(int op, const T* __restrict__ x, const T* __restr
   }
 }
 
+// Unary operators with two scalar parameters: CLIP y = max(min(x, b), a) (planer/layer.py:247-251),
+// HARDSIGMOID y = max(min(x*a + b, 1), 0) (planer/layer.py:66-69).  fp16 data is computed in fp32 and rounded once.
+template <typename T, int V>
+__global__ void unary2_kernel(int op, const T* __restrict__ x, T* __restrict__ y, int64_t total_vec, float a, float b) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const Vec<T, V> v = *reinterpret_cast<const Vec<T, V>*>(x + i * V);
+    Vec<T, V> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float f = ld_f(&v.v[k]);
+      st_f(&o.v[k], op == PLNR_EW_CLIP ? fmaxf(fminf(f, b), a) : fmaxf(fminf(fmaf(f, a, b), 1.f), 0.f));
+    }
+    *reinterpret_cast<Vec<T, V>*>(y + i * V) = o;
+  }
+}
+
+// Softmax over the last, contiguous axis of a dense (rows, c) array (planer/layer.py:141-146: y = x - max; e = exp(y);
+// y - log(sum e); exp) -- channel softmax of pixel-major activations, or the class axis of 2-D logits.  One warp per row.
+template <typename T>
+__global__ void softmax_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int c) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const T* xr = x + r * c;
+    float m = -3.0e38f;
+    for (int i = lane; i < c; i += 32) m = fmaxf(m, ld_f(xr + i));
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    float sum = 0.f;
+    for (int i = lane; i < c; i += 32) sum += __expf(ld_f(xr + i) - m);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    const float lg = __logf(sum);
+    for (int i = lane; i < c; i += 32) st_f(y + r * c + i, __expf(ld_f(xr + i) - m - lg));
+  }
+}
+
 template <typename T, int V>
 __global__ void gap_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int HW, int C, int xld, int xcoff) {
   const int CV = C / V;
@@ -822,6 +859,28 @@ int plnr_eltwise(plnr_ctx* ctx, int op, int dtype, const void* x, const void* p0
           op, (const T*)x, (const T*)p0, (const T*)p1, (T*)y, total, c, alpha);
   })
   return plnr_after_launch(ctx, "eltwise");
+}
+
+int plnr_unary2(plnr_ctx* ctx, int op, int dtype, const void* x, void* y, int64_t n, float a, float b) {
+  PLNR_REQUIRE(ctx && x && y && n >= 0, "unary2: bad argument");
+  PLNR_REQUIRE(op == PLNR_EW_CLIP || op == PLNR_EW_HARDSIGMOID, "unary2: unknown op %d", op);
+  if (n == 0) return PLNR_OK;
+  DISPATCH_T(dtype, {
+    constexpr int V = VecWidth<T>::value;
+    if (n % V == 0 && aligned16(x) && aligned16(y))
+      unary2_kernel<T, V><<<grid_for(n / V, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(op, (const T*)x, (T*)y, n / V, a, b);
+    else
+      unary2_kernel<T, 1><<<grid_for(n, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(op, (const T*)x, (T*)y, n, a, b);
+  })
+  return plnr_after_launch(ctx, "unary2");
+}
+
+int plnr_softmax(plnr_ctx* ctx, int dtype, const void* x, void* y, int64_t rows, int c) {
+  PLNR_REQUIRE(ctx && x && y && rows >= 0 && c >= 1, "softmax: bad argument");
+  if (rows == 0) return PLNR_OK;
+  DISPATCH_T(dtype, softmax_kernel<T><<<grid_for(rows * 32, ctx->sm_count * 4), kThreads, 0, ctx->stream>>>(
+                        (const T*)x, (T*)y, rows, c);)
+  return plnr_after_launch(ctx, "softmax");
 }
 
 int plnr_global_avgpool(plnr_ctx* ctx, int dtype, const plnr_tensor* x, void* y) {

@@ -327,6 +327,14 @@ class Executor:
         if op == 'upsample':
             x, y, a = self._view(st.ins[0]), alloc(st.out), st.attrs
             return lambda: ops.upsample_into(x, y, a['fh'], a['fw'])
+        if op in ('hardsigmoid', 'clip'):
+            x, y, a = self._view(st.ins[0]), alloc(st.out), st.attrs
+            code = ops.EW_CLIP if op == 'clip' else ops.EW_HARDSIGMOID
+            p0, p1 = (a.get('min', 0), a.get('max', 1)) if op == 'clip' else (a.get('alpha', 0.2), a.get('beta', 0.5))
+            return lambda: ops.unary2(code, _dense(x), y, p0, p1)
+        if op == 'softmax':
+            x, y = self._view(st.ins[0]), alloc(st.out)
+            return lambda: ops.softmax_into(_dense(x), y)
         if op == 'averagepool':
             x, y, a = self._view(st.ins[0]), alloc(st.out), st.attrs
             return lambda: ops.avgpool_into(x, y, a['w'], a['pads'], a['strides'])

@@ -132,6 +132,32 @@ def Sigmoid(x):
     return ops.eltwise(ops.EW_SIGMOID, x, _like(x))
 
 
+def HardSigmoid(x, alpha=0.2, beta=0.5):
+    """planer/layer.py:66-69: max(min(x*alpha + beta, 1), 0)."""
+    x = _dense_rows(x)
+    return ops.unary2(ops.EW_HARDSIGMOID, x, _like(x), alpha, beta)
+
+
+def Clip(x, min=0, max=1):
+    """planer/layer.py:247-251: np.maximum(np.minimum(x, max), min)."""
+    x = _dense_rows(x)
+    return ops.unary2(ops.EW_CLIP, x, _like(x), min, max)
+
+
+def Softmax(x, axis=-1):
+    """planer/layer.py:141-146 along the channel axis of a 4-D tensor (axis 1) or the last axis of a 2-D one."""
+    if not isinstance(x, DeviceArray):
+        x = B.asarray(x)
+    if x.ndim == 4 and axis in (1, -3):
+        x = _dense_rows(x)
+    elif x.ndim == 2 and axis in (1, -1):
+        x = B.to_flat(x)
+    else:
+        raise NotImplementedError('Softmax: only the channel axis of 4-D tensors and the last axis of 2-D tensors are '
+                                  'implemented (got %d-D, axis %d)' % (x.ndim, axis))
+    return ops.softmax_into(x, _like(x))
+
+
 def Add(x1, x2):
     """planer/layer.py:93-95 for equal-shape operands (the residual adds of the hot path)."""
     x1, x2 = _dense_rows(x1), _dense_rows(x2)
@@ -266,6 +292,6 @@ layer_map = _HotPathOnly({
     'flatten': Flatten, 'sigmoid': Sigmoid, 'maxpool': Maxpool, 'upsample': UpSample,
     'concat': Concatenate, 'add': Add, 'gap': GlobalAveragePool, 'identity': Identity, 'return': Return,
     # SURVEY 8f rank 2 (the callers either side of the path): same kernels, same parity bar
-    'averagepool': AveragePool, 'convtranspose': ConvTranspose2d,
+    'averagepool': AveragePool, 'convtranspose': ConvTranspose2d, 'hardsigmoid': HardSigmoid, 'clip': Clip, 'softmax': Softmax,
 })
 """Hot-path subset of planer/layer.py:262-281."""

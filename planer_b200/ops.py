@@ -11,7 +11,7 @@ import numpy as np
 from . import _capi
 from . import backend as B
 from ._capi import (ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ALGO_AUTO, ALGO_TCGEN05, ALGO_DIRECT,
-                    EW_RELU, EW_LEAKY, EW_SIGMOID, EW_ADD, EW_SCALE_SHIFT)
+                    EW_RELU, EW_LEAKY, EW_SIGMOID, EW_ADD, EW_SCALE_SHIFT, EW_CLIP, EW_HARDSIGMOID)
 
 
 def out_size(n_in, pad_lo, pad_hi, k, dil, stride):
@@ -193,6 +193,23 @@ def eltwise(op, x, y, p0=None, p1=None, alpha=0.0):
     p = lambda a: a.ptr if a is not None else None
     _capi.check(B.lib().plnr_eltwise(B.ctx(), op, _capi.dtype_code(x.dtype), x.ptr, p(p0), p(p1), y.ptr, npix, c,
                                      float(alpha)), 'plnr_eltwise')
+    return y
+
+
+def unary2(op, x, y, a, b):
+    """CLIP (a = min, b = max) / HARDSIGMOID (a = alpha, b = beta) on dense arrays of equal size."""
+    _capi.check(B.lib().plnr_unary2(B.ctx(), op, _capi.dtype_code(x.dtype), x.ptr, y.ptr, x.size, float(a), float(b)), 'plnr_unary2')
+    return y
+
+
+def softmax_into(x, y):
+    """Softmax over the innermost stored axis: channels of a dense nhwc array, or the last axis of a flat array."""
+    if x.layout == 'nhwc':
+        assert x.ld == x.shape[1] and x.coff == 0, 'softmax needs dense rows'
+        c = x.shape[1]
+    else:
+        c = x.shape[-1]
+    _capi.check(B.lib().plnr_softmax(B.ctx(), _capi.dtype_code(x.dtype), x.ptr, y.ptr, x.size // c, c), 'plnr_softmax')
     return y
 
 

@@ -19,7 +19,7 @@ import numpy as np
 
 HOT_OPS = ('conv', 'dense', 'relu', 'leakyrelu', 'sigmoid', 'add', 'batchnorm', 'flatten', 'gap', 'concat',
            'maxpool', 'upsample', 'identity', 'return',
-           'averagepool', 'convtranspose')          # the same kernels either side of the path
+           'averagepool', 'convtranspose', 'hardsigmoid', 'clip', 'softmax')          # the same kernels either side of the path
 ACTS = {'relu': 1, 'leakyrelu': 2, 'sigmoid': 3}
 
 
@@ -139,7 +139,13 @@ def infer(values, nodes, host_consts=None):
                 raise ValueError('dense %r: x is %s, K is %s' % (nd.name, sh[0], sh[1]))
             out = (m, nn)
             nd.flops = 2 * m * nn * kk
-        elif k in ('relu', 'leakyrelu', 'sigmoid', 'batchnorm', 'identity'):
+        elif k in ('relu', 'leakyrelu', 'sigmoid', 'batchnorm', 'identity', 'hardsigmoid', 'clip'):
+            out = sh[0]
+        elif k == 'softmax':
+            ax = a.get('axis', -1)
+            if not ((len(sh[0]) == 4 and ax in (1, -3)) or (len(sh[0]) == 2 and ax in (1, -1))):
+                raise NotImplementedError('softmax %r: only the channel axis of 4-D tensors / the last axis of 2-D tensors '
+                                          '(got %d-D, axis %d)' % (nd.name, len(sh[0]), ax))
             out = sh[0]
         elif k == 'add':
             if sh[0] != sh[1]:
@@ -320,7 +326,7 @@ def fuse(values, nodes, outputs):
         elif k == 'batchnorm':
             st = emit(Step('scale_shift', nd.name, [x], out))
             st.bn = (nd.ins[1], nd.ins[2])
-        elif k in ('maxpool', 'averagepool', 'zero_stuff'):
+        elif k in ('maxpool', 'averagepool', 'zero_stuff', 'hardsigmoid', 'clip', 'softmax'):
             emit(Step(k, nd.name, [x], out, nd.attrs))
         elif k == 'upsample':
             emit(Step('upsample', nd.name, [x], out, nd.attrs))

@@ -92,6 +92,13 @@ OP_CASES = {
                                      {'w': (3, 3), 'pads': (1, 1, 1, 1), 'strides': (2, 2)}),
     'averagepool_k3s1p1_f16': lambda n: ('averagepool', [_x(_rng(n), (2, 16, 12, 12), 'float16')],
                                          {'w': (3, 3), 'pads': (1, 1, 1, 1), 'strides': (1, 1)}),
+    'hardsigmoid': lambda n: ('hardsigmoid', [_x(_rng(n), (2, 8, 5, 7), 'float32') * 3], {'alpha': 0.25, 'beta': 0.5}),
+    'hardsigmoid_f16': lambda n: ('hardsigmoid', [_x(_rng(n), (2, 8, 5, 7), 'float16') * 3], {}),
+    'clip': lambda n: ('clip', [_x(_rng(n), (2, 8, 5, 7), 'float32') * 3], {'min': -1.0, 'max': 2.0}),
+    'clip_f16': lambda n: ('clip', [_x(_rng(n), (2, 8, 5, 7), 'float16') * 3], {'min': 0, 'max': 6}),
+    'softmax_logits': lambda n: ('softmax', [_x(_rng(n), (5, 1000), 'float32') * 4], {'axis': -1}),
+    'softmax_logits_f16': lambda n: ('softmax', [_x(_rng(n), (3, 77), 'float16') * 4], {'axis': 1}),
+    'softmax_channels': lambda n: ('softmax', [_x(_rng(n), (2, 21, 6, 5), 'float32') * 2], {'axis': 1}),
     'convtranspose_k4s2p1': lambda n: _convt(n, (2, 16, 7, 9), (16, 8, 4, 4), strides=(2, 2), pads=(1, 1, 1, 1)),
     'convtranspose_k3s2_outpad': lambda n: _convt(n, (1, 8, 6, 6), (8, 12, 3, 3), strides=(2, 2), pads=(1, 1, 1, 1),
                                                    output_padding=(1, 1)),

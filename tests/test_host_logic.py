@@ -55,7 +55,7 @@ def test_no_cpu_fallback(lib):
     with pytest.raises(NotImplementedError):
         planer.core(np)
     with pytest.raises(NotImplementedError):
-        planer.layer_map['softmax']
+        planer.layer_map['lstm']
     assert planer.core(planer.b200) is planer.b200
 
 
@@ -242,11 +242,16 @@ def test_resnet18_executor_patterns_are_planned():
 
 
 def test_unknown_operator_raises_by_name():
-    model = {'input': ['x'], 'inits': [], 'layers': [['sm', 'softmax', {}]], 'flow': [['x', ['sm'], 'y']]}
+    model = {'input': ['x'], 'inits': [], 'layers': [['sm', 'logsoftmax', {}]], 'flow': [['x', ['sm'], 'y']]}
+    with pytest.raises(NotImplementedError, match='logsoftmax'):
+        P.compile_graph(model, {'x': (1, 10)})
+    with pytest.raises(NotImplementedError, match='logsoftmax'):
+        planer.Net().load_json(model['input'], model['inits'], model['layers'], model['flow'])
+    # softmax is implemented along the stored innermost axis only: anything else is refused by name, not computed wrongly
+    model['layers'][0][1] = 'softmax'
+    model['layers'][0][2] = {'axis': 0}
     with pytest.raises(NotImplementedError, match='softmax'):
         P.compile_graph(model, {'x': (1, 10)})
-    with pytest.raises(NotImplementedError, match='softmax'):
-        planer.Net().load_json(model['input'], model['inits'], model['layers'], model['flow'])
 
 
 def test_bad_pads_rejected_like_documented():
