@@ -45,7 +45,23 @@ class Executor:
         v = self.values[vid]
         if v.kind == 'input' and len(v.shape) == 4:
             return self._input_cpad(vid)
-        return v.shape[1]
+        return self._out_cpad(vid)
+
+    def _out_cpad(self, vid):
+        """Stored channels of a conv output that only leaves the graph (YOLO heads: 255 channels): padded to a multiple of 8
+        in fp16 so that rows stay 16-byte aligned and the conv epilogue keeps its vector path; the filter gets zero rows for
+        the pad channels and the NHWC -> NCHW exit reads the logical channels only."""
+        v = self.values[vid]
+        c = v.shape[1]
+        if self.dtype != np.float16 or len(v.shape) != 4 or c % 8 == 0 or not v.is_output:
+            return c
+        prod = [st for st in self.plan.steps if st.out == vid]
+        users = [st for st in self.plan.steps if vid in [self._root(r) for r in st.reads()]]
+        if len(prod) != 1 or prod[0].op != 'conv' or users or prod[0].shortcut is not None or prod[0].attrs.get('group', 1) != 1:
+            return c
+        if self._fused_stem_of(self._root(prod[0].ins[0])) is not None or self._stem_of(self._root(prod[0].ins[0])) is not None:
+            return c
+        return _round_up(c, 8)
 
     def _input_cpad(self, vid):
         """Graph inputs feeding only group-1 convs are channel-padded to a multiple of 16 in fp16 so that the
@@ -176,7 +192,8 @@ class Executor:
             if pool[b] is None:
                 pool[b] = B.empty((gp.buffer_bytes[b],), np.uint8).buf
             layout = 'nhwc' if len(shape) == 4 else 'flat'
-            self.arr[r] = DeviceArray(pool[b], shape, dt, layout)
+            ld = self._out_cpad(r) if layout == 'nhwc' else None
+            self.arr[r] = DeviceArray(pool[b], shape, dt, layout, ld=ld)
             return self.arr[r]
 
         # graph inputs: pixel-major staging filled by an eager transform at every forward
@@ -289,9 +306,19 @@ class Executor:
             if op == 'conv':
                 a = st.attrs
                 g = a['group']
+                kh, kw = K.shape[2], K.shape[3]
+                if y.layout == 'nhwc' and y.ld != y.shape[1]:
+                    # channel-padded graph output (_out_cpad): run the kernel on ld channels, pad filter rows are zero
+                    cop = y.ld
+                    wp = ops.pack_weight(K, x.shape[1], dt, co_pad=cop)
+                    pad1 = lambda v: None if v is None else ops.pad_vector(v, cop)
+                    scale, shift = pad1(scale), pad1(shift)
+                    y = DeviceArray(y.buf, (y.shape[0], cop) + y.shape[2:], dt, 'nhwc', ld=cop, offset=y.offset)
+                    self._keep += [wp, scale, shift]
+                    return lambda: ops.conv2d_into(x, wp, y, kh, kw, a['strides'], a['dilations'], a['pads'], 1,
+                                                   scale, shift, res, st.act, st.alpha, res_after_act=st.res_after)
                 wp = ops.pack_weight(K, x.shape[1] // g, dt)
                 self._keep.append(wp)
-                kh, kw = K.shape[2], K.shape[3]
                 return lambda: ops.conv2d_into(x, wp, y, kh, kw, a['strides'], a['dilations'], a['pads'], g,
                                                scale, shift, res, st.act, st.alpha, res_after_act=st.res_after)
             Kc = K.astype(dt)

@@ -46,13 +46,20 @@ def _epilogue(scale, shift, residual, act, alpha, res_after_act=False):
     return ep, keep
 
 
-def pack_weight(K, cin_pad, dtype):
-    """OIHW -> [Cout][kh][kw][cin_pad] in ``dtype`` (one-off per layer)."""
+def pack_weight(K, cin_pad, dtype, co_pad=None):
+    """OIHW -> [Cout][kh][kw][cin_pad] in ``dtype`` (one-off per layer); ``co_pad`` > Cout appends zero filters."""
     co, cg, kh, kw = K.shape
-    out = B.empty((co, kh, kw, cin_pad), dtype)
+    out = B.empty((co, kh, kw, cin_pad), dtype) if not co_pad or co_pad == co else B.zeros((co_pad, kh, kw, cin_pad), dtype)
     _capi.check(B.lib().plnr_pack_conv_weight(B.ctx(), K.ptr, _capi.dtype_code(K.dtype), out.ptr,
                                               _capi.dtype_code(dtype), co, cg, kh, kw, cin_pad),
                 'plnr_pack_conv_weight')
+    return out
+
+
+def pad_vector(v, n):
+    """fp32 per-channel vector -> length n, zero-filled tail (channel-padded conv outputs)."""
+    out = B.zeros((n,), v.dtype)
+    out[0:v.shape[0]] = v
     return out
 
 

@@ -31,12 +31,18 @@ print(json.dumps({'model': 'yolov3-416 fp16', 'batch': n, 'ms_per_step': per, 'i
                   'tflops': flops / per / 1e9, 'gflop_per_step': flops / 1e9, 'launches_per_step': len(ex.launches)}))
 # per-kind split
 ex._load_inputs([xs[0]])
-kinds = {}
-for fn, kind in zip(ex.launches, ex.kinds):
+kinds, per_step = {}, []
+for fn, kind, name in zip(ex.launches, ex.kinds, ex.names):
     e0, e1 = C.c_void_p(), C.c_void_p()
     lib.plnr_event_create(C.byref(e0)); lib.plnr_event_create(C.byref(e1))
     lib.plnr_event_record(ctx, e0); fn(); lib.plnr_event_record(ctx, e1)
     B.synchronize()
     t = C.c_float(); lib.plnr_event_elapsed_ms(e0, e1, C.byref(t))
     kinds[kind] = kinds.get(kind, 0.0) + t.value
+    per_step.append((t.value, kind, name))
 print('eager per-kind ms (includes launch gaps):', {k: round(v, 3) for k, v in kinds.items()})
+fl = {nd.name: nd.flops for nd in ex.plan.nodes}
+print('slowest launches (ms, TFLOP/s, fused step):')
+for t, kind, name in sorted(per_step, reverse=True)[:14]:
+    f = fl.get(name.split('+')[0], 0)
+    print('  %.3f  %6.0f  %s %s' % (t, f / t / 1e9 if t > 0 else 0, kind, name[:70]))
