@@ -337,7 +337,10 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     long long t_tfull = 0;
     const long long t_all0 = clock64();
     const int nchunks = p.n_tile >> 5, half = (nchunks + 1) >> 1;
-    const int c_begin = eg * half * 32, c_end = min(nchunks, (eg + 1) * half) * 32;
+    // one 32-channel chunk per tile (Cout <= 32): the two column groups take the tiles in turn (group = accumulator buffer)
+    // instead of one group idling -- such layers (YOLO's 3 -> 32 and 64 -> 32 convs) are epilogue-bound
+    const bool alternate = nchunks == 1;
+    const int c_begin = alternate ? 0 : eg * half * 32, c_end = alternate ? 32 : min(nchunks, (eg + 1) * half) * 32;
     const bool has_res = p.res != nullptr;
     const uint32_t HvWv = (uint32_t)p.HvWv, uWv = (uint32_t)Wv, uMv = (uint32_t)p.Mv;
     uint8_t* st_o = stage + (warp - 4) * 1024;
@@ -375,7 +378,7 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             dst[2 * h + i] = *reinterpret_cast<const uint4*>(p.res + (size_t)g.row[i] * p.rld + p.rcoff + cb + h * 16 + piece * 8);
     };
     Geo gn = tile_geo(unit < p.num_tiles ? unit : 0);
-    if (has_res && p.vec_ok && c_begin < c_end && unit < p.num_tiles) {
+    if (has_res && p.vec_ok && c_begin < c_end && unit < p.num_tiles && (!alternate || eg == 0)) {
       const int cb = (int)fast_div((uint32_t)unit, p.div_mt) * p.n_tile + c_begin;
       if (cb + 32 <= p.Cout) fetch_res(gn, cb, rvp);
     }
@@ -407,7 +410,7 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       const int tile_n = tile + nunits;
       if (tile_n < p.num_tiles) {
         gn = tile_geo(tile_n);
-        if (has_res && p.vec_ok && c_begin < c_end) {
+        if (has_res && p.vec_ok && c_begin < c_end && (!alternate || ((it + 1) & 1u) == (uint32_t)eg)) {
           const int cb = (int)fast_div((uint32_t)tile_n, p.div_mt) * p.n_tile + c_begin;
           if (cb + 32 <= p.Cout) fetch_res(gn, cb, rvp);
         }
@@ -418,20 +421,21 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       t_tfull += clock64() - tt0;
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + a * (uint32_t)p.n_tile;
-      if (c_begin >= c_end) {               // nothing to read for this group (n_tile == 32): release at once
+      const int ce_ = (alternate && (it & 1u) != (uint32_t)eg) ? c_begin : c_end;      // not this group's tile
+      if (c_begin >= ce_) {               // nothing to read for this group: release at once
         ptx::tc_fence_before();
         if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
         else ptx::mbar_arrive(bar_tempty + 8 * a);
       }
-      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+      for (int c0 = c_begin; c0 < ce_; c0 += 32) {
         __syncwarp();
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(t_row + c0, v);
         const int cb = n0 + c0;
         const bool fast = p.vec_ok && (cb + 32 <= p.Cout);
-        if (has_res && p.vec_ok && c0 + 32 < c_end && cb + 64 <= p.Cout) fetch_res(g, cb + 32, rvn);   // one chunk ahead
+        if (has_res && p.vec_ok && c0 + 32 < ce_ && cb + 64 <= p.Cout) fetch_res(g, cb + 32, rvn);   // one chunk ahead
         ptx::tmem_ld_wait();
-        if (c0 + 32 >= c_end) {
+        if (c0 + 32 >= ce_) {
           ptx::tc_fence_before();
           if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
           else ptx::mbar_arrive(bar_tempty + 8 * a);
