@@ -33,8 +33,8 @@ with open('profiles/%s_launches_summary.md' % tag, 'w') as f:
     if len(idx) >= 3:
         fw = min((launches[a:b] for a, b in zip(idx[:-1], idx[1:])), key=len)     # a forward with no build kernels in between
         f.write('\nOne forward (%d launches), us: %s = %.1f us\n' % (len(fw), ', '.join('%.1f' % v for _, v in fw), sum(v for _, v in fw)))
-        conv = sum(v for k, v in fw if k.startswith(('conv_', 'stem_pool')))
-        f.write('Share of the tcgen05 conv kernels (stem_pool + conv_stack + conv_shift + conv_igemm) in that forward: %.1f%% '
+        conv = sum(v for k, v in fw if k.startswith(('conv_', 'stem_pool', 'gap_dense')))
+        f.write('Share of the roofline kernel set (stem_pool + conv_stack + conv_shift + conv_igemm + gap_dense: every conv / dense layer) in that forward: %.1f%% '
                 '(bench.py `roofline.kernel_share_of_step`, timed live with CUDA events, must agree with this share).\n'
                 % (100 * conv / sum(v for _, v in fw)))
 print('wrote profiles/%s_launches_summary.md (%d launches)' % (tag, len(launches)))
