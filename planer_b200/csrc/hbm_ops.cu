@@ -3,6 +3,7 @@
 // All are coalesced, 16-byte-vectorised streaming kernels over the pixel-major (NHWC) layout; their
 // roofline is HBM bandwidth (algorithmic bytes = (elements_in + elements_out) * sizeof(dtype)).
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace {
 
@@ -615,6 +616,208 @@ __global__ void __launch_bounds__(512) gap_dense_kernel(const T* __restrict__ x,
   }
 }
 
+// The same tail with the CTA's slice of the weight matrix BULK-COPIED to shared memory (one cp.async.bulk of och*C elements,
+// issued before the pooling phase and waited for after it): the dense phase then has no global-memory round trips at all.
+// ncu on the kernel above: its time is the number of dependent load rounds (pixels, then weights), not bytes or FLOPs.
+template <typename T, int V, int IMGS, int SPLIT, int PB, int OPW>
+__global__ void __launch_bounds__(512) gap_dense_smem_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                              const float* __restrict__ scale, const float* __restrict__ shift,
+                                                              T* __restrict__ y, int N, int HW, int C, int xld, int xcoff,
+                                                              int OUT, int och, int act, float alpha) {
+  extern __shared__ __align__(128) uint8_t gd_smem[];
+  float* pooled = reinterpret_cast<float*>(gd_smem);                                   // [IMGS][C]
+  T* wsm = reinterpret_cast<T*>(gd_smem + (size_t)IMGS * C * sizeof(float));           // [och][C]
+  const uint32_t bar = ptx::smem_u32(gd_smem + (size_t)IMGS * C * sizeof(float) + (size_t)och * C * sizeof(T));
+  const int n0 = blockIdx.x * IMGS, o0 = blockIdx.y * och;
+  const int o_end = min(o0 + och, OUT);
+  if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)((size_t)(o_end - o0) * C * sizeof(T));
+    ptx::mbar_arrive_expect_tx(bar, bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ptx::smem_u32(wsm)), "l"(reinterpret_cast<uint64_t>(w + (size_t)o0 * C)), "r"(bytes), "r"(bar) : "memory");
+  }
+  const int CV = C / V;
+  const float inv = 1.f / (float)HW;
+  const int items = IMGS * CV * SPLIT;
+  for (int idx = threadIdx.x; idx < ((items + 31) & ~31); idx += blockDim.x) {      // whole warps: shuffles below
+    const int item = idx / SPLIT, part = idx - item * SPLIT;
+    const int img = item / CV, cv = item - img * CV;
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    if (idx < items && n0 + img < N) {
+      const T* xp = x + (size_t)(n0 + img) * HW * xld + xcoff + cv * V;
+      for (int p0 = part; p0 < HW; p0 += PB * SPLIT) {
+        Vec<T, V> v[PB];
+#pragma unroll
+        for (int j = 0; j < PB; ++j)
+          if (p0 + j * SPLIT < HW) v[j] = *reinterpret_cast<const Vec<T, V>*>(xp + (size_t)(p0 + j * SPLIT) * xld);
+#pragma unroll
+        for (int j = 0; j < PB; ++j)
+          if (p0 + j * SPLIT < HW) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] += ld_f(&v[j].v[k]);
+          }
+      }
+    }
+#pragma unroll
+    for (int d = 1; d < SPLIT; d <<= 1) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
+    }
+    if (part == 0 && idx < items) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) pooled[img * C + cv * V + k] = acc[k] * inv;
+    }
+  }
+  __syncthreads();
+  while (!ptx::mbar_try_wait(bar, 0)) {}
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int ob = o0 + warp * OPW; ob < o_end; ob += nwarps * OPW) {
+    float acc[OPW][IMGS];
+#pragma unroll
+    for (int j = 0; j < OPW; ++j)
+#pragma unroll
+      for (int i = 0; i < IMGS; ++i) acc[j][i] = 0.f;
+    for (int cv = lane; cv < CV; cv += 32) {
+      Vec<T, V> wv[OPW];
+#pragma unroll
+      for (int j = 0; j < OPW; ++j)
+        wv[j] = *reinterpret_cast<const Vec<T, V>*>(wsm + (size_t)(min(ob + j, o_end - 1) - o0) * C + cv * V);
+#pragma unroll
+      for (int i = 0; i < IMGS; ++i) {
+        float pf[V];
+#pragma unroll
+        for (int k = 0; k < V; k += 4)
+          *reinterpret_cast<float4*>(&pf[k]) = *reinterpret_cast<const float4*>(pooled + i * C + cv * V + k);
+#pragma unroll
+        for (int j = 0; j < OPW; ++j)
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[j][i] = fmaf(ld_f(&wv[j].v[k]), pf[k], acc[j][i]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < OPW; ++j) {
+#pragma unroll
+      for (int i = 0; i < IMGS; ++i) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) acc[j][i] += __shfl_xor_sync(0xffffffffu, acc[j][i], d);
+      }
+      const int o = ob + j;
+      if (o < o_end && lane < IMGS && n0 + lane < N) {
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < IMGS; ++i) v = lane == i ? acc[j][i] : v;
+        v = fmaf(v, scale ? scale[o] : 1.f, shift ? shift[o] : 0.f);
+        st_f(y + (size_t)(n0 + lane) * OUT + o, plnr_apply_act(v, act, alpha));
+      }
+    }
+  }
+}
+
+// fp16 tail on the (legacy) warp-level tensor-core instruction: the CUDA-core versions above execute 8.6 M warp instructions
+// (ncu: issue slots 52 % busy -- 2 M FMA, 0.5 M half->float conversions of the weights, 1.3 M shuffle-reduction steps), i.e.
+// they are INSTRUCTION-bound at ~20 us for 65 MFLOP.  Here a CTA pools 8 images to fp16 (the reference's GlobalAveragePool
+// returns an fp16 array too) and each warp computes a 16-feature x 8-image block with mma.sync.m16n8k16 (fp32 accumulate):
+// D[f, n] = sum_k W[f, k] * pooled[n, k].  A fragments come straight from the (L2-resident, row-major) weight matrix, B
+// fragments from the pooled vectors in shared memory (row pitch C + 8 halves: conflict-free).  tcgen05 would need a
+// 128-row tile for an 8-column problem; this op is 0.014 % of the step's FLOPs.
+template <int IMGS>
+__global__ void __launch_bounds__(512) gap_dense_mma_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift,
+                                                             __half* __restrict__ y, int N, int HW, int C, int xld, int xcoff,
+                                                             int OUT, int och, int act, float alpha) {
+  static_assert(IMGS == 8, "the n8 dimension of mma.m16n8k16 is the image group");
+  extern __shared__ __align__(16) uint8_t gm_smem[];
+  __half* pooled = reinterpret_cast<__half*>(gm_smem);          // [8][C + 8]
+  const int pitch = C + 8;
+  const int n0 = blockIdx.x * IMGS, o0 = blockIdx.y * och;
+  const int o_end = min(o0 + och, OUT);
+  constexpr int V = 8, SPLIT = 2, PB = 13;
+  const int CV = C / V;
+  const float inv = 1.f / (float)HW;
+  const int items = IMGS * CV * SPLIT;
+  for (int idx = threadIdx.x; idx < ((items + 31) & ~31); idx += blockDim.x) {
+    const int item = idx / SPLIT, part = idx - item * SPLIT;
+    const int img = item / CV, cv = item - img * CV;
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    if (idx < items && n0 + img < N) {
+      const __half* xp = x + (size_t)(n0 + img) * HW * xld + xcoff + cv * V;
+      for (int p0 = part; p0 < HW; p0 += PB * SPLIT) {
+        Vec<__half, V> v[PB];
+#pragma unroll
+        for (int j = 0; j < PB; ++j)
+          if (p0 + j * SPLIT < HW) v[j] = *reinterpret_cast<const Vec<__half, V>*>(xp + (size_t)(p0 + j * SPLIT) * xld);
+#pragma unroll
+        for (int j = 0; j < PB; ++j)
+          if (p0 + j * SPLIT < HW) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] += ld_f(&v[j].v[k]);
+          }
+      }
+    }
+#pragma unroll
+    for (int d = 1; d < SPLIT; d <<= 1) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
+    }
+    if (part == 0 && idx < items) {
+      Vec<__half, V> o;
+#pragma unroll
+      for (int k = 0; k < V; ++k) o.v[k] = __float2half_rn(acc[k] * inv);
+      *reinterpret_cast<Vec<__half, V>*>(pooled + img * pitch + cv * V) = o;
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int gid = lane >> 2, tig = lane & 3;               // fragment coordinates of mma.m16n8k16
+  for (int m0 = o0 + warp * 16; m0 < o_end; m0 += nwarps * 16) {
+    const int r0 = min(m0 + gid, OUT - 1), r1 = min(m0 + gid + 8, OUT - 1);
+    const uint32_t* w0 = reinterpret_cast<const uint32_t*>(w + (size_t)r0 * C) + tig;
+    const uint32_t* w1 = reinterpret_cast<const uint32_t*>(w + (size_t)r1 * C) + tig;
+    const uint32_t* pb = reinterpret_cast<const uint32_t*>(pooled + gid * pitch) + tig;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    constexpr int U = 8;                                   // k-steps of 16 whose loads are in flight together
+    for (int k0 = 0; k0 < C; k0 += 16 * U) {
+      uint32_t a[U][4];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int kw = (k0 + 16 * u) >> 1;                 // 32-bit word index of column k
+        if (k0 + 16 * u < C) {
+          a[u][0] = __ldg(w0 + kw); a[u][1] = __ldg(w1 + kw); a[u][2] = __ldg(w0 + kw + 4); a[u][3] = __ldg(w1 + kw + 4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k0 + 16 * u < C) {
+          const int kw = (k0 + 16 * u) >> 1;
+          const uint32_t b0 = pb[kw], b1 = pb[kw + 4];
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)
+                       : "r"(a[u][0]), "r"(a[u][1]), "r"(a[u][2]), "r"(a[u][3]), "r"(b0), "r"(b1));
+        }
+      }
+    }
+    // D fragment: (feature m0 + gid, images 2*tig, 2*tig + 1) and (feature m0 + gid + 8, same images)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int f = m0 + gid + 8 * h;
+      if (f < o_end) {
+        const float sc = scale ? scale[f] : 1.f, sf = shift ? shift[f] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int n = n0 + 2 * tig + j;
+          if (n < N) y[(size_t)n * OUT + f] = __float2half_rn(plnr_apply_act(fmaf(h ? (j ? d3 : d2) : (j ? d1 : d0), sc, sf), act, alpha));
+        }
+      }
+    }
+  }
+}
+
 static inline bool view_vec_ok(const plnr_tensor* t, int V, size_t esz) {
   return t->c % V == 0 && t->ld % V == 0 && t->coff % V == 0 && aligned16(t->ptr) && (V * esz == 16);
 }
@@ -910,8 +1113,43 @@ int plnr_gap_dense_fwd(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const voi
     constexpr int V = VecWidth<T>::value;
     PLNR_REQUIRE(view_vec_ok(x, V, sizeof(T)) && aligned16(w) && x->c % V == 0,
                  "gap_dense: channels (%d) must be a multiple of %d and pointers 16-byte aligned", x->c, V);
-    const size_t smem = (size_t)IMGS * x->c * sizeof(float);
-    PLNR_REQUIRE(smem <= 96 * 1024, "gap_dense: %d channels do not fit the pooled-vector stage", x->c);
+    const size_t pooled_bytes = (size_t)IMGS * x->c * sizeof(float);
+    PLNR_REQUIRE(pooled_bytes <= 96 * 1024, "gap_dense: %d channels do not fit the pooled-vector stage", x->c);
+    const size_t row_bytes = (size_t)x->c * sizeof(T);
+    // (1) weights in shared memory: images in groups of 8, output features in slices of <= 160 KB of weight rows, about one
+    //     CTA per SM; (2) otherwise the streaming kernel.
+    constexpr int IMGS8 = 8;
+    const int gx8 = (x->n + IMGS8 - 1) / IMGS8;
+    int gy8 = ctx->sm_count / gx8;
+    if (gy8 < 1) gy8 = 1;
+    if (gy8 > 16) gy8 = 16;
+    int och8 = (out_features + gy8 - 1) / gy8;
+    och8 = (och8 + OPW - 1) / OPW * OPW;
+    const size_t smem8 = (size_t)IMGS8 * x->c * sizeof(float) + (size_t)och8 * row_bytes + 16;
+    const char* nomma = getenv("PLNR_GAP_DENSE_NO_MMA");
+    if (sizeof(T) == 2 && x->c % 16 == 0 && (size_t)IMGS8 * (x->c + 8) * 2 <= 48 * 1024 && !(nomma && atoi(nomma))) {
+      // fp16: 16 image groups x feature slices of a multiple of 16, about one CTA per SM
+      int gym = ctx->sm_count / gx8;
+      if (gym < 1) gym = 1;
+      int ochm = (out_features + gym - 1) / gym;
+      ochm = (ochm + 15) / 16 * 16;
+      gym = (out_features + ochm - 1) / ochm;
+      const size_t smemm = (size_t)IMGS8 * (x->c + 8) * sizeof(__half);
+      gap_dense_mma_kernel<IMGS8><<<dim3(gx8, gym), 512, smemm, ctx->stream>>>(
+          (const __half*)x->ptr, (const __half*)w, scale, shift, (__half*)y, x->n, HW, x->c, x->ld, x->coff, out_features, ochm,
+          act, alpha);
+      return plnr_after_launch(ctx, "gap_dense");
+    }
+    const char* nos = getenv("PLNR_GAP_DENSE_STREAM");
+    if (smem8 <= 200 * 1024 && !(nos && atoi(nos))) {
+      gy8 = (out_features + och8 - 1) / och8;
+      auto kern8 = gap_dense_smem_kernel<T, V, IMGS8, SPLIT, PB, OPW>;
+      PLNR_CHECK_CUDA(cudaFuncSetAttribute(kern8, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
+      kern8<<<dim3(gx8, gy8), 512, smem8, ctx->stream>>>(
+          (const T*)x->ptr, (const T*)w, scale, shift, (T*)y, x->n, HW, x->c, x->ld, x->coff, out_features, och8, act, alpha);
+      return plnr_after_launch(ctx, "gap_dense");
+    }
+    const size_t smem = pooled_bytes;
     // ~one CTA per SM: images in groups of IMGS, output features in slices.  Every slice re-reads its images' pixels and
     // every image group re-reads the weights (both from L2): 32 x 4 for ResNet-18 at batch 128 keeps the two about equal.
     const int gx = (x->n + IMGS - 1) / IMGS;

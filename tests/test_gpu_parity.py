@@ -354,7 +354,8 @@ def test_map_pipelined_stream_equals_blocking_calls(planer):
     assert np.array_equal(keep, first)
 
 
-@pytest.mark.parametrize('cfg', [(5, 24, 3, 3, 37, np.float16), (9, 512, 7, 7, 1000, np.float16),
+@pytest.mark.parametrize('cfg', [(5, 24, 3, 3, 37, np.float16), (9, 512, 7, 7, 1000, np.float16), (11, 64, 2, 3, 37, np.float16),
+                                 (130, 128, 1, 1, 300, np.float16),
                                  (3, 8, 1, 5, 3, np.float16), (6, 20, 4, 4, 70, np.float32)])
 def test_gap_dense_tail_kernel_vs_oracle(planer, cfg):
     """gap -> flatten -> dense in one launch (planer/layer.py:77-78, :59, :15-18) on ragged sizes: image groups and
