@@ -114,7 +114,7 @@ def run_reference(args, rank):
                                    'batch 8 per step'},
             'cpu_baseline': cb,
             'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def per_kernel_profile(net, x_dev, flops_by_step, reps=3):
@@ -147,7 +147,27 @@ def per_kernel_profile(net, x_dev, flops_by_step, reps=3):
     return [{'kind': k, 'name': nm, 'ms': t} for k, nm, t in zip([in_kind] + list(ex.kinds), [in_name] + list(ex.names), best)]
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything a library prints on fd 1 while the bench runs (NCCL's version banner, for one) goes to stderr: stdout carries
+    exactly ONE line, the JSON result."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)
@@ -309,7 +329,7 @@ def main():
                     'steps': e2e_steps, 'api': 'for y in net.map(batches): pinned numpy batch in, numpy logits out, 2 batches in flight',
                     'blocking_call': {'value': e2e_blocking, 'unit': UNIT, 'api': 'y = net(x) per batch (upload in two halves, one synchronisation)'}},
             'roofline': roofline, 'cpu_baseline': cb}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 if __name__ == '__main__':
