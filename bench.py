@@ -90,13 +90,21 @@ def cpu_baseline_run(steps, warmup, batch=8):
     model, blob = zoo.resnet18(0)
     net = oracle.build_net(model, blob)
     x = np.random.default_rng(1).standard_normal((batch,) + IN_SHAPE).astype(np.float32)
-    for _ in range(warmup):
-        net(x.copy())
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        net(x.copy())
-    dt = time.perf_counter() - t0
     cores = len(os.sched_getaffinity(0))
+    # torchrun exports OMP_NUM_THREADS=1, which OpenBLAS obeys at import: give the reference path every host core back
+    import contextlib
+    try:
+        from threadpoolctl import threadpool_limits
+        blas = threadpool_limits(limits=cores)
+    except ImportError:
+        blas = contextlib.nullcontext()
+    with blas:
+        for _ in range(warmup):
+            net(x.copy())
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            net(x.copy())
+        dt = time.perf_counter() - t0
     return {'value': batch * steps / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
             'sample': 'ResNet-18 fp32 (numpy fp16 matmul has no BLAS: 18 s/img) batch %d x %d forwards, numpy %s '
                       'BLAS threads=all cores' % (batch, steps, np.__version__)}, dt / steps
