@@ -84,9 +84,23 @@ def graph_cases():
     np.savez_compressed(os.path.join(OUT, 'graphs.npz'), **out)
 
 
+def tile_cases():
+    """The reference's sliding-window decorator (planer/util.py:291-348) around deterministic per-window functions."""
+    from tests.cases import TILE_CASES, make_tile_case
+    out = {}
+    for name in TILE_CASES:
+        img, kw, fn = make_tile_case(name)
+        y = planer.util.tile(progress=lambda *a: None, **kw)(fn)(img.copy())
+        out[name] = np.ascontiguousarray(y)
+        out[name + '.sha'] = np.array(digest(img))
+    np.savez_compressed(os.path.join(OUT, 'tile.npz'), **out)
+    print('tile.npz', len(TILE_CASES), 'cases')
+
+
 # ``--add``: keep the fixtures already in the .npz files and run the reference only for cases that are not there yet
 INCREMENTAL = '--add' in sys.argv
 
 if __name__ == '__main__':
+    tile_cases()
     op_cases()
     graph_cases()

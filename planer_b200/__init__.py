@@ -19,6 +19,8 @@ from .layer import wrap, layer_map
 from .net import Net
 from .io import read_net, from_model
 from . import zoo
+from . import util
+from .util import tile, resize
 
 InferenceSession = read_net          # planer/__init__.py:7
 

@@ -163,3 +163,36 @@ def rel_err(y, ref):
     """Range-relative error  max|y - ref| / max|ref|  (SURVEY 8d primary metric)."""
     y, ref = np.asarray(y, np.float64), np.asarray(ref, np.float64)
     return float(np.abs(y - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+# ---------------------------------------------------------------------------------------------
+# sliding-window inference (planer/util.py:291-348): name -> (image shape, decorator kwargs, per-window function id)
+# ---------------------------------------------------------------------------------------------
+def tile_fn(kind):
+    """Deterministic per-window functions standing in for a network: resolution-preserving, x2 up, /2 down, HWC -> HW."""
+    if kind == 'same':
+        return lambda im: im * np.float32(0.5) + np.float32(1)
+    if kind == 'up2':
+        return lambda im: np.repeat(np.repeat(im, 2, axis=0), 2, axis=1) * np.float32(0.25)
+    if kind == 'down2':
+        return lambda im: im[::2, ::2] + np.float32(3)
+    if kind == 'gray':
+        return lambda im: im.mean(axis=2)
+    raise KeyError(kind)
+
+
+TILE_CASES = {
+    'grid_3x4': ((150, 210), dict(window=64, margin=0.25), 'same'),
+    'rgb_margin_int': ((97, 131, 3), dict(window=48, margin=7), 'same'),
+    'up2_rgb': ((80, 100, 3), dict(window=40, margin=0.2), 'up2'),
+    'down2': ((128, 96), dict(window=64, margin=0.25), 'down2'),
+    'sample_half': ((160, 120), dict(sample=0.5, window=32, margin=0.25), 'same'),
+    'sample_tuple_rgb': ((90, 70, 3), dict(sample=(120, 100), window=64, margin=0.1), 'gray'),
+    'single_window_glob': ((50, 70), dict(window=128, glob=32), 'same'),
+    'single_window_sampled': ((50, 70, 3), dict(sample=1.5, window=256, glob=16), 'up2'),
+}
+
+
+def make_tile_case(name):
+    shape, kw, kind = TILE_CASES[name]
+    return _rng(name).standard_normal(shape).astype('float32') * 10, dict(kw), tile_fn(kind)

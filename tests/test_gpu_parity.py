@@ -407,3 +407,33 @@ def test_shift_conv_cta_pair_equals_single_cta(planer, cfg):
     if with_res:
         ref = oracle.add(ref, r.get().astype(np.float32))
     assert rel_err(outs['2'], oracle.relu(ref)) <= 1e-2
+
+
+def test_tiled_inference_windows_on_the_batch_axis(planer):
+    """the sliding-window decorator (planer/util.py:291-348) around a network.  All windows stacked on
+    the batch axis of ONE forward give what one forward per window gives, and both match the oracle network under the
+    same decorator (fp32, 1e-3)."""
+    model, blob = cases.get_model('decoder')
+    net = planer.from_model(model, blob)
+    onet = oracle.build_net(model, blob)
+    img = np.random.default_rng(3).standard_normal((96, 120, 3)).astype(np.float32)
+    chw = lambda hwc: np.ascontiguousarray(hwc.transpose(2, 0, 1))
+    hwc = lambda c: np.ascontiguousarray(c.transpose(1, 2, 0))
+    kw = dict(window=32, margin=0.25, progress=lambda *a: None)
+    forwards = []
+
+    def per_window(win):
+        forwards.append(1)
+        return hwc(net(chw(win)[None])[0])
+
+    def all_windows(batch):
+        forwards.append(batch.shape[0])
+        return np.stack([hwc(y) for y in net(np.ascontiguousarray(batch.transpose(0, 3, 1, 2)))])
+
+    y1 = planer.tile(**kw)(per_window)(img)
+    n1 = len(forwards)
+    y2 = planer.tile(batched=True, **kw)(all_windows)(img)
+    assert n1 == 20 and forwards[n1:] == [20]
+    ref = planer.tile(**kw)(lambda win: hwc(onet(chw(win)[None].copy())[0]))(img)
+    assert y1.shape == ref.shape == (96, 120, 3)
+    assert rel_err(y1, ref) <= 1e-3 and rel_err(y2, ref) <= 1e-3 and rel_err(y1, y2) <= 1e-4

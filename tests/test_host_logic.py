@@ -388,3 +388,36 @@ def test_decoder_plan_expands_convtranspose_into_zero_stuff_plus_conv():
     assert shp['up.stuff'] == (2, 64, 35, 43) and shp['up'] == (2, 32, 32, 40) and shp['out'] == (2, 3, 32, 40)
     # 2 * N * Cout * Cin * kh * kw * OH * OW of the stride-1 conv over the stuffed buffer (what the kernels execute)
     assert [n.flops for n in gp.nodes if n.name == 'up'] == [2 * 2 * 32 * 64 * 16 * 32 * 40]
+
+
+# ---------------------------------------------------------------------------------------------
+# sliding-window inference
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('name', list(cases.TILE_CASES))
+def test_tile_decorator_equals_the_reference(name):
+    """planer_b200.util.tile vs the reference's decorator (planer/util.py:291-348) on the same seeded image and per-window
+    function: bit-identical (same float32 arithmetic, same window grid, same uint16 blending weights) -- window by window
+    and with all windows stacked on the batch axis (``batched=True``)."""
+    import hashlib
+    from planer_b200 import util
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'tile.npz'))
+    img, kw, fn = cases.make_tile_case(name)
+    assert hashlib.sha256(img.tobytes()).hexdigest() == str(gold[name + '.sha'])
+    seen = []
+    y = util.tile(progress=lambda i, n: seen.append((i, n)), **kw)(fn)(img.copy())
+    ref = gold[name]
+    assert y.shape == ref.shape and y.dtype == ref.dtype and y.tobytes() == ref.tobytes()
+    if seen:
+        assert seen == [(i + 1, seen[0][1]) for i in range(seen[0][1])]          # one progress call per window, in order
+    calls = []
+
+    def stacked(batch):
+        calls.append(batch.shape[0])
+        return np.stack([fn(b) for b in batch])
+    yb = util.tile(batched=True, **kw)(stacked)(img.copy())
+    assert len(calls) == 1 and calls[0] == max(len(seen), 1)
+    assert yb.tobytes() == ref.tobytes()
+    # per-call keyword overrides, like the reference's wrapper
+    y2 = util.tile(window=9999)(fn)(img.copy(), **{**kw, 'progress': lambda *a: None})
+    assert y2.tobytes() == ref.tobytes()
