@@ -267,7 +267,8 @@ def test_bad_pads_rejected_like_documented():
 # chaining, liveness).  The table/array module are injected by the test; the package itself has no CPU path.
 # ---------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize('name', ['readme_f32', 'readme_f16', 'resnet18_small_f32', 'yolov3_quarter_f32'])
+@pytest.mark.parametrize('name', ['readme_f32', 'readme_f16', 'resnet18_small_f32', 'yolov3_quarter_f32', 'decoder_f32',
+                                  'decoder_f16'])
 def test_net_plumbing_bit_exact_with_injected_numpy_table(name):
     g = np.load(os.path.join(GOLD, 'graphs.npz'))
     model, blob, x, half = cases.make_graph_case(name)
@@ -281,6 +282,13 @@ def test_net_plumbing_bit_exact_with_injected_numpy_table(name):
     for i, t in enumerate(ys):
         assert cases.sample(t).tobytes() == g['%s.out%d' % (name, i)].tobytes()
     assert set(net.timer) >= {'conv'}
+    # Net.map (a stream of batches) degrades to one call per batch off the GPU path: same results, same order
+    xs = [x.copy(), x[:1].copy(), x.copy()]
+    got = list(net.map(iter(xs)))
+    for xi, gi in zip(xs, got):
+        want = net(xi.copy())
+        for a, b in zip(gi if isinstance(gi, tuple) else (gi,), want if isinstance(want, tuple) else (want,)):
+            assert np.asarray(a).tobytes() == np.asarray(b).tobytes()
 
 
 def test_c1_single_conv_plumbing_bit_exact():
