@@ -182,6 +182,10 @@ int plnr_flip_weight(plnr_ctx* ctx, int dtype, const void* w, void* out, int ci,
 /* Integer-factor nearest upsample, zero pixel shift (planer/util.py:184-192 with the default mode
  * strings of planer/util.py:212). */
 int plnr_upsample_nearest(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y, int fh, int fw);
+/* Bilinear upsample by integer factors >= 2 (planer/util.py:121-153, upsample_blinear): edge-replicated input, 4-tap blend
+ * with the (4, fh*fw) fp32 weight table `wmat` (device pointer; the reference's make_upmat, planer/util.py:121-131). */
+int plnr_upsample_linear(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y, int fh, int fw,
+                         const float* wmat);
 /* Channel-slice copy x -> y (same n,h,w,c; different ld/coff): the building block of
  * np.concatenate(axis=1) (planer/layer.py:90-91). */
 int plnr_copy_channels(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y);

@@ -301,14 +301,54 @@ def upsample_nearest(x, k, trans_mode='half-pixel', round_mode='round_prefer_cei
                             _nearest_shift(k[1], trans_mode, round_mode))
 
 
+def _bilinear_taps(k):
+    """(4, kh*kw) blend weights of the four corners (left-top, right-top, left-bottom, right-bottom) for every output position
+    inside one input cell -- computed in FLOAT16 like the reference.  reference: planer/util.py:121-131 (make_upmat);
+    kh == 1 or kw == 1 degenerate to two taps there and are not restated (the B200 path requires both factors >= 2)."""
+    ys = np.linspace(0.5 / k[0], 1 - 0.5 / k[0], k[0], dtype=np.float16)[:, None]
+    xs = np.linspace(0.5 / k[1], 1 - 0.5 / k[1], k[1], dtype=np.float16)[None, :]
+    return np.vstack([((1 - xs) * (1 - ys)).reshape(1, -1), (xs * (1 - ys)).reshape(1, -1),
+                      ((1 - xs) * ys).reshape(1, -1), (xs * ys).reshape(1, -1)])
+
+
+def upsample_bilinear(x, k):
+    """Integer-factor bilinear upsample: replicate the border by one pixel, blend every 2x2 neighbourhood into a kh x kw
+    block with ONE matmul (cells, 4) @ (4, kh*kw), interleave the blocks and crop kh//2, kw//2 on each side.
+    reference: planer/util.py:133-153 (upsample_blinear), both factors >= 2."""
+    n, c, h, w = x.shape
+    assert k[0] >= 2 and k[1] >= 2
+    xp = np.concatenate((x[:, :, :1, :], x, x[:, :, -1:, :]), axis=2)
+    xp = np.concatenate((xp[:, :, :, :1], xp, xp[:, :, :, -1:]), axis=3)
+    corners = [xp[:, :, :-1, :-1], xp[:, :, :-1, 1:], xp[:, :, 1:, :-1], xp[:, :, 1:, 1:]]
+    cells = np.concatenate([t[:, :, :, :, None] for t in corners], axis=-1)
+    out = np.matmul(cells.reshape((-1, 4)), _bilinear_taps(k))
+    hh, ww = h + 1, w + 1
+    out = out.reshape((-1, ww, k[0], k[1])).transpose((0, 2, 1, 3)).reshape((n, c, hh * k[0], ww * k[1]))
+    return out[:, :, k[0] // 2:h * k[0] + k[0] // 2, k[1] // 2:w * k[1] + k[1] // 2]
+
+
+def _upsample(x, k, mode, trans_mode, round_mode):
+    """reference: planer/util.py:212-219 (upsample) for whole-number factors."""
+    kint = [int(k[0]), int(k[1])]
+    if mode == 'nearest':
+        return upsample_nearest(x, kint, trans_mode, round_mode)
+    if mode == 'linear' and k[0] == int(k[0]) and k[1] == int(k[1]):
+        return upsample_bilinear(x, kint)
+    raise NotImplementedError('oracle: fractional-scale resize (planer/util.py:194-210) is not restated')
+
+
 def upsample(x, k, mode='nearest'):
     """``k`` is the ONNX scales tensor; its last two entries, truncated to int, are the factors.
     reference: planer/layer.py:80-82 (UpSample) -> planer/util.py:212-216 (upsample; note the
     default mode strings 'half-pixcel' / 'round_prefer_ceil' select a zero shift)."""
-    if mode != 'nearest':
-        raise NotImplementedError('oracle covers the nearest mode of the hot path only')
     kk = np.asarray(k)[-2:].astype(int).tolist()
-    return upsample_nearest(x, [int(kk[0]), int(kk[1])], 'half-pixcel', 'round_prefer_ceil')
+    return _upsample(x, kk, mode, 'half-pixcel', 'round_prefer_ceil')
+
+
+def resize(x, roi, k, size=None, mode='nearest', coordinate_transformation_mode='half_pixel',
+           nearest_mode='round_prefer_floor'):
+    """reference: planer/layer.py:84-88 (Resize) with a scales tensor."""
+    return _upsample(x, np.asarray(k)[-2:].tolist(), mode, coordinate_transformation_mode, nearest_mode)
 
 
 # --------------------------------------------------------------------------------------
@@ -319,7 +359,7 @@ layer_map = {
     'conv': conv2d, 'dense': dense, 'matmul': matmul, 'relu': relu, 'leakyrelu': leakyrelu,
     'sigmoid': sigmoid, 'add': add, 'batchnorm': batchnorm, 'flatten': flatten, 'gap': gap,
     'concat': concat, 'maxpool': maxpool, 'averagepool': avgpool, 'upsample': upsample,
-    'convtranspose': convtranspose2d, 'hardsigmoid': hardsigmoid, 'clip': clip, 'softmax': softmax, 'return': ret,
+    'convtranspose': convtranspose2d, 'hardsigmoid': hardsigmoid, 'clip': clip, 'softmax': softmax, 'resize': resize, 'return': ret,
 }
 """Hot-path subset of planer/layer.py:262-281 (layer_map)."""
 

@@ -319,6 +319,40 @@ __global__ void upsample_kernel(const T* __restrict__ x, T* __restrict__ y, int 
   }
 }
 
+// Bilinear upsample by integer factors (planer/util.py:121-153: upsample_blinear): the image is edge-replicated by one
+// pixel, every 2x2 neighbourhood of the padded image yields an fh x fw block of outputs as a 4-tap blend with weights
+// wmat[tap][a*fw + b] (the reference's make_upmat, computed in fp16 on the host exactly as it does and passed as fp32),
+// and the result is cropped by (fh/2, fw/2).  One thread per output vector; the 4 taps hit L1/L2.
+template <typename T, int V>
+__global__ void upsample_linear_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ wmat, int N, int H,
+                                       int W, int C, int xld, int xcoff, int yld, int ycoff, int fh, int fw) {
+  const int CV = C / V, OH = H * fh, OW = W * fw, kk = fh * fw;
+  const int64_t total = (int64_t)N * OH * OW * CV;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    int64_t t = i / CV;
+    int ox = (int)(t % OW);
+    t /= OW;
+    int oy = (int)(t % OH);
+    int n = (int)(t / OH);
+    const int yp = oy + fh / 2, xp = ox + fw / 2;
+    const int cy = yp / fh, a = yp - cy * fh, cx = xp / fw, b = xp - cx * fw;        // cell of the padded image, position in it
+    const int r0 = max(cy - 1, 0), r1 = min(cy, H - 1), c0 = max(cx - 1, 0), c1 = min(cx, W - 1);
+    const T* xb = x + (size_t)n * H * W * xld + xcoff + cv * V;
+    const Vec<T, V> p00 = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)r0 * W + c0) * xld);
+    const Vec<T, V> p01 = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)r0 * W + c1) * xld);
+    const Vec<T, V> p10 = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)r1 * W + c0) * xld);
+    const Vec<T, V> p11 = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)r1 * W + c1) * xld);
+    const int wi = a * fw + b;
+    const float w0 = wmat[wi], w1 = wmat[kk + wi], w2 = wmat[2 * kk + wi], w3 = wmat[3 * kk + wi];
+    Vec<T, V> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+      st_f(&o.v[k], fmaf(ld_f(&p11.v[k]), w3, fmaf(ld_f(&p10.v[k]), w2, fmaf(ld_f(&p01.v[k]), w1, ld_f(&p00.v[k]) * w0))));
+    *reinterpret_cast<Vec<T, V>*>(y + (((size_t)n * OH + oy) * OW + ox) * yld + ycoff + cv * V) = o;
+  }
+}
+
 template <typename T, int V>
 __global__ void copy_channels_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t npix, int C, int xld,
                                      int xcoff, int yld, int ycoff) {
@@ -1024,6 +1058,25 @@ int plnr_upsample_nearest(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const 
     }
   })
   return plnr_after_launch(ctx, "upsample_nearest");
+}
+
+int plnr_upsample_linear(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y, int fh, int fw, const float* wmat) {
+  PLNR_REQUIRE(ctx && x && y && x->ptr && y->ptr && wmat, "upsample_linear: NULL argument");
+  PLNR_REQUIRE(fh >= 2 && fw >= 2 && y->h == x->h * fh && y->w == x->w * fw && y->n == x->n && y->c == x->c,
+               "upsample_linear: factors must be >= 2 in both axes and match the output extents (%d,%d)", fh, fw);
+  DISPATCH_T(dtype, {
+    constexpr int V = VecWidth<T>::value;
+    if (view_vec_ok(x, V, sizeof(T)) && view_vec_ok(y, V, sizeof(T))) {
+      const int64_t work = (int64_t)y->n * y->h * y->w * (y->c / V);
+      upsample_linear_kernel<T, V><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
+          (const T*)x->ptr, (T*)y->ptr, wmat, x->n, x->h, x->w, x->c, x->ld, x->coff, y->ld, y->coff, fh, fw);
+    } else {
+      const int64_t work = (int64_t)y->n * y->h * y->w * y->c;
+      upsample_linear_kernel<T, 1><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
+          (const T*)x->ptr, (T*)y->ptr, wmat, x->n, x->h, x->w, x->c, x->ld, x->coff, y->ld, y->coff, fh, fw);
+    }
+  })
+  return plnr_after_launch(ctx, "upsample_linear");
 }
 
 int plnr_copy_channels(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y) {

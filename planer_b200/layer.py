@@ -241,14 +241,58 @@ def upsample_factors(k):
     return int(f[0]), int(f[1])
 
 
-def UpSample(x, k, mode='nearest'):
-    """planer/layer.py:80-82 -> planer/util.py:184-192 (nearest, integer factors, zero pixel shift)."""
-    if mode != 'nearest':
-        raise NotImplementedError("UpSample mode %r: only 'nearest' is on the B200 hot path" % mode)
-    fh, fw = upsample_factors(k)
+def _int_scales(k):
+    """Last two ONNX scales as integers, or None when they are not whole numbers."""
+    k = k.get() if isinstance(k, DeviceArray) else np.asarray(k)
+    f = k.reshape(-1)[-2:].astype(np.float64)
+    return (int(f[0]), int(f[1])) if f.size == 2 and np.all(f == np.floor(f)) and np.all(f >= 1) else None
+
+
+def _upsample(x, fh, fw, mode, what):
     x = _as_nhwc(x)
     n, c, h, w = x.shape
-    return ops.upsample_into(x, B.empty((n, c, h * fh, w * fw), x.dtype, 'nhwc'), fh, fw)
+    y = B.empty((n, c, h * fh, w * fw), x.dtype, 'nhwc')
+    if mode == 'nearest':
+        return ops.upsample_into(x, y, fh, fw)
+    if mode == 'linear' and fh >= 2 and fw >= 2:
+        return ops.upsample_linear_into(x, y, fh, fw)
+    raise NotImplementedError("%s: mode %r with factors (%d, %d) is not implemented (nearest, or linear with both factors >= 2)"
+                              % (what, mode, fh, fw))
+
+
+def UpSample(x, k, mode='nearest'):
+    """planer/layer.py:80-82 -> planer/util.py:212-219: integer factors; 'nearest' (util.py:184-192, zero pixel shift) or
+    'linear' (util.py:133-153, edge-replicated 4-tap blend)."""
+    fh, fw = upsample_factors(k)
+    return _upsample(x, fh, fw, mode, 'UpSample')
+
+
+def Resize(x, roi, k, size=None, mode='nearest', coordinate_transformation_mode='half_pixel',
+           nearest_mode='round_prefer_floor'):
+    """planer/layer.py:84-88 for whole-number scales: the reference then takes the same two paths as UpSample
+    (planer/util.py:212-219).  Nearest is implemented for the mode pairs whose pixel shift is zero (util.py:155-170: the
+    ONNX defaults, asymmetric+floor, ...); fractional scales (util.py:194-210) are not."""
+    if k is None or getattr(k, 'size', 0) == 0:
+        raise NotImplementedError('Resize with `sizes` instead of `scales` is not implemented')
+    f = _int_scales(k)
+    if f is None:
+        raise NotImplementedError('Resize with fractional scales (planer/util.py:194-210) is not implemented')
+    if mode == 'nearest' and (nearest_shift(f[0], coordinate_transformation_mode, nearest_mode) or
+                              nearest_shift(f[1], coordinate_transformation_mode, nearest_mode)):
+        raise NotImplementedError('Resize nearest with a non-zero pixel shift (%s, %s) is not implemented'
+                                  % (coordinate_transformation_mode, nearest_mode))
+    return _upsample(x, f[0], f[1], mode, 'Resize')
+
+
+def nearest_shift(k, trans_mode, round_mode):
+    """Pixel shift the reference applies after a nearest upsample for an ONNX mode pair (planer/util.py:155-170): the
+    position of the first source index that maps to 0."""
+    idx = np.arange(-64, 64).astype(np.float64)
+    if trans_mode == 'half_pixel': idx = (idx + 0.5) / k - 0.5
+    if trans_mode == 'asymmetric': idx = idx / k
+    idx = {'round_prefer_floor': lambda v: np.round(v - 1e-3), 'round_prefer_ceil': lambda v: np.round(v + 1e-3),
+           'ceil': np.ceil, 'floor': np.floor}.get(round_mode, lambda v: v)(idx)
+    return int(np.argmax(idx.astype(np.int16) == 0) - 64)
 
 
 def Concatenate(*xs, axis=0):
@@ -293,5 +337,6 @@ layer_map = _HotPathOnly({
     'concat': Concatenate, 'add': Add, 'gap': GlobalAveragePool, 'identity': Identity, 'return': Return,
     # SURVEY 8f rank 2 (the callers either side of the path): same kernels, same parity bar
     'averagepool': AveragePool, 'convtranspose': ConvTranspose2d, 'hardsigmoid': HardSigmoid, 'clip': Clip, 'softmax': Softmax,
+    'resize': Resize,
 })
 """Hot-path subset of planer/layer.py:262-281."""

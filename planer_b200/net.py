@@ -59,12 +59,12 @@ class Net:
         sliced out of it in ``inits`` order, each ``nbytes`` long (scalar inits occupy one element).
         ``broadcast``: None = automatically when torch.distributed is initialised, True/False to force."""
         np = self._array
-        total = sum(max(int(numpy.prod(s)), 1) * d.itemsize for _, s, d in self._init_meta)
+        total = sum(int(numpy.prod(s)) * d.itemsize for _, s, d in self._init_meta)
         if np is not B:                                   # injected array module (tests): plain slicing
             blob = np.asarray(data).reshape(-1).view(numpy.uint8)
             self.weights, s = [], 0
             for name, shape, dt in self._init_meta:
-                nb = max(int(numpy.prod(shape)), 1) * dt.itemsize
+                nb = int(numpy.prod(shape)) * dt.itemsize
                 w = np.zeros(shape, dtype=dt)
                 w.reshape(-1).view(numpy.uint8)[:] = blob[s:s + nb]
                 self.weights.append(w)
@@ -83,7 +83,7 @@ class Net:
         self._blob = blob
         self.weights, s = [], 0
         for name, shape, dt in self._init_meta:
-            nb = max(int(numpy.prod(shape)), 1) * dt.itemsize
+            nb = int(numpy.prod(shape)) * dt.itemsize
             self.weights.append(DeviceArray(blob.buf, shape, dt, 'flat', offset=blob.offset + s))
             s += nb
         self._executors = {}
@@ -134,6 +134,8 @@ class Net:
                 first = ls[0] if isinstance(ls, list) else ls
                 if kinds.get(first) == 'upsample' and not isinstance(xs, str) and len(xs) > 1:
                     consts[xs[1]] = self.host_const(xs[1])
+                if kinds.get(first) == 'resize' and not isinstance(xs, str) and len(xs) > 2 and xs[2] in self.inits:
+                    consts[xs[2]] = self.host_const(xs[2])
             gp = P.compile_graph(self._model(), dict(zip(names, sig[0])), consts)
             self._executors[sig] = Executor(self, gp, self.compute_dtype(), self.use_graph)
         return self._executors[sig]

@@ -169,6 +169,28 @@ def flip_weight(K):
     return out
 
 
+_upmat_cache = {}
+
+
+def upsample_linear_weights(fh, fw):
+    """The reference's 4-tap weight table for integer-factor bilinear upsampling (planer/util.py:121-131, make_upmat):
+    sample positions and products in FLOAT16, rows = (left-top, right-top, left-bottom, right-bottom); device fp32 (4, fh*fw)."""
+    if (fh, fw) not in _upmat_cache:
+        ys = np.linspace(0.5 / fh, 1 - 0.5 / fh, fh, dtype=np.float16)[:, None]
+        xs = np.linspace(0.5 / fw, 1 - 0.5 / fw, fw, dtype=np.float16)[None, :]
+        taps = [(1 - xs) * (1 - ys), xs * (1 - ys), (1 - xs) * ys, xs * ys]
+        _upmat_cache[(fh, fw)] = B.asarray(np.stack([t.reshape(-1) for t in taps]).astype(np.float32))
+    return _upmat_cache[(fh, fw)]
+
+
+def upsample_linear_into(x, y, fh, fw):
+    tx, ty = x.tensor(), y.tensor()
+    wm = upsample_linear_weights(fh, fw)
+    _capi.check(B.lib().plnr_upsample_linear(B.ctx(), _capi.dtype_code(x.dtype), C.byref(tx), C.byref(ty), fh, fw, wm.ptr),
+                'plnr_upsample_linear')
+    return y
+
+
 def upsample_into(x, y, fh, fw):
     tx, ty = x.tensor(), y.tensor()
     _capi.check(B.lib().plnr_upsample_nearest(B.ctx(), _capi.dtype_code(x.dtype), C.byref(tx), C.byref(ty), fh, fw),

@@ -19,7 +19,7 @@ import numpy as np
 
 HOT_OPS = ('conv', 'dense', 'relu', 'leakyrelu', 'sigmoid', 'add', 'batchnorm', 'flatten', 'gap', 'concat',
            'maxpool', 'upsample', 'identity', 'return',
-           'averagepool', 'convtranspose', 'hardsigmoid', 'clip', 'softmax')          # the same kernels either side of the path
+           'averagepool', 'convtranspose', 'hardsigmoid', 'clip', 'softmax', 'resize')          # the same kernels either side of the path
 ACTS = {'relu': 1, 'leakyrelu': 2, 'sigmoid': 3}
 
 
@@ -169,16 +169,27 @@ def infer(values, nodes, host_consts=None):
             kw_, pd, st = a.get('w', (2, 2)), a.get('pads', (0, 0, 0, 0)), a.get('strides', (2, 2))
             out = (n, c, (h + pd[0] + pd[2] - kw_[0] + st[0]) // st[0], (w + pd[1] + pd[3] - kw_[1] + st[1]) // st[1])
             nd.attrs = dict(w=tuple(kw_), pads=tuple(pd), strides=tuple(st))
-        elif k == 'upsample':
-            if a.get('mode', 'nearest') != 'nearest':
-                raise NotImplementedError("upsample %r: mode %r is outside the B200 hot path" % (nd.name, a.get('mode')))
-            scales = host_consts.get(values[nd.ins[1]].name)
+        elif k in ('upsample', 'resize'):
+            mode = a.get('mode', 'nearest')
+            sname = values[nd.ins[1 if k == 'upsample' else 2]].name if len(nd.ins) > (1 if k == 'upsample' else 2) and \
+                nd.ins[1 if k == 'upsample' else 2] is not None else None
+            scales = host_consts.get(sname)
             if scales is None:
-                raise ValueError('upsample %r: scales tensor %r must be a constant init' % (nd.name, values[nd.ins[1]].name))
-            f = np.asarray(scales).reshape(-1)[-2:].astype(int).tolist()          # planer/layer.py:82
+                raise ValueError('%s %r: scales tensor %r must be a constant init' % (k, nd.name, sname))
+            sc = np.asarray(scales, np.float64).reshape(-1)[-2:]
+            if k == 'resize' and (sc.size != 2 or np.any(sc != np.floor(sc))):
+                raise NotImplementedError('resize %r: fractional scales (planer/util.py:194-210) are not implemented' % nd.name)
+            f = sc.astype(int).tolist()                                           # planer/layer.py:82
+            if mode not in ('nearest', 'linear') or (mode == 'linear' and min(f) < 2):
+                raise NotImplementedError("%s %r: mode %r with factors %s is not implemented" % (k, nd.name, mode, f))
+            if k == 'resize' and mode == 'nearest':
+                from .layer import nearest_shift
+                tm, rm = a.get('coordinate_transformation_mode', 'half_pixel'), a.get('nearest_mode', 'round_prefer_floor')
+                if nearest_shift(f[0], tm, rm) or nearest_shift(f[1], tm, rm):
+                    raise NotImplementedError('resize %r: nearest with a non-zero pixel shift (%s, %s)' % (nd.name, tm, rm))
             n, c, h, w = sh[0]
             out = (n, c, h * int(f[0]), w * int(f[1]))
-            nd.attrs = dict(fh=int(f[0]), fw=int(f[1]))
+            nd.attrs = dict(fh=int(f[0]), fw=int(f[1]), mode=mode)
         elif k == 'concat':
             if a.get('axis', 0) != 1 or any(len(s) != 4 for s in sh):
                 raise NotImplementedError('concat %r: only channel concat (axis=1) of 4-D tensors is on the hot path' % nd.name)
@@ -328,7 +339,7 @@ def fuse(values, nodes, outputs):
             st.bn = (nd.ins[1], nd.ins[2])
         elif k in ('maxpool', 'averagepool', 'zero_stuff', 'hardsigmoid', 'clip', 'softmax'):
             emit(Step(k, nd.name, [x], out, nd.attrs))
-        elif k == 'upsample':
+        elif k in ('upsample', 'resize'):
             emit(Step('upsample', nd.name, [x], out, nd.attrs))
         elif k == 'concat':
             emit(Step('concat', nd.name, list(nd.ins), out))

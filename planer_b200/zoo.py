@@ -135,6 +135,23 @@ def decoder_net(seed=0, width=32):
     return b.finish(['x'], [y])
 
 
+def upsample_net(seed=0, width=16):
+    """conv+relu -> bilinear x2 (UpSample, mode 'linear') -> conv+relu -> Resize nearest x2 (ONNX default modes) -> conv ->
+    softmax over channels: the interpolation operators of SURVEY 8f rank 2 in the real IR (planer/layer.py:80-88, :141-146)."""
+    b = _Builder(seed)
+    w = width
+    x = b.conv('x', 3, w, 3, name='c1', bias=True)
+    x = b.op('relu', {}, [x], name='c1.relu')
+    x = b.op('upsample', {'mode': 'linear'}, [x, b.init('up1.scales', np.array([1, 1, 2, 2], np.float32))], name='up1')
+    x = b.conv(x, w, w, 3, name='c2')
+    x = b.op('relu', {}, [x], name='c2.relu')
+    x = b.op('resize', {'mode': 'nearest', 'coordinate_transformation_mode': 'half_pixel', 'nearest_mode': 'round_prefer_floor'},
+             [x, b.init('up2.roi', np.zeros(0, np.float32)), b.init('up2.scales', np.array([1, 1, 2, 2], np.float32))], name='up2')
+    x = b.conv(x, w, 5, 1, name='c3', bias=True)
+    y = b.op('softmax', {'axis': 1}, [x], name='prob')
+    return b.finish(['x'], [y])
+
+
 def readme_net(seed=0):
     """The README's CustomNet in the real IR: conv+relu chained in one flow,
     maxpool(2), upsample(x2, nearest), concat(axis=1)+sigmoid chained, return."""

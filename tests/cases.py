@@ -81,6 +81,18 @@ OP_CASES = {
                               {'mode': 'nearest'}),
     'upsample_2x3_f16': lambda n: ('upsample', [_x(_rng(n), (1, 8, 4, 5), 'float16'), np.array([1, 1, 2, 3], 'float32')],
                                    {'mode': 'nearest'}),
+    'upsample_linear_x2': lambda n: ('upsample', [_x(_rng(n), (2, 8, 5, 7), 'float32'), np.array([1, 1, 2, 2], 'float32')],
+                                     {'mode': 'linear'}),
+    'upsample_linear_3x2_f16': lambda n: ('upsample', [_x(_rng(n), (1, 16, 6, 5), 'float16'), np.array([1, 1, 3, 2], 'float32')],
+                                          {'mode': 'linear'}),
+    'resize_linear_x2': lambda n: ('resize', [_x(_rng(n), (1, 8, 9, 6), 'float32'), np.zeros(0, 'float32'),
+                                              np.array([1, 1, 2, 2], 'float32')], {'mode': 'linear'}),
+    'resize_nearest_x2': lambda n: ('resize', [_x(_rng(n), (2, 8, 4, 6), 'float32'), np.zeros(0, 'float32'),
+                                               np.array([1, 1, 2, 2], 'float32')], {'mode': 'nearest'}),
+    'resize_nearest_asym_floor_x3': lambda n: ('resize', [_x(_rng(n), (1, 8, 4, 5), 'float16'), np.zeros(0, 'float32'),
+                                                          np.array([1, 1, 3, 3], 'float32')],
+                                               {'mode': 'nearest', 'coordinate_transformation_mode': 'asymmetric',
+                                                'nearest_mode': 'floor'}),
     'concat_c': lambda n: ('concat', [_x(_rng(n), (2, 8, 5, 7), 'float32'), _x(_rng(n + '2'), (2, 16, 5, 7), 'float32')],
                            {'axis': 1}),
     'gap': lambda n: ('gap', [_x(_rng(n), (2, 16, 7, 7), 'float32')], {}),
@@ -121,6 +133,7 @@ BUILDERS = {
     'yolov3_quarter': lambda: zoo.yolov3(0, width=0.25),
     'yolov3': lambda: zoo.yolov3(0),
     'decoder': lambda: zoo.decoder_net(0),
+    'upsample_net': lambda: zoo.upsample_net(0),
 }
 GRAPH_CASES = {
     'readme_f32': ('readme', (2, 3, 32, 32), False),
@@ -133,6 +146,8 @@ GRAPH_CASES = {
     'yolov3_416_f32_n1': ('yolov3', (1, 3, 416, 416), False),     # BASELINE config 4 graph
     'decoder_f32': ('decoder', (2, 3, 32, 40), False),            # averagepool + convtranspose in a graph
     'decoder_f16': ('decoder', (2, 3, 32, 40), True),
+    'upsample_net_f32': ('upsample_net', (2, 3, 12, 20), False),  # bilinear upsample, resize, channel softmax in a graph
+    'upsample_net_f16': ('upsample_net', (2, 3, 12, 20), True),
 }
 
 _model_cache = {}

@@ -268,7 +268,7 @@ def test_bad_pads_rejected_like_documented():
 # ---------------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize('name', ['readme_f32', 'readme_f16', 'resnet18_small_f32', 'yolov3_quarter_f32', 'decoder_f32',
-                                  'decoder_f16'])
+                                  'decoder_f16', 'upsample_net_f32'])
 def test_net_plumbing_bit_exact_with_injected_numpy_table(name):
     g = np.load(os.path.join(GOLD, 'graphs.npz'))
     model, blob, x, half = cases.make_graph_case(name)
