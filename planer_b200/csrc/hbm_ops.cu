@@ -326,30 +326,41 @@ __global__ void upsample_kernel(const T* __restrict__ x, T* __restrict__ y, int 
 template <typename T, int V>
 __global__ void upsample_linear_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ wmat, int N, int H,
                                        int W, int C, int xld, int xcoff, int yld, int ycoff, int fh, int fw) {
-  const int CV = C / V, OH = H * fh, OW = W * fw, kk = fh * fw;
-  const int64_t total = (int64_t)N * OH * OW * CV;
+  // one thread per CELL of the edge-replicated image (2x2 neighbourhood) and 16-byte channel vector: its four corner loads
+  // feed the fh x fw outputs of the cell (one thread per OUTPUT vector re-loaded the corners fh*fw times and was bound by
+  // load issue at 0.27 of the copy bandwidth, tools/hbm_bench.py)
+  const int CV = C / V, OH = H * fh, OW = W * fw, kk = fh * fw, HC = H + 1, WC = W + 1;
+  const int64_t total = (int64_t)N * HC * WC * CV;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int cv = (int)(i % CV);
     int64_t t = i / CV;
-    int ox = (int)(t % OW);
-    t /= OW;
-    int oy = (int)(t % OH);
-    int n = (int)(t / OH);
-    const int yp = oy + fh / 2, xp = ox + fw / 2;
-    const int cy = yp / fh, a = yp - cy * fh, cx = xp / fw, b = xp - cx * fw;        // cell of the padded image, position in it
+    int cx = (int)(t % WC);
+    t /= WC;
+    int cy = (int)(t % HC);
+    int n = (int)(t / HC);
     const int r0 = max(cy - 1, 0), r1 = min(cy, H - 1), c0 = max(cx - 1, 0), c1 = min(cx, W - 1);
     const T* xb = x + (size_t)n * H * W * xld + xcoff + cv * V;
     const Vec<T, V> p00 = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)r0 * W + c0) * xld);
     const Vec<T, V> p01 = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)r0 * W + c1) * xld);
     const Vec<T, V> p10 = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)r1 * W + c0) * xld);
     const Vec<T, V> p11 = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)r1 * W + c1) * xld);
-    const int wi = a * fw + b;
-    const float w0 = wmat[wi], w1 = wmat[kk + wi], w2 = wmat[2 * kk + wi], w3 = wmat[3 * kk + wi];
-    Vec<T, V> o;
+    float f00[V], f01[V], f10[V], f11[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k)
-      st_f(&o.v[k], fmaf(ld_f(&p11.v[k]), w3, fmaf(ld_f(&p10.v[k]), w2, fmaf(ld_f(&p01.v[k]), w1, ld_f(&p00.v[k]) * w0))));
-    *reinterpret_cast<Vec<T, V>*>(y + (((size_t)n * OH + oy) * OW + ox) * yld + ycoff + cv * V) = o;
+    for (int k = 0; k < V; ++k) { f00[k] = ld_f(&p00.v[k]); f01[k] = ld_f(&p01.v[k]); f10[k] = ld_f(&p10.v[k]); f11[k] = ld_f(&p11.v[k]); }
+    for (int a = 0; a < fh; ++a) {
+      const int oy = cy * fh + a - fh / 2;                 // the crop of planer/util.py:153
+      if (oy < 0 || oy >= OH) continue;
+      for (int b = 0; b < fw; ++b) {
+        const int ox = cx * fw + b - fw / 2;
+        if (ox < 0 || ox >= OW) continue;
+        const int wi = a * fw + b;
+        const float w0 = wmat[wi], w1 = wmat[kk + wi], w2 = wmat[2 * kk + wi], w3 = wmat[3 * kk + wi];
+        Vec<T, V> o;
+#pragma unroll
+        for (int k = 0; k < V; ++k) st_f(&o.v[k], fmaf(f11[k], w3, fmaf(f10[k], w2, fmaf(f01[k], w1, f00[k] * w0))));
+        *reinterpret_cast<Vec<T, V>*>(y + (((size_t)n * OH + oy) * OW + ox) * yld + ycoff + cv * V) = o;
+      }
+    }
   }
 }
 
@@ -440,6 +451,43 @@ __global__ void softmax_kernel(const T* __restrict__ x, T* __restrict__ y, int64
     for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
     const float lg = __logf(sum);
     for (int i = lane; i < c; i += 32) st_f(y + r * c + i, __expf(ld_f(xr + i) - m - lg));
+  }
+}
+
+// Softmax of short rows (c = G * V elements, G a power of two <= 32): G adjacent lanes hold one row in registers -- one
+// 16-byte load and one 16-byte store per lane, max and sum by xor-shuffles inside the lane group; 32 / G rows per warp.
+// (The warp-per-row kernel above reads a 64-channel row three times through 2-byte loads: 0.19 of the copy bandwidth.)
+template <typename T, int V>
+__global__ void softmax_rows_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int G) {
+  const int64_t total = rows * G;
+  const int64_t n_iter = (total + (int64_t)gridDim.x * blockDim.x - 1) / ((int64_t)gridDim.x * blockDim.x);
+  for (int64_t it = 0; it < n_iter; ++it) {                 // whole warps stay in the loop: the shuffles are warp-wide
+    const int64_t i = it * (int64_t)gridDim.x * blockDim.x + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool ok = i < total;
+    float f[V];
+    if (ok) {
+      const Vec<T, V> v = *reinterpret_cast<const Vec<T, V>*>(x + i * V);
+#pragma unroll
+      for (int k = 0; k < V; ++k) f[k] = ld_f(&v.v[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) f[k] = 0.f;
+    }
+    float m = f[0];
+#pragma unroll
+    for (int k = 1; k < V; ++k) m = fmaxf(m, f[k]);
+    for (int d = 1; d < G; d <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) sum += __expf(f[k] - m);
+    for (int d = 1; d < G; d <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    const float lg = __logf(sum);
+    if (ok) {
+      Vec<T, V> o;
+#pragma unroll
+      for (int k = 0; k < V; ++k) st_f(&o.v[k], __expf(f[k] - m - lg));
+      *reinterpret_cast<Vec<T, V>*>(y + i * V) = o;
+    }
   }
 }
 
@@ -1067,11 +1115,11 @@ int plnr_upsample_linear(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const p
   DISPATCH_T(dtype, {
     constexpr int V = VecWidth<T>::value;
     if (view_vec_ok(x, V, sizeof(T)) && view_vec_ok(y, V, sizeof(T))) {
-      const int64_t work = (int64_t)y->n * y->h * y->w * (y->c / V);
+      const int64_t work = (int64_t)x->n * (x->h + 1) * (x->w + 1) * (x->c / V);
       upsample_linear_kernel<T, V><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
           (const T*)x->ptr, (T*)y->ptr, wmat, x->n, x->h, x->w, x->c, x->ld, x->coff, y->ld, y->coff, fh, fw);
     } else {
-      const int64_t work = (int64_t)y->n * y->h * y->w * y->c;
+      const int64_t work = (int64_t)x->n * (x->h + 1) * (x->w + 1) * x->c;
       upsample_linear_kernel<T, 1><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
           (const T*)x->ptr, (T*)y->ptr, wmat, x->n, x->h, x->w, x->c, x->ld, x->coff, y->ld, y->coff, fh, fw);
     }
@@ -1134,8 +1182,14 @@ int plnr_unary2(plnr_ctx* ctx, int op, int dtype, const void* x, void* y, int64_
 int plnr_softmax(plnr_ctx* ctx, int dtype, const void* x, void* y, int64_t rows, int c) {
   PLNR_REQUIRE(ctx && x && y && rows >= 0 && c >= 1, "softmax: bad argument");
   if (rows == 0) return PLNR_OK;
-  DISPATCH_T(dtype, softmax_kernel<T><<<grid_for(rows * 32, ctx->sm_count * 4), kThreads, 0, ctx->stream>>>(
-                        (const T*)x, (T*)y, rows, c);)
+  DISPATCH_T(dtype, {
+    constexpr int V = VecWidth<T>::value;
+    const int G = c / V;
+    if (c % V == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0 && aligned16(x) && aligned16(y))
+      softmax_rows_kernel<T, V><<<grid_for(rows * G, ctx->sm_count * 4), kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, rows, G);
+    else
+      softmax_kernel<T><<<grid_for(rows * 32, ctx->sm_count * 4), kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, rows, c);
+  })
   return plnr_after_launch(ctx, "softmax");
 }
 

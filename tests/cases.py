@@ -110,6 +110,8 @@ OP_CASES = {
     'clip_f16': lambda n: ('clip', [_x(_rng(n), (2, 8, 5, 7), 'float16') * 3], {'min': 0, 'max': 6}),
     'softmax_logits': lambda n: ('softmax', [_x(_rng(n), (5, 1000), 'float32') * 4], {'axis': -1}),
     'softmax_logits_f16': lambda n: ('softmax', [_x(_rng(n), (3, 77), 'float16') * 4], {'axis': 1}),
+    'softmax_channels_64_f16': lambda n: ('softmax', [_x(_rng(n), (3, 64, 5, 7), 'float16') * 2], {'axis': 1}),
+    'softmax_logits_16': lambda n: ('softmax', [_x(_rng(n), (37, 16), 'float32') * 3], {'axis': -1}),
     'softmax_channels': lambda n: ('softmax', [_x(_rng(n), (2, 21, 6, 5), 'float32') * 2], {'axis': 1}),
     'convtranspose_k4s2p1': lambda n: _convt(n, (2, 16, 7, 9), (16, 8, 4, 4), strides=(2, 2), pads=(1, 1, 1, 1)),
     'convtranspose_k3s2_outpad': lambda n: _convt(n, (1, 8, 6, 6), (8, 12, 3, 3), strides=(2, 2), pads=(1, 1, 1, 1),

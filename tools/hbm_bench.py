@@ -80,5 +80,21 @@ report('eltwise_kernel scale_shift (BN)', 'planer/layer.py:125-127', 2 * n_e * 2
 # graph-exit layout transpose NHWC -> NCHW
 flat = [B.empty((128, 64, 112, 112), np.float16) for _ in range(NB)]
 report('nhwc_to_nchw_kernel', 'planer/net.py:100', 2 * n_e * 2, timed(lambda i: ops.nhwc_to_nchw_into(e_in[i % NB], flat[i % NB])))
+# ---- the operators next to the path ----
+ya = [rnd((128, 64, 56, 56)) for _ in range(NB)]
+report('avgpool_kernel 2x2/s2', 'planer/util.py:97-100', (xs[0].size + ya[0].size) * 2,
+       timed(lambda i: ops.avgpool_into(xs[i % NB], ya[i % NB], (2, 2), (0, 0, 0, 0), (2, 2))))
+report('avgpool_kernel 3x3/s2/p1', 'planer/util.py:97-100', (xs[0].size + ya[0].size) * 2,
+       timed(lambda i: ops.avgpool_into(xs[i % NB], ya[i % NB], (3, 3), (1, 1, 1, 1), (2, 2))))
+report('upsample_linear_kernel x2', 'planer/util.py:133-153', (xu[0].size + yu[0].size) * 2,
+       timed(lambda i: ops.upsample_linear_into(xu[i % NB], yu[i % NB], 2, 2)))
+# zero stuffing of ConvTranspose2d(k4, s2, p1): 256 x 256 x 26 x 26 -> 55 x 55
+yz = [rnd((256, 256, 55, 55)) for _ in range(NB)]
+report('zero_stuff_kernel s2 (convtranspose)', 'planer/layer.py:32-33', (xu[0].size + yz[0].size) * 2,
+       timed(lambda i: ops.zero_stuff_into(xu[i % NB], yz[i % NB], 2, 2, (2, 2))))
+report('unary2_kernel clip', 'planer/layer.py:247-251', 2 * n_e * 2, timed(lambda i: ops.unary2(ops.EW_CLIP, e_in[i % NB], e_out[i % NB], 0, 6)))
+report('unary2_kernel hardsigmoid', 'planer/layer.py:66-69', 2 * n_e * 2,
+       timed(lambda i: ops.unary2(ops.EW_HARDSIGMOID, e_in[i % NB], e_out[i % NB], 0.2, 0.5)))
+report('softmax_kernel (64 channels per pixel)', 'planer/layer.py:141-146', 2 * n_e * 2, timed(lambda i: ops.softmax_into(e_in[i % NB], e_out[i % NB])))
 if len(sys.argv) > 1:
     json.dump(dict(peak_gbs=peak, rows=rows), open(sys.argv[1], 'w'), indent=1)
