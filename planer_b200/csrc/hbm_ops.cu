@@ -516,32 +516,50 @@ __global__ void gap_kernel(const T* __restrict__ x, T* __restrict__ y, int N, in
 // ---------------------------------------------------------------------------------------------
 // averagepool: zero padding, the divisor is ALWAYS kh*kw (planer/util.py:97-100: pool(np.add) then rst /= c[0]*c[1])
 // ---------------------------------------------------------------------------------------------
-template <typename T, int V>
+template <typename T, int V, int KH, int KW>
 __global__ void avgpool_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int xld,
-                               int xcoff, int OH, int OW, int yld, int ycoff, int kh, int kw, int pt, int pl, int sh, int sw) {
+                               int xcoff, int OH, int OW, int yld, int ycoff, int kh_rt, int kw_rt, int pt, int pl, int sh, int sw) {
+  // blockIdx.y walks output rows (n, oh), blockIdx.x * blockDim.x + threadIdx.x the (ow, channel vector) pairs of a row: no
+  // 64-bit divisions per thread; KH/KW > 0: compile-time window, every tap an unconditional clamped load, all in flight
+  const int kh = KH > 0 ? KH : kh_rt, kw = KW > 0 ? KW : kw_rt;
   const int CV = C / V;
-  const int64_t total = (int64_t)N * OH * OW * CV;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= OW * CV) return;
+  const int ow = t / CV, cv = t - ow * CV;
   const float inv = 1.f / (float)(kh * kw);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(i % CV);
-    int64_t t = i / CV;
-    int ow = (int)(t % OW);
-    t /= OW;
-    int oh = (int)(t % OH);
-    int n = (int)(t / OH);
+  for (int64_t row = blockIdx.y; row < (int64_t)N * OH; row += gridDim.y) {
+    const int n = (int)(row / OH), oh = (int)(row - (int64_t)n * OH);
     float acc[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) acc[k] = 0.f;
     const T* xb = x + (size_t)n * H * W * xld + xcoff + cv * V;
-    for (int r = 0; r < kh; ++r) {
-      const int ih = oh * sh + r - pt;
-      if (ih < 0 || ih >= H) continue;
-      for (int q = 0; q < kw; ++q) {
-        const int iw = ow * sw + q - pl;
-        if (iw < 0 || iw >= W) continue;
-        const Vec<T, V> v = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)ih * W + iw) * xld);
+    if (KH > 0) {
+      Vec<T, V> v[(KH > 0 ? KH : 1) * (KW > 0 ? KW : 1)];
+      bool ok[(KH > 0 ? KH : 1) * (KW > 0 ? KW : 1)];
 #pragma unroll
-        for (int k = 0; k < V; ++k) acc[k] += ld_f(&v.v[k]);
+      for (int r = 0; r < KH; ++r)
+#pragma unroll
+        for (int q = 0; q < KW; ++q) {
+          const int ih = oh * sh + r - pt, iw = ow * sw + q - pl;
+          ok[r * KW + q] = ih >= 0 && ih < H && iw >= 0 && iw < W;
+          const int ihc = min(max(ih, 0), H - 1), iwc = min(max(iw, 0), W - 1);
+          v[r * KW + q] = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)ihc * W + iwc) * xld);
+        }
+#pragma unroll
+      for (int j = 0; j < KH * KW; ++j)
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += ok[j] ? ld_f(&v[j].v[k]) : 0.f;
+    } else {
+      for (int r = 0; r < kh; ++r) {
+        const int ih = oh * sh + r - pt;
+        if (ih < 0 || ih >= H) continue;
+        for (int q = 0; q < kw; ++q) {
+          const int iw = ow * sw + q - pl;
+          if (iw < 0 || iw >= W) continue;
+          const Vec<T, V> v = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)ih * W + iw) * xld);
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[k] += ld_f(&v.v[k]);
+        }
       }
     }
     Vec<T, V> o;
@@ -560,21 +578,23 @@ __global__ void avgpool_kernel(const T* __restrict__ x, T* __restrict__ y, int N
 template <typename T, int V>
 __global__ void zero_stuff_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int xld, int xcoff,
                                   int OH, int OW, int yld, int ycoff, int lo_h, int lo_w, int sh, int sw) {
+  // blockIdx.y walks output rows (n, oh): whether a row carries input pixels at all is decided once per row, and a thread
+  // needs one small division (by the channel-vector count) instead of three 64-bit ones
   const int CV = C / V;
-  const int64_t total = (int64_t)N * OH * OW * CV;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(i % CV);
-    int64_t t = i / CV;
-    int ow = (int)(t % OW);
-    t /= OW;
-    int oh = (int)(t % OH);
-    int n = (int)(t / OH);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= OW * CV) return;
+  const int ow = t / CV, cv = t - ow * CV;
+  const int b = ow - lo_w;
+  const bool col_hit = b >= 0 && b % sw == 0 && b / sw < W;
+  const int iw = col_hit ? b / sw : 0;
+  for (int64_t row = blockIdx.y; row < (int64_t)N * OH; row += gridDim.y) {
+    const int n = (int)(row / OH), oh = (int)(row - (int64_t)n * OH);
+    const int a = oh - lo_h;
     Vec<T, V> v;
 #pragma unroll
     for (int k = 0; k < V; ++k) st_f(&v.v[k], 0.f);
-    const int a = oh - lo_h, b = ow - lo_w;
-    if (a >= 0 && b >= 0 && a % sh == 0 && b % sw == 0 && a / sh < H && b / sw < W)
-      v = *reinterpret_cast<const Vec<T, V>*>(x + (((size_t)n * H + a / sh) * W + b / sw) * xld + xcoff + cv * V);
+    if (col_hit && a >= 0 && a % sh == 0 && a / sh < H)
+      v = *reinterpret_cast<const Vec<T, V>*>(x + (((size_t)n * H + a / sh) * W + iw) * xld + xcoff + cv * V);
     *reinterpret_cast<Vec<T, V>*>(y + (((size_t)n * OH + oh) * OW + ow) * yld + ycoff + cv * V) = v;
   }
 }
@@ -1035,25 +1055,37 @@ int plnr_maxpool2d(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_te
   return plnr_after_launch(ctx, "maxpool2d");
 }
 
+static inline dim3 row_grid(int row_items, int64_t rows, int sm_count) {
+  // x covers one output row; y = enough row walkers for ~16 resident CTAs per SM, each walking rows with stride gridDim.y
+  // (one block per row made 100 k one-vector blocks for a 55-pixel row: block scheduling, not HBM, bounded the kernel)
+  const int gx = (row_items + kThreads - 1) / kThreads;
+  int64_t gy = ((int64_t)sm_count * 16 + gx - 1) / gx;
+  if (gy > rows) gy = rows;
+  if (gy < 1) gy = 1;
+  if (gy > 65535) gy = 65535;
+  return dim3((unsigned)gx, (unsigned)gy);
+}
+
 int plnr_avgpool2d(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y, int kh, int kw, int pad_t,
                    int pad_l, int stride_h, int stride_w) {
   PLNR_REQUIRE(ctx && x && y && x->ptr && y->ptr, "avgpool2d: NULL argument");
   PLNR_REQUIRE(x->n == y->n && x->c == y->c, "avgpool2d: batch/channel mismatch");
   PLNR_REQUIRE(kh >= 1 && kw >= 1 && stride_h >= 1 && stride_w >= 1 && pad_t >= 0 && pad_l >= 0, "avgpool2d: bad window");
+#define AP_LAUNCH(VV, KH_, KW_)                                                                                            \
+  avgpool_kernel<T, VV, KH_, KW_><<<row_grid(y->w * (y->c / VV), (int64_t)y->n * y->h, ctx->sm_count), kThreads, 0, ctx->stream>>>(        \
+      (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, kh, kw, pad_t, pad_l, \
+      stride_h, stride_w)
   DISPATCH_T(dtype, {
     constexpr int V = VecWidth<T>::value;
     if (view_vec_ok(x, V, sizeof(T)) && view_vec_ok(y, V, sizeof(T))) {
-      const int64_t work = (int64_t)y->n * y->h * y->w * (y->c / V);
-      avgpool_kernel<T, V><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
-          (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, kh, kw, pad_t,
-          pad_l, stride_h, stride_w);
+      if (kh == 2 && kw == 2) AP_LAUNCH(V, 2, 2);
+      else if (kh == 3 && kw == 3) AP_LAUNCH(V, 3, 3);
+      else AP_LAUNCH(V, 0, 0);
     } else {
-      const int64_t work = (int64_t)y->n * y->h * y->w * y->c;
-      avgpool_kernel<T, 1><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
-          (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, kh, kw, pad_t,
-          pad_l, stride_h, stride_w);
+      AP_LAUNCH(1, 0, 0);
     }
   })
+#undef AP_LAUNCH
   return plnr_after_launch(ctx, "avgpool2d");
 }
 
@@ -1066,13 +1098,11 @@ int plnr_zero_stuff(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_t
   DISPATCH_T(dtype, {
     constexpr int V = VecWidth<T>::value;
     if (view_vec_ok(x, V, sizeof(T)) && view_vec_ok(y, V, sizeof(T))) {
-      const int64_t work = (int64_t)y->n * y->h * y->w * (y->c / V);
-      zero_stuff_kernel<T, V><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
+      zero_stuff_kernel<T, V><<<row_grid(y->w * (y->c / V), (int64_t)y->n * y->h, ctx->sm_count), kThreads, 0, ctx->stream>>>(
           (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, lo_h, lo_w,
           stride_h, stride_w);
     } else {
-      const int64_t work = (int64_t)y->n * y->h * y->w * y->c;
-      zero_stuff_kernel<T, 1><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
+      zero_stuff_kernel<T, 1><<<row_grid(y->w * y->c, (int64_t)y->n * y->h, ctx->sm_count), kThreads, 0, ctx->stream>>>(
           (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, lo_h, lo_w,
           stride_h, stride_w);
     }
