@@ -330,14 +330,12 @@ __global__ void upsample_linear_kernel(const T* __restrict__ x, T* __restrict__ 
   // feed the fh x fw outputs of the cell (one thread per OUTPUT vector re-loaded the corners fh*fw times and was bound by
   // load issue at 0.27 of the copy bandwidth, tools/hbm_bench.py)
   const int CV = C / V, OH = H * fh, OW = W * fw, kk = fh * fw, HC = H + 1, WC = W + 1;
-  const int64_t total = (int64_t)N * HC * WC * CV;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(i % CV);
-    int64_t t = i / CV;
-    int cx = (int)(t % WC);
-    t /= WC;
-    int cy = (int)(t % HC);
-    int n = (int)(t / HC);
+  // blockIdx.y walks cell rows (n, cy), x the (cell column, channel vector) pairs of a row
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= WC * CV) return;
+  const int cx = t / CV, cv = t - cx * CV;
+  for (int64_t row = blockIdx.y; row < (int64_t)N * HC; row += gridDim.y) {
+    const int n = (int)(row / HC), cy = (int)(row - (int64_t)n * HC);
     const int r0 = max(cy - 1, 0), r1 = min(cy, H - 1), c0 = max(cx - 1, 0), c1 = min(cx, W - 1);
     const T* xb = x + (size_t)n * H * W * xld + xcoff + cv * V;
     const Vec<T, V> p00 = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)r0 * W + c0) * xld);
@@ -1145,12 +1143,10 @@ int plnr_upsample_linear(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const p
   DISPATCH_T(dtype, {
     constexpr int V = VecWidth<T>::value;
     if (view_vec_ok(x, V, sizeof(T)) && view_vec_ok(y, V, sizeof(T))) {
-      const int64_t work = (int64_t)x->n * (x->h + 1) * (x->w + 1) * (x->c / V);
-      upsample_linear_kernel<T, V><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
+      upsample_linear_kernel<T, V><<<row_grid((x->w + 1) * (x->c / V), (int64_t)x->n * (x->h + 1), ctx->sm_count), kThreads, 0, ctx->stream>>>(
           (const T*)x->ptr, (T*)y->ptr, wmat, x->n, x->h, x->w, x->c, x->ld, x->coff, y->ld, y->coff, fh, fw);
     } else {
-      const int64_t work = (int64_t)x->n * (x->h + 1) * (x->w + 1) * x->c;
-      upsample_linear_kernel<T, 1><<<grid_for(work, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
+      upsample_linear_kernel<T, 1><<<row_grid((x->w + 1) * x->c, (int64_t)x->n * (x->h + 1), ctx->sm_count), kThreads, 0, ctx->stream>>>(
           (const T*)x->ptr, (T*)y->ptr, wmat, x->n, x->h, x->w, x->c, x->ld, x->coff, y->ld, y->coff, fh, fw);
     }
   })
