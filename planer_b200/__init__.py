@@ -18,6 +18,7 @@ from . import backend as b200
 from .layer import wrap, layer_map
 from .net import Net
 from .io import read_net, from_model
+from .onnx_import import read_onnx, onnx2pla
 from . import zoo
 from . import util
 from .util import tile, resize

@@ -4,8 +4,8 @@ Formats: ``<name>.pla`` (zip of ``<name>.json`` + ``<name>.npy``, io.py:12-18,29
 ``<name>.npy`` (io.py:19-24); the ``.npy`` is the flat uint8 concatenation of every init (io.py:286).  Files
 written by the reference load here byte for byte and vice versa (``zoo.save_model``).
 
-ONNX import (io.py:36-299) is a "next" row of SURVEY 8f: it needs the ``onnx`` package, which this image
-does not have, so ``.onnx`` paths raise instead of silently doing something else.
+``<name>.onnx`` goes through ``onnx_import.read_onnx`` (io.py:36-299 restated without the ``onnx`` package, SURVEY 8f
+rank 1): graphs made of the implemented operators load, anything else raises NotImplementedError naming the operator.
 """
 import json
 import os
@@ -36,8 +36,10 @@ def read_net(path, debug=False):
         if reader:
             weights = numpy.load(path + '.npy')
     elif os.path.exists(path + '.onnx'):
-        raise NotImplementedError('read_net: ONNX import (planer/io.py:53-287) is not part of the B200 hot path and '
-                                  'the onnx package is absent; convert with the reference\'s onnx2pla first')
+        from .onnx_import import read_onnx                    # planer/io.py:25-29; unsupported operators raise by name
+        body, weights = read_onnx(path + '.onnx')
+        if not reader:
+            weights = None
     else:
         return print('model %s not found!' % path)           # planer/io.py:30-31
     net.load_json(body['input'], body['inits'], body['layers'], body['flow'], debug)

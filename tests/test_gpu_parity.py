@@ -437,3 +437,22 @@ def test_tiled_inference_windows_on_the_batch_axis(planer):
     ref = planer.tile(**kw)(lambda win: hwc(onet(chw(win)[None].copy())[0]))(img)
     assert y1.shape == ref.shape == (96, 120, 3)
     assert rel_err(y1, ref) <= 1e-3 and rel_err(y2, ref) <= 1e-3 and rel_err(y1, y2) <= 1e-4
+
+
+@pytest.mark.parametrize('name', ['mini_resnet', 'mini_decoder'])
+def test_onnx_file_from_the_torch_exporter_runs_on_the_gpu(planer, name):
+    """``read_net('<name>.onnx')`` (planer/io.py:8-34 with the ONNX branch of io.py:25-29) on a file written by
+    PyTorch's exporter, against PyTorch's own outputs stored next to it: fp32 within 1e-3, fp16 within 1e-2."""
+    d = os.path.join(GOLD, 'onnx')
+    g = np.load(os.path.join(d, name + '.npz'))
+    for half, tol in ((False, 1e-3), (True, 1e-2)):
+        net = planer.read_net(os.path.join(d, name + '.onnx'))
+        x = g['x']
+        if half:
+            net.half()
+            x = x.astype(np.float16)
+        y = net(x)
+        ys = y if isinstance(y, tuple) else (y,)
+        for i, t in enumerate(ys):
+            ref = g['y%d' % i]
+            assert t.shape == ref.shape and rel_err(t, ref) <= tol, (name, half, i, rel_err(t, ref))

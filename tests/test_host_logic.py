@@ -429,3 +429,67 @@ def test_tile_decorator_equals_the_reference(name):
     # per-call keyword overrides, like the reference's wrapper
     y2 = util.tile(window=9999)(fn)(img.copy(), **{**kw, 'progress': lambda *a: None})
     assert y2.tobytes() == ref.tobytes()
+
+
+# ---------------------------------------------------------------------------------------------
+# ONNX importer against files written by PyTorch's own exporter (oracle/gen_onnx_fixtures.py)
+# ---------------------------------------------------------------------------------------------
+ONNX_DIR = os.path.join(ROOT, 'tests', 'golden', 'onnx')
+
+
+def _onnx_consts(model, blob):
+    """Host copies of the small constant inits the planner needs as numbers (upsample / resize scales)."""
+    out, s = {}, 0
+    for name, shape, dt in model['inits']:
+        nb = int(np.prod(shape)) * np.dtype(dt).itemsize
+        if nb <= 64:
+            out[name] = blob[s:s + nb].view(dt).reshape(shape)
+        s += nb
+    return out
+
+
+@pytest.mark.parametrize('name', ['mini_resnet', 'mini_decoder'])
+def test_onnx_import_reproduces_torch_through_the_oracle(name):
+    """read_onnx (planer/io.py:53-287 restated, no onnx package) on a real exporter file: the IR, run by the numpy oracle,
+    reproduces PyTorch's outputs; the IR follows the reference's conventions; the planner compiles it."""
+    from planer_b200 import onnx_import
+    model, blob = onnx_import.read_onnx(os.path.join(ONNX_DIR, name + '.onnx'))
+    g = np.load(os.path.join(ONNX_DIR, name + '.npz'))
+    y = oracle.build_net(model, blob)(g['x'].copy())
+    ys = y if isinstance(y, tuple) else (y,)
+    for i, t in enumerate(ys):
+        assert t.shape == g['y%d' % i].shape and cases.rel_err(t, g['y%d' % i]) <= 1e-5
+    # IR conventions of the reference importer (SURVEY App. A)
+    assert model['input'][0] == 'x' and model['layers'][-1] == ['return', 'return', {}] and model['flow'][-1][2] == 'plrst'
+    assert blob.dtype == np.uint8 and blob.size == sum(int(np.prod(s)) * np.dtype(d).itemsize for _, s, d in model['inits'])
+    for xs, names, out in model['flow'][:-1]:
+        assert len(names) == 1 and isinstance(out, str) and (isinstance(xs, str) or len(xs) > 1)      # io.py:70-73
+    kinds = [l[1] for l in model['layers']]
+    if name == 'mini_decoder':
+        bn = [l[0] for l in model['layers'] if l[1] == 'batchnorm'][0]
+        flow = [f for f in model['flow'] if f[1] == [bn]][0]
+        assert flow[0][1].endswith('_invK') and flow[0][2].endswith('_invB')                           # io.py:85-90
+        names = [i[0] for i in model['inits']]
+        assert flow[0][1][:-5] in names                            # the original gamma stays in the blob (io.py:78,89)
+        assert {'clip', 'resize', 'convtranspose', 'averagepool', 'hardsigmoid', 'softmax', 'leakyrelu'} <= set(kinds)
+        clip = [l for l in model['layers'] if l[1] == 'clip'][0]
+        assert clip[2] == {'min': 0.0, 'max': 6.0}                 # ReLU6: bounds arrive as inputs in opset 13
+    gp = P.compile_graph(model, {'x': g['x'].shape}, _onnx_consts(model, blob))
+    assert gp.summary().get('conv', 0) >= 4
+
+
+def test_onnx_import_names_what_it_cannot_do(tmp_path):
+    from planer_b200 import onnx_import
+    # a one-node graph with an operator outside the table: field numbers per the ONNX schema (NodeProto.op_type = 4, ...)
+    def msg(fields):
+        out = b''
+        for num, payload in fields:
+            out += bytes([(num << 3) | 2, len(payload)]) + payload
+        return out
+    node = msg([(1, b'x'), (2, b'y'), (3, b'n0'), (4, b'Erf')])
+    vi = lambda n: msg([(1, n)])
+    graph = msg([(1, node), (11, vi(b'x')), (12, vi(b'y'))])
+    with pytest.raises(NotImplementedError, match='Erf'):
+        onnx_import.read_onnx(msg([(7, graph)]))
+    with pytest.raises(ValueError, match='GraphProto'):
+        onnx_import.read_onnx(b'')
