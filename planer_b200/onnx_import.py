@@ -206,10 +206,8 @@ def read_onnx(path_or_bytes):
             flow[0] = [ins[0], kname, bname]
             layers.append([lname, 'batchnorm', {}])
         elif op == 'Conv':
-            kshape = const(ins[1]).shape if const(ins[1]) is not None else (0, 0, 1, 1)
             layers.append([lname, 'conv', {'group': int(a.get('group') or 1), 'strides': _ints(a, 'strides', (1, 1)),
                                            'dilations': _ints(a, 'dilations', (1, 1)), 'pads': _ints(a, 'pads', (0, 0, 0, 0))}])
-            del kshape
         elif op == 'ConvTranspose':
             layers.append([lname, 'convtranspose', {'group': int(a.get('group') or 1), 'strides': _ints(a, 'strides', (1, 1)),
                                                     'dilations': _ints(a, 'dilations', (1, 1)),
