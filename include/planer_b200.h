@@ -169,6 +169,11 @@ int plnr_dense_fwd(plnr_ctx* ctx, int dtype, const void* x, const void* w, void*
 /* Maxpool with the reference's semantics: ZERO padding and a -1e4 floor (planer/util.py:79-95). */
 int plnr_maxpool2d(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y,
                    int kh, int kw, int pad_t, int pad_l, int stride_h, int stride_w);
+/* Bilinear resize to any output size (planer/util.py:194-210, upsample_size; fractional ONNX scales).  The per-row and
+ * per-column tables (device pointers; y->h and y->w entries) hold the lower source index, the weight of index + 1 and the
+ * weight of the index itself, computed by the caller in the image dtype as the reference does. */
+int plnr_resize_linear(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y, const int* row_lo, const float* row_w,
+                       const float* row_w1, const int* col_lo, const float* col_w, const float* col_w1);
 /* AveragePool with the reference's semantics: ZERO padding, divisor kh*kw whatever the window covers
  * (planer/layer.py:74-75 -> planer/util.py:97-100). */
 int plnr_avgpool2d(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y,

@@ -327,6 +327,26 @@ def upsample_bilinear(x, k):
     return out[:, :, k[0] // 2:h * k[0] + k[0] // 2, k[1] // 2:w * k[1] + k[1] // 2]
 
 
+def upsample_size(x, size):
+    """Bilinear resize to an arbitrary (H, W): centre-aligned source coordinates computed IN THE IMAGE DTYPE, clipped to the
+    image, gather + lerp along columns, then along rows.  reference: planer/util.py:194-210 (upsample_size)."""
+    lead, (h, w) = x.shape[:-2], x.shape[-2:]
+    kh, kw = size[0] / h, size[1] / w
+    rs = np.linspace(-0.5 + 0.5 / kh, h - 0.5 - 0.5 / kh, size[0], dtype=x.dtype)
+    cs = np.linspace(-0.5 + 0.5 / kw, w - 0.5 - 0.5 / kw, size[1], dtype=x.dtype)
+    rs = np.clip(rs, 0, h - 1, out=rs)
+    cs = np.clip(cs, 0, w - 1, out=cs)
+    ra = np.floor(np.clip(rs, 0, h - 1.001)).astype(int)
+    ca = np.floor(np.clip(cs, 0, w - 1.001)).astype(int)
+    rs -= ra
+    cs -= ca
+    rs = rs.reshape(-1, 1)
+    img = x.reshape(-1, h, w)
+    cols = img[:, :, ca] * (1 - cs) + img[:, :, ca + 1] * cs
+    out = cols[:, ra, :] * (1 - rs) + cols[:, ra + 1, :] * rs
+    return out.reshape(lead + tuple(size))
+
+
 def _upsample(x, k, mode, trans_mode, round_mode):
     """reference: planer/util.py:212-219 (upsample) for whole-number factors."""
     kint = [int(k[0]), int(k[1])]
@@ -334,7 +354,9 @@ def _upsample(x, k, mode, trans_mode, round_mode):
         return upsample_nearest(x, kint, trans_mode, round_mode)
     if mode == 'linear' and k[0] == int(k[0]) and k[1] == int(k[1]):
         return upsample_bilinear(x, kint)
-    raise NotImplementedError('oracle: fractional-scale resize (planer/util.py:194-210) is not restated')
+    if mode == 'linear':
+        return upsample_size(x, (int(round(k[0] * x.shape[2])), int(round(k[1] * x.shape[3]))))
+    raise NotImplementedError('oracle: unknown resize mode %r' % mode)
 
 
 def upsample(x, k, mode='nearest'):

@@ -66,6 +66,7 @@ PROTOTYPES = {
     'plnr_dense_fwd': [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(Epilogue), C.c_int],
     'plnr_maxpool2d': [_P, C.c_int, _TP, _TP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
     'plnr_upsample_linear': [_P, C.c_int, _TP, _TP, C.c_int, C.c_int, _P],
+    'plnr_resize_linear': [_P, C.c_int, _TP, _TP, _P, _P, _P, _P, _P, _P],
     'plnr_avgpool2d': [_P, C.c_int, _TP, _TP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
     'plnr_zero_stuff': [_P, C.c_int, _TP, _TP, C.c_int, C.c_int, C.c_int, C.c_int],
     'plnr_flip_weight': [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int],

@@ -362,6 +362,41 @@ __global__ void upsample_linear_kernel(const T* __restrict__ x, T* __restrict__ 
   }
 }
 
+// Bilinear resize to an arbitrary size (planer/util.py:194-210, upsample_size): separable gather + lerp, columns first.  The
+// source indices and weights of every output row / column come from the host, computed in the image dtype exactly as the
+// reference does (a float16 image gets float16 coordinates there); tables: lo index, weight of lo + 1, one minus that weight.
+template <typename T, int V>
+__global__ void resize_linear_kernel(const T* __restrict__ x, T* __restrict__ y, const int* __restrict__ rlo, const float* __restrict__ rw,
+                                     const float* __restrict__ rw1, const int* __restrict__ clo, const float* __restrict__ cw,
+                                     const float* __restrict__ cw1, int N, int H, int W, int C, int xld, int xcoff, int OH, int OW,
+                                     int yld, int ycoff) {
+  const int CV = C / V;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= OW * CV) return;
+  const int ox = t / CV, cv = t - ox * CV;
+  const int c0 = clo[ox], c1 = min(c0 + 1, W - 1);
+  const float fc = cw[ox], gc = cw1[ox];
+  for (int64_t row = blockIdx.y; row < (int64_t)N * OH; row += gridDim.y) {
+    const int n = (int)(row / OH), oy = (int)(row - (int64_t)n * OH);
+    const int r0 = rlo[oy], r1 = min(r0 + 1, H - 1);
+    const float fr = rw[oy], gr = rw1[oy];
+    const T* xb = x + (size_t)n * H * W * xld + xcoff + cv * V;
+    const Vec<T, V> p00 = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)r0 * W + c0) * xld);
+    const Vec<T, V> p01 = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)r0 * W + c1) * xld);
+    const Vec<T, V> p10 = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)r1 * W + c0) * xld);
+    const Vec<T, V> p11 = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)r1 * W + c1) * xld);
+    Vec<T, V> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      T top, bot;                                            // the column pass is rounded to the image dtype (buf in util.py:208)
+      st_f(&top, ld_f(&p00.v[k]) * gc + ld_f(&p01.v[k]) * fc);
+      st_f(&bot, ld_f(&p10.v[k]) * gc + ld_f(&p11.v[k]) * fc);
+      st_f(&o.v[k], ld_f(&top) * gr + ld_f(&bot) * fr);
+    }
+    *reinterpret_cast<Vec<T, V>*>(y + (((size_t)n * OH + oy) * OW + ox) * yld + ycoff + cv * V) = o;
+  }
+}
+
 template <typename T, int V>
 __global__ void copy_channels_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t npix, int C, int xld,
                                      int xcoff, int yld, int ycoff) {
@@ -1151,6 +1186,26 @@ int plnr_upsample_linear(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const p
     }
   })
   return plnr_after_launch(ctx, "upsample_linear");
+}
+
+int plnr_resize_linear(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y, const int* row_lo, const float* row_w,
+                       const float* row_w1, const int* col_lo, const float* col_w, const float* col_w1) {
+  PLNR_REQUIRE(ctx && x && y && x->ptr && y->ptr && row_lo && row_w && row_w1 && col_lo && col_w && col_w1,
+               "resize_linear: NULL argument");
+  PLNR_REQUIRE(y->n == x->n && y->c == x->c && x->h >= 1 && x->w >= 1, "resize_linear: batch/channel mismatch");
+  DISPATCH_T(dtype, {
+    constexpr int V = VecWidth<T>::value;
+    if (view_vec_ok(x, V, sizeof(T)) && view_vec_ok(y, V, sizeof(T))) {
+      resize_linear_kernel<T, V><<<row_grid(y->w * (y->c / V), (int64_t)y->n * y->h, ctx->sm_count), kThreads, 0, ctx->stream>>>(
+          (const T*)x->ptr, (T*)y->ptr, row_lo, row_w, row_w1, col_lo, col_w, col_w1, x->n, x->h, x->w, x->c, x->ld, x->coff,
+          y->h, y->w, y->ld, y->coff);
+    } else {
+      resize_linear_kernel<T, 1><<<row_grid(y->w * y->c, (int64_t)y->n * y->h, ctx->sm_count), kThreads, 0, ctx->stream>>>(
+          (const T*)x->ptr, (T*)y->ptr, row_lo, row_w, row_w1, col_lo, col_w, col_w1, x->n, x->h, x->w, x->c, x->ld, x->coff,
+          y->h, y->w, y->ld, y->coff);
+    }
+  })
+  return plnr_after_launch(ctx, "resize_linear");
 }
 
 int plnr_copy_channels(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_tensor* y) {

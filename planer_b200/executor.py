@@ -353,6 +353,8 @@ class Executor:
             return lambda: ops.maxpool_into(x, y, a['w'], a['pads'], a['strides'])
         if op == 'upsample':
             x, y, a = self._view(st.ins[0]), alloc(st.out), st.attrs
+            if a.get('mode') == 'linear_size':
+                return lambda: ops.resize_linear_into(x, y)
             if a.get('mode', 'nearest') == 'linear':
                 ops.upsample_linear_weights(a['fh'], a['fw'])            # uploaded now, outside graph capture
                 return lambda: ops.upsample_linear_into(x, y, a['fh'], a['fw'])

@@ -276,12 +276,24 @@ def Resize(x, roi, k, size=None, mode='nearest', coordinate_transformation_mode=
         raise NotImplementedError('Resize with `sizes` instead of `scales` is not implemented')
     f = _int_scales(k)
     if f is None:
-        raise NotImplementedError('Resize with fractional scales (planer/util.py:194-210) is not implemented')
+        if mode != 'linear':
+            raise NotImplementedError('Resize nearest with fractional scales truncates them in the reference '
+                                      '(planer/util.py:213,216); not implemented')
+        kk = (k.get() if isinstance(k, DeviceArray) else np.asarray(k)).reshape(-1)[-2:].tolist()
+        x = _as_nhwc(x)
+        n, c, h, w = x.shape
+        size = resize_size((h, w), kk)
+        return ops.resize_linear_into(x, B.empty((n, c) + size, x.dtype, 'nhwc'))
     if mode == 'nearest' and (nearest_shift(f[0], coordinate_transformation_mode, nearest_mode) or
                               nearest_shift(f[1], coordinate_transformation_mode, nearest_mode)):
         raise NotImplementedError('Resize nearest with a non-zero pixel shift (%s, %s) is not implemented'
                                   % (coordinate_transformation_mode, nearest_mode))
     return _upsample(x, f[0], f[1], mode, 'Resize')
+
+
+def resize_size(hw, scales):
+    """Output size of a fractional-scale resize (planer/util.py:214)."""
+    return int(round(scales[0] * hw[0])), int(round(scales[1] * hw[1]))
 
 
 def nearest_shift(k, trans_mode, round_mode):

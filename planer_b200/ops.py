@@ -191,6 +191,35 @@ def upsample_linear_into(x, y, fh, fw):
     return y
 
 
+def resize_linear_tables(n_in, n_out, dtype):
+    """Source index / weights of every output sample along one axis, computed in the IMAGE dtype exactly like the reference
+    (planer/util.py:196-206): centre-aligned coordinates, clipped; -> (lo int32, weight of lo+1, weight of lo) as fp32."""
+    dtype = np.dtype(dtype)
+    k = n_out / n_in
+    pos = np.linspace(-0.5 + 0.5 / k, n_in - 0.5 - 0.5 / k, n_out, dtype=dtype)
+    pos = np.clip(pos, 0, n_in - 1, out=pos)
+    lo = np.floor(np.clip(pos, 0, n_in - 1.001)).astype(int)
+    pos -= lo
+    return lo.astype(np.int32), pos.astype(np.float32), (1 - pos).astype(np.float32)
+
+
+_resize_cache = {}
+
+
+def resize_linear_into(x, y):
+    """Bilinear resize of x (n, c, h, w) to y's spatial size (planer/util.py:194-210)."""
+    key = (x.shape[2], x.shape[3], y.shape[2], y.shape[3], str(x.dtype))
+    if key not in _resize_cache:
+        if len(_resize_cache) > 256: _resize_cache.clear()
+        _resize_cache[key] = [B.asarray(t) for t in resize_linear_tables(x.shape[2], y.shape[2], x.dtype) +
+                              resize_linear_tables(x.shape[3], y.shape[3], x.dtype)]
+    rl, rw, rw1, cl, cw, cw1 = _resize_cache[key]
+    tx, ty = x.tensor(), y.tensor()
+    _capi.check(B.lib().plnr_resize_linear(B.ctx(), _capi.dtype_code(x.dtype), C.byref(tx), C.byref(ty), rl.ptr, rw.ptr, rw1.ptr,
+                                           cl.ptr, cw.ptr, cw1.ptr), 'plnr_resize_linear')
+    return y
+
+
 def upsample_into(x, y, fh, fw):
     tx, ty = x.tensor(), y.tensor()
     _capi.check(B.lib().plnr_upsample_nearest(B.ctx(), _capi.dtype_code(x.dtype), C.byref(tx), C.byref(ty), fh, fw),

@@ -177,8 +177,16 @@ def infer(values, nodes, host_consts=None):
             if scales is None:
                 raise ValueError('%s %r: scales tensor %r must be a constant init' % (k, nd.name, sname))
             sc = np.asarray(scales, np.float64).reshape(-1)[-2:]
-            if k == 'resize' and (sc.size != 2 or np.any(sc != np.floor(sc))):
-                raise NotImplementedError('resize %r: fractional scales (planer/util.py:194-210) are not implemented' % nd.name)
+            if k == 'resize' and sc.size == 2 and np.any(sc != np.floor(sc)):
+                if mode != 'linear':
+                    raise NotImplementedError('resize %r: nearest with fractional scales is not implemented' % nd.name)
+                n, c, h, w = sh[0]
+                out = (n, c, int(round(float(sc[0]) * h)), int(round(float(sc[1]) * w)))      # planer/util.py:214
+                nd.attrs = dict(mode='linear_size')
+                values[nd.outs[0]].shape = tuple(int(v) for v in out)
+                continue
+            if k == 'resize' and sc.size != 2:
+                raise NotImplementedError('resize %r: needs a 4-entry scales tensor' % nd.name)
             f = sc.astype(int).tolist()                                           # planer/layer.py:82
             if mode not in ('nearest', 'linear') or (mode == 'linear' and min(f) < 2):
                 raise NotImplementedError("%s %r: mode %r with factors %s is not implemented" % (k, nd.name, mode, f))

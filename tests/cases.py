@@ -87,6 +87,12 @@ OP_CASES = {
                                           {'mode': 'linear'}),
     'resize_linear_x2': lambda n: ('resize', [_x(_rng(n), (1, 8, 9, 6), 'float32'), np.zeros(0, 'float32'),
                                               np.array([1, 1, 2, 2], 'float32')], {'mode': 'linear'}),
+    'resize_linear_1p5': lambda n: ('resize', [_x(_rng(n), (2, 8, 9, 6), 'float32'), np.zeros(0, 'float32'),
+                                               np.array([1, 1, 1.5, 2.5], 'float32')], {'mode': 'linear'}),
+    # (fp32 only: with a float16 image the reference computes the coordinates in float16, where w - 1.001 rounds up to w - 1
+    #  for w >= 5 and its own gather then indexes one past the edge, planer/util.py:204-208)
+    'resize_linear_down': lambda n: ('resize', [_x(_rng(n), (1, 16, 12, 10), 'float32'), np.zeros(0, 'float32'),
+                                                np.array([1, 1, 0.75, 1.3], 'float32')], {'mode': 'linear'}),
     'resize_nearest_x2': lambda n: ('resize', [_x(_rng(n), (2, 8, 4, 6), 'float32'), np.zeros(0, 'float32'),
                                                np.array([1, 1, 2, 2], 'float32')], {'mode': 'nearest'}),
     'resize_nearest_asym_floor_x3': lambda n: ('resize', [_x(_rng(n), (1, 8, 4, 5), 'float16'), np.zeros(0, 'float32'),
