@@ -5,8 +5,10 @@ batch 128 per GPU (configs[2]; configs[4] = 8 x 128 is the same workload weak-sc
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 Prints ONE JSON line (rank 0).  A "step" is one forward of the whole graph over one batch of synthetic
-NCHW input.  `value` is device-timed with inputs resident in HBM; `e2e` goes through the public
-``net(numpy_array)`` call with pinned-host H2D and the D2H of the logits inside the timed region.
+NCHW input.  `value` is device-timed with inputs resident in HBM; `e2e` goes through the public API from
+HOST memory -- ``for y in net.map(batches)``, a pinned numpy batch uploaded and the logits read back for
+every step inside the timed region, two batches in flight -- and `e2e.blocking_call` is the same through
+the reference-shaped blocking ``y = net(x)`` per batch.
 The reference arm times the numpy restatement of the reference (oracle/planer_oracle.py, "port") on the
 host cores -- the only place outside tests/ and smoke() where oracle/ is executed.
 """
