@@ -635,6 +635,12 @@ static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
     pl.cg = 2;
     pl.b_stage_bytes = (uint32_t)(pl.n_tile / 2) * 128;
   }
+  // streamed N = 256 weights: a pair halves the B bytes each CTA moves (TMA writes + MMA reads: 20 KB -> 12 KB per K=16 step,
+  // under the 128-clk tensor time); measured +1.2 % on the ResNet-18 step (PLNR_SHIFT_CTA_GROUP A/B)
+  if (forced == 0 && pl.cg == 1 && !resident_fits(1, 2) && pl.n_tile == 256 && m_tiles_128 >= 2) {
+    pl.cg = 2;
+    pl.b_stage_bytes = (uint32_t)(pl.n_tile / 2) * 128;
+  }
   if (resident_fits(pl.cg, 2)) {
     pl.b_resident = 1;
     pl.nb = kst;
