@@ -18,7 +18,9 @@
  *     [coff, coff+C) of the row.  (The reference itself hands non-contiguous CNHW views between
  *     layers -- planer/util.py:44 -- so inter-layer layout is not part of its contract; NCHW is
  *     restored at the graph boundary by plnr_nhwc_to_nchw.)
- *   - dtype codes: PLNR_F32 / PLNR_F16.
+ *   - dtype codes: PLNR_F32 / PLNR_F16 for everything the path computes on; PLNR_U8 is accepted as the SOURCE dtype of
+ *     the graph-entry functions (plnr_nchw_to_nhwc, plnr_stem_pack, plnr_stem_pool_fwd_u8, plnr_cast): the numpy reference
+ *     promotes a uint8 image against float weights (planer/layer.py:22-26 on a uint8 x), i.e. computes on x.astype(w.dtype).
  */
 #ifndef PLANER_B200_H
 #define PLANER_B200_H
@@ -32,7 +34,7 @@ extern "C" {
 
 #define PLNR_ABI_VERSION 1
 
-enum { PLNR_F32 = 0, PLNR_F16 = 1 };
+enum { PLNR_F32 = 0, PLNR_F16 = 1, PLNR_U8 = 2 /* graph INPUTS only: uint8 images, converted by the input-time kernel */ };
 enum { PLNR_ACT_NONE = 0, PLNR_ACT_RELU = 1, PLNR_ACT_LEAKY = 2, PLNR_ACT_SIGMOID = 3 };
 enum { PLNR_ALGO_AUTO = 0, PLNR_ALGO_TCGEN05 = 1, PLNR_ALGO_DIRECT = 2 };
 enum {
@@ -127,6 +129,11 @@ int plnr_stem_pool_geometry(int kh, int pad_t, int pad_l, int* e_min, int* taps,
 int plnr_stem_pool_fwd(plnr_ctx* ctx, const void* x, int n, int c, int h, int w, const void* w_packed,
                        const float* scale, const float* shift, int kh, int kw, int stride, int pad_t, int pad_l,
                        int pad_b, int pad_r, int act, int pool_k, int pool_stride, int pool_pad, const plnr_tensor* y);
+/* The same with a uint8 image x (n, 3, h, w): the producer warps convert while staging (exact: 0..255 are fp16 numbers).
+ * Replaces planer/net.py:96-98 + planer/layer.py:22-26 on a uint8 array (numpy promotes uint8 x float16 to float16). */
+int plnr_stem_pool_fwd_u8(plnr_ctx* ctx, const void* x, int n, int c, int h, int w, const void* w_packed,
+                          const float* scale, const float* shift, int kh, int kw, int stride, int pad_t, int pad_l,
+                          int pad_b, int pad_r, int act, int pool_k, int pool_stride, int pool_pad, const plnr_tensor* y);
 /* pixel-major view x -> NCHW dense y.  Graph exit: planer/net.py:100. */
 int plnr_nhwc_to_nchw(plnr_ctx* ctx, const plnr_tensor* x, int x_dtype, void* y, int y_dtype);
 /* flat cast, n elements (Net.half, planer/net.py:26-29). */

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # PLNR_LIB: another build of the same library (A/B timing of two kernel versions on one box); never a different backend
 LIB_PATH = os.environ.get('PLNR_LIB') or os.path.join(HERE, 'libplaner_b200.so')
 
-F32, F16 = 0, 1
+F32, F16, U8 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
 ALGO_AUTO, ALGO_TCGEN05, ALGO_DIRECT = 0, 1, 2
 EW_RELU, EW_LEAKY, EW_SIGMOID, EW_ADD, EW_SCALE_SHIFT, EW_CLIP, EW_HARDSIGMOID = 0, 1, 2, 3, 4, 5, 6
@@ -56,6 +56,7 @@ PROTOTYPES = {
     'plnr_stem_pool_supported': [C.c_int] * 16,
     'plnr_stem_pool_geometry': [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
     'plnr_stem_pool_fwd': [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P] + [C.c_int] * 11 + [_TP],
+    'plnr_stem_pool_fwd_u8': [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P] + [C.c_int] * 11 + [_TP],
     'plnr_nhwc_to_nchw': [_P, _TP, C.c_int, _P, C.c_int],
     'plnr_cast': [_P, _P, C.c_int, _P, C.c_int, C.c_int64],
     'plnr_pack_conv_weight': [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
@@ -123,6 +124,13 @@ def check(rc, what=''):
         msg = _lib.plnr_last_error().decode(errors='replace') if _lib is not None else ''
         raise PlanerB200Error('%s failed (rc=%d): %s' % (what or 'libplaner_b200 call', rc, msg))
     return rc
+
+
+def src_dtype_code(dt):
+    """dtype code of a graph INPUT as the caller hands it over: float32 / float16, or uint8 images (converted by the
+    graph-entry kernels: plnr_nchw_to_nhwc, plnr_stem_pack, plnr_stem_pool_fwd_u8, plnr_cast)."""
+    import numpy as np
+    return U8 if np.dtype(dt) == np.uint8 else dtype_code(dt)
 
 
 def dtype_code(dt):

@@ -280,6 +280,16 @@ def asarray_async(a):
     return out, ev
 
 
+def clone(a):
+    """Device copy of a flat array on the library stream (results handed to the caller must outlive the next forward)."""
+    src = to_flat(a)
+    out = empty(src.shape, src.dtype)
+    if src.nbytes:
+        with _torch().cuda.stream(stream()):
+            out.buf[:src.nbytes].copy_(src.buf[src.offset:src.offset + src.nbytes], non_blocking=True)
+    return out
+
+
 def asnumpy(a):
     return a.get() if isinstance(a, DeviceArray) else np.asarray(a)
 
@@ -310,6 +320,6 @@ def to_nhwc(a, dtype=None, cpad=None):
     cp = c if cpad is None else cpad
     out = empty((n, cp, h, w), dtype, 'nhwc')
     t = out.tensor()
-    _capi.check(lib().plnr_nchw_to_nhwc(ctx(), a.ptr, _capi.dtype_code(a.dtype), c, C.byref(t),
+    _capi.check(lib().plnr_nchw_to_nhwc(ctx(), a.ptr, _capi.src_dtype_code(a.dtype), c, C.byref(t),
                                         _capi.dtype_code(dtype)), 'plnr_nchw_to_nhwc')
     return out

@@ -82,7 +82,7 @@ static inline bool plnr_pdl_enabled() {
   return v == 1;
 }
 
-static inline size_t plnr_dtype_size(int dt) { return dt == PLNR_F16 ? 2 : 4; }
+static inline size_t plnr_dtype_size(int dt) { return dt == PLNR_F16 ? 2 : (dt == PLNR_U8 ? 1 : 4); }
 
 static inline int plnr_out_size(int n_in, int pad_lo, int pad_hi, int k, int dil, int stride) {
   // planer/util.py:25-26
@@ -93,6 +93,7 @@ static inline int plnr_out_size(int n_in, int pad_lo, int pad_hi, int k, int dil
 template <typename T> __device__ __forceinline__ float ld_f(const T* p);
 template <> __device__ __forceinline__ float ld_f<float>(const float* p) { return *p; }
 template <> __device__ __forceinline__ float ld_f<__half>(const __half* p) { return __half2float(*p); }
+template <> __device__ __forceinline__ float ld_f<uint8_t>(const uint8_t* p) { return (float)*p; }
 template <typename T> __device__ __forceinline__ void st_f(T* p, float v);
 template <> __device__ __forceinline__ void st_f<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void st_f<__half>(__half* p, float v) { *p = __float2half_rn(v); }

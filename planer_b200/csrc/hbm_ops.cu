@@ -974,7 +974,10 @@ int plnr_nchw_to_nhwc(plnr_ctx* ctx, const void* x, int x_dtype, int c_src, cons
 #define LAUNCH(TI, TO)                                                                                       \
   nchw_to_nhwc_kernel<TI, TO><<<grid, block, 0, ctx->stream>>>((const TI*)x, (TO*)y->ptr, c_src, HW, y->c, y->ld, \
                                                                y->coff)
-  if (x_dtype == PLNR_F32 && y_dtype == PLNR_F32) LAUNCH(float, float);
+  PLNR_REQUIRE(y_dtype == PLNR_F32 || y_dtype == PLNR_F16, "nchw_to_nhwc: the output dtype must be F32 or F16");
+  if (x_dtype == PLNR_U8 && y_dtype == PLNR_F16) LAUNCH(uint8_t, __half);        // uint8 images: value-preserving cast
+  else if (x_dtype == PLNR_U8) LAUNCH(uint8_t, float);
+  else if (x_dtype == PLNR_F32 && y_dtype == PLNR_F32) LAUNCH(float, float);
   else if (x_dtype == PLNR_F32 && y_dtype == PLNR_F16) LAUNCH(float, __half);
   else if (x_dtype == PLNR_F16 && y_dtype == PLNR_F16) LAUNCH(__half, __half);
   else LAUNCH(__half, float);
@@ -993,7 +996,10 @@ int plnr_stem_pack(plnr_ctx* ctx, const void* x, int x_dtype, int n, int c, int 
   const size_t smem = (size_t)((stride * c * Wp + 7) / 8) * 8 * 2 + (size_t)y->c * 4;
   PLNR_REQUIRE(smem <= 48 * 1024, "stem_pack: source rows do not fit shared memory (%zu bytes)", smem);
   const int grid = n * y->h;
-  if (x_dtype == PLNR_F16)
+  if (x_dtype == PLNR_U8)
+    stem_pack_kernel<uint8_t><<<grid, 256, smem, ctx->stream>>>((const uint8_t*)x, (__half*)y->ptr, n, c, h, w, y->h, y->w,
+                                                                y->c, kw, stride, pad_l, Wp);
+  else if (x_dtype == PLNR_F16)
     stem_pack_kernel<__half><<<grid, 256, smem, ctx->stream>>>((const __half*)x, (__half*)y->ptr, n, c, h, w, y->h, y->w,
                                                                y->c, kw, stride, pad_l, Wp);
   else
@@ -1021,7 +1027,12 @@ int plnr_cast(plnr_ctx* ctx, const void* x, int x_dtype, void* y, int y_dtype, i
   PLNR_REQUIRE(ctx && x && y && n >= 0, "cast: bad argument");
   if (n == 0) return PLNR_OK;
   int grid = grid_for(n, ctx->sm_count);
-  if (x_dtype == PLNR_F32 && y_dtype == PLNR_F16)
+  PLNR_REQUIRE(y_dtype == PLNR_F32 || y_dtype == PLNR_F16, "cast: the output dtype must be F32 or F16");
+  if (x_dtype == PLNR_U8 && y_dtype == PLNR_F16)
+    cast_kernel<uint8_t, __half><<<grid, kThreads, 0, ctx->stream>>>((const uint8_t*)x, (__half*)y, n);
+  else if (x_dtype == PLNR_U8)
+    cast_kernel<uint8_t, float><<<grid, kThreads, 0, ctx->stream>>>((const uint8_t*)x, (float*)y, n);
+  else if (x_dtype == PLNR_F32 && y_dtype == PLNR_F16)
     cast_kernel<float, __half><<<grid, kThreads, 0, ctx->stream>>>((const float*)x, (__half*)y, n);
   else if (x_dtype == PLNR_F16 && y_dtype == PLNR_F32)
     cast_kernel<__half, float><<<grid, kThreads, 0, ctx->stream>>>((const __half*)x, (float*)y, n);

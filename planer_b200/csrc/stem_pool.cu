@@ -43,7 +43,7 @@ constexpr int kProducerWarps = 4;
 constexpr long long kWatchdogCycles = 4000000000ll;
 
 struct StemParams {
-  const __half* x;                      // NCHW
+  const void* x;                        // NCHW, fp16 or (U8 instantiation) uint8
   int N, H, W, OH, OW, POH, POW;
   int e_min, T;
   int P;                                // staging position of image column 0 (pad_l rounded up to even)
@@ -96,6 +96,17 @@ __device__ __forceinline__ uint32_t h2_u32(__half2 h) { return *reinterpret_cast
 __device__ __forceinline__ __half2 u32_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) { return h2_u32(__hmax2(u32_h2(a), u32_h2(b))); }
 
+// eight uint8 pixels -> eight fp16 values, exactly: byte b under exponent byte 0x64 is the fp16 number 1024 + b
+__device__ __forceinline__ uint4 u8x8_to_h8(uint2 r) {
+  const __half2 k1024 = u32_h2(0x64006400u);
+  uint4 o;
+  o.x = h2_u32(__hsub2(u32_h2(__byte_perm(r.x, 0x64646464u, 0x5140)), k1024));
+  o.y = h2_u32(__hsub2(u32_h2(__byte_perm(r.x, 0x64646464u, 0x7362)), k1024));
+  o.z = h2_u32(__hsub2(u32_h2(__byte_perm(r.y, 0x64646464u, 0x5140)), k1024));
+  o.w = h2_u32(__hsub2(u32_h2(__byte_perm(r.y, 0x64646464u, 0x7362)), k1024));
+  return o;
+}
+
 // rows of one work item: pooled rows [p0, p0 + np), conv rows [h0, h1] (the ones that exist), packed rows from t0
 struct ItemGeom { int img, p0, np, h0, h1, nrows, npk; };
 __device__ __forceinline__ ItemGeom item_geom(const StemParams& p, int item) {
@@ -111,6 +122,7 @@ __device__ __forceinline__ ItemGeom item_geom(const StemParams& p, int item) {
   return g;
 }
 
+template <bool U8>
 __global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -245,12 +257,17 @@ __global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const StemParams
     const int two_w = 2 * p.W;
     auto load_row = [&](const Cur& c) {                     // global -> registers
       const int t = c.g.h0 + p.e_min + c.i;
-      const __half* xrow = p.x + (size_t)c.g.img * 3 * p.H * p.W + (long long)t * two_w;
+      const long long row0 = (long long)c.g.img * 3 * p.H * p.W + (long long)t * two_w;     // in elements
 #pragma unroll
       for (int k = 0; k < kMaxLd; ++k) {
         const int ih = 2 * t + ld_ph[k];
         q[k] = make_uint4(0u, 0u, 0u, 0u);
-        if (ld_goff[k] >= 0 && ih >= 0 && ih < p.H) q[k] = __ldg(reinterpret_cast<const uint4*>(xrow + ld_goff[k]));
+        if (ld_goff[k] >= 0 && ih >= 0 && ih < p.H) {
+          if (U8)       // uint8 image: 8-byte loads, converted here so that staging and gather are those of the fp16 path
+            q[k] = u8x8_to_h8(__ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(p.x) + row0 + ld_goff[k])));
+          else
+            q[k] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.x) + row0 + ld_goff[k]));
+        }
       }
     };
     auto store_row = [&](uint8_t* stg) {                    // registers -> planar staging rows [channel][phase][position]
@@ -488,10 +505,10 @@ extern "C" int plnr_stem_pool_geometry(int kh, int pad_t, int pad_l, int* e_min,
   return PLNR_OK;
 }
 
-extern "C" int plnr_stem_pool_fwd(plnr_ctx* ctx, const void* x, int n, int c, int h, int w, const void* w_packed,
-                                  const float* scale, const float* shift, int kh, int kw, int stride, int pad_t,
-                                  int pad_l, int pad_b, int pad_r, int act, int pool_k, int pool_stride, int pool_pad,
-                                  const plnr_tensor* y) {
+static int stem_pool_launch(plnr_ctx* ctx, const void* x, bool u8, int n, int c, int h, int w, const void* w_packed,
+                            const float* scale, const float* shift, int kh, int kw, int stride, int pad_t,
+                            int pad_l, int pad_b, int pad_r, int act, int pool_k, int pool_stride, int pool_pad,
+                            const plnr_tensor* y) {
   PLNR_REQUIRE(ctx && x && w_packed && y && y->ptr, "stem_pool: NULL argument");
   PLNR_REQUIRE(act == PLNR_ACT_RELU, "stem_pool: only the ReLU epilogue makes the pooling pad neutral (act=%d)", act);
   const StemPlan pl = make_plan(c, h, w, y->c, kh, kw, stride, pad_t, pad_l, pad_b, pad_r, pool_k, pool_stride, pool_pad);
@@ -499,13 +516,13 @@ extern "C" int plnr_stem_pool_fwd(plnr_ctx* ctx, const void* x, int n, int c, in
                kh, kw, stride, pool_k, pool_stride, pool_pad);
   PLNR_REQUIRE(y->n == n && y->h == pl.POH && y->w == pl.POW, "stem_pool: output is (%d,%d,%d), expected (%d,%d,%d)",
                y->n, y->h, y->w, n, pl.POH, pl.POW);
-  PLNR_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 &&
+  PLNR_REQUIRE((reinterpret_cast<uintptr_t>(x) & (u8 ? 7 : 15)) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && y->ld % 8 == 0 && y->coff % 8 == 0,
                "stem_pool: pointers must be 16-byte aligned, ld/coff multiples of 8");
 
   StemParams p;
   memset(&p, 0, sizeof(p));
-  p.x = (const __half*)x;
+  p.x = x;
   p.N = n; p.H = h; p.W = w; p.OH = pl.OH; p.OW = pl.OW; p.POH = pl.POH; p.POW = pl.POW;
   p.e_min = pl.e_min; p.T = pl.T; p.P = pl.P;
   // bands of PB pooled rows: enough items to balance the persistent grid, few enough that the one-row halo stays cheap
@@ -523,10 +540,28 @@ extern "C" int plnr_stem_pool_fwd(plnr_ctx* ctx, const void* x, int n, int c, in
 
   static bool attr_set = false;
   if (!attr_set) {
-    PLNR_CHECK_CUDA(cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    PLNR_CHECK_CUDA(cudaFuncSetAttribute(stem_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    PLNR_CHECK_CUDA(cudaFuncSetAttribute(stem_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   int grid = ctx->sm_count < p.items ? ctx->sm_count : p.items;
-  stem_pool_kernel<<<grid, kThreads, pl.smem_bytes, ctx->stream>>>(p);
+  if (u8) stem_pool_kernel<true><<<grid, kThreads, pl.smem_bytes, ctx->stream>>>(p);
+  else stem_pool_kernel<false><<<grid, kThreads, pl.smem_bytes, ctx->stream>>>(p);
   return plnr_after_launch(ctx, "stem_pool");
+}
+
+extern "C" int plnr_stem_pool_fwd(plnr_ctx* ctx, const void* x, int n, int c, int h, int w, const void* w_packed,
+                                  const float* scale, const float* shift, int kh, int kw, int stride, int pad_t,
+                                  int pad_l, int pad_b, int pad_r, int act, int pool_k, int pool_stride, int pool_pad,
+                                  const plnr_tensor* y) {
+  return stem_pool_launch(ctx, x, false, n, c, h, w, w_packed, scale, shift, kh, kw, stride, pad_t, pad_l, pad_b, pad_r, act,
+                          pool_k, pool_stride, pool_pad, y);
+}
+
+extern "C" int plnr_stem_pool_fwd_u8(plnr_ctx* ctx, const void* x, int n, int c, int h, int w, const void* w_packed,
+                                     const float* scale, const float* shift, int kh, int kw, int stride, int pad_t,
+                                     int pad_l, int pad_b, int pad_r, int act, int pool_k, int pool_stride, int pool_pad,
+                                     const plnr_tensor* y) {
+  return stem_pool_launch(ctx, x, true, n, c, h, w, w_packed, scale, shift, kh, kw, stride, pad_t, pad_l, pad_b, pad_r, act,
+                          pool_k, pool_stride, pool_pad, y);
 }

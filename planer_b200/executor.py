@@ -20,9 +20,11 @@ def _round_up(v, m):
 
 
 class Executor:
-    def __init__(self, net, gplan, dtype, use_graph=True):
+    def __init__(self, net, gplan, dtype, use_graph=True, input_dtypes=None):
         self.net, self.plan, self.dtype = net, gplan, np.dtype(dtype)
         self.use_graph = use_graph
+        # dtype each graph input arrives in (uint8 images and fp32 arrays are converted by the input-time kernel)
+        self.input_dtypes = [np.dtype(d) for d in input_dtypes] if input_dtypes else [self.dtype] * len(gplan.inputs)
         self.values = gplan.values
         self.arr = {}             # root value id -> DeviceArray
         self.launches = []        # closures, in order
@@ -32,6 +34,7 @@ class Executor:
         self.input_ids = list(gplan.inputs)
         self.in_arrays, self.out_arrays, self.out_flat = [], [], []
         self._keep = []
+        self._in_stage = {}       # graph input -> fp16 staging array (fp32 images on the fused first layer)
         self._build()
 
     # ------------------------------------------------------------------------------------------
@@ -59,6 +62,8 @@ class Executor:
         users = [st for st in self.plan.steps if vid in [self._root(r) for r in st.reads()]]
         if len(prod) != 1 or prod[0].op != 'conv' or users or prod[0].shortcut is not None or prod[0].attrs.get('group', 1) != 1:
             return c
+        if prod[0].res is not None:
+            return c                 # a fused residual operand has the logical channel count: keep the unpadded path
         if self._fused_stem_of(self._root(prod[0].ins[0])) is not None or self._stem_of(self._root(prod[0].ins[0])) is not None:
             return c
         return _round_up(c, 8)
@@ -67,8 +72,8 @@ class Executor:
         """Graph inputs feeding only group-1 convs are channel-padded to a multiple of 16 in fp16 so that the
         first layer runs on the tensor cores (Cin=3 -> 16; the packed weights carry zeros there)."""
         c = self.values[vid].shape[1]
-        if self.dtype != np.float16 or c % 16 == 0:
-            return c
+        if self.dtype != np.float16 or c % 16 == 0 or self.values[vid].is_output:
+            return c                 # an input that is also returned keeps its logical channels
         for st in self.plan.steps:
             if vid in [self._root(r) for r in st.reads()]:
                 if not (st.op == 'conv' and st.attrs['group'] == 1 and self._root(st.ins[0]) == vid):
@@ -353,17 +358,25 @@ class Executor:
             return lambda: ops.maxpool_into(x, y, a['w'], a['pads'], a['strides'])
         if op == 'upsample':
             x, y, a = self._view(st.ins[0]), alloc(st.out), st.attrs
+            # the interpolation tables are uploaded now (outside graph capture) and OWNED by this executor: its CUDA graph
+            # keeps their addresses
             if a.get('mode') == 'linear_size':
-                return lambda: ops.resize_linear_into(x, y)
+                tabs = ops.resize_linear_device_tables(x, y)
+                self._keep.append(tabs)
+                return lambda: ops.resize_linear_into(x, y, tabs)
             if a.get('mode', 'nearest') == 'linear':
-                ops.upsample_linear_weights(a['fh'], a['fw'])            # uploaded now, outside graph capture
-                return lambda: ops.upsample_linear_into(x, y, a['fh'], a['fw'])
+                wm = ops.upsample_linear_weights(a['fh'], a['fw'])
+                self._keep.append(wm)
+                return lambda: ops.upsample_linear_into(x, y, a['fh'], a['fw'], wm)
             return lambda: ops.upsample_into(x, y, a['fh'], a['fw'])
-        if op in ('hardsigmoid', 'clip'):
+        if op == 'clip':
+            x, a = self._get(st.ins[0]), st.attrs         # in place on the root storage, like relu (planer/layer.py:250-251)
+            if self._root(st.ins[0]) not in self.arr:
+                raise AssertionError('clip input not materialised')
+            return lambda: ops.unary2(ops.EW_CLIP, _dense(x), _dense(x), a.get('min', 0), a.get('max', 1))
+        if op == 'hardsigmoid':
             x, y, a = self._view(st.ins[0]), alloc(st.out), st.attrs
-            code = ops.EW_CLIP if op == 'clip' else ops.EW_HARDSIGMOID
-            p0, p1 = (a.get('min', 0), a.get('max', 1)) if op == 'clip' else (a.get('alpha', 0.2), a.get('beta', 0.5))
-            return lambda: ops.unary2(code, _dense(x), y, p0, p1)
+            return lambda: ops.unary2(ops.EW_HARDSIGMOID, _dense(x), y, a.get('alpha', 0.2), a.get('beta', 0.5))
         if op == 'softmax':
             x, y = self._view(st.ins[0]), alloc(st.out)
             return lambda: ops.softmax_into(_dense(x), y)
@@ -414,13 +427,21 @@ class Executor:
 
     # ------------------------------------------------------------------------------------------
     def _load_inputs(self, xs):
-        for a, x, vid in zip(self.in_arrays, xs, self.input_ids):
+        for k, (a, x, vid) in enumerate(zip(self.in_arrays, xs, self.input_ids)):
             shp = self.values[vid].shape
             if tuple(x.shape) != tuple(shp):
                 raise ValueError('input %r: plan compiled for shape %s, got %s' % (self.values[vid].name, shp, x.shape))
+            if x.dtype != self.input_dtypes[k]:
+                raise ValueError('input %r: plan compiled for dtype %s, got %s' % (self.values[vid].name,
+                                                                                  self.input_dtypes[k], x.dtype))
             if x.layout != 'flat':
                 x = B.to_flat(x)
             if vid in self.fused_stems:
+                if x.dtype not in (np.float16, np.uint8):           # fp32 host image on an fp16 net: one cast, then the fused kernel
+                    stage = self._in_stage.setdefault(vid, B.empty(shp, np.float16))
+                    _capi.check(B.lib().plnr_cast(B.ctx(), x.ptr, _capi.src_dtype_code(x.dtype), stage.ptr, _capi.F16, x.size),
+                                'plnr_cast')
+                    x = stage
                 self.fused_stems[vid]['run'](x)
             elif vid in self.stems:
                 sm = self.stems[vid]
@@ -428,7 +449,7 @@ class Executor:
             elif len(shp) == 4:
                 ops.nchw_to_nhwc_into(x, a, shp[1])
             else:
-                _capi.check(B.lib().plnr_cast(B.ctx(), x.ptr, _capi.dtype_code(x.dtype), a.ptr,
+                _capi.check(B.lib().plnr_cast(B.ctx(), x.ptr, _capi.src_dtype_code(x.dtype), a.ptr,
                                               _capi.dtype_code(a.dtype), x.size), 'plnr_cast')
 
     def run(self, xs):

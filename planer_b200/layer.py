@@ -49,7 +49,8 @@ def _cast_nhwc(x, dtype):
 
 
 def _compute_dtype(*arrs):
-    dts = {np.dtype(a.dtype) for a in arrs if a is not None}
+    # a uint8 image takes the dtype of the float operand (numpy: uint8 x float16 -> float16)
+    dts = {np.dtype(a.dtype) for a in arrs if a is not None and np.dtype(a.dtype) != np.uint8}
     return dts.pop() if len(dts) == 1 else np.dtype(np.float32)     # numpy would promote to fp32
 
 
@@ -139,9 +140,10 @@ def HardSigmoid(x, alpha=0.2, beta=0.5):
 
 
 def Clip(x, min=0, max=1):
-    """planer/layer.py:247-251: np.maximum(np.minimum(x, max), min)."""
-    x = _dense_rows(x)
-    return ops.unary2(ops.EW_CLIP, x, _like(x), min, max)
+    """planer/layer.py:247-251: np.minimum(x, max, out=x); np.maximum(x, min, out=x) -- IN PLACE, returns its input (the
+    numexpr branch of the reference, which allocates, is not the path the oracle pins)."""
+    d = _dense_rows(x)           # x itself when it is dense; a dense copy of a strided view / NCHW graph input otherwise
+    return ops.unary2(ops.EW_CLIP, d, d, min, max)
 
 
 def Softmax(x, axis=-1):

@@ -3,17 +3,23 @@
 Same attributes (``weights, body, flow, life, timer, input, inits, layer``) and methods (``load_json,
 load_weights, half, info, forward, timeit, run, __call__``).  Differences that matter:
 
-  * ``forward`` does not interpret the flow layer by layer; it compiles it once per input shape into a fused
-    launch list captured in a CUDA graph (plan.py / executor.py) and replays that.  ``forward(debug=True)``
-    keeps the reference's per-layer interpreter (net.py:43-70) over the eager operator table, prints the same
-    trace and fills ``timer`` per operator type -- with device time from CUDA events (the reference's timers
-    are unsynchronised wall clock).
+  * ``forward`` does not interpret the flow layer by layer; it compiles it once per input signature into a
+    fused launch list captured in a CUDA graph (plan.py / executor.py) and replays that.
+    ``forward(debug=True)`` runs the flow operator by operator over the eager table instead: the flow is
+    lowered ONCE (at ``load_json``) into a linear schedule of ``_Op`` records with explicit argument keys
+    and the keys that die after each operator, and the debug run walks that schedule, prints the
+    reference's trace format and fills ``timer`` per operator type -- with device time from CUDA events
+    (the reference's timers are unsynchronised wall clock).
   * weights live in ONE device blob (the uint8 ``.npy`` of planer/io.py:286 uploaded as is); ``self.weights``
     are views into it.  With ``torch.distributed`` initialised the blob is read by rank 0 only and broadcast
     once over NCCL (dist.py); there is no collective on the forward path.
+  * graph inputs may be ``uint8`` images: the first layer reads them as they are (the numpy reference promotes
+    ``uint8 x float16 -> float16``, i.e. computes on ``x.astype(weights.dtype)``), which halves the host -> device bytes.
   * operators outside the hot path raise ``NotImplementedError`` at ``load_json`` time.
 """
+import os
 import time
+from collections import OrderedDict
 
 import numpy
 
@@ -22,7 +28,37 @@ from .backend import DeviceArray
 from .layer import wrap, layer_map as key
 
 
+class _Op:
+    """One operator application of the lowered flow: ``outs = layer(*[env[k] for k in ins])``."""
+    __slots__ = ('layer', 'ins', 'outs', 'strict', 'single_out', 'dead')
+
+    def __init__(self, layer, ins, outs, strict, single_out, dead):
+        self.layer, self.ins, self.outs = layer, ins, outs
+        self.strict, self.single_out, self.dead = strict, single_out, dead
+
+
+def _lower_flow(flow, life):
+    """flow entries ``(x, layer | [layers], y)`` -> [_Op].  Semantics of planer/net.py:43-66: the first layer of an entry
+    reads the entry's input key(s), every chained layer reads the entry's output key(s); a single string key must exist
+    (KeyError), a key list is looked up leniently (missing -> None); input keys whose last use (``life``) is this entry
+    are dropped from the environment right after the arguments were fetched."""
+    sched = []
+    for pos, (src, names, dst) in enumerate(flow):
+        chain = names if isinstance(names, list) else [names]
+        src_keys = [src] if isinstance(src, str) else list(src)
+        dead = tuple(sorted({k for k in src_keys if life.get(k, pos + 1) <= pos}))
+        outs = (dst,) if isinstance(dst, str) else tuple(dst)
+        for j, lname in enumerate(chain):
+            feed = src if j == 0 else dst
+            strict = isinstance(feed, str)
+            ins = (feed,) if strict else tuple(feed)
+            sched.append(_Op(lname, ins, outs, strict, isinstance(dst, str), dead if j == 0 else ()))
+    return sched
+
+
 class Net:
+    max_executors = int(os.environ.get('PLNR_MAX_EXECUTORS', '8'))     # compiled input signatures kept alive (LRU)
+
     def __init__(self, table=None, array_module=None):
         self.weights, self.body, self.flow = [], [], []
         self.life, self.timer = {}, {}
@@ -30,24 +66,31 @@ class Net:
         self._table = key if table is None else table                 # tests may inject another operator table
         self._array = B if array_module is None else array_module     # ... and array module (Level A protocol)
         self._init_meta, self._host_blob, self._blob = [], None, None
-        self._executors, self.use_graph, self._host_rings = {}, True, {}
+        self._executors, self.use_graph, self._host_rings = OrderedDict(), True, {}
+        self._schedule = []
+        self.output_copy = True      # forward() on device arrays returns fresh arrays, like the reference (net.py:60,72)
+
+    def _invalidate(self):
+        for ex in self._executors.values():
+            ex.close()
+        self._executors = OrderedDict()
+        self._host_rings = {}
 
     # -- planer/net.py:10-24 ---------------------------------------------------------------------
     def load_json(self, inputs, inits, body, flow, debug=False):
-        self.body, self.flow, self.life = [], [], {}
-        for i in body:
-            para = i[2]
-            if debug: print(i)
-            self.body.append((i[0], wrap(self._table[i[1]], i[1])(**para)))
-        for i in range(len(flow)):
-            keys = flow[i][0]
-            if isinstance(keys, str): keys = [keys]
-            for j in keys: self.life[j] = i
+        if debug:
+            for entry in body: print(entry)
+        self.body = [(name, wrap(self._table[kind], kind)(**para)) for name, kind, para in body]
+        self.life = {}
+        for pos, entry in enumerate(flow):
+            for k in ([entry[0]] if isinstance(entry[0], str) else entry[0]):
+                self.life[k] = pos                                   # last flow entry that reads key k
         self._init_meta = [(i[0], tuple(i[1]), numpy.dtype(i[2])) for i in inits]
         self.weights = []            # created by load_weights as views into one blob
         self.input, self.inits = inputs, [i[0] for i in inits]
         self.layer, self.flow = body, flow
-        self._executors = {}
+        self._schedule = _lower_flow(flow, self.life)
+        self._invalidate()
 
     def _model(self):
         return {'input': self.input, 'inits': [[n, list(s), str(d)] for n, s, d in self._init_meta],
@@ -86,20 +129,17 @@ class Net:
             nb = int(numpy.prod(shape)) * dt.itemsize
             self.weights.append(DeviceArray(blob.buf, shape, dt, 'flat', offset=blob.offset + s))
             s += nb
-        self._executors = {}
+        self._invalidate()
 
     # -- planer/net.py:26-29 -----------------------------------------------------------------------
     def half(self):
-        for i in range(len(self.weights)):
-            if self.weights[i].dtype == numpy.float32:
-                self.weights[i] = self.weights[i].astype('float16')
-        self._executors = {}
+        self.weights = [w.astype('float16') if w.dtype == numpy.float32 else w for w in self.weights]
+        self._invalidate()
 
     def info(self, obj):
         if isinstance(obj, list):
             return [self.info(i) for i in obj]
-        if hasattr(obj, 'shape'): return obj.shape
-        return obj
+        return obj.shape if hasattr(obj, 'shape') else obj
 
     def host_const(self, name):
         """Host copy of a (small) init, e.g. the upsample scales the planner needs as numbers."""
@@ -110,80 +150,102 @@ class Net:
         dts = {numpy.dtype(w.dtype) for w in self.weights if numpy.dtype(w.dtype).kind == 'f' and w.size > 4}
         return numpy.dtype(numpy.float16) if dts == {numpy.dtype(numpy.float16)} else numpy.dtype(numpy.float32)
 
+    def blob_crc32(self):
+        """CRC-32 of the device weight blob as this rank holds it (multi-GPU load check: every rank must report the value
+        rank 0 computed from the file)."""
+        import zlib
+        if self._blob is None:
+            return None
+        n = sum(int(numpy.prod(s)) * d.itemsize for _, s, d in self._init_meta)
+        flat = DeviceArray(self._blob.buf, (n,), numpy.uint8, 'flat', offset=self._blob.offset)
+        return zlib.crc32(flat.get().tobytes())
+
     # -- planer/net.py:37-72 -----------------------------------------------------------------------
     def forward(self, *x, debug=False):
         if debug or self._array is not B:
             return self._forward_layers(*x, debug=debug)
         xs = [B.asarray(i) for i in x]
-        ex = self.executor([i.shape for i in xs])
+        ex = self.executor([i.shape for i in xs], [i.dtype for i in xs])
         start = time.time()
         out = ex.run(xs)
+        if self.output_copy:
+            out = tuple(B.clone(o) for o in out)          # the executor's own output buffers are overwritten by the next run
         self.timer['plan'] = self.timer.get('plan', 0) + time.time() - start
         return out
 
-    def executor(self, shapes):
-        """Compile (once per input-shape signature) and return the fused executor."""
+    def _forward_device(self, xs):
+        """forward() for internal callers that consume the outputs before the next run (no output copies)."""
+        return self.executor([i.shape for i in xs], [i.dtype for i in xs]).run(xs)
+
+    def executor(self, shapes, dtypes=None):
+        """Compile (once per input shape / dtype signature) and return the fused executor; the ``max_executors`` most
+        recently used signatures stay alive (each owns an activation arena, packed weights and a CUDA graph)."""
         from . import plan as P
         from .executor import Executor
-        sig = (tuple(tuple(int(v) for v in s) for s in shapes), str(self.compute_dtype()), self.use_graph)
-        if sig not in self._executors:
-            names = [n for n in self.input if n not in self.inits]
-            consts = {}
-            kinds = {l[0]: l[1] for l in self.layer}
-            for xs, ls, y in self.flow:
-                first = ls[0] if isinstance(ls, list) else ls
-                if kinds.get(first) == 'upsample' and not isinstance(xs, str) and len(xs) > 1:
-                    consts[xs[1]] = self.host_const(xs[1])
-                if kinds.get(first) == 'resize' and not isinstance(xs, str) and len(xs) > 2 and xs[2] in self.inits:
-                    consts[xs[2]] = self.host_const(xs[2])
-            gp = P.compile_graph(self._model(), dict(zip(names, sig[0])), consts)
-            self._executors[sig] = Executor(self, gp, self.compute_dtype(), self.use_graph)
-        return self._executors[sig]
+        cdt = self.compute_dtype()
+        in_dts = tuple(str(numpy.dtype(d)) for d in dtypes) if dtypes is not None else (str(cdt),) * len(shapes)
+        sig = (tuple(tuple(int(v) for v in s) for s in shapes), in_dts, str(cdt), self.use_graph)
+        if sig in self._executors:
+            self._executors.move_to_end(sig)
+            return self._executors[sig]
+        names = [n for n in self.input if n not in self.inits]
+        consts = {}
+        kinds = {l[0]: l[1] for l in self.layer}
+        for xs, ls, y in self.flow:
+            first = ls[0] if isinstance(ls, list) else ls
+            if kinds.get(first) == 'upsample' and not isinstance(xs, str) and len(xs) > 1:
+                consts[xs[1]] = self.host_const(xs[1])
+            if kinds.get(first) == 'resize' and not isinstance(xs, str) and len(xs) > 2 and xs[2] in self.inits:
+                consts[xs[2]] = self.host_const(xs[2])
+        gp = P.compile_graph(self._model(), dict(zip(names, sig[0])), consts)
+        ex = Executor(self, gp, cdt, self.use_graph, input_dtypes=[numpy.dtype(d) for d in in_dts])
+        self._executors[sig] = ex
+        while len(self._executors) > max(1, self.max_executors):
+            _, old = self._executors.popitem(last=False)
+            old.close()
+            self._host_rings = {}
+        return ex
 
     def _forward_layers(self, *x, debug=False):
-        """The reference interpreter, identical in behaviour (net.py:38-72), over the eager operator table."""
+        """Operator-by-operator run of the lowered flow over the eager table (``forward(debug=True)``, injected array
+        modules): behaviour of the reference interpreter (planer/net.py:37-72), device timers instead of wall clock."""
         np = self._array
-        dic = dict(self.body)
-        rst = {'None': None}
-        for k, v in zip(self.inits, self.weights): rst[k] = v
-        for k, v in zip(self.input, x): rst[k] = v
-        y = None
-        for i in range(len(self.flow)):
-            x, ls, y = self.flow[i]
-            if not isinstance(ls, list): ls = [ls]
-            for l in ls:
-                out = x if l == ls[0] else y
-                if not isinstance(out, str):
-                    p = [rst.get(i) for i in out]
-                else: p = [rst[out]]
-                xs = x if isinstance(x, list) else [x]
-                for k in set(xs):
-                    if k in rst and self.life[k] <= i: del rst[k]
-                obj = dic[l]
-                if debug:
-                    print(l, obj.name, ':', obj.para())
-                    print('\t--> ', out, ':', self.info(p))
-                t0 = _tick(np)
-                if isinstance(y, str): rst[y] = obj(*p)
-                else:
-                    for k, v in zip(y, obj(*p)): rst[k] = v
-                cost = _tock(np, t0)
-                if debug:
-                    for k in (y, [y])[isinstance(y, str)]:
-                        print('\t<-- ', k, ':', self.info(rst[k]))
-                self.timer[obj.name] = self.timer.get(obj.name, 0) + cost
-        out = rst[y]
-        if np is B and isinstance(out, tuple):             # graph boundary: NCHW, like the planned path
-            out = tuple(B.to_flat(o) if isinstance(o, DeviceArray) else o for o in out)
-        return out
+        layers = dict(self.body)
+        env = {'None': None}
+        env.update(zip(self.inits, self.weights))
+        env.update(zip(self.input, x))
+        result = None
+        for op in self._schedule:
+            layer = layers[op.layer]
+            args = [env[k] for k in op.ins] if op.strict else [env.get(k) for k in op.ins]
+            for k in op.dead:
+                env.pop(k, None)
+            if debug:
+                print(op.layer, layer.name, ':', layer.para())
+                print('\t--> ', op.ins[0] if op.strict else list(op.ins), ':', self.info(args))
+            t0 = _tick(np)
+            result = layer(*args)
+            if op.single_out:
+                env[op.outs[0]] = result
+            else:
+                env.update(zip(op.outs, result))
+            self.timer[layer.name] = self.timer.get(layer.name, 0) + _tock(np, t0)
+            if debug:
+                for k in op.outs:
+                    print('\t<-- ', k, ':', self.info(env[k]))
+        if np is B and isinstance(result, tuple):            # graph boundary: NCHW, like the planned path
+            result = tuple(B.to_flat(o) if isinstance(o, DeviceArray) else o for o in result)
+        return result
 
     def timeit(self, status='start'):
-        if status == 'start': self.timer = {}
-        if status == 'end':
-            for i in self.timer: print(i, self.timer[i])
+        if status == 'start':
+            self.timer = {}
+        elif status == 'end':
+            for name, cost in self.timer.items(): print(name, cost)
 
     def run(self, output=None, input={}):
-        rst = self(input)   # compatible with onnxruntime (planer/net.py:79-81)
+        """onnxruntime-shaped call (planer/net.py:79-81): always a tuple."""
+        rst = self(input)
         return rst if isinstance(rst, tuple) else (rst,)
 
     def show(self):
@@ -194,19 +256,22 @@ class Net:
     def __call__(self, *x, **key):
         np = self._array
         if type(x[0]) is dict: x = [x[0][i] for i in self.input]
-        tp = [isinstance(i, numpy.ndarray) for i in x]
-        need = sum(tp) > 0 and numpy is not np
-        if need and np is B and len(x) == 1 and not key and self._chunks(x[0]) > 1:
-            return self._call_chunked(x[0], self._chunks(x[0]))
-        if need: x = [np.asarray(i) if b else i for i, b in zip(x, tp)]
+        from_host = [isinstance(i, numpy.ndarray) for i in x]
+        need = any(from_host) and numpy is not np
+        if need and np is B and not key:
+            if len(x) == 1 and self._chunks(x[0]) > 1:
+                return self._call_chunked(x[0], self._chunks(x[0]))
+            # host in, host out: the outputs are downloaded before anything can overwrite them -- no device copies
+            rst = self._forward_device([B.asarray(i) for i in x])
+            rst = tuple(i.get() for i in rst)
+            return rst[0] if len(rst) == 1 else rst
+        if need: x = [np.asarray(i) if b else i for i, b in zip(x, from_host)]
         rst = self.forward(*x, **key)
-        if need: rst = tuple([i.get() for i in rst])
+        if need: rst = tuple(i.get() for i in rst)
         return rst[0] if len(rst) == 1 else rst
 
 
 def _chunked_methods():
-    import os
-
     def _chunks(self, x):
         """Host batches of images are uploaded in two halves so that the PCIe copy of the second half overlaps the forward
         of the first (the forward path has no cross-image dependency: planer/util.py:33,42).  PLNR_E2E_CHUNKS overrides."""
@@ -221,7 +286,7 @@ def _chunked_methods():
     def _host_ring(self, key, outs, slots):
         """Pinned host buffers for the outputs of one executor signature: ``slots`` sets of one buffer per output."""
         ring = self._host_rings.get(key)
-        if ring is None or len(ring) < slots:
+        if ring is None or len(ring) < slots or any(h.numel() < o.nbytes for h, o in zip(ring[0], outs)):
             torch = B._torch()
             ring = [[torch.empty(o.nbytes, dtype=torch.uint8).pin_memory() for o in outs] for _ in range(slots)]
             self._host_rings[key] = ring
@@ -247,9 +312,9 @@ def _chunked_methods():
         ring, metas = None, None
         for j, (dev, ev) in enumerate(parts):
             B.stream().wait_event(ev)
-            rst = self.forward(dev)
+            rst = self._forward_device([dev])
             if ring is None:
-                ring = self._host_ring(('chunked', dev.shape, chunks), rst, chunks)
+                ring = self._host_ring(('chunked', dev.shape, str(dev.dtype), chunks), rst, chunks)
             metas = rst
             self._download_async(rst, ring[j])
         B.synchronize()
@@ -264,7 +329,11 @@ def _chunked_methods():
         their sum (``Net.__call__``, planer/net.py:94-101, is upload -> forward -> download, blocking, per call).  The
         forward path has no cross-batch state (BatchNorm is pre-folded, planer/io.py:76-91), so the results are those of
         separate calls.  Batches should live in pinned host memory (``planer_b200.pinned_empty``) -- pageable arrays work
-        but are staged by the driver at a fraction of the PCIe rate.  ``depth`` = batches in flight behind the one yielded."""
+        but are staged by the driver at a fraction of the PCIe rate -- and may be ``uint8`` images (half the bytes of
+        fp16; the first layer converts).  ``depth`` = batches in flight behind the one yielded.
+
+        Buffer ownership: ``map`` pulls the next batch from ``batches`` only after the upload of the previous one has
+        COMPLETED, so a producer may refill the same (pinned) buffer for every batch -- one buffer is enough."""
         if self._array is not B:
             for x in batches:
                 yield self(x)
@@ -281,8 +350,15 @@ def _chunked_methods():
             rst = _from_pinned(metas, ring[slot])
             return rst[0] if len(rst) == 1 else rst
 
-        i = 0
-        for x in batches:
+        i, up = 0, None
+        it = iter(batches)
+        while True:
+            if up is not None:
+                up.synchronize()                              # the previous batch has left its host buffer: it may be refilled
+            try:
+                x = next(it)
+            except StopIteration:
+                break
             if type(x) is dict: x = x[self.input[0]]
             x = numpy.ascontiguousarray(x)
             slot = i % slots
@@ -296,11 +372,11 @@ def _chunked_methods():
                 up = torch.cuda.Event()
                 up.record(cs)
             ls.wait_event(up)
-            rst = self.forward(dev_in[slot])
+            rst = self._forward_device([dev_in[slot]])
             if ring is None or tuple(o.shape for o in rst) != tuple(o.shape for o in metas):
                 while pending:
                     yield finish(pending.pop(0))
-                ring = self._host_ring(('map', x.shape, slots), rst, slots)
+                ring = self._host_ring(('map', x.shape, str(x.dtype), slots), rst, slots)
             metas = rst
             self._download_async(rst, ring[slot])
             done[slot] = torch.cuda.Event()

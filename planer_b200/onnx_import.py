@@ -108,8 +108,11 @@ def _tensor(buf):
 
 
 def _attribute(buf):
-    name, f, i, s, t, floats, ints = '', None, None, None, None, [], []
+    """AttributeProto -> (name, value).  Field 20 (``type``: 1 FLOAT, 2 INT, 3 STRING, 4 TENSOR, 6 FLOATS, 7 INTS) tells a
+    scalar whose value is the wire default (0 / 0.0 / '' may be left out by a writer) from an empty list."""
+    name, f, i, s, t, floats, ints, kind = '', None, None, None, None, [], [], 0
     for num, wt, val in _fields(buf):
+        if num == 20: kind = int(val)
         if num == 1: name = bytes(val).decode()
         elif num == 2: f = struct.unpack('<f', val)[0]
         elif num == 3: i = _signed(val)
@@ -120,7 +123,9 @@ def _attribute(buf):
     for v in (t, s, f, i):
         if v is not None:
             return name, v
-    return name, (ints if ints else floats)
+    if kind in (1, 2, 3):
+        return name, {1: 0.0, 2: 0, 3: ''}[kind]
+    return name, (ints if ints or kind == 7 else floats)
 
 
 def _node(buf):

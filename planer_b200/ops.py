@@ -183,9 +183,11 @@ def upsample_linear_weights(fh, fw):
     return _upmat_cache[(fh, fw)]
 
 
-def upsample_linear_into(x, y, fh, fw):
+def upsample_linear_into(x, y, fh, fw, wm=None):
+    """``wm``: the weight table from ``upsample_linear_weights`` when the caller owns it (an executor whose CUDA graph
+    holds its address); None = the module cache (eager calls)."""
     tx, ty = x.tensor(), y.tensor()
-    wm = upsample_linear_weights(fh, fw)
+    wm = upsample_linear_weights(fh, fw) if wm is None else wm
     _capi.check(B.lib().plnr_upsample_linear(B.ctx(), _capi.dtype_code(x.dtype), C.byref(tx), C.byref(ty), fh, fw, wm.ptr),
                 'plnr_upsample_linear')
     return y
@@ -206,14 +208,24 @@ def resize_linear_tables(n_in, n_out, dtype):
 _resize_cache = {}
 
 
-def resize_linear_into(x, y):
-    """Bilinear resize of x (n, c, h, w) to y's spatial size (planer/util.py:194-210)."""
-    key = (x.shape[2], x.shape[3], y.shape[2], y.shape[3], str(x.dtype))
-    if key not in _resize_cache:
-        if len(_resize_cache) > 256: _resize_cache.clear()
-        _resize_cache[key] = [B.asarray(t) for t in resize_linear_tables(x.shape[2], y.shape[2], x.dtype) +
-                              resize_linear_tables(x.shape[3], y.shape[3], x.dtype)]
-    rl, rw, rw1, cl, cw, cw1 = _resize_cache[key]
+def resize_linear_device_tables(x, y):
+    """The six device tables of one (input size, output size, dtype) resize."""
+    return [B.asarray(t) for t in resize_linear_tables(x.shape[2], y.shape[2], x.dtype) +
+            resize_linear_tables(x.shape[3], y.shape[3], x.dtype)]
+
+
+def resize_linear_into(x, y, tables=None):
+    """Bilinear resize of x (n, c, h, w) to y's spatial size (planer/util.py:194-210).  ``tables``: device tables owned by
+    the caller (an executor: its captured CUDA graph keeps reading them); None = a small module-level cache for eager calls
+    (entries are evicted one at a time, oldest first, never while a captured graph can refer to them)."""
+    if tables is None:
+        key = (x.shape[2], x.shape[3], y.shape[2], y.shape[3], str(x.dtype))
+        if key not in _resize_cache:
+            while len(_resize_cache) >= 256:
+                _resize_cache.pop(next(iter(_resize_cache)))
+            _resize_cache[key] = resize_linear_device_tables(x, y)
+        tables = _resize_cache[key]
+    rl, rw, rw1, cl, cw, cw1 = tables
     tx, ty = x.tensor(), y.tensor()
     _capi.check(B.lib().plnr_resize_linear(B.ctx(), _capi.dtype_code(x.dtype), C.byref(tx), C.byref(ty), rl.ptr, rw.ptr, rw1.ptr,
                                            cl.ptr, cw.ptr, cw1.ptr), 'plnr_resize_linear')
@@ -289,7 +301,7 @@ def gap_dense_into(x, w, y, scale=None, shift=None, act=ACT_NONE, alpha=0.0):
 
 def nchw_to_nhwc_into(x_flat, y, c_src=None):
     t = y.tensor()
-    _capi.check(B.lib().plnr_nchw_to_nhwc(B.ctx(), x_flat.ptr, _capi.dtype_code(x_flat.dtype),
+    _capi.check(B.lib().plnr_nchw_to_nhwc(B.ctx(), x_flat.ptr, _capi.src_dtype_code(x_flat.dtype),
                                           x_flat.shape[1] if c_src is None else c_src, C.byref(t),
                                           _capi.dtype_code(y.dtype)), 'plnr_nchw_to_nhwc')
     return y
@@ -330,7 +342,7 @@ def stem_pack_weight(K, stride, pads, cp):
 def stem_pack_into(x_flat, y, kw, stride, pad_l):
     n, c, h, w = x_flat.shape
     t = y.tensor()
-    _capi.check(B.lib().plnr_stem_pack(B.ctx(), x_flat.ptr, _capi.dtype_code(x_flat.dtype), n, c, h, w, C.byref(t), kw,
+    _capi.check(B.lib().plnr_stem_pack(B.ctx(), x_flat.ptr, _capi.src_dtype_code(x_flat.dtype), n, c, h, w, C.byref(t), kw,
                                        stride, pad_l), 'plnr_stem_pack')
     return y
 
@@ -365,9 +377,14 @@ def stem_pool_into(x_flat, w_packed, scale, shift, y, kh, kw, stride, pads, act=
     n, c, h, w = x_flat.shape
     t = y.tensor()
     p = lambda a: a.ptr if a is not None else None
-    _capi.check(B.lib().plnr_stem_pool_fwd(B.ctx(), x_flat.ptr, n, c, h, w, w_packed.ptr, p(scale), p(shift), kh, kw,
-                                           stride, pads[0], pads[1], pads[2], pads[3], act, 3, 2, 1, C.byref(t)),
-                'plnr_stem_pool_fwd')
+    if x_flat.dtype == np.uint8:                  # uint8 image: converted by the kernel's producer warps (exact)
+        fn, what = B.lib().plnr_stem_pool_fwd_u8, 'plnr_stem_pool_fwd_u8'
+    elif x_flat.dtype == np.float16:
+        fn, what = B.lib().plnr_stem_pool_fwd, 'plnr_stem_pool_fwd'
+    else:
+        raise _capi.PlanerB200Error('stem_pool: the image must be float16 or uint8, got %s' % x_flat.dtype)
+    _capi.check(fn(B.ctx(), x_flat.ptr, n, c, h, w, w_packed.ptr, p(scale), p(shift), kh, kw,
+                   stride, pads[0], pads[1], pads[2], pads[3], act, 3, 2, 1, C.byref(t)), what)
     return y
 
 

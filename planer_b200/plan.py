@@ -97,8 +97,9 @@ def flatten(model, input_shapes):
             out = new(None, 'act', y)
             out.producer = len(nodes)
             nodes.append(Node(lname, kind, dict(attrs), ins, [out.id]))
-            if kind in ('relu', 'identity'):
-                # in-place: every key that named the input now sees the mutated / same array
+            if kind in ('relu', 'identity', 'clip'):
+                # in-place (planer/layer.py:44-46 ReLU, :250-251 Clip): every key that named the input now sees the
+                # mutated / same array
                 out.alias_of = ins[0]
                 for k, vid in list(cur.items()):
                     if vid == ins[0]:
@@ -345,7 +346,10 @@ def fuse(values, nodes, outputs):
         elif k == 'batchnorm':
             st = emit(Step('scale_shift', nd.name, [x], out))
             st.bn = (nd.ins[1], nd.ins[2])
-        elif k in ('maxpool', 'averagepool', 'zero_stuff', 'hardsigmoid', 'clip', 'softmax'):
+        elif k == 'clip':
+            st = emit(Step('clip', nd.name, [x], out, nd.attrs))
+            st.inplace = True
+        elif k in ('maxpool', 'averagepool', 'zero_stuff', 'hardsigmoid', 'softmax'):
             emit(Step(k, nd.name, [x], out, nd.attrs))
         elif k in ('upsample', 'resize'):
             emit(Step('upsample', nd.name, [x], out, nd.attrs))
@@ -409,7 +413,7 @@ def assign_buffers(plan, elem_bytes, storage_channels):
     values, steps = plan.values, plan.steps
     root = lambda v: _root(values, v)
     for st in steps:                                   # aliases created by standalone steps
-        if st.op in ('relu', 'alias') or (st.op == 'flatten' and values[st.ins[0]].shape[2:] == (1, 1)):
+        if st.op in ('relu', 'clip', 'alias') or (st.op == 'flatten' and values[st.ins[0]].shape[2:] == (1, 1)):
             values[st.out].alias_of = st.ins[0]
     last_use, size = {}, {}
     for pos, st in enumerate(steps):
