@@ -237,6 +237,9 @@ int plnr_event_destroy(plnr_event* ev);
  * [0] producer wait-for-empty, [1] producer total, [2] MMA wait-for-full, [3] MMA wait-for-accumulator,
  * [4] MMA total, [5] epilogue wait-for-accumulator, [6] epilogue total.  enable=1 arms it, out (host) may be NULL. */
 int plnr_debug_conv_profile(plnr_ctx* ctx, int enable, int64_t* out, int n);
+/* Family name of the kernel the most recent call on this ctx launched ("conv2d_shift", "conv2d_stack", "conv2d_tcgen05",
+ * "conv2d_direct", "stem_pool", "gap_dense", ...): lets a host label a per-launch timing table (bench.py). */
+int plnr_last_kernel(plnr_ctx* ctx, char* out, int n);
 /* Which kernel plnr_conv2d_fwd would pick for this problem: PLNR_ALGO_TCGEN05 or PLNR_ALGO_DIRECT. */
 int plnr_conv2d_algo(const plnr_conv_desc* desc, const plnr_tensor* x, const plnr_tensor* y);
 

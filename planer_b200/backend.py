@@ -85,6 +85,13 @@ def launch_count():
     return n.value
 
 
+def last_kernel():
+    """Family name of the kernel the most recent library call launched (diagnostics / bench tables)."""
+    buf = C.create_string_buffer(64)
+    _capi.check(lib().plnr_last_kernel(ctx(), buf, 64))
+    return buf.value.decode()
+
+
 def device_info():
     out = (C.c_int64 * 4)()
     _capi.check(lib().plnr_device_info(ctx(), out))

@@ -92,6 +92,13 @@ int plnr_debug_conv_profile(plnr_ctx* ctx, int enable, int64_t* out, int n) {
   return PLNR_OK;
 }
 
+int plnr_last_kernel(plnr_ctx* ctx, char* out, int n) {
+  PLNR_REQUIRE(ctx && out && n > 0, "plnr_last_kernel: bad argument");
+  strncpy(out, ctx->last_kernel ? ctx->last_kernel : "", (size_t)n - 1);
+  out[n - 1] = 0;
+  return PLNR_OK;
+}
+
 int plnr_launch_count(plnr_ctx* ctx, int64_t* out) {
   PLNR_REQUIRE(ctx && out, "plnr_launch_count: NULL argument");
   *out = ctx->launches;

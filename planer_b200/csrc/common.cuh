@@ -26,6 +26,7 @@ struct plnr_ctx {
   // device-side error word written by kernels that time out on a barrier (debug aid)
   int* dev_error = nullptr;
   long long* prof = nullptr;       // debug: per-CTA role cycle counters of the last tcgen05 conv launch
+  const char* last_kernel = "";   // name handed to plnr_after_launch by the most recent launch (diagnostics)
   bool shift_attr_set = false;
   bool igemm_attr_set = false;     // cudaFuncSetAttribute(max dynamic smem) done for this device
   // cache of TMA descriptors keyed by a byte string of their parameters
@@ -70,6 +71,7 @@ static inline int plnr_after_launch(plnr_ctx* ctx, const char* what) {
   }
   if (ctx->capturing) ctx->capture_launches++;
   else ctx->launches++;
+  ctx->last_kernel = what;
   return PLNR_OK;
 }
 

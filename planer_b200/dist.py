@@ -96,3 +96,17 @@ def max_over_ranks(value):
 def barrier():
     if initialized() and rank_world()[1] > 1:
         _dist().barrier()
+
+
+def gather_ints(value):
+    """All-gather of one python int per rank (load-time checks: every rank reports the CRC of the weight blob it
+    received and of its logits on a shared input; rank 0 compares).  Returns the list indexed by rank."""
+    if not initialized() or rank_world()[1] == 1:
+        return [int(value)]
+    import torch
+    d = _dist()
+    dev = 'cuda' if d.get_backend() == 'nccl' else 'cpu'
+    mine = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+    out = [torch.zeros_like(mine) for _ in range(d.get_world_size())]
+    d.all_gather(out, mine)
+    return [int(t.item()) for t in out]

@@ -166,6 +166,24 @@ class Executor:
             return None
         return chain
 
+    def _nbytes(self, vid, itemsize=None):
+        shp = self.values[vid].shape
+        return int(np.prod(shp)) * (self.dtype.itemsize if itemsize is None else itemsize)
+
+    def _step_bytes(self, st, extra_weights=()):
+        """Algorithmic bytes of one fused launch: logical operands read once, result written once."""
+        n = sum(self._nbytes(r) for r in st.reads()) + self._nbytes(st.out)
+        for w in (st.w, st.bias) + tuple(st.bn or ()) + tuple(extra_weights):
+            if w is not None:
+                n += self._nbytes(w)
+        if st.shortcut is not None:
+            n += self._nbytes(st.shortcut[2].w)
+        return n
+
+    def algorithmic_bytes(self):
+        """Algorithmic HBM bytes of one forward as this executor fuses it: input-time kernels + every graph launch."""
+        return int(self.input_bytes + sum(self.launch_bytes))
+
     def _get(self, vid):
         return self.arr[self._root(vid)]
 
@@ -227,13 +245,25 @@ class Executor:
             self.arr[vid] = a
             self.in_arrays.append(a)
 
+        self.launch_bytes = []    # algorithmic bytes per launch: every operand read once + the result written once
         for st in gp.steps:
+            self._io_override = None
             fn = self._make(st, alloc)
             if fn is not None:
                 self.launches.append(fn)
                 self.kinds.append(st.op)
                 self.names.append(getattr(self, 'names_override', None) or '+'.join(st.fused))
                 self.names_override = None
+                self.launch_bytes.append(self._io_override if self._io_override is not None else self._step_bytes(st))
+        self.input_bytes = 0      # input-time kernels (fused first layer / layout): graph input in its own dtype + what they write
+        for k, vid in enumerate(self.input_ids):
+            self.input_bytes += self._nbytes(vid, self.input_dtypes[k].itemsize)
+            fs = self.fused_stems.get(vid)
+            if fs is not None:
+                self.input_bytes += self._nbytes(fs['pool'].out) + self._nbytes(fs['conv'].w)
+            elif self.arr.get(vid) is not None:
+                a = self.arr[vid]
+                self.input_bytes += int(np.prod(a.shape)) * a.dtype.itemsize
 
         # graph outputs: restore NCHW (planer/net.py:100 hands NCHW arrays back)
         for o in gp.outputs:
@@ -243,6 +273,7 @@ class Executor:
                 self.launches.append(lambda a=a, flat=flat: ops.nhwc_to_nchw_into(a, flat))
                 self.kinds.append('to_nchw')
                 self.names.append('to_nchw')
+                self.launch_bytes.append(2 * self._nbytes(o))
                 self.out_flat.append(flat)
             else:
                 self.out_flat.append(a)
@@ -413,6 +444,7 @@ class Executor:
                 self._keep += [scale, shift, Kc]
                 self.fused_dense |= {id(fl), id(dn)}
                 self.names_override = '+'.join(st.fused + dn.fused)
+                self._io_override = self._nbytes(st.ins[0]) + self._nbytes(dn.out) + self._nbytes(dn.w)
                 return lambda: ops.gap_dense_into(x, Kc, y, scale, shift, dn.act, dn.alpha)
             x, y = self._view(st.ins[0]), alloc(st.out)
             return lambda: ops.gap_into(x, y)

@@ -456,3 +456,131 @@ def test_onnx_file_from_the_torch_exporter_runs_on_the_gpu(planer, name):
         for i, t in enumerate(ys):
             ref = g['y%d' % i]
             assert t.shape == ref.shape and rel_err(t, ref) <= tol, (name, half, i, rel_err(t, ref))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The drop-in: the UNMODIFIED reference package drives the B200 kernels after planer_b200.install(planer)
+# ---------------------------------------------------------------------------------------------------------------------
+def _import_reference():
+    ref_root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_root, 'planer')):
+        pytest.skip('baseline/_ref (pip-installed copy of the unmodified reference) is not in this checkout: '
+                    'run __graft_entry__.build() where /root/reference exists')
+    import sys
+    if not os.access(os.path.expanduser('~'), os.W_OK):
+        os.environ['HOME'] = '/tmp'
+    sys.path.insert(0, ref_root)
+    try:
+        import planer as ref                     # prints its banner, creates ~/.planer_zoo (planer/__init__.py:19-20,50-51)
+    finally:
+        sys.path.remove(ref_root)
+    assert os.path.realpath(ref.__file__).startswith(os.path.realpath(ref_root)), ref.__file__
+    return ref
+
+
+@pytest.mark.parametrize('name', ['readme_f32', 'readme_f16', 'resnet18_small_f32', 'resnet18_f32_n1', 'yolov3_quarter_f32'])
+def test_reference_net_on_b200_after_install(planer, graphs_gold, name):
+    """``planer_b200.install(planer)`` (planer/__init__.py:22-38 + planer/layer.py:262-281): the reference's own Net --
+    its load_json / load_weights / half / forward interpreter / __call__, unmodified -- runs every layer on the B200
+    kernels and reproduces the outputs the reference computed with numpy (tests/golden/graphs.npz)."""
+    import numpy
+    ref = _import_reference()
+    saved = dict(ref.layer.layer_map)
+    try:
+        planer.install(ref)
+        assert ref.net.np is planer.b200 and ref.layer.layer_map['conv'] is planer.layer_map['conv']
+        model, blob, x, half = cases.make_graph_case(name)
+        net = ref.Net()                                     # the reference's class, not ours
+        assert type(net).__module__ == 'planer.net'
+        net.load_json(model['input'], model['inits'], model['layers'], model['flow'])
+        net.load_weights(blob)
+        if half:
+            net.half()
+        y = net(x)                                          # numpy in, numpy out (planer/net.py:94-101)
+        ys = y if isinstance(y, tuple) else (y,)
+        assert all(isinstance(t, numpy.ndarray) for t in ys)
+        assert len(ys) == int(graphs_gold[name + '.nout'])
+        tol = 1e-2 if half else 1e-3
+        for i, t in enumerate(ys):
+            assert t.shape == tuple(graphs_gold['%s.shape%d' % (name, i)])
+            ref_out = graphs_gold['%s.out%d' % (name, i)]
+            scale = float(graphs_gold['%s.absmax%d' % (name, i)])
+            err = float(np.abs(cases.sample(t).astype(np.float64) - ref_out.astype(np.float64)).max() / scale)
+            assert err <= tol, (name, i, err)
+    finally:
+        ref.core(numpy, True)
+        ref.layer.layer_map.clear()
+        ref.layer.layer_map.update(saved)
+
+
+def test_uint8_images_equal_their_float16_cast(planer):
+    """A uint8 NCHW batch through Net (fused first layer converts in its producer warps; other nets through the layout
+    kernels) gives bit-for-bit the result of the same pixels handed over as float16 -- what numpy's promotion
+    uint8 x float16 -> float16 computes in the reference (planer/layer.py:22-26)."""
+    rng = np.random.default_rng(3)
+    model, blob = zoo_model('resnet18')
+    net = planer.from_model(model, blob, half=True)
+    x8 = rng.integers(0, 256, (4, 3, 224, 224), dtype=np.uint8)
+    a = net(x8)
+    b = net(x8.astype(np.float16))
+    assert a.dtype == np.float16 and np.array_equal(a, b)
+    assert len(net.executor([x8.shape], [np.uint8]).fused_stems) == 1
+    # a net without the fused first layer: README net (3 -> 64 stride-1 conv) in fp16 and fp32
+    model, blob = zoo_model('readme')
+    for half in (True, False):
+        net = planer.from_model(model, blob, half=half)
+        x8 = rng.integers(0, 256, (2, 3, 32, 32), dtype=np.uint8)
+        assert np.array_equal(net(x8), net(x8.astype(np.float16 if half else np.float32)))
+
+
+def zoo_model(key):
+    return cases.get_model(key)
+
+
+def test_forward_results_survive_the_next_forward(planer):
+    """net(device array) hands back fresh arrays like the reference (planer/net.py:60,72): a second forward of the same
+    signature must not overwrite the first result."""
+    from planer_b200 import backend as B
+    model, blob = cases.get_model('readme')
+    net = planer.from_model(model, blob, half=True)
+    rng = np.random.default_rng(5)
+    x1, x2 = [rng.standard_normal((2, 3, 32, 32)).astype(np.float16) for _ in range(2)]
+    y1 = net(B.asarray(x1))
+    keep = y1.get().copy()
+    y2 = net(B.asarray(x2))
+    assert np.array_equal(y1.get(), keep) and not np.array_equal(y2.get(), keep)
+    assert np.array_equal(keep, net(x1))
+
+
+def test_map_allows_refilling_one_pinned_buffer(planer):
+    """Net.map pulls the next batch only after the previous upload has completed: a producer that refills ONE pinned buffer
+    for every batch gets the results of separate calls."""
+    model, blob = cases.get_model('readme')
+    net = planer.from_model(model, blob, half=True)
+    rng = np.random.default_rng(6)
+    batches = [rng.standard_normal((64, 3, 32, 32)).astype(np.float16) for _ in range(6)]
+    buf = planer.pinned_empty(batches[0].shape, np.float16)
+
+    def feed():
+        for b in batches:
+            buf[...] = b
+            yield buf
+    got = list(net.map(feed()))
+    for b, y in zip(batches, got):
+        assert np.array_equal(y, net(b))
+
+
+def test_fp16_residual_head_with_three_channels(planer):
+    """out = x + conv(...) with C = 3 as a graph output in fp16: the output-channel padding of conv-only heads must not be
+    applied when a residual operand is fused (it has the logical channel count)."""
+    from planer_b200 import zoo
+    b = zoo._Builder(11)
+    y = b.conv('x', 3, 16, 3, 1, 1, name='c1', bias=True)
+    y = b.op('relu', {}, [y], name='r1')
+    y = b.conv(y, 16, 3, 3, 1, 1, name='c2', bias=True)
+    out = b.op('add', {}, [y, 'x'], name='add')
+    model, blob = b.finish(['x'], [out])
+    x = np.random.default_rng(2).standard_normal((2, 3, 20, 24)).astype(np.float16)
+    ref = oracle.build_net(model, blob)(x.astype(np.float32))
+    got = planer.from_model(model, blob, half=True)(x)
+    assert got.shape == ref.shape and rel_err(got, ref) <= 1e-2

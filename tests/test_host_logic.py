@@ -348,7 +348,9 @@ def _gloo_worker(rank, world, port, q):
         x = np.random.default_rng(1).standard_normal((5, 3, 16, 16)).astype(np.float32)
         y = net(x[lo:hi].copy())
         t = dist.max_over_ranks(float(rank + 1))
-        q.put((rank, lo, hi, got.tobytes() == blob.tobytes(), y, t))
+        import zlib
+        crcs = dist.gather_ints(zlib.crc32(got.tobytes()))                       # bench.py's load check: one CRC per rank
+        q.put((rank, lo, hi, got.tobytes() == blob.tobytes(), y, t, crcs))
     finally:
         td.destroy_process_group()
 
@@ -365,7 +367,9 @@ def test_gloo_world2_blob_broadcast_and_batch_shard():
     assert [(r[1], r[2]) for r in res] == [(0, 3), (3, 5)]
     assert all(r[3] for r in res), 'rank did not receive the exact blob bytes'
     assert all(r[5] == 2.0 for r in res)
+    import zlib
     model, blob = zoo.readme_net(0)
+    assert all(r[6] == [zlib.crc32(blob.tobytes())] * 2 for r in res), 'gather_ints: every rank must see both CRCs'
     x = np.random.default_rng(1).standard_normal((5, 3, 16, 16)).astype(np.float32)
     full = oracle.build_net(model, blob)(x.copy())
     assert np.array_equal(np.concatenate([res[0][4], res[1][4]]), full)      # shards concatenate to the full batch
@@ -493,3 +497,58 @@ def test_onnx_import_names_what_it_cannot_do(tmp_path):
         onnx_import.read_onnx(msg([(7, graph)]))
     with pytest.raises(ValueError, match='GraphProto'):
         onnx_import.read_onnx(b'')
+
+
+# ---------------------------------------------------------------------------------------------
+# the drop-in into the reference package (Level B): what install() rebinds, checked without a GPU
+# ---------------------------------------------------------------------------------------------
+
+def test_install_rebinds_the_reference_package():
+    """planer_b200.install(planer) on the pip-installed, unmodified reference (baseline/_ref): the array module of
+    util / layer / net / io and every hot-path entry of planer.layer.layer_map now point at the B200 implementation; the
+    entries outside the hot path stay the reference's.  (The run on the GPU is tests/test_gpu_parity.py.)"""
+    import sys
+    ref_root = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_root, 'planer')):
+        pytest.skip('baseline/_ref not present (created by __graft_entry__.build() where /root/reference exists)')
+    os.environ.setdefault('HOME', '/tmp')
+    sys.path.insert(0, ref_root)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            import planer as ref
+    finally:
+        sys.path.remove(ref_root)
+    saved = dict(ref.layer.layer_map)
+    try:
+        planer.install(ref)
+        for mod in (ref.util, ref.layer, ref.net, ref.io):
+            assert mod.np is planer.b200
+        for kind, fn in planer.layer_map.items():
+            assert ref.layer.layer_map[kind] is fn
+        outside = set(saved) - set(planer.layer_map)
+        assert outside and all(ref.layer.layer_map[k] is saved[k] for k in outside)
+        assert ref.net.key is ref.layer.layer_map            # the reference's Net reads the patched table
+    finally:
+        ref.core(np, True)
+        ref.layer.layer_map.clear()
+        ref.layer.layer_map.update(saved)
+
+
+def test_debug_trace_and_schedule_follow_the_reference_interpreter():
+    """forward(debug=True) walks the schedule lowered at load_json: same trace lines, same liveness (a key is dropped
+    after the last flow entry that reads it), same results as the fused-free reference loop (planer/net.py:37-72)."""
+    model, blob, x, _ = cases.make_graph_case('readme_f32')
+    net = planer.Net(table=oracle.layer_map, array_module=np)
+    net.load_json(model['input'], model['inits'], model['layers'], model['flow'])
+    net.load_weights(blob)
+    ops_ = net._schedule
+    assert [o.layer for o in ops_] == ['conv', 'relu', 'pool', 'up', 'concat', 'sigmoid', 'return']
+    assert ops_[0].ins == ('x', 'K', 'B') and not ops_[0].strict and ops_[1].ins == ('a',) and ops_[1].strict
+    assert 'x' in ops_[0].dead and ops_[1].dead == ()          # chained layers never drop keys a second time
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        y = net.forward(x.copy(), debug=True)
+    out = buf.getvalue()
+    assert 'conv conv : ' in out and "\t-->  ['x', 'K', 'B'] :" in out and '\t<--  a :' in out
+    g = np.load(os.path.join(GOLD, 'graphs.npz'))
+    assert cases.sample(y[0]).tobytes() == g['readme_f32.out0'].tobytes()
