@@ -240,6 +240,9 @@ int plnr_debug_conv_profile(plnr_ctx* ctx, int enable, int64_t* out, int n);
 /* Family name of the kernel the most recent call on this ctx launched ("conv2d_shift", "conv2d_stack", "conv2d_tcgen05",
  * "conv2d_direct", "stem_pool", "gap_dense", ...): lets a host label a per-launch timing table (bench.py). */
 int plnr_last_kernel(plnr_ctx* ctx, char* out, int n);
+/* Test aid: virtual grid and per-plane tap tables the shift-GEMM kernel (csrc/conv_shift.cu) uses for a problem; out[0] = 0
+ * when the kernel does not apply.  Layout in the source.  x->ptr only needs to be 16-byte aligned (not dereferenced). */
+int plnr_debug_shift_geometry(const plnr_conv_desc* desc, const plnr_tensor* x, const plnr_tensor* y, int* out, int n);
 /* Which kernel plnr_conv2d_fwd would pick for this problem: PLNR_ALGO_TCGEN05 or PLNR_ALGO_DIRECT. */
 int plnr_conv2d_algo(const plnr_conv_desc* desc, const plnr_tensor* x, const plnr_tensor* y);
 

@@ -88,6 +88,7 @@ PROTOTYPES = {
     'plnr_event_destroy': [_P],
     'plnr_conv2d_algo': [C.POINTER(ConvDesc), _TP, _TP],
     'plnr_last_kernel': [_P, C.c_char_p, C.c_int],
+    'plnr_debug_shift_geometry': [C.POINTER(ConvDesc), _TP, _TP, C.POINTER(C.c_int), C.c_int],
     'plnr_debug_conv_profile': [_P, C.c_int, C.POINTER(C.c_int64), C.c_int],
 }
 

@@ -30,8 +30,8 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kThreads = 384;          // warps 0-3: producer / MMA / TMEM / table; warps 4-11: two epilogue groups
-constexpr uint32_t kEpiBytes = 2 * 2 * 256 * 2;   // [buffer][scale | shift][256] fp16 (the epilogue math is packed fp16)
 constexpr int kMaxA = 4, kMaxB = 40;
+constexpr uint32_t kEpiBytes = 2 * 2 * 256 * 2;   // [buffer][scale | shift][256] fp16 (the epilogue math is packed fp16)
 constexpr uint32_t kStageBytes = 8 * 1024;        // epilogue transposition stage (per epilogue warp: 32 rows x 32 B = 16 channels)
 constexpr long long kWatchdogCycles = 4000000000ll;
 
@@ -42,6 +42,16 @@ struct ShiftParams {
   long long Mv;             // N * Hv * Wv virtual output positions
   int halo;                 // (R-1)*dil_h*Wv + (S-1)*dil_w
   int R, S, dh, dw;
+  // Phase planes.  Stride 1: ONE plane holding every tap.  Stride 2: the input splits into (row parity, column parity)
+  // planes x[2i + a, 2j + b]; tap (r, s) reads plane ((r - pad_t) mod 2, (s - pad_l) mod 2) at the shifted position
+  // (floor((r - pad_t) / 2), floor((s - pad_l) / 2)), so the strided convolution is a sum of up to four stride-1 shift
+  // GEMMs, one per plane, over the SAME virtual output grid.  A plane is fetched by a tiled TMA box with element stride
+  // `cs` along W (every other pixel: whole 128-byte channel rows, no wasted sectors) and row coordinate hrow * cs + h0.
+  int nplanes, cs;
+  int pl_w0[4], pl_h0[4];   // TMA start coordinates of a plane's virtual column 0 / virtual row 0
+  int pl_first[5];          // taps [pl_first[i], pl_first[i + 1]) of the tables below belong to plane i
+  uint32_t tap_aoff[kMaxB]; // A descriptor offset of a tap inside its plane buffer: (r' * Wv + s') * 8
+  uint8_t tap_w[kMaxB];     // index r * S + s of the tap in the packed filter
   int C, cchunks;
   int c2chunks, s2;         // fused 1x1 shortcut convolution: extra 64-channel chunks read from a second tensor at stride s2
   uint32_t ctr;             // descriptor offset of the un-shifted (centre) view: (pad_t * dil_h * Wv + pad_l * dil_w) * 8
@@ -184,8 +194,12 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       const uint32_t row0_off = (uint32_t)(Wv - off) * 128u;
       // chunks [0, cchunks): 64 input channels of the convolution, RS taps each; chunks [cchunks, +c2chunks): 64
       // channels of the fused 1x1 shortcut, read from the second tensor at stride s2 into the same row layout, ONE tap
-      for (int cc = 0; cc < p.cchunks + p.c2chunks; ++cc) {
-        const bool sc = cc >= p.cchunks;
+      const int nmain = p.cchunks * p.nplanes;
+      for (int lu = 0; lu < nmain + p.c2chunks; ++lu) {
+        // load unit = (64-channel chunk, plane) of the convolution, then the chunks of the fused shortcut
+        const bool sc = lu >= nmain;
+        const int cc = sc ? lu - nmain : lu / p.nplanes;
+        const int pi = sc ? 0 : lu - cc * p.nplanes;
         const long long tw0 = clock64();
         mbar_wait(bar_aempty + 8 * ab, aph ^ 1, p.err, 0);
         t_wait += clock64() - tw0;
@@ -196,9 +210,10 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           long long v = v0;
           int img = (int)(v / p.Hv), hrow = (int)(v - (long long)img * p.Hv);
           const CUtensorMap* mA = sc ? &mapA2 : &mapA;
-          const int cs = sc ? p.s2 : 1, c0 = (sc ? cc - p.cchunks : cc) * 64;
+          const int cs = sc ? p.s2 : p.cs, c0 = cc * 64;
+          const int w0 = sc ? -p.pad_l * p.s2 : p.pl_w0[pi], h0 = sc ? -p.pad_t * p.s2 : p.pl_h0[pi];
           for (int i = 0; i < nrows; ++i) {
-            tma_load_4d<CG>(dst, mA, full, c0, -p.pad_l * cs, (hrow - p.pad_t) * cs, img);
+            tma_load_4d<CG>(dst, mA, full, c0, w0, hrow * cs + h0, img);
             dst += row_bytes;
             if (++hrow == p.Hv) { hrow = 0; ++img; }
           }
@@ -206,9 +221,8 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         __syncwarp();
         if (++ab == na) { ab = 0; aph ^= 1; }
         if (!p.b_resident || first) {
-          const int ntaps = sc ? 1 : RS;
-          const int kbase = sc ? RS * p.C + (cc - p.cchunks) * 64 : cc * 64;
-          for (int tap = 0; tap < ntaps; ++tap) {
+          const int t0 = sc ? 0 : p.pl_first[pi], t1 = sc ? 1 : p.pl_first[pi + 1];
+          for (int t = t0; t < t1; ++t) {
             if (!p.b_resident) {
               const long long tb0 = clock64();
               mbar_wait(bar_bempty + 8 * bs, bph ^ 1, p.err, 4);
@@ -216,9 +230,10 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             }
             if (ptx::elect_one()) {
               const uint32_t full = bar_bfull + 8 * bs;
+              const int kcol = sc ? RS * p.C + cc * 64 : (int)p.tap_w[t] * p.C + cc * 64;
               if (leader) ptx::mbar_arrive_expect_tx(full, (uint32_t)CG * p.b_stage_bytes);
-              if (CG == 2) ptx::tma_load_2d_pair(sB + bs * p.b_stage_bytes, &mapB, full, tap * p.C + kbase, n_row);
-              else ptx::tma_load_2d(sB + bs * p.b_stage_bytes, &mapB, full, tap * p.C + kbase, n_row);
+              if (CG == 2) ptx::tma_load_2d_pair(sB + bs * p.b_stage_bytes, &mapB, full, kcol, n_row);
+              else ptx::tma_load_2d(sB + bs * p.b_stage_bytes, &mapB, full, kcol, n_row);
             }
             __syncwarp();
             if (++bs == nb) { bs = 0; bph ^= 1; }
@@ -242,7 +257,6 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     const uint32_t a_lo0 = (uint32_t)ptx::make_smem_desc(sA + (uint32_t)Wv * 128u, 1024, 2);
     const uint32_t b_lo0 = (uint32_t)ptx::make_smem_desc(sB, 1024, 2);
     const uint32_t a_step = p.a_buf_bytes >> 4, b_step = p.b_stage_bytes >> 4;
-    const uint32_t r_step = (uint32_t)(p.dh * Wv) * 8u, s_step = (uint32_t)p.dw * 8u;
     const int R = p.R, S = p.S, cchunks = p.cchunks, n_tile = p.n_tile;
     const bool resident = p.b_resident != 0;
     const bool elected = ptx::elect_one();       // the same lane issues every MMA and every commit
@@ -255,17 +269,20 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       const uint32_t d_tmem = tmem_base + a * (uint32_t)n_tile;
       uint32_t acc = 0u;
       uint32_t b_lo = b_lo0;                     // resident: (chunk, tap) boxes in order from the start of sB
-      const int nchunks_all = cchunks + p.c2chunks;
-      for (int cc = 0; cc < nchunks_all; ++cc) {
-        const bool sc = cc >= cchunks;           // chunk of the fused 1x1 shortcut: one tap, the un-shifted view
+      const int nmain = cchunks * p.nplanes, nchunks_all = nmain + p.c2chunks;
+      uint32_t ridx = 0;                         // resident: running index of the next weight box
+      for (int cc = 0; cc < nchunks_all; ++cc) { // cc = load unit: (chunk, plane), then the fused-shortcut chunks
+        const bool sc = cc >= nmain;             // chunk of the fused 1x1 shortcut: one tap, the un-shifted view
+        const int pi = sc ? 0 : cc % p.nplanes;
+        const int t0 = sc ? 0 : p.pl_first[pi], t1 = sc ? 1 : p.pl_first[pi + 1];
         const long long tf0 = clock64();
         mbar_wait(bar_afull + 8 * ab, aph, p.err, 2);
         t_full += clock64() - tf0;
         if (stamp && it == 0 && cc == 0 && lane == 0) p.prof[1402] = clock64() - t_entry;
         ptx::tc_fence_after();
-        uint32_t a_row = a_lo0 + ab * a_step;
+        const uint32_t a_row = a_lo0 + ab * a_step;
         if (sc) {
-          const uint32_t bi = resident ? (uint32_t)(cchunks * R * S + (cc - cchunks)) : bs;
+          const uint32_t bi = resident ? (uint32_t)(cchunks * R * S + (cc - nmain)) : bs;
           if (!resident || it == 0) {
             mbar_wait(bar_bfull + 8 * bi, resident ? 0u : bph, p.err, 5);
             ptx::tc_fence_after();
@@ -280,31 +297,26 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           acc = 1u;
           if (!resident) { if (++bs == nb) { bs = 0; bph ^= 1; } }
         } else if (resident) {
-          if (it == 0) {                         // weights are loaded once per CTA, chunk by chunk behind the A rows
-            for (int i = 0; i < R * S; ++i) mbar_wait(bar_bfull + 8 * (uint32_t)(cc * R * S + i), 0, p.err, 5);
+          if (it == 0) {                         // weights are loaded once per CTA, unit by unit behind the A rows
+            for (int t = t0; t < t1; ++t) mbar_wait(bar_bfull + 8 * (ridx + (uint32_t)(t - t0)), 0, p.err, 5);
             ptx::tc_fence_after();
           }
-          for (int r = 0; r < R; ++r, a_row += r_step) {
-            uint32_t a_lo = a_row;
-            for (int sx = 0; sx < S; ++sx, a_lo += s_step, b_lo += b_step) {
-              if (elected) ptx::umma_f16_x4<CG>(d_tmem, a_lo, b_lo, desc_hi, idesc, acc);
-              acc = 1u;
-            }
+          for (int t = t0; t < t1; ++t, b_lo += b_step) {
+            if (elected) ptx::umma_f16_x4<CG>(d_tmem, a_row + p.tap_aoff[t], b_lo, desc_hi, idesc, acc);
+            acc = 1u;
           }
+          ridx += (uint32_t)(t1 - t0);
         } else {
-          for (int r = 0; r < R; ++r, a_row += r_step) {
-            uint32_t a_lo = a_row;
-            for (int sx = 0; sx < S; ++sx, a_lo += s_step) {
-              mbar_wait(bar_bfull + 8 * bs, bph, p.err, 5);
-              ptx::tc_fence_after();
-              if (elected) {
-                ptx::umma_f16_x4<CG>(d_tmem, a_lo, b_lo0 + bs * b_step, desc_hi, idesc, acc);
-                if (CG == 2) ptx::umma_commit_pair(bar_bempty + 8 * bs, 3);
-                else ptx::umma_commit(bar_bempty + 8 * bs);
-              }
-              acc = 1u;
-              if (++bs == nb) { bs = 0; bph ^= 1; }
+          for (int t = t0; t < t1; ++t) {
+            mbar_wait(bar_bfull + 8 * bs, bph, p.err, 5);
+            ptx::tc_fence_after();
+            if (elected) {
+              ptx::umma_f16_x4<CG>(d_tmem, a_row + p.tap_aoff[t], b_lo0 + bs * b_step, desc_hi, idesc, acc);
+              if (CG == 2) ptx::umma_commit_pair(bar_bempty + 8 * bs, 3);
+              else ptx::umma_commit(bar_bempty + 8 * bs);
             }
+            acc = 1u;
+            if (++bs == nb) { bs = 0; bph ^= 1; }
           }
         }
         if (elected) {
@@ -575,8 +587,11 @@ static void small_tensor_fixup(CUtensorMap* m, uint64_t tensor_bytes) {
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+static inline int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
 struct ShiftPlan {
   int cg, n_tile, na, nb, b_resident, rows_max, Wv, Hv, halo;
+  int cs, pv_t, pv_l;       // conv stride (1 | 2); virtual padding rows / columns of the (plane) grid
   uint32_t a_buf_bytes, b_stage_bytes;
   size_t smem_bytes;
   bool ok;
@@ -587,13 +602,31 @@ static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
                            int c2 = 0) {
   ShiftPlan pl;
   memset(&pl, 0, sizeof(pl));
-  if (d->dtype != PLNR_F16 || d->groups != 1 || d->stride_h != 1 || d->stride_w != 1) return pl;
+  if (d->dtype != PLNR_F16 || d->groups != 1 || d->stride_h != d->stride_w || d->stride_h < 1 || d->stride_h > 2) return pl;
   if (x->c % 64 != 0 || x->ld % 8 != 0 || x->coff % 8 != 0 || (reinterpret_cast<uintptr_t>(x->ptr) & 15)) return pl;
   if (d->pad_b > d->pad_t || d->pad_r > d->pad_l) return pl;
-  pl.Wv = x->w + d->pad_l;
-  pl.Hv = x->h + d->pad_t;
-  if (pl.Wv > 256 || d->kh * d->kw > kMaxB) return pl;
-  pl.halo = (d->kh - 1) * d->dil_h * pl.Wv + (d->kw - 1) * d->dil_w;
+  if (d->kh * d->kw > kMaxB) return pl;
+  pl.cs = d->stride_h;
+  if (pl.cs == 1) {
+    pl.pv_t = d->pad_t; pl.pv_l = d->pad_l;
+    pl.Wv = x->w + d->pad_l;
+    pl.Hv = x->h + d->pad_t;
+    pl.halo = (d->kh - 1) * d->dil_h * pl.Wv + (d->kw - 1) * d->dil_w;
+  } else {
+    // stride 2 (phase planes, see ShiftParams): tap r reads plane row p + floor((r - pad_t) / 2); the grid needs
+    // ceil(pad / 2) virtual padding rows / columns and holds the larger plane (ceil(H / 2) x ceil(W / 2))
+    if (d->dil_h != 1 || d->dil_w != 1 || c2 != 0) return pl;
+    if (const char* e = getenv("PLNR_NO_SHIFT_S2")) { if (atoi(e)) return pl; }
+    pl.pv_t = (d->pad_t + 1) / 2; pl.pv_l = (d->pad_l + 1) / 2;
+    pl.Wv = (x->w + 1) / 2 + pl.pv_l;
+    pl.Hv = (x->h + 1) / 2 + pl.pv_t;
+    const int r_max = floor_div(d->kh - 1 - d->pad_t, 2) + pl.pv_t, s_max = floor_div(d->kw - 1 - d->pad_l, 2) + pl.pv_l;
+    pl.halo = r_max * pl.Wv + s_max;
+    // reads past the end of a virtual row / image must land in the zero padding of the next one
+    if (y->w - 1 + s_max - pl.Wv >= pl.pv_l || y->h - 1 + r_max - pl.Hv >= pl.pv_t) return pl;
+    if (y->w > pl.Wv || y->h > pl.Hv) return pl;
+  }
+  if (pl.Wv * pl.cs > 256) return pl;
   pl.rows_max = (pl.Wv - 1 + kTileM - 1 + pl.halo) / pl.Wv + 1;
   // position o0 sits at row offset Wv whatever its column `off` (see the producer): the rows of a tile start at
   // Wv - off and there are floor((off + 127 + halo) / Wv) + 1 of them -- the buffer is sized for the worst `off`
@@ -645,6 +678,7 @@ static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
     pl.b_resident = 1;
     pl.nb = kst;
     if (resident_fits(pl.cg, 3)) pl.na = 3;
+    if (pl.cs == 2 && resident_fits(pl.cg, 4)) pl.na = 4;      // planes with one or two taps: keep more A loads in flight
   } else {
     if (fixed + 2 * (size_t)pl.a_buf_bytes + 3 * (size_t)pl.b_stage_bytes > budget) return pl;
     size_t left = budget - fixed - 2 * (size_t)pl.a_buf_bytes;
@@ -662,6 +696,59 @@ static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
   return pl;
 }
 
+// Tap tables of a problem, grouped by phase plane (see ShiftParams); stride 1 = one plane in filter order.
+static bool fill_planes(ShiftParams& p, const ShiftPlan& pl, const plnr_conv_desc* d) {
+  p.cs = pl.cs;
+  int nt = 0;
+  p.nplanes = 0;
+  for (int a = 0; a < pl.cs; ++a) {
+    for (int b = 0; b < pl.cs; ++b) {
+      const int first = nt;
+      for (int r = 0; r < d->kh; ++r) {
+        for (int sx = 0; sx < d->kw; ++sx) {
+          int rp, sp;
+          if (pl.cs == 1) { rp = r * d->dil_h; sp = sx * d->dil_w; }
+          else {
+            const int dr = floor_div(r - d->pad_t, 2), dq = floor_div(sx - d->pad_l, 2);
+            if (r - d->pad_t - 2 * dr != a || sx - d->pad_l - 2 * dq != b) continue;
+            rp = dr + pl.pv_t; sp = dq + pl.pv_l;
+          }
+          p.tap_aoff[nt] = (uint32_t)(rp * pl.Wv + sp) * 8u;
+          p.tap_w[nt] = (uint8_t)(r * d->kw + sx);
+          ++nt;
+        }
+      }
+      if (nt == first) continue;                         // no tap reads this plane (e.g. 1x1 / stride 2)
+      p.pl_first[p.nplanes] = first;
+      p.pl_w0[p.nplanes] = pl.cs == 1 ? -d->pad_l : -2 * pl.pv_l + b;
+      p.pl_h0[p.nplanes] = pl.cs == 1 ? -d->pad_t : -2 * pl.pv_t + a;
+      ++p.nplanes;
+    }
+  }
+  p.pl_first[p.nplanes] = nt;
+  return nt == d->kh * d->kw && p.nplanes >= 1;
+}
+
+}  // namespace
+
+// Debug / test aid: the virtual grid and tap tables the shift kernel would use for a problem, as integers:
+// out = [ok, cs, Hv, Wv, halo, nplanes, ntaps, (w0, h0, first) x 4, (aoff / 8, filter tap) x ntaps]; tests/test_host_logic.py
+// replays them in numpy against the oracle convolution, so the plane algebra is pinned without a GPU.
+extern "C" int plnr_debug_shift_geometry(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y, int* out, int n) {
+  if (!d || !x || !y || !out || n < 19 + 2 * kMaxB) return PLNR_ERR_INVALID;
+  memset(out, 0, sizeof(int) * (size_t)n);
+  const ShiftPlan pl = make_plan(d, x, y, 148);
+  if (!pl.ok) return PLNR_OK;
+  ShiftParams p;
+  memset(&p, 0, sizeof(p));
+  if (!fill_planes(p, pl, d)) return PLNR_OK;
+  out[0] = 1; out[1] = pl.cs; out[2] = pl.Hv; out[3] = pl.Wv; out[4] = pl.halo; out[5] = p.nplanes; out[6] = p.pl_first[p.nplanes];
+  for (int i = 0; i < 4; ++i) { out[7 + 3 * i] = p.pl_w0[i]; out[8 + 3 * i] = p.pl_h0[i]; out[9 + 3 * i] = p.pl_first[i]; }
+  for (int t = 0; t < out[6]; ++t) { out[19 + 2 * t] = (int)(p.tap_aoff[t] / 8u); out[20 + 2 * t] = p.tap_w[t]; }
+  return PLNR_OK;
+}
+
+namespace {
 }  // namespace
 
 bool plnr_conv2d_shift_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y) {
@@ -700,6 +787,7 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
   p.Mv = (long long)x->n * pl.Hv * pl.Wv;
   p.halo = pl.halo;
   p.R = d->kh; p.S = d->kw; p.dh = d->dil_h; p.dw = d->dil_w;
+  PLNR_REQUIRE(fill_planes(p, pl, d), "conv2d(shift): tap table is inconsistent");
   p.C = x->c; p.cchunks = x->c / 64;
   p.c2chunks = c2 / 64; p.s2 = x2 ? s2 : 1;
   p.ctr = (uint32_t)(d->pad_t * pl.Wv + d->pad_l) * 8u;      // the view whose tap reads input pixel (p, q) itself
@@ -735,8 +823,9 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
     const cuuint64_t dims[4] = {(cuuint64_t)x->c, (cuuint64_t)x->w, (cuuint64_t)x->h, (cuuint64_t)x->n};
     const cuuint64_t strides[3] = {(cuuint64_t)x->ld * 2, (cuuint64_t)x->w * x->ld * 2,
                                    (cuuint64_t)x->h * x->w * x->ld * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)pl.Wv, 1, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    // stride 2: Wv positions of a plane = every other pixel of a 2*Wv-wide box (element stride 2 along W)
+    const cuuint32_t box[4] = {64, (cuuint32_t)(pl.Wv * pl.cs), 1, 1};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)pl.cs, 1, 1};
     void* gaddr = (void*)((__half*)x->ptr + x->coff);
     CUresult r = g_encode_tiled(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, gaddr, dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -101,6 +101,9 @@ CONV_SWEEP = [
     # 3-wide filters over 64-channel output blocks (also the shapes of the opt-in stacked kernel, conv_stack.cu)
     (4, 64, 56, 56, 64, 3, 1, 1, 1), (2, 128, 28, 28, 128, 3, 1, 1, 1), (3, 64, 20, 24, 192, 3, 1, 1, 1),
     (2, 64, 17, 19, 64, 3, 1, 0, 1), (5, 64, 9, 11, 64, 3, 1, 1, 1),
+    # stride 2 with Cin % 64 == 0: the phase-plane shift GEMM (resident weights / streamed CTA pairs / two channel blocks)
+    (2, 64, 56, 56, 128, 3, 2, 1, 1), (2, 128, 28, 28, 256, 3, 2, 1, 1), (3, 256, 14, 14, 512, 3, 2, 1, 1),
+    (2, 64, 21, 23, 64, 1, 2, 0, 1), (2, 64, 26, 30, 96, 5, 2, 2, 1), (1, 128, 40, 36, 64, 3, 2, 0, 1),
 ]
 
 
@@ -584,3 +587,26 @@ def test_fp16_residual_head_with_three_channels(planer):
     ref = oracle.build_net(model, blob)(x.astype(np.float32))
     got = planer.from_model(model, blob, half=True)(x)
     assert got.shape == ref.shape and rel_err(got, ref) <= 1e-2
+
+
+@pytest.mark.parametrize('cfg', [(4, 64, 56, 56, 128), (2, 128, 28, 28, 256), (4, 256, 14, 14, 512)])
+def test_stride2_shift_gemm_equals_im2col_kernel(planer, cfg, monkeypatch):
+    """The two tensor-core formulations of a 3x3 / stride-2 convolution -- four phase planes through the shift GEMM
+    (conv_shift.cu) and TMA im2col (conv_tcgen05.cu) -- accumulate the same products in fp32 and round once: they must
+    agree to fp16 rounding of differently ordered fp32 sums."""
+    from planer_b200 import ops, backend as B
+    n, cin, h, w, cout = cfg
+    rng = np.random.default_rng(cin + cout)
+    x = B.to_nhwc(B.asarray(rng.standard_normal((n, cin, h, w)).astype(np.float16)))
+    K = (rng.standard_normal((cout, cin, 3, 3)) * np.sqrt(2.0 / (cin * 9))).astype(np.float16)
+    wp = ops.pack_weight(B.asarray(K), cin, np.float16)
+    outs, kernels = [], []
+    for no_s2 in ('0', '1'):
+        monkeypatch.setenv('PLNR_NO_SHIFT_S2', no_s2)
+        y = B.empty((n, cout, h // 2, w // 2), np.float16, 'nhwc')
+        ops.conv2d_into(x, wp, y, 3, 3, (2, 2), (1, 1), (1, 1, 1, 1), 1, None, None, None, ops.ACT_RELU, 0.0, ops.ALGO_TCGEN05)
+        kernels.append(B.last_kernel())
+        B.synchronize()
+        outs.append(y.get().astype(np.float32))
+    assert kernels == ['conv2d_shift', 'conv2d_tcgen05'], kernels
+    assert rel_err(outs[0], outs[1]) <= 2e-3

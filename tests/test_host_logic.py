@@ -552,3 +552,75 @@ def test_debug_trace_and_schedule_follow_the_reference_interpreter():
     assert 'conv conv : ' in out and "\t-->  ['x', 'K', 'B'] :" in out and '\t<--  a :' in out
     g = np.load(os.path.join(GOLD, 'graphs.npz'))
     assert cases.sample(y[0]).tobytes() == g['readme_f32.out0'].tobytes()
+
+
+# ---------------------------------------------------------------------------------------------
+# shift-GEMM geometry (csrc/conv_shift.cu): the virtual grid, phase planes and tap tables the kernel uses, replayed in
+# numpy against the oracle convolution -- pins the stride-2 plane algebra and the TMA start coordinates without a GPU
+# ---------------------------------------------------------------------------------------------
+
+def _shift_geometry(lib, xshape, cout, k, stride, pads, dil=1):
+    n, c, h, w = xshape
+    d = _capi.ConvDesc(_capi.F16, k[0], k[1], pads[0], pads[1], pads[2], pads[3], stride, stride, dil, dil, 1, 0)
+    oh = (h + pads[0] + pads[2] - (k[0] - 1) * dil - 1 + stride) // stride
+    ow = (w + pads[1] + pads[3] - (k[1] - 1) * dil - 1 + stride) // stride
+    tx, ty = _capi.Tensor(256, n, h, w, c, c, 0), _capi.Tensor(256, n, oh, ow, cout, cout, 0)
+    out = (ctypes.c_int * 128)()
+    assert lib.plnr_debug_shift_geometry(ctypes.byref(d), ctypes.byref(tx), ctypes.byref(ty), out, 128) == 0
+    return list(out), oh, ow
+
+
+@pytest.mark.parametrize('cfg', [
+    # n, c, h, w, cout, (kh, kw), stride, pads (t, l, b, r), dilation
+    (2, 64, 12, 12, 8, (3, 3), 2, (1, 1, 1, 1), 1),       # ResNet down-sampling conv: four planes, 4 + 2 + 2 + 1 taps
+    (1, 64, 13, 11, 8, (3, 3), 2, (1, 1, 1, 1), 1),       # odd sizes: the odd-phase planes are one row / column shorter
+    (2, 64, 10, 14, 8, (1, 1), 2, (0, 0, 0, 0), 1),       # 1x1 / stride 2 shortcut conv: one plane, one tap
+    (1, 64, 20, 22, 8, (3, 3), 2, (0, 0, 0, 0), 1),       # no padding
+    (1, 64, 16, 16, 8, (5, 5), 2, (2, 2, 2, 2), 1),       # 5x5: 9 + 6 + 6 + 4 taps
+    (1, 64, 12, 12, 8, (3, 3), 2, (1, 1, 0, 0), 1),       # top / left padding only
+    (2, 64, 9, 10, 8, (3, 3), 1, (1, 1, 1, 1), 1),        # stride 1: one plane in filter order
+    (1, 64, 12, 12, 8, (3, 3), 1, (2, 2, 2, 2), 2),       # stride 1, dilation 2
+])
+def test_shift_gemm_plane_geometry_reproduces_the_convolution(lib, cfg):
+    n, c, h, w, cout, k, stride, pads, dil = cfg
+    g, oh, ow = _shift_geometry(lib, (n, c, h, w), cout, k, stride, pads, dil)
+    assert g[0] == 1, 'the shift kernel must apply to this problem'
+    cs, Hv, Wv, halo, nplanes, ntaps = g[1:7]
+    assert cs == stride and ntaps == k[0] * k[1]
+    rng = np.random.default_rng(sum(cfg[:5]) + stride)
+    x = rng.integers(-3, 4, (n, c, h, w)).astype(np.float64)           # small integers: exact arithmetic
+    K = rng.integers(-2, 3, (cout, c, k[0], k[1])).astype(np.float64)
+    ref = oracle.conv2d(x.astype(np.float32), K.astype(np.float32), None, 1, (stride, stride), (dil, dil), pads).astype(np.float64)
+    M = n * Hv * Wv
+    acc = np.zeros((M + halo + 1, cout))
+    for pi in range(nplanes):
+        w0, h0, first = g[7 + 3 * pi: 10 + 3 * pi]
+        last = g[7 + 3 * (pi + 1) + 2] if pi + 1 < nplanes else ntaps
+        # what the TMA boxes put into shared memory: virtual position (img, p', q') <- x[img, :, p' * cs + h0, q' * cs + w0], 0 outside
+        plane = np.zeros((M + halo + 1, c))
+        for img in range(n):
+            for pv in range(Hv):
+                ih = pv * cs + h0
+                if not 0 <= ih < h:
+                    continue
+                for qv in range(Wv):
+                    iw = qv * cs + w0
+                    if 0 <= iw < w:
+                        plane[(img * Hv + pv) * Wv + qv] = x[img, :, ih, iw]
+        for t in range(first, last):
+            aoff, wt = g[19 + 2 * t], g[20 + 2 * t]
+            assert 0 <= aoff <= halo
+            r, s = divmod(wt, k[1])
+            shifted = np.zeros_like(plane)
+            shifted[:M + halo + 1 - aoff] = plane[aoff:]
+            acc += shifted @ K[:, :, r, s].T                           # one tcgen05.mma chain: D += A(shifted view) * W_tap^T
+    got = acc[:M].reshape(n, Hv, Wv, cout)[:, :oh, :ow].transpose(0, 3, 1, 2)
+    assert np.array_equal(got, ref)
+
+
+def test_shift_gemm_rejects_what_it_cannot_do(lib):
+    for cfg in [((1, 64, 12, 12), 8, (3, 3), 3, (1, 1, 1, 1), 1),     # stride 3
+                ((1, 64, 12, 12), 8, (3, 3), 2, (2, 2, 2, 2), 2),     # stride 2 with dilation
+                ((1, 48, 12, 12), 8, (3, 3), 1, (1, 1, 1, 1), 1),     # Cin % 64 != 0
+                ((1, 64, 12, 300), 8, (3, 3), 2, (1, 1, 1, 1), 1)]:   # 2 * Wv > 256: the TMA box limit
+        assert _shift_geometry(lib, *cfg)[0][0] == 0
