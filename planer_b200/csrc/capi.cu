@@ -51,6 +51,8 @@ int plnr_destroy(plnr_ctx* ctx) {
   if (!ctx) return PLNR_OK;
   cudaSetDevice(ctx->device);
   if (ctx->dev_error) cudaFree(ctx->dev_error);
+  if (ctx->sk_ws) cudaFree(ctx->sk_ws);
+  if (ctx->sk_flags) cudaFree(ctx->sk_flags);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return PLNR_OK;
@@ -73,6 +75,7 @@ int plnr_stream_sync(plnr_ctx* ctx) {
   if (err[0] != 0) {
     plnr_set_error("device-side watchdog fired: code %d (block %d, role %d, aux %d)", err[0], err[1], err[2], err[3]);
     cudaMemset(ctx->dev_error, 0, sizeof(err));
+    if (ctx->sk_flags) cudaMemset(ctx->sk_flags, 0, sizeof(int) * 16 * 256);
     return PLNR_ERR_CUDA;
   }
   return PLNR_OK;

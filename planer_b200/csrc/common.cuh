@@ -26,6 +26,8 @@ struct plnr_ctx {
   // device-side error word written by kernels that time out on a barrier (debug aid)
   int* dev_error = nullptr;
   long long* prof = nullptr;       // debug: per-CTA role cycle counters of the last tcgen05 conv launch
+  float* sk_ws = nullptr;          // stream-K workspace of the shift conv kernel: fp32 partial tiles, one slot per unit
+  int* sk_flags = nullptr;         // ... and their ready flags (self-cleaning: the consumer resets them)
   const char* last_kernel = "";   // name handed to plnr_after_launch by the most recent launch (diagnostics)
   bool shift_attr_set = false;
   bool igemm_attr_set = false;     // cudaFuncSetAttribute(max dynamic smem) done for this device

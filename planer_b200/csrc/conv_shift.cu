@@ -30,10 +30,12 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kThreads = 384;          // warps 0-3: producer / MMA / TMEM / table; warps 4-11: two epilogue groups
-constexpr int kMaxA = 4, kMaxB = 40;
+constexpr int kMaxA = 8, kMaxB = 40;
 constexpr uint32_t kEpiBytes = 2 * 2 * 256 * 2;   // [buffer][scale | shift][256] fp16 (the epilogue math is packed fp16)
 constexpr uint32_t kStageBytes = 8 * 1024;        // epilogue transposition stage (per epilogue warp: 32 rows x 32 B = 16 channels)
 constexpr long long kWatchdogCycles = 4000000000ll;
+
+struct AMaps { CUtensorMap m[4]; };     // the A operand's tensor map with boxes of 1, 2, 4, 8 rows
 
 struct ShiftParams {
   FastDiv div_hvwv, div_wv, div_mt;     // / (Hv*Wv), / Wv, / num_m_tiles
@@ -48,6 +50,7 @@ struct ShiftParams {
   // GEMMs, one per plane, over the SAME virtual output grid.  A plane is fetched by a tiled TMA box with element stride
   // `cs` along W (every other pixel: whole 128-byte channel rows, no wasted sectors) and row coordinate hrow * cs + h0.
   int nplanes, cs;
+  int max_hlog;             // log2 of the tallest A box in use (0..3)
   int pl_w0[4], pl_h0[4];   // TMA start coordinates of a plane's virtual column 0 / virtual row 0
   int pl_first[5];          // taps [pl_first[i], pl_first[i + 1]) of the tables below belong to plane i
   uint32_t tap_aoff[kMaxB]; // A descriptor offset of a tap inside its plane buffer: (r' * Wv + s') * 8
@@ -65,6 +68,63 @@ struct ShiftParams {
   int vec_ok;
   int* err;
   long long* prof;
+  // stream-K (see SegList): iterations per tile = weight boxes per tile; fp32 partial tiles and their ready flags
+  int streamk, ipt;
+  float* sk_ws;             // [unit][CG * 128 rows][n_tile] fp32: the partial accumulator a unit contributes to another unit's tile
+  int* sk_flags;            // [unit][2 ranks][8 epilogue warps]: 1 = that warp's part of the partial is in sk_ws
+};
+
+// Work of one persistent unit (CTA or CTA pair) as a list of segments.  Without stream-K a segment is a whole tile
+// (tiles unit, unit + nunits, ...).  With stream-K the (tile, k-iteration) space -- an iteration is one weight box = one
+// (64-channel chunk, tap) = four tcgen05.mma -- is cut into nunits equal contiguous ranges, so that a last, partly filled
+// wave (225 tiles on 148 SMs at 14x14) costs its share instead of a whole round.  A range covers: the tail of a tile
+// another unit started (CONTRIB: the fp32 partial accumulator goes to sk_ws), whole tiles, and the head of a tile
+// (OWNER: waits for the partials of the units that continue the tile, adds them in unit order -- deterministic -- and runs
+// the epilogue).  Order inside a unit: CONTRIB first, OWNER second, whole tiles last: every partial is produced at the very
+// start of its unit's timeline, so an owner never waits in practice and no wait can depend on another wait.
+enum { SEG_FULL = 0, SEG_OWNER = 1, SEG_CONTRIB = 2 };
+struct Seg { int tile, it0, it1, mode; };
+struct SegList {
+  int nseg, first_tile, it0_first, it1_last, ipt, unit, nunits, streamk;
+  bool has_contrib, has_owner;
+  __device__ __forceinline__ static void range(const ShiftParams& p, int u, int nunits, long long& g0, long long& g1) {
+    const long long T = (long long)p.num_tiles * p.ipt;
+    g0 = T * u / nunits;
+    g1 = T * (u + 1) / nunits;
+  }
+  __device__ __forceinline__ void init(const ShiftParams& p, int unit_, int nunits_) {
+    unit = unit_; nunits = nunits_; ipt = p.ipt; streamk = p.streamk;
+    has_contrib = has_owner = false;
+    first_tile = 0; it0_first = 0; it1_last = ipt;
+    if (!streamk) {
+      nseg = unit < p.num_tiles ? (p.num_tiles - unit + nunits - 1) / nunits : 0;
+      return;
+    }
+    long long g0, g1;
+    range(p, unit, nunits, g0, g1);
+    if (g1 <= g0) { nseg = 0; return; }
+    first_tile = (int)(g0 / ipt);
+    const int last_tile = (int)((g1 - 1) / ipt);
+    nseg = last_tile - first_tile + 1;
+    it0_first = (int)(g0 - (long long)first_tile * ipt);
+    it1_last = (int)(g1 - (long long)last_tile * ipt);
+    has_contrib = it0_first > 0;
+    has_owner = it1_last < ipt && (nseg > 1 || it0_first == 0);
+  }
+  __device__ __forceinline__ Seg at(int k) const {
+    Seg sg;
+    if (!streamk) { sg.tile = unit + k * nunits; sg.it0 = 0; sg.it1 = ipt; sg.mode = SEG_FULL; return sg; }
+    int j = k;
+    if (has_owner) {
+      if (has_contrib) j = k == 0 ? 0 : (k == 1 ? nseg - 1 : k - 1);
+      else j = k == 0 ? nseg - 1 : k - 1;
+    }
+    sg.tile = first_tile + j;
+    sg.it0 = j == 0 ? it0_first : 0;
+    sg.it1 = j == nseg - 1 ? it1_last : ipt;
+    sg.mode = sg.it0 > 0 ? SEG_CONTRIB : (sg.it1 < ipt ? SEG_OWNER : SEG_FULL);
+    return sg;
+  }
 };
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int role) {
@@ -115,7 +175,7 @@ __device__ __forceinline__ void tile_rows(long long o0, int Wv, int halo, long l
 
 template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant__ CUtensorMap mapB,
                       const __grid_constant__ CUtensorMap mapA2, const ShiftParams p) {
   extern __shared__ uint8_t smem_raw[];
   const long long t_entry = clock64();
@@ -144,7 +204,7 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   const uint32_t row_bytes = (uint32_t)Wv * 128u;       // one virtual row of 64 channels in shared memory
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&mapA);
+    for (int i = 0; i <= p.max_hlog; ++i) ptx::prefetch_tmap(&mapsA.m[i]);
     ptx::prefetch_tmap(&mapB);
     if (p.c2chunks) ptx::prefetch_tmap(&mapA2);
   }
@@ -177,7 +237,11 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     bool first = true;
     long long t_wait = 0;
     const long long t_all0 = clock64();
-    for (int tile = unit; tile < p.num_tiles; tile += nunits) {
+    SegList segs;
+    segs.init(p, unit, nunits);
+    for (int k = 0; k < segs.nseg; ++k) {
+      const Seg sg = segs.at(k);
+      const int tile = sg.tile;
       const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
       const long long o0 = ((long long)m_idx * CG + rank) * kTileM;
       long long v0; int nrows, off;
@@ -200,6 +264,12 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         const bool sc = lu >= nmain;
         const int cc = sc ? lu - nmain : lu / p.nplanes;
         const int pi = sc ? 0 : lu - cc * p.nplanes;
+        // taps of this unit inside the segment's iteration range (iteration of tap t: cc * RS + t; shortcut chunks follow)
+        int t0 = sc ? 0 : p.pl_first[pi], t1 = sc ? 1 : p.pl_first[pi + 1];
+        const int ibase = sc ? p.cchunks * RS + cc : cc * RS;
+        t0 = max(t0, sg.it0 - ibase);
+        t1 = min(t1, sg.it1 - ibase);
+        if (t0 >= t1) continue;
         const long long tw0 = clock64();
         mbar_wait(bar_aempty + 8 * ab, aph ^ 1, p.err, 0);
         t_wait += clock64() - tw0;
@@ -209,19 +279,30 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           uint32_t dst = sA + ab * p.a_buf_bytes + row0_off;
           long long v = v0;
           int img = (int)(v / p.Hv), hrow = (int)(v - (long long)img * p.Hv);
-          const CUtensorMap* mA = sc ? &mapA2 : &mapA;
           const int cs = sc ? p.s2 : p.cs, c0 = cc * 64;
           const int w0 = sc ? -p.pad_l * p.s2 : p.pl_w0[pi], h0 = sc ? -p.pad_t * p.s2 : p.pl_h0[pi];
-          for (int i = 0; i < nrows; ++i) {
-            tma_load_4d<CG>(dst, mA, full, c0, w0, hrow * cs + h0, img);
-            dst += row_bytes;
-            if (++hrow == p.Hv) { hrow = 0; ++img; }
+          // The rows of one image go out as boxes of 8 / 4 / 2 / 1 rows: the issuing thread pays ~100-150 clk per TMA
+          // instruction whatever its size, and at 7x7 / 14x14 a tile is 12-21 rows per chunk (per plane at stride 2) --
+          // issued row by row this warp, not the tensor pipe, paced those layers (profiles/r02_tma_issue.md)
+          const int max_hlog = sc ? 0 : p.max_hlog;
+          int left = nrows;
+          while (left > 0) {
+            int seg = min(left, p.Hv - hrow);                // rows of this image
+            left -= seg;
+            while (seg > 0) {
+              int k = seg >= 8 ? 3 : (seg >= 4 ? 2 : (seg >= 2 ? 1 : 0));
+              if (k > max_hlog) k = max_hlog;
+              tma_load_4d<CG>(dst, sc ? &mapA2 : &mapsA.m[k], full, c0, w0, hrow * cs + h0, img);
+              dst += row_bytes << k;
+              hrow += 1 << k;
+              seg -= 1 << k;
+            }
+            if (hrow == p.Hv) { hrow = 0; ++img; }
           }
         }
         __syncwarp();
         if (++ab == na) { ab = 0; aph ^= 1; }
         if (!p.b_resident || first) {
-          const int t0 = sc ? 0 : p.pl_first[pi], t1 = sc ? 1 : p.pl_first[pi + 1];
           for (int t = t0; t < t1; ++t) {
             if (!p.b_resident) {
               const long long tb0 = clock64();
@@ -260,7 +341,10 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     const int R = p.R, S = p.S, cchunks = p.cchunks, n_tile = p.n_tile;
     const bool resident = p.b_resident != 0;
     const bool elected = ptx::elect_one();       // the same lane issues every MMA and every commit
-    for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
+    SegList segs;
+    segs.init(p, unit, nunits);
+    for (int k = 0; k < segs.nseg; ++k, ++it) {
+      const Seg sg = segs.at(k);
       const uint32_t a = it & 1, tph = (it >> 1) & 1;
       const long long te0 = clock64();
       mbar_wait(bar_tempty + 8 * a, tph ^ 1, p.err, 1);
@@ -274,7 +358,14 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       for (int cc = 0; cc < nchunks_all; ++cc) { // cc = load unit: (chunk, plane), then the fused-shortcut chunks
         const bool sc = cc >= nmain;             // chunk of the fused 1x1 shortcut: one tap, the un-shifted view
         const int pi = sc ? 0 : cc % p.nplanes;
-        const int t0 = sc ? 0 : p.pl_first[pi], t1 = sc ? 1 : p.pl_first[pi + 1];
+        int t0 = sc ? 0 : p.pl_first[pi], t1 = sc ? 1 : p.pl_first[pi + 1];
+        {                                        // the part of this unit inside the segment (see the producer)
+          const int ibase = sc ? cchunks * R * S + (cc - nmain) : (cc / p.nplanes) * R * S;
+          const int nt = t1 - t0;
+          t0 = max(t0, sg.it0 - ibase);
+          t1 = min(t1, sg.it1 - ibase);
+          if (t0 >= t1) { if (resident && !sc) { ridx += (uint32_t)nt; b_lo += (uint32_t)nt * b_step; } continue; }
+        }
         const long long tf0 = clock64();
         mbar_wait(bar_afull + 8 * ab, aph, p.err, 2);
         t_full += clock64() - tf0;
@@ -320,15 +411,14 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           }
         }
         if (elected) {
-          if (CG == 2) {
-            ptx::umma_commit_pair(bar_aempty + 8 * ab, 3);
-            if (cc == nchunks_all - 1) ptx::umma_commit_pair(bar_tfull + 8 * a, 3);
-          } else {
-            ptx::umma_commit(bar_aempty + 8 * ab);
-            if (cc == nchunks_all - 1) ptx::umma_commit(bar_tfull + 8 * a);
-          }
+          if (CG == 2) ptx::umma_commit_pair(bar_aempty + 8 * ab, 3);
+          else ptx::umma_commit(bar_aempty + 8 * ab);
         }
         if (++ab == na) { ab = 0; aph ^= 1; }
+      }
+      if (elected) {                             // accumulator of this segment complete (commits are ordered)
+        if (CG == 2) ptx::umma_commit_pair(bar_tfull + 8 * a, 3);
+        else ptx::umma_commit(bar_tfull + 8 * a);
       }
     }
     if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 2] = t_full; p.prof[blockIdx.x * 8 + 3] = t_tempty; p.prof[blockIdx.x * 8 + 4] = clock64() - t_all0; }
@@ -389,13 +479,18 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           if (g.row[i] >= 0)
             dst[2 * h + i] = *reinterpret_cast<const uint4*>(p.res + (size_t)g.row[i] * p.rld + p.rcoff + cb + h * 16 + piece * 8);
     };
-    Geo gn = tile_geo(unit < p.num_tiles ? unit : 0);
-    if (has_res && p.vec_ok && c_begin < c_end && unit < p.num_tiles && (!alternate || eg == 0)) {
-      const int cb = (int)fast_div((uint32_t)unit, p.div_mt) * p.n_tile + c_begin;
+    SegList segs;
+    segs.init(p, unit, nunits);
+    const Seg sg0 = segs.at(0);
+    Geo gn = tile_geo(segs.nseg > 0 ? sg0.tile : 0);
+    if (has_res && p.vec_ok && c_begin < c_end && segs.nseg > 0 && sg0.mode != SEG_CONTRIB && (!alternate || eg == 0)) {
+      const int cb = (int)fast_div((uint32_t)sg0.tile, p.div_mt) * p.n_tile + c_begin;
       if (cb + 32 <= p.Cout) fetch_res(gn, cb, rvp);
     }
 
-    for (int tile = unit; tile < p.num_tiles; tile += nunits, ++it) {
+    for (int k = 0; k < segs.nseg; ++k, ++it) {
+      const Seg sg = segs.at(k);
+      const int tile = sg.tile;
       const uint32_t a = it & 1, tph = (it >> 1) & 1;
       const int n_idx = (int)fast_div((uint32_t)tile, p.div_mt);
       const int n0 = n_idx * p.n_tile;
@@ -418,12 +513,12 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       uint4 rv[4], rvn[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { rv[i] = rvp[i]; rvn[i] = make_uint4(0u, 0u, 0u, 0u); }
-      // next tile: geometry + residual of its first chunk (in flight during this whole epilogue)
-      const int tile_n = tile + nunits;
-      if (tile_n < p.num_tiles) {
-        gn = tile_geo(tile_n);
-        if (has_res && p.vec_ok && c_begin < c_end && (!alternate || ((it + 1) & 1u) == (uint32_t)eg)) {
-          const int cb = (int)fast_div((uint32_t)tile_n, p.div_mt) * p.n_tile + c_begin;
+      // next segment: geometry + residual of its first chunk (in flight during this whole epilogue)
+      if (k + 1 < segs.nseg) {
+        const Seg sn = segs.at(k + 1);
+        gn = tile_geo(sn.tile);
+        if (has_res && p.vec_ok && c_begin < c_end && sn.mode != SEG_CONTRIB && (!alternate || ((it + 1) & 1u) == (uint32_t)eg)) {
+          const int cb = (int)fast_div((uint32_t)sn.tile, p.div_mt) * p.n_tile + c_begin;
           if (cb + 32 <= p.Cout) fetch_res(gn, cb, rvp);
         }
       }
@@ -434,6 +529,57 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + a * (uint32_t)p.n_tile;
       const int ce_ = (alternate && (it & 1u) != (uint32_t)eg) ? c_begin : c_end;      // not this group's tile
+      if (sg.mode == SEG_CONTRIB) {
+        // stream-K: this unit computed the tail of a tile another unit owns -- the raw fp32 accumulator goes to the
+        // workspace (row-major [256 rows of the unit][n_tile]; a thread's 32 columns of a chunk are 128 contiguous bytes)
+        float* wrow = p.sk_ws + ((size_t)unit * (CG * kTileM) + rank * kTileM + (uint32_t)(ew * 32 + lane)) * (uint32_t)p.n_tile;
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+          __syncwarp();
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(t_row + c0, v);
+          ptx::tmem_ld_wait();
+          if (c0 + 32 >= c_end) {
+            ptx::tc_fence_before();
+            if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
+            else ptx::mbar_arrive(bar_tempty + 8 * a);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            __stcg(reinterpret_cast<float4*>(wrow + c0) + j,
+                   make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3])));
+        }
+        __threadfence();                  // the partial is visible device-wide before its flag
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile int*>(p.sk_flags + (unit * 2 + (int)rank) * 8 + (warp - 4)) = 1;
+        continue;
+      }
+      int npieces = 0;                    // stream-K owner: units unit+1 .. unit+npieces hold the rest of this tile
+      if (sg.mode == SEG_OWNER) {
+        const long long tile_end = (long long)(tile + 1) * p.ipt;
+        for (int v = unit + 1; v < nunits; ++v) {
+          long long g0, g1;
+          SegList::range(p, v, nunits, g0, g1);
+          if (g0 >= tile_end) break;
+          if (g1 > g0) npieces = v - unit;
+        }
+        if (lane == 0) {
+          for (int pc = 1; pc <= npieces; ++pc) {
+            volatile int* f = p.sk_flags + ((unit + pc) * 2 + (int)rank) * 8 + (warp - 4);
+            const long long t0 = clock64();
+            while (*f == 0) {
+              if (*reinterpret_cast<volatile int*>(p.err) != 0) break;
+              if (clock64() - t0 > kWatchdogCycles) {
+                if (atomicCAS(p.err, 0, 4) == 0) { p.err[1] = blockIdx.x; p.err[2] = 6; p.err[3] = unit + pc; }
+                break;
+              }
+            }
+            *f = 0;                       // consumed: the next launch starts from clean flags
+          }
+          __threadfence();
+        }
+        __syncwarp();
+      }
       if (c_begin >= ce_) {               // nothing to read for this group: release at once
         ptx::tc_fence_before();
         if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
@@ -451,6 +597,17 @@ conv_shift_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           ptx::tc_fence_before();
           if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
           else ptx::mbar_arrive(bar_tempty + 8 * a);
+        }
+        for (int pc = 1; pc <= npieces; ++pc) {     // stream-K owner: add the other units' partial sums, in unit order
+          const float* prow = p.sk_ws + ((size_t)(unit + pc) * (CG * kTileM) + rank * kTileM + (uint32_t)(ew * 32 + lane)) * (uint32_t)p.n_tile + c0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 q4 = __ldcg(reinterpret_cast<const float4*>(prow) + j);
+            v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + q4.x);
+            v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + q4.y);
+            v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + q4.z);
+            v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + q4.w);
+          }
         }
         if (fast) {
           // The math of a chunk is compiled twice, once with the activation fixed to ReLU: with the generic runtime
@@ -674,11 +831,25 @@ static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
     pl.cg = 2;
     pl.b_stage_bytes = (uint32_t)(pl.n_tile / 2) * 128;
   }
+  // stride 2: a plane buffer feeds only 1-4 taps (4-16 MMAs), so the A ring must be deep enough to cover the TMA latency
+  // -- a CTA pair halves the weight bytes per CTA, which is what buys the extra A buffers
+  int na_cap = kMaxA;
+  if (const char* e = getenv("PLNR_SHIFT_S2_NA")) { int v = atoi(e); if (v >= 2 && v <= kMaxA) na_cap = v; }
+  if (pl.cs == 2 && forced == 0 && pl.cg == 1 && m_tiles_128 >= 2 && pl.n_tile % 32 == 0 && pl.n_tile >= 64) {
+    pl.cg = 2;
+    pl.b_stage_bytes = (uint32_t)(pl.n_tile / 2) * 128;
+  }
   if (resident_fits(pl.cg, 2)) {
     pl.b_resident = 1;
     pl.nb = kst;
     if (resident_fits(pl.cg, 3)) pl.na = 3;
-    if (pl.cs == 2 && resident_fits(pl.cg, 4)) pl.na = 4;      // planes with one or two taps: keep more A loads in flight
+    if (pl.cs == 2) for (int na = 4; na <= na_cap; ++na) if (resident_fits(pl.cg, na)) pl.na = na;
+  } else if (pl.cs == 2) {
+    if (fixed + 2 * (size_t)pl.a_buf_bytes + 3 * (size_t)pl.b_stage_bytes > budget) return pl;
+    for (int na = 2; na <= na_cap; ++na)
+      if (fixed + (size_t)na * pl.a_buf_bytes + 4 * (size_t)pl.b_stage_bytes <= budget) pl.na = na;
+    pl.nb = (int)((budget - fixed - (size_t)pl.na * pl.a_buf_bytes) / pl.b_stage_bytes);
+    if (pl.nb > 12) pl.nb = 12;
   } else {
     if (fixed + 2 * (size_t)pl.a_buf_bytes + 3 * (size_t)pl.b_stage_bytes > budget) return pl;
     size_t left = budget - fixed - 2 * (size_t)pl.a_buf_bytes;
@@ -818,24 +989,30 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
   p.err = ctx->dev_error;
   p.prof = ctx->prof;
 
-  CUtensorMap mapA, mapB;
-  {
+  AMaps mapsA;
+  CUtensorMap mapB;
+  memset(&mapsA, 0, sizeof(mapsA));
+  // boxes of up to 256 positions (32 KB); PLNR_SHIFT_ROWBOX=0 keeps the row-by-row loads (A/B)
+  p.max_hlog = 0;
+  while (p.max_hlog < 3 && (2 << p.max_hlog) * pl.Wv <= 256 && (2 << p.max_hlog) <= pl.Hv) ++p.max_hlog;
+  if (const char* e = getenv("PLNR_SHIFT_ROWBOX")) { int v = atoi(e); if (v >= 0 && v < p.max_hlog) p.max_hlog = v; }
+  for (int k = 0; k <= p.max_hlog; ++k) {
     const cuuint64_t dims[4] = {(cuuint64_t)x->c, (cuuint64_t)x->w, (cuuint64_t)x->h, (cuuint64_t)x->n};
     const cuuint64_t strides[3] = {(cuuint64_t)x->ld * 2, (cuuint64_t)x->w * x->ld * 2,
                                    (cuuint64_t)x->h * x->w * x->ld * 2};
-    // stride 2: Wv positions of a plane = every other pixel of a 2*Wv-wide box (element stride 2 along W)
-    const cuuint32_t box[4] = {64, (cuuint32_t)(pl.Wv * pl.cs), 1, 1};
-    const cuuint32_t estr[4] = {1, (cuuint32_t)pl.cs, 1, 1};
+    // stride 2: Wv positions of a plane = every other pixel of a 2*Wv-wide box (element stride 2 along W), rows likewise
+    const cuuint32_t box[4] = {64, (cuuint32_t)(pl.Wv * pl.cs), (cuuint32_t)((1 << k) * pl.cs), 1};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)pl.cs, (cuuint32_t)pl.cs, 1};
     void* gaddr = (void*)((__half*)x->ptr + x->coff);
-    CUresult r = g_encode_tiled(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, gaddr, dims, strides, box, estr,
+    CUresult r = g_encode_tiled(&mapsA.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, gaddr, dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-      plnr_set_error("cuTensorMapEncodeTiled(A) failed with CUresult %d (C=%d W=%d H=%d N=%d Wv=%d)", (int)r, x->c, x->w,
-                     x->h, x->n, pl.Wv);
+      plnr_set_error("cuTensorMapEncodeTiled(A, %d rows) failed with CUresult %d (C=%d W=%d H=%d N=%d Wv=%d stride=%d)", 1 << k,
+                     (int)r, x->c, x->w, x->h, x->n, pl.Wv, pl.cs);
       return PLNR_ERR_DRIVER;
     }
-    small_tensor_fixup(&mapA, (uint64_t)x->n * x->h * x->w * x->ld * 2);
+    small_tensor_fixup(&mapsA.m[k], (uint64_t)x->n * x->h * x->w * x->ld * 2);
   }
   {
     const int Ktot = d->kh * d->kw * x->c + c2;
@@ -853,7 +1030,7 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
     small_tensor_fixup(&mapB, (uint64_t)Ktot * y->c * 2);
   }
 
-  CUtensorMap mapA2 = mapA;
+  CUtensorMap mapA2 = mapsA.m[0];
   if (x2) {
     // x2 sampled at stride s2 in W (element stride) and H (row coordinate): one box = Wv positions of one virtual row
     const cuuint64_t dims[4] = {(cuuint64_t)x2->c, (cuuint64_t)x2->w, (cuuint64_t)x2->h, (cuuint64_t)x2->n};
@@ -879,7 +1056,30 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
     ctx->shift_attr_set = true;
   }
   int units = ctx->sm_count / cg;
-  if (p.num_tiles < units) units = p.num_tiles;
+  // stream-K (SegList): worth it when the last data-parallel round is poorly filled.  Streamed weights only (a resident
+  // filter is loaded during a unit's first WHOLE tile), at least two 32-channel chunks per epilogue group, and enough
+  // iterations that every unit gets a non-empty range.  PLNR_STREAMK=0 off, 1 auto (default), 2 whenever legal.
+  p.ipt = d->kh * d->kw * p.cchunks + p.c2chunks;
+  {
+    int mode = 1;
+    if (const char* e = getenv("PLNR_STREAMK")) mode = atoi(e);
+    const double waves = (double)p.num_tiles / units;
+    const double dp_rounds = (double)((p.num_tiles + units - 1) / units);
+    const bool legal = !p.b_resident && p.n_tile >= 64 && (long long)p.num_tiles * p.ipt >= 4ll * units && p.num_tiles >= 2 &&
+                       !(ctx->capturing && !ctx->sk_ws);
+    if (legal && mode > 0 && (mode >= 2 || dp_rounds / (waves + 0.12) >= 1.06)) {
+      const size_t ws_bytes = (size_t)units * cg * kTileM * 256 * sizeof(float);
+      if (!ctx->sk_ws) {
+        PLNR_CHECK_CUDA(cudaMalloc(&ctx->sk_ws, ws_bytes));
+        PLNR_CHECK_CUDA(cudaMalloc(&ctx->sk_flags, sizeof(int) * 16 * 256));
+        PLNR_CHECK_CUDA(cudaMemsetAsync(ctx->sk_flags, 0, sizeof(int) * 16 * 256, ctx->stream));
+      }
+      p.streamk = 1;
+      p.sk_ws = ctx->sk_ws;
+      p.sk_flags = ctx->sk_flags;
+    }
+  }
+  if (!p.streamk && p.num_tiles < units) units = p.num_tiles;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(units * cg));
@@ -897,8 +1097,8 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = plnr_pdl_enabled() ? 2 : 1;
-  cudaError_t le = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<2>, mapA, mapB, mapA2, p)
-                           : cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<1>, mapA, mapB, mapA2, p);
+  cudaError_t le = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<2>, mapsA, mapB, mapA2, p)
+                           : cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<1>, mapsA, mapB, mapA2, p);
   if (le != cudaSuccess) {
     plnr_set_error("launch of conv_shift_f16_kernel<%d> failed: %s", cg, cudaGetErrorString(le));
     return PLNR_ERR_CUDA;

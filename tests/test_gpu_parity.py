@@ -318,7 +318,7 @@ def test_yolov3_fp16_batch_runs_and_matches_fp32_golden(planer, graphs_gold):
         scale = float(graphs_gold['yolov3_416_f32_n1.absmax%d' % i])
         err = float(np.abs(cases.sample(t[0]).astype(np.float64) - ref.astype(np.float64)).max() / scale)
         assert err <= 1e-2, (i, err)
-        assert np.array_equal(t[0], t[1])
+        assert rel_err(t[0], t[1]) <= 1e-3       # the same image twice: other tiles, other stream-K split points, same values to fp16 rounding
 
 
 def test_map_pipelined_stream_equals_blocking_calls(planer):
@@ -340,8 +340,12 @@ def test_map_pipelined_stream_equals_blocking_calls(planer):
     for depth in (1, 2, 3):
         got = list(net.map(iter(batches), depth=depth))
         assert len(got) == len(want)
+        # net(x) uploads a 64-image batch as two 32-image halves, map() runs it as one batch: the tile decomposition (and,
+        # with stream-K, the split points of the fp32 sums) differ, so the logits agree to fp16 rounding, not bit for bit
         for g, w in zip(got, want):
-            assert g.shape == w.shape and np.array_equal(g, w)
+            assert g.shape == w.shape and rel_err(g, w) <= 1e-3
+        for a, b in zip(got, list(net.map(iter(batches), depth=2))):
+            assert np.array_equal(a, b)                      # the same call twice IS bit-identical (fixed summation order)
     # chunked blocking call (two halves on the copy stream) == one upload
     x = batches[0]
     os.environ['PLNR_E2E_CHUNKS'] = '1'
@@ -349,7 +353,7 @@ def test_map_pipelined_stream_equals_blocking_calls(planer):
         one = net(x)
     finally:
         del os.environ['PLNR_E2E_CHUNKS']
-    assert np.array_equal(net(x), one)
+    assert rel_err(net(x), one) <= 1e-3
     # results do not alias the pinned ring: a later call must not change an earlier result
     first = net(x).copy()
     keep = net(x)
@@ -610,3 +614,45 @@ def test_stride2_shift_gemm_equals_im2col_kernel(planer, cfg, monkeypatch):
         outs.append(y.get().astype(np.float32))
     assert kernels == ['conv2d_shift', 'conv2d_tcgen05'], kernels
     assert rel_err(outs[0], outs[1]) <= 2e-3
+
+
+@pytest.mark.parametrize('cfg', [
+    # n, cin, h, w, cout, k, stride, with residual -- shapes whose last data-parallel round is poorly filled
+    (128, 256, 14, 14, 256, 3, 1, True),      # ResNet layer3: 113 pair tiles on 74 pairs
+    (128, 512, 7, 7, 512, 3, 1, False),       # ResNet layer4: 64 pair tiles on 74 pairs
+    (32, 512, 13, 13, 1024, 3, 1, False),     # YOLOv3 at 13x13
+    (7, 256, 14, 14, 256, 3, 1, True),        # fewer tiles than units
+    (16, 128, 14, 14, 320, 3, 1, False),      # ragged last channel block
+    (64, 256, 14, 14, 256, 1, 1, False),      # 1x1: four iterations per tile
+])
+def test_stream_k_equals_data_parallel_and_oracle(planer, cfg, monkeypatch):
+    """Stream-K (conv_shift.cu, SegList): tiles cut along K between units, fp32 partials added in unit order.  Forced on
+    (PLNR_STREAMK=2) it must agree with the data-parallel schedule of the same kernel (PLNR_STREAMK=0) to fp16 rounding of
+    re-associated fp32 sums, with the oracle within the fp16 bar, and with itself bit for bit (deterministic)."""
+    from planer_b200 import ops, backend as B
+    n, cin, h, w, cout, k, s, with_res = cfg
+    rng = np.random.default_rng(cin + cout + n)
+    x = rng.standard_normal((n, cin, h, w)).astype(np.float16)
+    K = (rng.standard_normal((cout, cin, k, k)) * np.sqrt(2.0 / (cin * k * k))).astype(np.float16)
+    bk = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bb = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    pad = k // 2
+    r = rng.standard_normal((n, cout, h, w)).astype(np.float16) if with_res else None
+    xd, wp = B.to_nhwc(B.asarray(x)), ops.pack_weight(B.asarray(K), cin, np.float16)
+    scale, shift = ops.fold_affine(None, B.asarray(bk), B.asarray(bb), cout)
+    rd = B.to_nhwc(B.asarray(r)) if with_res else None
+    outs = {}
+    for mode in ('0', '2', '2b'):
+        monkeypatch.setenv('PLNR_STREAMK', mode[0])
+        y = B.empty((n, cout, h, w), np.float16, 'nhwc')
+        ops.conv2d_into(xd, wp, y, k, k, (s, s), (1, 1), (pad,) * 4, 1, scale, shift, rd, ops.ACT_RELU, 0.0, ops.ALGO_TCGEN05)
+        B.synchronize()
+        outs[mode] = y.get()
+    assert np.array_equal(outs['2'], outs['2b'])
+    assert rel_err(outs['2'], outs['0']) <= 1e-3
+    if n <= 32:
+        ref = oracle.conv2d(x.astype(np.float32), K.astype(np.float32), None, 1, (s, s), (1, 1), (pad,) * 4)
+        ref = oracle.batchnorm(ref, bk.reshape(1, -1, 1, 1), bb.reshape(1, -1, 1, 1))
+        if with_res:
+            ref = oracle.add(ref, r.astype(np.float32))
+        assert rel_err(outs['2'], oracle.relu(ref)) <= 1e-2

@@ -61,6 +61,7 @@ cfgs = {
     'g': ('layer2.0 64->128 s2', 128, 64, 56, 56, 128, 3, 2, False),
     'h': ('layer3.0 128->256 s2', 128, 128, 28, 28, 256, 3, 2, False),
     'i': ('down 64->128 1x1 s2', 128, 64, 56, 56, 128, 1, 2, False),
+    'l': ('layer4.0 256->512 s2', 128, 256, 14, 14, 512, 3, 2, False),
     'j': ('128->128 @14 x512 (layer2 FLOPs)', 512, 128, 14, 14, 128, 3, 1, False),
     'k': ('64->64 @28 x512 (layer1 FLOPs)', 512, 64, 28, 28, 64, 3, 1, False),
 }
