@@ -526,13 +526,18 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
       const long long tt0 = clock64();
       mbar_wait(bar_tfull + 8 * a, tph, p.err, 3);
       t_tfull += clock64() - tt0;
+      const bool estamp = stamp && threadIdx.x == 128 && k == segs.nseg - 1;     // debug: time stamps of the last epilogue
+      int estamp_i = 1408;
+      if (estamp) p.prof[estamp_i++] = clock64() - t_entry;
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + a * (uint32_t)p.n_tile;
       const int ce_ = (alternate && (it & 1u) != (uint32_t)eg) ? c_begin : c_end;      // not this group's tile
       if (sg.mode == SEG_CONTRIB) {
         // stream-K: this unit computed the tail of a tile another unit owns -- the raw fp32 accumulator goes to the
-        // workspace (row-major [256 rows of the unit][n_tile]; a thread's 32 columns of a chunk are 128 contiguous bytes)
-        float* wrow = p.sk_ws + ((size_t)unit * (CG * kTileM) + rank * kTileM + (uint32_t)(ew * 32 + lane)) * (uint32_t)p.n_tile;
+        // workspace in the order the registers hold it: [unit][rank][lane quarter][32-column chunk][4-column group][lane],
+        // so that every store / load instruction of a warp moves 512 contiguous bytes (row-major rows cost 32 sectors each)
+        float4* wq = reinterpret_cast<float4*>(p.sk_ws) +
+                     (size_t)((unit * CG + (int)rank) * 4 + ew) * (size_t)(p.n_tile >> 5) * 256 + lane;
         for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           __syncwarp();
           uint32_t v[32];
@@ -545,7 +550,7 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            __stcg(reinterpret_cast<float4*>(wrow + c0) + j,
+            __stcg(wq + ((c0 >> 5) * 8 + j) * 32,
                    make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                                __uint_as_float(v[4 * j + 3])));
         }
@@ -593,16 +598,18 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
         const bool fast = p.vec_ok && (cb + 32 <= p.Cout);
         if (has_res && p.vec_ok && c0 + 32 < ce_ && cb + 64 <= p.Cout) fetch_res(g, cb + 32, rvn);   // one chunk ahead
         ptx::tmem_ld_wait();
+        if (estamp && estamp_i < 1424) p.prof[estamp_i++] = clock64() - t_entry;
         if (c0 + 32 >= ce_) {
           ptx::tc_fence_before();
           if (CG == 2 && !leader) ptx::mbar_arrive_remote(bar_tempty + 8 * a, 0);
           else ptx::mbar_arrive(bar_tempty + 8 * a);
         }
         for (int pc = 1; pc <= npieces; ++pc) {     // stream-K owner: add the other units' partial sums, in unit order
-          const float* prow = p.sk_ws + ((size_t)(unit + pc) * (CG * kTileM) + rank * kTileM + (uint32_t)(ew * 32 + lane)) * (uint32_t)p.n_tile + c0;
+          const float4* pq = reinterpret_cast<const float4*>(p.sk_ws) +
+                             (size_t)(((unit + pc) * CG + (int)rank) * 4 + ew) * (size_t)(p.n_tile >> 5) * 256 + lane;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 q4 = __ldcg(reinterpret_cast<const float4*>(prow) + j);
+            const float4 q4 = __ldcg(pq + ((c0 >> 5) * 8 + j) * 32);
             v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + q4.x);
             v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + q4.y);
             v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + q4.z);
@@ -680,6 +687,7 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
           else chunk_math(ActTag<0>{});
 #pragma unroll
           for (int i = 0; i < 4; ++i) rv[i] = rvn[i];
+          if (estamp && estamp_i < 1424) p.prof[estamp_i++] = clock64() - t_entry;
         } else if (g.own >= 0) {
           __half* yrow = p.y + (size_t)g.own * p.yld + p.ycoff;
           const __half* rrow = has_res ? p.res + (size_t)g.own * p.rld + p.rcoff : nullptr;
@@ -773,7 +781,11 @@ static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
     // stride 2 (phase planes, see ShiftParams): tap r reads plane row p + floor((r - pad_t) / 2); the grid needs
     // ceil(pad / 2) virtual padding rows / columns and holds the larger plane (ceil(H / 2) x ceil(W / 2))
     if (d->dil_h != 1 || d->dil_w != 1 || c2 != 0) return pl;
-    if (const char* e = getenv("PLNR_NO_SHIFT_S2")) { if (atoi(e)) return pl; }
+    // Opt-in (PLNR_SHIFT_S2=1): measured on ResNet-18 batch 128 the three 3x3/s2 convolutions take 31-35 us this way
+    // against 23-29 us through TMA im2col (profiles/r02_kernel_experiments.md) -- the phase planes leave the tile
+    // quantisation of the N=256 CTA-pair schedule (2 rounds for 1.5) where the im2col kernel picks N=128 tiles that fill
+    // 2.65 of 3 rounds.  Correct (tests force it on), kept for shapes where the im2col TMA rate binds.
+    { const char* e = getenv("PLNR_SHIFT_S2"); if (!(e && atoi(e))) return pl; }
     pl.pv_t = (d->pad_t + 1) / 2; pl.pv_l = (d->pad_l + 1) / 2;
     pl.Wv = (x->w + 1) / 2 + pl.pv_l;
     pl.Hv = (x->h + 1) / 2 + pl.pv_t;
@@ -1055,13 +1067,42 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
     PLNR_CHECK_CUDA(cudaFuncSetAttribute(conv_shift_f16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     ctx->shift_attr_set = true;
   }
+  // Persistent grid = the number of units (CTAs / CTA pairs) that can be RESIDENT AT ONCE.  For pairs that is not
+  // sm_count / 2: a cluster needs both SMs in one GPC, and GPCs with an odd number of usable SMs leave one over
+  // (cudaOccupancyMaxActiveClusters; cached per shared-memory size).  Stream-K depends on it -- a unit that starts only
+  // after another has finished delivers its partial tiles a whole unit-time late.
   int units = ctx->sm_count / cg;
+  {
+    const long long key = ((long long)cg << 32) | (long long)pl.smem_bytes;
+    auto it = ctx->shift_max_units.find(key);
+    if (it == ctx->shift_max_units.end()) {
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3((unsigned)(ctx->sm_count / cg * cg));
+      q.blockDim = dim3(kThreads);
+      q.dynamicSmemBytes = pl.smem_bytes;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = (unsigned)cg; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int n = 0;
+      cudaError_t qe = cg == 2 ? cudaOccupancyMaxActiveClusters(&n, conv_shift_f16_kernel<2>, &q)
+                               : cudaOccupancyMaxActiveClusters(&n, conv_shift_f16_kernel<1>, &q);
+      if (qe != cudaSuccess || n < 1) { cudaGetLastError(); n = units; }
+      it = ctx->shift_max_units.emplace(key, n).first;
+    }
+    if (it->second < units) units = it->second;
+    if (const char* e = getenv("PLNR_SHIFT_UNITS")) { int v = atoi(e); if (v >= 1 && v < units) units = v; }
+  }
   // stream-K (SegList): worth it when the last data-parallel round is poorly filled.  Streamed weights only (a resident
   // filter is loaded during a unit's first WHOLE tile), at least two 32-channel chunks per epilogue group, and enough
-  // iterations that every unit gets a non-empty range.  PLNR_STREAMK=0 off, 1 auto (default), 2 whenever legal.
+  // iterations that every unit gets a non-empty range.  PLNR_STREAMK=0 off (default), 1 auto, 2 whenever legal.
   p.ipt = d->kh * d->kw * p.cchunks + p.c2chunks;
   {
-    int mode = 1;
+    // Default OFF: measured (profiles/r02_kernel_experiments.md) the balanced schedule shortens the MMA phase of the
+    // 14x14 layers by 6k clk per CTA but costs as much again -- units at different K offsets stream DIFFERENT weight boxes
+    // from L2 at the same time (the data-parallel schedule has all 148 SMs on the same box), 18 % more clk per iteration.
+    int mode = 0;
     if (const char* e = getenv("PLNR_STREAMK")) mode = atoi(e);
     const double waves = (double)p.num_tiles / units;
     const double dp_rounds = (double)((p.num_tiles + units - 1) / units);

@@ -593,7 +593,8 @@ def test_fp16_residual_head_with_three_channels(planer):
     assert got.shape == ref.shape and rel_err(got, ref) <= 1e-2
 
 
-@pytest.mark.parametrize('cfg', [(4, 64, 56, 56, 128), (2, 128, 28, 28, 256), (4, 256, 14, 14, 512)])
+@pytest.mark.parametrize('cfg', [(4, 64, 56, 56, 128), (2, 128, 28, 28, 256), (4, 256, 14, 14, 512), (3, 64, 30, 26, 96),
+                                 (128, 128, 28, 28, 256)])
 def test_stride2_shift_gemm_equals_im2col_kernel(planer, cfg, monkeypatch):
     """The two tensor-core formulations of a 3x3 / stride-2 convolution -- four phase planes through the shift GEMM
     (conv_shift.cu) and TMA im2col (conv_tcgen05.cu) -- accumulate the same products in fp32 and round once: they must
@@ -606,7 +607,7 @@ def test_stride2_shift_gemm_equals_im2col_kernel(planer, cfg, monkeypatch):
     wp = ops.pack_weight(B.asarray(K), cin, np.float16)
     outs, kernels = [], []
     for no_s2 in ('0', '1'):
-        monkeypatch.setenv('PLNR_NO_SHIFT_S2', no_s2)
+        monkeypatch.setenv('PLNR_SHIFT_S2', '0' if no_s2 == '1' else '1')
         y = B.empty((n, cout, h // 2, w // 2), np.float16, 'nhwc')
         ops.conv2d_into(x, wp, y, 3, 3, (2, 2), (1, 1), (1, 1, 1, 1), 1, None, None, None, ops.ACT_RELU, 0.0, ops.ALGO_TCGEN05)
         kernels.append(B.last_kernel())

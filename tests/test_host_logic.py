@@ -581,7 +581,8 @@ def _shift_geometry(lib, xshape, cout, k, stride, pads, dil=1):
     (2, 64, 9, 10, 8, (3, 3), 1, (1, 1, 1, 1), 1),        # stride 1: one plane in filter order
     (1, 64, 12, 12, 8, (3, 3), 1, (2, 2, 2, 2), 2),       # stride 1, dilation 2
 ])
-def test_shift_gemm_plane_geometry_reproduces_the_convolution(lib, cfg):
+def test_shift_gemm_plane_geometry_reproduces_the_convolution(lib, cfg, monkeypatch):
+    monkeypatch.setenv('PLNR_SHIFT_S2', '1')          # the stride-2 phase-plane path is opt-in (csrc/conv_shift.cu)
     n, c, h, w, cout, k, stride, pads, dil = cfg
     g, oh, ow = _shift_geometry(lib, (n, c, h, w), cout, k, stride, pads, dil)
     assert g[0] == 1, 'the shift kernel must apply to this problem'
@@ -618,7 +619,10 @@ def test_shift_gemm_plane_geometry_reproduces_the_convolution(lib, cfg):
     assert np.array_equal(got, ref)
 
 
-def test_shift_gemm_rejects_what_it_cannot_do(lib):
+def test_shift_gemm_rejects_what_it_cannot_do(lib, monkeypatch):
+    assert _shift_geometry(lib, (1, 64, 12, 12), 8, (3, 3), 2, (1, 1, 1, 1), 1)[0][0] == 0      # stride 2 is opt-in
+    monkeypatch.setenv('PLNR_SHIFT_S2', '1')
+    assert _shift_geometry(lib, (1, 64, 12, 12), 8, (3, 3), 2, (1, 1, 1, 1), 1)[0][0] == 1
     for cfg in [((1, 64, 12, 12), 8, (3, 3), 3, (1, 1, 1, 1), 1),     # stride 3
                 ((1, 64, 12, 12), 8, (3, 3), 2, (2, 2, 2, 2), 2),     # stride 2 with dilation
                 ((1, 48, 12, 12), 8, (3, 3), 1, (1, 1, 1, 1), 1),     # Cin % 64 != 0

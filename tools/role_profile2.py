@@ -45,9 +45,18 @@ def run(name, n, cin, h, w, cout, k, stride=1, res=False):
     print('%-28s %.4f ms  %6.0f TFLOP/s | producer wait %3.0f%% of %7.0f | mma wait_full %3.0f%% wait_acc %3.0f%% of %7.0f | '
           'epilogue wait %3.0f%% of %7.0f' % (name, best, gflop / best, 100 * m[0] / max(m[1], 1), m[1], 100 * m[2] / max(m[4], 1),
                                              100 * m[3] / max(m[4], 1), m[4], 100 * m[5] / max(m[6], 1), m[6]), flush=True)
+    worst = int(np.argmax(a[:, 6]))
+    print('      epilogue role total per CTA: min %.0f  mean %.0f  max %.0f (CTA row %d: mma total %.0f, tfull wait %.0f) | mma total min %.0f max %.0f'
+          % (a[:, 6].min(), a[:, 6].mean(), a[:, 6].max(), worst, a[worst, 4], a[worst, 5], a[:, 4].min(), a[:, 4].max()), flush=True)
+    if os.environ.get('ROLE_DUMP'):
+        print('      per-CTA epilogue totals:', ' '.join('%.0f' % (v / 1000) for v in a[:, 6]))
+        print('      per-CTA mma totals:     ', ' '.join('%.0f' % (v / 1000) for v in a[:, 4]))
     st = [int(v) for v in out[1400:1408]]
     print('      CTA0 stamps (clk since kernel entry): setup done %d | first A landed %d | mma loop done %d | epilogue done %d | '
           'final barrier %d | dealloc %d | setup->dealloc %.1f us (globaltimer)' % (tuple(st[1:7]) + ((st[7] - st[0]) / 1e3,)), flush=True)
+    es = [int(v) for v in out[1408:1424]]
+    print('      last epilogue of CTA0 warp 4 (clk since entry): accumulator ready %d | then (tmem_ld done, chunk done) x chunks: %s'
+          % (es[0], ' '.join('%d' % (v - es[0]) for v in es[1:] if v)), flush=True)
     _capi.check(lib.plnr_debug_conv_profile(ctx, 0, None, 0))
 
 
