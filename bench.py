@@ -241,14 +241,16 @@ def time_graph_steps(net, xs, steps):
     return e0.elapsed_time(e1) / steps
 
 
-def parity_check(net, config):
+def parity_check(net, config, half=True):
     """The timed net on the committed golden input vs the unmodified reference's output (tests/golden/graphs.npz)."""
     from tests import cases
-    cfg = CONFIGS[config]
+    cfg = dict(CONFIGS[config])
+    if not half:
+        cfg['tol'] = 1e-3                              # north star: 1e-3 for fp32, 1e-2 for fp16
     gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'graphs.npz'))
     name = cfg['golden']
     _, shape, _ = cases.GRAPH_CASES[name]
-    x = np.random.default_rng(1).standard_normal(shape).astype(np.float16)      # cases.make_graph_case, in the net's dtype
+    x = np.random.default_rng(1).standard_normal(shape).astype(np.float16 if half else np.float32)   # cases.make_graph_case, in the net's dtype
     y = net(x)
     ys = y if isinstance(y, tuple) else (y,)
     assert len(ys) == int(gold[name + '.nout']), 'output count differs from the reference'
@@ -258,8 +260,8 @@ def parity_check(net, config):
         ref, scale = gold['%s.out%d' % (name, i)], float(gold['%s.absmax%d' % (name, i)])
         worst = max(worst, float(np.abs(cases.sample(t).astype(np.float64) - ref.astype(np.float64)).max() / scale))
     if not worst <= cfg['tol']:
-        raise SystemExit('[bench] PARITY FAILURE: %s fp16 vs reference golden %s: range-relative error %.3e > %.0e'
-                         % (config, name, worst, cfg['tol']))
+        raise SystemExit('[bench] PARITY FAILURE: %s %s vs reference golden %s: range-relative error %.3e > %.0e'
+                         % (config, 'fp16' if half else 'fp32', name, worst, cfg['tol']))
     import zlib
     crc = zlib.crc32(b''.join(np.ascontiguousarray(t).tobytes() for t in ys))
     return {'golden': 'tests/golden/graphs.npz:' + name, 'rel_err': worst, 'tol': cfg['tol']}, crc
@@ -319,6 +321,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='resnet18', choices=sorted(CONFIGS))
     ap.add_argument('--batch', type=int, default=None, help='images per GPU (default: the BASELINE config: 128 / 32)')
+    ap.add_argument('--dtype', default='f16', choices=['f16', 'f32'],
+                    help='f32 = BASELINE configs[1] arithmetic (CUDA-core FFMA path; roofline against the FFMA peak)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer legs (profiling runs)')
     ap.add_argument('--min-warm-sec', type=float, default=1.5, help='keep warming up at least this long (clock sampling)')
@@ -353,12 +357,15 @@ def main():
     n_init = sum(int(np.prod(s)) * np.dtype(d).itemsize for _, s, d in model['inits'])
     file_crc = zlib.crc32(np.ascontiguousarray(blob).reshape(-1).view(np.uint8)[:n_init].tobytes())
     blob_crcs = dist.gather_ints(net.blob_crc32())
-    net.half()
+    half = args.dtype == 'f16'
+    if half:
+        net.half()
     del blob
+    npdt = np.float16 if half else np.float32
 
     # ---- checks before timing: parity against the reference's golden output; all ranks hold the same weights and
     #      produce the same logits on the shared golden input ----
-    parity, logit_crc = parity_check(net, args.config)
+    parity, logit_crc = parity_check(net, args.config, half)
     logit_crcs = dist.gather_ints(logit_crc)
     if rank == 0:
         if any(c != file_crc for c in blob_crcs):
@@ -370,11 +377,11 @@ def main():
 
     rng = np.random.default_rng(100 + rank)
     shape = (batch, 3, cfg['hw'], cfg['hw'])
-    hosts = [rng.standard_normal(shape).astype(np.float16) for _ in range(2)]
+    hosts = [rng.standard_normal(shape).astype(npdt) for _ in range(2)]
     xs = [B.asarray(hosts[i % 2] if i < 2 else np.roll(hosts[i % 2], i, axis=0)) for i in range(N_INPUT_BUFFERS)]
     B.synchronize()
 
-    ex = net.executor([shape], [np.float16])
+    ex = net.executor([shape], [npdt])
     flops = ex.plan.flops
     # clocks are sampled from the start of the warm-up to the end of the timed region: the same load throughout.
     # The warm-up runs at least W steps AND at least ~1.5 s so that nvidia-smi (200 ms period) sees the loaded state.
@@ -418,6 +425,11 @@ def main():
     all_ms = sum(r['ms'] for r in table)
     ms_step = ms_total / steps
     pk = peaks()
+    if not half:
+        # fp32 runs on the CUDA cores: 148 SMs x 128 FFMA/clk x 2 FLOP at the clock sampled under this load
+        mhz = (clk or {}).get('sm_mhz') or 1965.0
+        ffma = B.device_info()['sm_count'] * 128 * 2 * mhz * 1e6 / 1e12
+        pk = dict(pk, tflops_sustained=ffma, tflops_burst=ffma, source='FFMA peak = SMs x 128 x 2 x sampled SM clock (%.0f MHz)' % mhz)
     achieved = flops / (ms_step / 1e3) / 1e12
     fl_by_name = {n.name: n.flops for n in ex.plan.nodes}
     fam = {}
@@ -448,9 +460,9 @@ def main():
         else:
             traffic_src = ('null: the newest committed capture (profiles/%s) is of another build of libplaner_b200.so'
                            % cands[-1])
-    roofline = {'bound': 'tensor',
-                'kernel': 'whole step: every launch is a tcgen05 conv / dense kernel (%d conv+dense layers in %d launches)'
-                          % (sum(1 for n in ex.plan.nodes if n.kind in ('conv', 'dense')), len(table)),
+    roofline = {'bound': 'tensor' if half else 'ffma',
+                'kernel': 'whole step: every launch is a %s conv / dense kernel (%d conv+dense layers in %d launches)'
+                          % ('tcgen05' if half else 'CUDA-core FFMA', sum(1 for n in ex.plan.nodes if n.kind in ('conv', 'dense')), len(table)),
                 'achieved': achieved, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved / pk['tflops_sustained'], 'traffic': traffic, 'traffic_source': traffic_src,
                 'peak_source': pk['source'] + ', sustained figure (kernels timed inside a long step)',
@@ -470,8 +482,8 @@ def main():
 
     line = {'metric': cfg['metric'], 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': args.warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f16', 'data': 'synthetic',
-            'config': {'workload': cfg['workload'] % batch, 'global_batch': world * batch,
+            'dtype': args.dtype, 'data': 'synthetic',
+            'config': {'workload': (cfg['workload'] % batch).replace('fp16', 'fp16' if half else 'fp32'), 'global_batch': world * batch,
                        'parallelism': 'dp%d batch split, no forward collective' % world,
                        'l2': 'inputs rotate over %d device buffers (%.0f MB > 126 MB L2)' % (N_INPUT_BUFFERS, N_INPUT_BUFFERS * hosts[0].nbytes / 1e6),
                        'launch': '%s + 1 CUDA graph (%d fused kernels) per step' % (
@@ -500,15 +512,15 @@ def run_e2e(net, hosts, batch, world, ms_step, torch, dist, B):
         p[...] = a
         return p
 
-    def leg_map(bufs, n):
+    def leg_map(bufs, n, copy=True):
         def feed(k):
             for i in range(k):
                 yield bufs[i % len(bufs)]
-        for y in net.map(feed(6)):
+        for y in net.map(feed(6), copy=copy):
             pass
         dist.barrier(); torch.cuda.synchronize()
         t0, nout, last = time.perf_counter(), 0, None
-        for y in net.map(feed(n)):
+        for y in net.map(feed(n), copy=copy):
             last = y
             nout += (y[0] if isinstance(y, tuple) else y).shape[0]
         torch.cuda.synchronize()
@@ -521,6 +533,9 @@ def run_e2e(net, hosts, batch, world, ms_step, torch, dist, B):
     d2h = int(sum(t.nbytes for t in (y if isinstance(y, tuple) else (y,))))
     f16 = [pin(h) for h in hosts]
     v_f16, _ = leg_map(f16, n_batches)
+    v_views = None
+    if d2h > (4 << 20):             # large results: the host memcpy into fresh arrays dominates; report the view-yielding call too
+        v_views, _ = leg_map(u8, n_batches, copy=False)
     # the blocking reference-shaped call: upload + forward + download per call, no overlap between calls
     nb = max(20, n_batches // 4)
     for i in range(3):
@@ -535,8 +550,12 @@ def run_e2e(net, hosts, batch, world, ms_step, torch, dist, B):
             'steps': n_batches, 'input': 'uint8 NCHW images in pinned host memory (the first layer converts; the numpy '
                                          'reference computes on x.astype(float16) for such an input)',
             'api': 'for y in net.map(batches): pinned numpy batch in, numpy result out, 2 batches in flight',
+            'result_views': None if v_views is None else {
+                'value': v_views, 'unit': UNIT, 'steps': n_batches,
+                'api': 'net.map(batches, copy=False): results are views of the pinned ring (valid for depth + 1 further results) '
+                       'instead of fresh numpy arrays -- no %d MB host memcpy per batch' % (d2h // 1000000)},
             'fp16_host': {'value': v_f16, 'unit': UNIT, 'h2d_bytes_per_step': int(f16[0].nbytes), 'steps': n_batches,
-                          'input': 'fp16 NCHW host batches (twice the PCIe bytes)'},
+                          'input': '%s NCHW host batches' % str(hosts[0].dtype)},
             'blocking_call': {'value': v_blk, 'unit': UNIT, 'steps': nb,
                               'api': 'y = net(x) per uint8 batch (upload in two halves, one synchronisation)'}}
 

@@ -17,7 +17,7 @@ all three at import: planer/__init__.py:19-20,50-51).
 from . import backend as b200
 from .layer import wrap, layer_map
 from .net import Net
-from .io import read_net, from_model
+from .io import read_net, from_model, save_pack, load_pack
 from .onnx_import import read_onnx, onnx2pla
 from . import zoo
 from . import util

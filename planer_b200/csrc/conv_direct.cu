@@ -115,6 +115,135 @@ __global__ void __launch_bounds__(NT) conv_direct_kernel(const DirectParams p) {
   }
 }
 
+// fp32 fast path (BASELINE config 2): 128 pixels x 128 channels per CTA, 8 x 8 outputs per thread, contraction slabs of 16
+// gathered with ONE tap decode and one 16-byte load per four channels (needs Cg % 4 == 0 and 16-byte aligned rows), shared
+// memory double buffered.  FFMA-bound: 64 FFMA per four 16-byte shared-memory loads.  Same arithmetic as the generic kernel
+// above (fp32 multiplies, fp32 accumulation in k order within a slab), same fused epilogue.
+constexpr int FM = 128, FN = 128, FK = 16;
+
+__global__ void __launch_bounds__(256) conv_direct_f32x8_kernel(const DirectParams p) {
+  __shared__ __align__(16) float As[2][FK][FM + 4];
+  __shared__ __align__(16) float Bs[2][FK][FN + 4];
+  const float* __restrict__ x = (const float*)p.x;
+  const float* __restrict__ w = (const float*)p.w;
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * FM, n0 = blockIdx.y * FN;
+  // loader role: thread -> rows (tid / 4) and (tid / 4 + 64), four consecutive k starting at (tid % 4) * 4
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;
+  int pn[2], ph[2], pw[2];
+  bool mvalid[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int m = m0 + lrow + 64 * i;
+    mvalid[i] = m < p.M;
+    const int mm = mvalid[i] ? m : 0;
+    pw[i] = mm % p.OW;
+    const int t = mm / p.OW;
+    ph[i] = (t % p.OH) * p.sh - p.pt;
+    pn[i] = t / p.OH;
+    pw[i] = pw[i] * p.sw - p.pl;
+  }
+  const float* wrow[2];
+  bool covalid[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int co = n0 + lrow + 64 * i;
+    covalid[i] = co < p.Cog;
+    wrow[i] = w + (size_t)(covalid[i] ? co : 0) * p.Ktot;
+  }
+  const int ty = tid >> 4, tx = tid & 15;      // thread -> rows ty*4 + {0..3} and 64 + ty*4 + {0..3}; channels likewise with tx
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float4 ra[2], rb[2];
+  auto gload = [&](int k0) {
+    const int k = k0 + lk;
+    const bool kvalid = k < p.Ktot;
+    const int tap = kvalid ? k / p.Cg : 0, c = k - tap * p.Cg;
+    const int r = tap / p.kw, s_ = tap - r * p.kw;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int ih = ph[i] + r * p.dh, iw = pw[i] + s_ * p.dw;
+      if (kvalid && mvalid[i] && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
+        ra[i] = __ldg(reinterpret_cast<const float4*>(x + (((size_t)pn[i] * p.H + ih) * p.W + iw) * p.xld + p.xcoff + c));
+      if (kvalid && covalid[i]) rb[i] = __ldg(reinterpret_cast<const float4*>(wrow[i] + k));
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = lrow + 64 * i;
+      As[buf][lk + 0][row] = ra[i].x; As[buf][lk + 1][row] = ra[i].y; As[buf][lk + 2][row] = ra[i].z; As[buf][lk + 3][row] = ra[i].w;
+      Bs[buf][lk + 0][row] = rb[i].x; Bs[buf][lk + 1][row] = rb[i].y; Bs[buf][lk + 2][row] = rb[i].z; Bs[buf][lk + 3][row] = rb[i].w;
+    }
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < p.Ktot; k0 += FK) {
+    const bool more = k0 + FK < p.Ktot;
+    if (more) gload(k0 + FK);                 // global loads of the next slab fly during this slab's FFMAs
+#pragma unroll
+    for (int kk = 0; kk < FK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) {
+      sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+  float* __restrict__ y = (float*)p.y;
+  const float* __restrict__ res = (const float*)p.res;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int mm = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+    if (mm >= p.M) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int co = n0 + jh * 64 + tx * 4;
+      if (co >= p.Cog) continue;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = acc[i][jh * 4 + j];
+      const bool full = co + 4 <= p.Cog;
+      float rv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (res) {
+        if (full) { const float4 r4 = *reinterpret_cast<const float4*>(res + (size_t)mm * p.rld + p.rcoff + co); rv[0] = r4.x; rv[1] = r4.y; rv[2] = r4.z; rv[3] = r4.w; }
+        else for (int j = 0; j < 4 && co + j < p.Cog; ++j) rv[j] = res[(size_t)mm * p.rld + p.rcoff + co + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (co + j < p.Cog) {
+          if (p.scale) v[j] *= p.scale[co + j];
+          if (p.shift) v[j] += p.shift[co + j];
+          if (!p.res_after) v[j] += rv[j];
+          v[j] = plnr_apply_act(v[j], p.act, p.alpha);
+          if (p.res_after) v[j] += rv[j];
+        }
+      }
+      if (full) *reinterpret_cast<float4*>(y + (size_t)mm * p.yld + p.ycoff + co) = make_float4(v[0], v[1], v[2], v[3]);
+      else for (int j = 0; j < 4 && co + j < p.Cog; ++j) y[(size_t)mm * p.yld + p.ycoff + co + j] = v[j];
+    }
+  }
+}
+
 }  // namespace
 
 int plnr_conv2d_direct(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w,
@@ -135,6 +264,20 @@ int plnr_conv2d_direct(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor
     p.scale = ep->scale; p.shift = ep->shift; p.act = ep->act; p.alpha = ep->alpha;
     p.res_after = ep->res_after_act;
     if (ep->residual) { p.res = ep->residual->ptr; p.rld = ep->residual->ld; p.rcoff = ep->residual->coff; }
+  }
+  // fp32, one group, channel counts and pitches that allow 16-byte gathers: the 128 x 128 x 16 FFMA kernel
+  {
+    const bool al16 = ((reinterpret_cast<uintptr_t>(x->ptr) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y->ptr)) & 15) == 0;
+    bool ok = d->dtype == PLNR_F32 && d->groups == 1 && p.Cg % 4 == 0 && x->ld % 4 == 0 && x->coff % 4 == 0 && y->ld % 4 == 0 &&
+              y->coff % 4 == 0 && al16 && p.Cog >= 32;
+    if (p.res) ok = ok && p.rld % 4 == 0 && p.rcoff % 4 == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0;
+    if (const char* e = getenv("PLNR_DIRECT_SMALL")) { if (atoi(e)) ok = false; }
+    if (ok) {
+      dim3 grid((p.M + FM - 1) / FM, (p.Cog + FN - 1) / FN, 1);
+      PLNR_REQUIRE(grid.y <= 65535, "conv2d(direct): too many channel tiles");
+      conv_direct_f32x8_kernel<<<grid, 256, 0, ctx->stream>>>(p);
+      return plnr_after_launch(ctx, "conv2d_direct_f32x8");
+    }
   }
   dim3 grid((p.M + BM - 1) / BM, (p.Cog + BN - 1) / BN, d->groups);
   PLNR_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv2d(direct): too many channel tiles / groups");

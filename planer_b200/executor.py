@@ -35,6 +35,7 @@ class Executor:
         self.in_arrays, self.out_arrays, self.out_flat = [], [], []
         self._keep = []
         self._in_stage = {}       # graph input -> fp16 staging array (fp32 images on the fused first layer)
+        self.pack_hits = self.pack_misses = 0
         self._build()
 
     # ------------------------------------------------------------------------------------------
@@ -166,6 +167,26 @@ class Executor:
             return None
         return chain
 
+    def _packed(self, key, build):
+        """One-off weight artefact of this net (packed filter, folded scale / shift, ...): taken from the Net's pack store when
+        an executor of another input shape -- or the on-disk pack cache (io.py) -- already made it, else built and kept
+        there.  ``build`` returns a DeviceArray or a tuple of DeviceArrays / None."""
+        store = self.net._pack_store
+        key = '%s|%s' % (self.dtype.name, key)
+        if key + '#n' in store:
+            n = store[key + '#n']
+            vals = tuple(store.get('%s#%d' % (key, i)) for i in range(abs(n)))
+            self.pack_hits += 1
+            return vals if n > 0 else vals[0]
+        val = build()
+        vals = val if isinstance(val, tuple) else (val,)
+        for i, v in enumerate(vals):
+            if v is not None:
+                store['%s#%d' % (key, i)] = v
+        store[key + '#n'] = len(vals) if isinstance(val, tuple) else -1
+        self.pack_misses += 1
+        return val
+
     def _nbytes(self, vid, itemsize=None):
         shp = self.values[vid].shape
         return int(np.prod(shp)) * (self.dtype.itemsize if itemsize is None else itemsize)
@@ -290,14 +311,15 @@ class Executor:
             x = self._view(st.ins[0]) if fused is None else None
             K = self._weight(st.w)
             if op == 'conv' and st.attrs.get('flip'):
-                K = ops.flip_weight(K)                   # convtranspose: (C_in, C_out, kh, kw) -> flipped (C_out, C_in, kh, kw)
+                K0 = K                                   # convtranspose: (C_in, C_out, kh, kw) -> flipped (C_out, C_in, kh, kw)
+                K = self._packed(st.name + '|flip', lambda: ops.flip_weight(K0))
                 self._keep.append(K)
             co = K.shape[0]
             bias = self._weight(st.bias) if st.bias is not None else None
             bn_k, bn_b = (self._weight(st.bn[0]), self._weight(st.bn[1])) if st.bn else (None, None)
             scale = shift = None
             if bias is not None or bn_k is not None:
-                scale, shift = ops.fold_affine(bias, bn_k, bn_b, co)
+                scale, shift = self._packed(st.name + '|fold', lambda: ops.fold_affine(bias, bn_k, bn_b, co))
                 if bn_k is None:
                     scale = None
             res = self._view(st.res) if st.res is not None else None
@@ -305,7 +327,8 @@ class Executor:
             if fused is not None:
                 a = st.attrs
                 yp = alloc(fused['pool'].out)
-                wp = B.asarray(ops.stem_pool_weight(K.get().astype(np.float16), a['pads'][0], a['pads'][1]))
+                wp = self._packed(st.name + '|stem_pool|%d|%d' % (a['pads'][0], a['pads'][1]),
+                                  lambda: B.asarray(ops.stem_pool_weight(K.get().astype(np.float16), a['pads'][0], a['pads'][1])))
                 self._keep.append(wp)
                 kh, kw = K.shape[2], K.shape[3]
                 fused['run'] = lambda xf: ops.stem_pool_into(xf, wp, scale, shift, yp, kh, kw, a['strides'][0], a['pads'],
@@ -318,13 +341,15 @@ class Executor:
                 x2_vid, s2, sh = st.shortcut
                 x2 = self._view(x2_vid)
                 a = st.attrs
-                Kd = self._weight(sh.w).get().astype(np.float32)[:, :, 0, 0]
-                s_main, t_main = self._step_affine(st, co)
-                s_short, t_short = self._step_affine(sh, co)
-                w2 = (Kd * (s_short / s_main)[:, None]).astype(np.float16)
-                wp = ops.pack_weight(K, x.shape[1], dt).get().reshape(co, -1)
-                wcat = B.asarray(np.ascontiguousarray(np.concatenate([wp, w2], axis=1)))
-                scale_c, shift_c = B.asarray(s_main.astype(np.float32)), B.asarray((t_main + t_short).astype(np.float32))
+                def build_shortcut():
+                    Kd = self._weight(sh.w).get().astype(np.float32)[:, :, 0, 0]
+                    s_main, t_main = self._step_affine(st, co)
+                    s_short, t_short = self._step_affine(sh, co)
+                    w2 = (Kd * (s_short / s_main)[:, None]).astype(np.float16)
+                    wp = ops.pack_weight(K, x.shape[1], dt).get().reshape(co, -1)
+                    return (B.asarray(np.ascontiguousarray(np.concatenate([wp, w2], axis=1))),
+                            B.asarray(s_main.astype(np.float32)), B.asarray((t_main + t_short).astype(np.float32)))
+                wcat, scale_c, shift_c = self._packed('%s|shortcut|%s|%d' % (st.name, sh.name, x.shape[1]), build_shortcut)
                 self._keep += [wcat, scale_c, shift_c]
                 kh, kw = K.shape[2], K.shape[3]
                 return lambda: ops.conv2d_shortcut_into(x, wcat, x2, s2, y, kh, kw, a['strides'], a['dilations'], a['pads'],
@@ -333,8 +358,9 @@ class Executor:
             if stem is not None:
                 # first layer on the packed input: (T x 1) stride-1 conv, taps re-ordered on the host (tiny, load time)
                 g = stem['geom']
-                w2 = ops.stem_pack_weight(K.get().astype(np.float16), stem['stride'], st.attrs['pads'], stem['cp'])
-                wp = B.asarray(w2)
+                wp = self._packed('%s|stem_pack|%d|%s|%d' % (st.name, stem['stride'], tuple(st.attrs['pads']), stem['cp']),
+                                  lambda: B.asarray(ops.stem_pack_weight(K.get().astype(np.float16), stem['stride'],
+                                                                         st.attrs['pads'], stem['cp'])))
                 self._keep.append(wp)
                 pads2 = (g['pad_t2'], 0, g['pad_b2'], 0)
                 return lambda: ops.conv2d_into(x, wp, y, g['T'], 1, (1, 1), (1, 1), pads2, 1, scale, shift, res,
@@ -346,18 +372,18 @@ class Executor:
                 if y.layout == 'nhwc' and y.ld != y.shape[1]:
                     # channel-padded graph output (_out_cpad): run the kernel on ld channels, pad filter rows are zero
                     cop = y.ld
-                    wp = ops.pack_weight(K, x.shape[1], dt, co_pad=cop)
+                    wp = self._packed('%s|pack|%d|%d' % (st.name, x.shape[1], cop), lambda: ops.pack_weight(K, x.shape[1], dt, co_pad=cop))
                     pad1 = lambda v: None if v is None else ops.pad_vector(v, cop)
-                    scale, shift = pad1(scale), pad1(shift)
+                    scale, shift = self._packed('%s|foldpad|%d' % (st.name, cop), lambda: (pad1(scale), pad1(shift)))
                     y = DeviceArray(y.buf, (y.shape[0], cop) + y.shape[2:], dt, 'nhwc', ld=cop, offset=y.offset)
                     self._keep += [wp, scale, shift]
                     return lambda: ops.conv2d_into(x, wp, y, kh, kw, a['strides'], a['dilations'], a['pads'], 1,
                                                    scale, shift, res, st.act, st.alpha, res_after_act=st.res_after)
-                wp = ops.pack_weight(K, x.shape[1] // g, dt)
+                wp = self._packed('%s|pack|%d' % (st.name, x.shape[1] // g), lambda: ops.pack_weight(K, x.shape[1] // g, dt))
                 self._keep.append(wp)
                 return lambda: ops.conv2d_into(x, wp, y, kh, kw, a['strides'], a['dilations'], a['pads'], g,
                                                scale, shift, res, st.act, st.alpha, res_after_act=st.res_after)
-            Kc = K.astype(dt)
+            Kc = self._packed(st.name + '|cast', lambda: K.astype(dt))
             self._keep.append(Kc)
             if x.layout != 'flat':
                 raise NotImplementedError('dense %r needs a 2-D input (got %s)' % (st.name, x.shape))
@@ -436,10 +462,10 @@ class Executor:
                 bn_k, bn_b = (self._weight(dn.bn[0]), self._weight(dn.bn[1])) if dn.bn else (None, None)
                 scale = shift = None
                 if bias is not None or bn_k is not None:
-                    scale, shift = ops.fold_affine(bias, bn_k, bn_b, K.shape[0])
+                    scale, shift = self._packed(dn.name + '|fold', lambda: ops.fold_affine(bias, bn_k, bn_b, K.shape[0]))
                     if bn_k is None:
                         scale = None
-                Kc = K.astype(dt)
+                Kc = self._packed(dn.name + '|cast', lambda: K.astype(dt))
                 y = alloc(dn.out)
                 self._keep += [scale, shift, Kc]
                 self.fused_dense |= {id(fl), id(dn)}

@@ -44,7 +44,74 @@ def read_net(path, debug=False):
         return print('model %s not found!' % path)           # planer/io.py:30-31
     net.load_json(body['input'], body['inits'], body['layers'], body['flow'], debug)
     net.load_weights(weights)
+    net._pack_path = path + PACK_SUFFIX           # pre-packed weight cache beside the model (save_pack / load at first use)
     return net
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Pre-packed weight cache.  The reference re-derives nothing at load (its weights are used as stored,
+# planer/net.py:83-88; Net.half() casts per call site, planer/net.py:26-29); here every executor build used to re-run the
+# one-off device work -- fp32 -> fp16 casts, OIHW -> [Cout][kh][kw][Cin] packing, BatchNorm / bias folding, first-layer and
+# shortcut packings: ~94 launches for ResNet-18.  `save_pack(net)` writes what the net's pack store holds to
+# `<model>.b200pack.npz`, keyed by the SHA-256 of the weight blob, the ABI version and the library's pack-format version;
+# a later `read_net` + first forward uploads the cached arrays instead (stale or foreign caches are ignored, never trusted).
+# ---------------------------------------------------------------------------------------------------------------------
+PACK_SUFFIX = '.b200pack.npz'
+PACK_FORMAT = 1
+
+
+def _blob_digest(net):
+    import hashlib
+    from . import backend as B
+    n = sum(int(numpy.prod(s)) * d.itemsize for _, s, d in net._init_meta)
+    flat = B.DeviceArray(net._blob.buf, (n,), numpy.uint8, 'flat', offset=net._blob.offset)
+    return hashlib.sha256(flat.get().tobytes()).hexdigest()
+
+
+def save_pack(net, path=None):
+    """Write the one-off weight artefacts the net has built so far (run at least one forward per input signature you
+    want covered) to ``path`` (default: beside the model file ``read_net`` loaded).  Returns the path."""
+    from . import backend as B, _capi
+    path = path or getattr(net, '_pack_path', None)
+    if path is None:
+        raise ValueError('save_pack: no path given and the net was not loaded from a file')
+    B.synchronize()
+    out = {'__meta__': numpy.array(json.dumps({'blob_sha256': _blob_digest(net), 'abi': _capi.load().plnr_abi_version(),
+                                               'format': PACK_FORMAT}))}
+    for k, v in net._pack_store.items():
+        out[k] = numpy.array(v) if k.endswith('#n') else v.get()
+    tmp = path + '.tmp.npz'
+    numpy.savez(tmp, **out)
+    os.replace(tmp, path)
+    return path
+
+
+def load_pack(net, path=None):
+    """Fill the net's pack store from a cache written by ``save_pack``.  Returns the number of arrays taken (0 when the
+    file is missing, was written for other weights / another ABI, or is unreadable)."""
+    from . import backend as B, _capi
+    path = path or getattr(net, '_pack_path', None)
+    if path is None or not os.path.exists(path) or net._blob is None:
+        return 0
+    try:
+        z = numpy.load(path, allow_pickle=False)
+        meta = json.loads(str(z['__meta__']))
+        if meta.get('format') != PACK_FORMAT or meta.get('abi') != _capi.load().plnr_abi_version() or \
+                meta.get('blob_sha256') != _blob_digest(net):
+            return 0
+        n = 0
+        for k in z.files:
+            if k == '__meta__':
+                continue
+            if k.endswith('#n'):
+                net._pack_store[k] = int(z[k])
+            else:
+                net._pack_store[k] = B.asarray(z[k])
+                n += 1
+        return n
+    except Exception:
+        net._pack_store = {}
+        return 0
 
 
 def from_model(model, blob, half=False):

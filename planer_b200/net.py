@@ -68,13 +68,16 @@ class Net:
         self._init_meta, self._host_blob, self._blob = [], None, None
         self._executors, self.use_graph, self._host_rings = OrderedDict(), True, {}
         self._schedule = []
+        self._pack_store = {}        # one-off weight artefacts (packed filters, folded scale / shift): shared by every executor
         self.output_copy = True      # forward() on device arrays returns fresh arrays, like the reference (net.py:60,72)
 
-    def _invalidate(self):
+    def _invalidate(self, weights_changed=True):
         for ex in self._executors.values():
             ex.close()
         self._executors = OrderedDict()
         self._host_rings = {}
+        if weights_changed:
+            self._pack_store = {}
 
     # -- planer/net.py:10-24 ---------------------------------------------------------------------
     def load_json(self, inputs, inits, body, flow, debug=False):
@@ -197,6 +200,10 @@ class Net:
                 consts[xs[1]] = self.host_const(xs[1])
             if kinds.get(first) == 'resize' and not isinstance(xs, str) and len(xs) > 2 and xs[2] in self.inits:
                 consts[xs[2]] = self.host_const(xs[2])
+        if not self._pack_store and getattr(self, '_pack_path', None) and not getattr(self, '_pack_tried', False):
+            from . import io as _io
+            self._pack_tried = True
+            _io.load_pack(self)                               # pre-packed weight cache beside the model file, if valid
         gp = P.compile_graph(self._model(), dict(zip(names, sig[0])), consts)
         ex = Executor(self, gp, cdt, self.use_graph, input_dtypes=[numpy.dtype(d) for d in in_dts])
         self._executors[sig] = ex
@@ -300,8 +307,9 @@ def _chunked_methods():
                 src = B.to_flat(o)
                 h[:src.nbytes].copy_(src.buf[src.offset:src.offset + src.nbytes], non_blocking=True)
 
-    def _from_pinned(outs, bufs):
-        return tuple(numpy.array(h[:o.nbytes].numpy().view(o.dtype).reshape(o.shape)) for o, h in zip(outs, bufs))
+    def _from_pinned(outs, bufs, copy=True):
+        views = tuple(h[:o.nbytes].numpy().view(o.dtype).reshape(o.shape) for o, h in zip(outs, bufs))
+        return tuple(numpy.array(v) for v in views) if copy else views
 
     def _call_chunked(self, x, chunks):
         # All uploads are queued on the copy stream first; each chunk's forward waits for its own upload only, its
@@ -322,7 +330,7 @@ def _chunked_methods():
         rst = tuple(numpy.concatenate([o[j] for o in outs], axis=0) for j in range(len(outs[0])))
         return rst[0] if len(rst) == 1 else rst
 
-    def map(self, batches, depth=2):
+    def map(self, batches, depth=2, copy=True):
         """Pipelined ``net(x)`` over an iterable of host batches: yields, in order, exactly what ``net(x)`` returns for
         each batch.  While batch *i* is computed, batch *i+1* is uploaded on a copy stream and the outputs of batch *i-1*
         travel back to pinned host memory, so that a stream of batches runs at max(PCIe, compute) per batch instead of
@@ -333,21 +341,24 @@ def _chunked_methods():
         fp16; the first layer converts).  ``depth`` = batches in flight behind the one yielded.
 
         Buffer ownership: ``map`` pulls the next batch from ``batches`` only after the upload of the previous one has
-        COMPLETED, so a producer may refill the same (pinned) buffer for every batch -- one buffer is enough."""
+        COMPLETED, so a producer may refill the same (pinned) buffer for every batch -- one buffer is enough.
+        ``copy=False`` yields views of the pinned result ring instead of fresh arrays: a result then stays valid until
+        ``depth + 1`` further results have been yielded -- for large outputs (YOLO heads: 58 MB per batch of 32) the host
+        memcpy into a fresh array otherwise costs more than the forward."""
         if self._array is not B:
             for x in batches:
                 yield self(x)
             return
         torch = B._torch()
         B.init()
-        slots = depth + 1
+        slots = depth + 1 if copy else 2 * depth + 2          # views handed out must outlive `depth + 1` further results
         cs, ls = B.copy_stream(), B.stream()
         dev_in, done, pending = [None] * slots, [None] * slots, []
         ring, metas = None, None
 
         def finish(slot):
             done[slot].synchronize()
-            rst = _from_pinned(metas, ring[slot])
+            rst = _from_pinned(metas, ring[slot], copy)
             return rst[0] if len(rst) == 1 else rst
 
         i, up = 0, None

@@ -657,3 +657,38 @@ def test_stream_k_equals_data_parallel_and_oracle(planer, cfg, monkeypatch):
         if with_res:
             ref = oracle.add(ref, r.astype(np.float32))
         assert rel_err(outs['2'], oracle.relu(ref)) <= 1e-2
+
+
+def test_pack_cache_roundtrip_and_sharing(planer, tmp_path):
+    """Pre-packed weight cache (io.save_pack / load_pack): a second load of the same model builds its executor without
+    re-running any cast / pack / fold launch and gives bit-identical outputs; executors of other input shapes share the
+    pack store in memory; a cache written for other weights is ignored."""
+    from planer_b200 import zoo, backend as B
+    model, blob = zoo.resnet18(0)
+    path = str(tmp_path / 'r18')
+    zoo.save_model(path, model, blob)
+    x = np.random.default_rng(9).standard_normal((2, 3, 224, 224)).astype(np.float16)
+    net = planer.read_net(path)
+    net.half()
+    y0 = net(x)
+    ex = net.executor([x.shape], [x.dtype])
+    assert ex.pack_misses > 20 and ex.pack_hits == 0
+    ex4 = net.executor([(4,) + x.shape[1:]], [x.dtype])          # another input shape: everything comes from the store
+    assert ex4.pack_misses == 0 and ex4.pack_hits == ex.pack_misses
+    cache = planer.save_pack(net)
+    assert cache.endswith('.b200pack.npz') and os.path.exists(cache)
+    net2 = planer.read_net(path)
+    net2.half()
+    l0 = B.launch_count()
+    ex2 = net2.executor([x.shape], [x.dtype])
+    assert ex2.pack_misses == 0 and ex2.pack_hits == ex.pack_misses
+    assert B.launch_count() - l0 == 0, 'executor build with a valid cache must not launch any packing kernel'
+    assert np.array_equal(net2(x), y0)
+    # other weights, same file name: the digest does not match, the cache is ignored
+    model3, blob3 = zoo.resnet18(1)
+    zoo.save_model(path, model3, blob3)
+    net3 = planer.read_net(path)
+    net3.half()
+    ex3 = net3.executor([x.shape], [x.dtype])
+    assert ex3.pack_hits == 0 and ex3.pack_misses == ex.pack_misses
+    assert not np.array_equal(net3(x), y0)
