@@ -73,6 +73,9 @@ typedef struct {
   int32_t act;              /* PLNR_ACT_* */
   float alpha;              /* leaky slope */
   int32_t res_after_act;    /* 0: act(v + residual) (ResNet);  1: act(v) + residual (Darknet shortcut) */
+  int32_t out_nchw;         /* 1: y->ptr is a DENSE NCHW array of y's logical shape -- the graph-exit transpose (planer/net.py:100
+                             *    hands NCHW arrays back) folded into the epilogue.  No residual; only where
+                             *    plnr_conv2d_out_nchw_supported says so (the shift-GEMM kernel). */
 } plnr_epilogue;
 
 typedef struct {
@@ -157,6 +160,7 @@ int plnr_fold_affine(plnr_ctx* ctx, const void* bias, const void* bn_k, const vo
  * the direct CUDA-core kernel (fp32 accumulate in both). */
 int plnr_conv2d_fwd(plnr_ctx* ctx, const plnr_conv_desc* desc, const plnr_tensor* x, const void* w_packed,
                     const plnr_tensor* y, const plnr_epilogue* ep);
+int plnr_conv2d_out_nchw_supported(const plnr_conv_desc* desc, const plnr_tensor* x, const plnr_tensor* y);
 /* Conv2d + fused 1x1 shortcut convolution: y = act((conv(x, W) + conv1x1_stride(x2, W2)) * scale + shift).  Replaces the
  * tail of a down-sampling residual block -- Conv2d -> BatchNorm on the main path, Conv2d(1x1, stride) -> BatchNorm on
  * the shortcut, Add, ReLU (planer/layer.py:22-26, :125-127, :93-95, :44-46) -- by ONE launch: the shortcut's k-chunks

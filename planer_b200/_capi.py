@@ -25,7 +25,7 @@ class Tensor(C.Structure):
 
 class Epilogue(C.Structure):
     _fields_ = [('scale', C.c_void_p), ('shift', C.c_void_p), ('residual', C.POINTER(Tensor)),
-                ('act', C.c_int32), ('alpha', C.c_float), ('res_after_act', C.c_int32)]
+                ('act', C.c_int32), ('alpha', C.c_float), ('res_after_act', C.c_int32), ('out_nchw', C.c_int32)]
 
 
 class ConvDesc(C.Structure):
@@ -62,6 +62,7 @@ PROTOTYPES = {
     'plnr_pack_conv_weight': [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
     'plnr_fold_affine': [_P, _P, _P, _P, C.c_int, _P, _P, C.c_int],
     'plnr_conv2d_fwd': [_P, C.POINTER(ConvDesc), _TP, _P, _TP, C.POINTER(Epilogue)],
+    'plnr_conv2d_out_nchw_supported': [C.POINTER(ConvDesc), _TP, _TP],
     'plnr_conv2d_shortcut_supported': [C.POINTER(ConvDesc), _TP, _TP, C.c_int, _TP],
     'plnr_conv2d_shortcut_fwd': [_P, C.POINTER(ConvDesc), _TP, _P, _TP, C.c_int, _TP, C.POINTER(Epilogue)],
     'plnr_dense_fwd': [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(Epilogue), C.c_int],

@@ -270,6 +270,12 @@ int plnr_conv2d_fwd(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x
     PLNR_REQUIRE(r->n == y->n && r->h == y->h && r->w == y->w && r->c == y->c,
                  "conv2d: residual shape differs from the output shape");
   }
+  if (ep && ep->out_nchw) {
+    PLNR_REQUIRE(!ep->residual, "conv2d: out_nchw cannot be combined with a residual operand");
+    PLNR_REQUIRE(d->algo != PLNR_ALGO_DIRECT && plnr_conv2d_shift_supported(d, x, y),
+                 "conv2d: out_nchw needs the shift-GEMM kernel (plnr_conv2d_out_nchw_supported)");
+    return plnr_conv2d_shift(ctx, d, x, w, y, ep);
+  }
   bool tc_ok = plnr_conv2d_tcgen05_supported(d, x, y);
   if (d->algo == PLNR_ALGO_TCGEN05 && !tc_ok) {
     plnr_set_error("conv2d: PLNR_ALGO_TCGEN05 requested but the problem is not eligible "
@@ -278,6 +284,11 @@ int plnr_conv2d_fwd(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x
   }
   if (d->algo != PLNR_ALGO_DIRECT && tc_ok) return plnr_conv2d_tcgen05(ctx, d, x, w, y, ep);
   return plnr_conv2d_direct(ctx, d, x, w, y, ep);
+}
+
+int plnr_conv2d_out_nchw_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y) {
+  if (!d || !x || !y || d->dtype != PLNR_F16 || d->groups != 1 || d->algo == PLNR_ALGO_DIRECT) return 0;
+  return plnr_conv2d_shift_supported(d, x, y) ? 1 : 0;
 }
 
 int plnr_conv2d_shortcut_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* x2, int stride2,

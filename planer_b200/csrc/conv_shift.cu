@@ -66,6 +66,7 @@ struct ShiftParams {
   const __half* res; int rld, rcoff;
   int act; float alpha; int res_after;
   int vec_ok;
+  int y_nchw, ohw;          // 1: y is a dense NCHW array (graph exit folded into the epilogue); OH * OW
   int* err;
   long long* prof;
   // stream-K (see SegList): iterations per tile = weight boxes per tile; fp32 partial tiles and their ready flags
@@ -689,7 +690,11 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
           for (int i = 0; i < 4; ++i) rv[i] = rvn[i];
           if (estamp && estamp_i < 1424) p.prof[estamp_i++] = clock64() - t_entry;
         } else if (g.own >= 0) {
-          __half* yrow = p.y + (size_t)g.own * p.yld + p.ycoff;
+          // NCHW exit: pixel g.own = img * OH*OW + pix  ->  y[(img * Cout + c) * OH*OW + pix]
+          const uint32_t img_ = p.y_nchw ? (uint32_t)g.own / (uint32_t)p.ohw : 0u;
+          __half* yrow = p.y_nchw ? p.y + ((size_t)img_ * p.Cout) * p.ohw + ((uint32_t)g.own - img_ * (uint32_t)p.ohw)
+                                  : p.y + (size_t)g.own * p.yld + p.ycoff;
+          const size_t cstride = p.y_nchw ? (size_t)p.ohw : 1;
           const __half* rrow = has_res ? p.res + (size_t)g.own * p.rld + p.rcoff : nullptr;
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
@@ -701,7 +706,7 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
               if (!p.res_after) o1 += rf;
               o1 = plnr_apply_act(o1, p.act, p.alpha);
               if (p.res_after) o1 += rf;
-              yrow[c] = __float2half_rn(o1);
+              yrow[(size_t)c * cstride] = __float2half_rn(o1);
             }
           }
         }
@@ -954,7 +959,7 @@ bool plnr_conv2d_shift_shortcut_supported(const plnr_conv_desc* d, const plnr_te
 int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w,
                       const plnr_tensor* y, const plnr_epilogue* ep, const plnr_tensor* x2, int s2) {
   // 3-wide filters over 64-channel output blocks whose taps fit in shared memory: the stacked variant (conv_stack.cu)
-  if (plnr_conv2d_stack_supported(d, x, y, ep, x2, s2)) return plnr_conv2d_stack(ctx, d, x, w, y, ep, x2, s2);
+  if (!(ep && ep->out_nchw) && plnr_conv2d_stack_supported(d, x, y, ep, x2, s2)) return plnr_conv2d_stack(ctx, d, x, w, y, ep, x2, s2);
   int rc = resolve_driver();
   if (rc != PLNR_OK) return rc;
   const int c2 = x2 ? x2->c : 0;
@@ -998,6 +1003,10 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
     }
   }
   p.vec_ok = vec ? 1 : 0;
+  if (ep && ep->out_nchw) {          // every thread stores its own pixel, channel by channel: lanes = consecutive pixels of a plane
+    PLNR_REQUIRE(!ep->residual, "conv2d(shift): out_nchw cannot be combined with a residual operand");
+    p.y_nchw = 1; p.ohw = y->h * y->w; p.vec_ok = 0;
+  }
   p.err = ctx->dev_error;
   p.prof = ctx->prof;
 

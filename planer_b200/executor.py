@@ -36,6 +36,7 @@ class Executor:
         self._keep = []
         self._in_stage = {}       # graph input -> fp16 staging array (fp32 images on the fused first layer)
         self.pack_hits = self.pack_misses = 0
+        self.nchw_exits = 0       # graph outputs written as NCHW by the producing conv's epilogue
         self._build()
 
     # ------------------------------------------------------------------------------------------
@@ -68,6 +69,20 @@ class Executor:
         if self._fused_stem_of(self._root(prod[0].ins[0])) is not None or self._stem_of(self._root(prod[0].ins[0])) is not None:
             return c
         return _round_up(c, 8)
+
+    def _nchw_exit_ok(self, st, x, K):
+        v = self.values[self._root(st.out)]
+        if self.dtype != np.float16 or os.environ.get('PLNR_NO_NCHW_EXIT') == '1' or not v.is_output or len(v.shape) != 4:
+            return False
+        if st.res is not None or st.shortcut is not None or st.attrs.get('group', 1) != 1 or st.attrs.get('flip'):
+            return False
+        root = self._root(st.out)
+        if any(root in [self._root(r) for r in u.reads()] for u in self.plan.steps) or v.slice_of is not None:
+            return False
+        if self.stems.get(self._root(st.ins[0])) is not None or x.layout != 'nhwc':
+            return False
+        a = st.attrs
+        return ops.conv2d_out_nchw_supported(x, v.shape, K.shape[2], K.shape[3], a['strides'], a['dilations'], a['pads'])
 
     def _input_cpad(self, vid):
         """Graph inputs feeding only group-1 convs are channel-padded to a multiple of 16 in fp16 so that the
@@ -224,12 +239,19 @@ class Executor:
         gp, vals, dt = self.plan, self.values, self.dtype
         if dt == np.float16 and os.environ.get('PLNR_NO_SHORTCUT_FUSION') != '1':
             P.absorb_shortcuts(gp, self._shortcut_eligible)
+        self.placed_concat_inputs = 0
+        if os.environ.get('PLNR_NO_ZERO_COPY_CONCAT') != '1':
+            self.placed_concat_inputs = P.place_concat_inputs(gp, align=16 // dt.itemsize)
         P.assign_buffers(gp, dt.itemsize, self._storage_c)
         pool = [None] * len(gp.buffer_bytes)
 
         def alloc(vid):
             r = self._root(vid)
             if r in self.arr:
+                return self.arr[r]
+            if vals[r].slice_of is not None:              # zero-copy concat: this value lives in a slice of the concat's buffer
+                out, off = vals[r].slice_of
+                self.arr[r] = ops.channel_slice(alloc(out), off, vals[r].shape[1])
                 return self.arr[r]
             shape = vals[r].shape
             b = gp.buffer_of[r]
@@ -324,6 +346,18 @@ class Executor:
                     scale = None
             res = self._view(st.res) if st.res is not None else None
             self._keep += [scale, shift]
+            if fused is None and op == 'conv' and self._nchw_exit_ok(st, x, K):
+                # graph output produced by this conv and read by nothing else: the epilogue writes the dense NCHW array
+                # itself (plnr_epilogue.out_nchw) -- no pixel-major copy, no transpose launch, no channel padding
+                a = st.attrs
+                flat = B.empty(vals[st.out].shape, dt)
+                self.arr[self._root(st.out)] = flat
+                wp = self._packed('%s|pack|%d' % (st.name, x.shape[1]), lambda: ops.pack_weight(K, x.shape[1], dt))
+                self._keep += [wp, flat]
+                kh, kw = K.shape[2], K.shape[3]
+                self.nchw_exits += 1
+                return lambda: ops.conv2d_into(x, wp, flat, kh, kw, a['strides'], a['dilations'], a['pads'], 1, scale, shift,
+                                               None, st.act, st.alpha, out_nchw=True)
             if fused is not None:
                 a = st.attrs
                 yp = alloc(fused['pool'].out)
@@ -444,11 +478,17 @@ class Executor:
             x, y, a = self._view(st.ins[0]), alloc(st.out), st.attrs
             return lambda: ops.zero_stuff_into(x, y, a['lo_h'], a['lo_w'], a['strides'])
         if op == 'concat':
-            xs, y = [self._view(i) for i in st.ins], alloc(st.out)
+            y = alloc(st.out)
+            xs = [self._view(i) for i in st.ins]
             offs = np.cumsum([0] + [x.shape[1] for x in xs]).tolist()
-            views = [ops.channel_slice(y, o, x.shape[1]) for x, o in zip(xs, offs)]
+            out_root = self._root(st.out)
+            # inputs the planner placed inside y (P.place_concat_inputs) are already there; copy only the others
+            todo = [(x, ops.channel_slice(y, o, x.shape[1])) for x, o, i in zip(xs, offs, st.ins)
+                    if vals[self._root(i)].slice_of != (out_root, o)]
+            if not todo:
+                return None
             def run():
-                for x, v in zip(xs, views):
+                for x, v in todo:
                     ops.copy_channels(x, v)
             return run
         if op == 'gap':

@@ -33,9 +33,10 @@ def pool_out_shape(xshape, w, pads, strides):
             (ww + pads[1] + pads[3] - w[1] + strides[1]) // strides[1])
 
 
-def _epilogue(scale, shift, residual, act, alpha, res_after_act=False):
+def _epilogue(scale, shift, residual, act, alpha, res_after_act=False, out_nchw=False):
     keep = []
     ep = _capi.Epilogue()
+    ep.out_nchw = int(bool(out_nchw))
     ep.scale = scale.ptr if scale is not None else None
     ep.shift = shift.ptr if shift is not None else None
     if residual is not None:
@@ -77,12 +78,28 @@ def fold_affine(bias, bn_k, bn_b, c):
     return scale, shift
 
 
+def nchw_out_tensor(y):
+    """plnr_tensor header of a FLAT (NCHW) 4-D array used as a conv output with ``out_nchw`` (extents only; ld = c)."""
+    n, c, h, w = y.shape
+    return _capi.Tensor(y.ptr, n, h, w, c, c, 0)
+
+
+def conv2d_out_nchw_supported(x, yshape, kh, kw, strides, dilations, pads):
+    """True when the conv epilogue can write the dense NCHW result itself (graph exit without a transpose launch)."""
+    d = _capi.ConvDesc(_capi.dtype_code(x.dtype), kh, kw, pads[0], pads[1], pads[2], pads[3],
+                       strides[0], strides[1], dilations[0], dilations[1], 1, ALGO_AUTO)
+    tx = x.tensor()
+    ty = _capi.Tensor(256, yshape[0], yshape[2], yshape[3], yshape[1], yshape[1], 0)
+    return bool(B.lib().plnr_conv2d_out_nchw_supported(C.byref(d), C.byref(tx), C.byref(ty)))
+
+
 def conv2d_into(x, w_packed, y, kh, kw, strides, dilations, pads, groups=1, scale=None, shift=None,
-                residual=None, act=ACT_NONE, alpha=0.0, algo=ALGO_AUTO, res_after_act=False):
+                residual=None, act=ACT_NONE, alpha=0.0, algo=ALGO_AUTO, res_after_act=False, out_nchw=False):
+    """``out_nchw``: y is a flat NCHW array and the epilogue writes it directly (plnr_epilogue.out_nchw)."""
     d = _capi.ConvDesc(_capi.dtype_code(x.dtype), kh, kw, pads[0], pads[1], pads[2], pads[3],
                        strides[0], strides[1], dilations[0], dilations[1], groups, algo)
-    tx, ty = x.tensor(), y.tensor()
-    ep, keep = _epilogue(scale, shift, residual, act, alpha, res_after_act)
+    tx, ty = x.tensor(), (nchw_out_tensor(y) if out_nchw else y.tensor())
+    ep, keep = _epilogue(scale, shift, residual, act, alpha, res_after_act, out_nchw)
     _capi.check(B.lib().plnr_conv2d_fwd(B.ctx(), C.byref(d), C.byref(tx), w_packed.ptr, C.byref(ty), C.byref(ep)),
                 'plnr_conv2d_fwd')
     return y

@@ -28,11 +28,12 @@ def _out(n_in, pad_lo, pad_hi, k, dil, stride):
 
 
 class Value:
-    __slots__ = ('id', 'shape', 'kind', 'name', 'producer', 'uses', 'is_output', 'alias_of')
+    __slots__ = ('id', 'shape', 'kind', 'name', 'producer', 'uses', 'is_output', 'alias_of', 'slice_of')
 
     def __init__(self, vid, shape, kind, name):
         self.id, self.shape, self.kind, self.name = vid, None if shape is None else tuple(shape), kind, name
         self.producer, self.uses, self.is_output, self.alias_of = None, 0, False, None
+        self.slice_of = None      # (concat output value id, first channel): this value LIVES in a channel slice of that buffer
 
 
 class Node:
@@ -406,12 +407,63 @@ def _root(values, vid):
     return vid
 
 
+def _storage_root(values, vid):
+    """The value whose buffer holds ``vid``: aliases, then channel slices of a concat output (zero-copy concat)."""
+    vid = _root(values, vid)
+    while values[vid].slice_of is not None:
+        vid = _root(values, values[vid].slice_of[0])
+    return vid
+
+
+def place_concat_inputs(plan, writes_strided=('conv', 'upsample'), reads_strided=('conv', 'concat'), align=8):
+    """Zero-copy concat (np.concatenate(axis=1), planer/layer.py:90-91): an input of a channel concat is PRODUCED in place,
+    as a channel slice of the concat's output buffer, when its producer can write a strided view (conv epilogues, nearest
+    upsample), every reader can read one (convs -- TMA takes any row pitch -- and the concat itself), its channel count and
+    offset keep 16-byte alignment, and it is neither a graph output nor already placed elsewhere.  The concat step then
+    copies only the inputs that could not be placed.  Returns the number of placed inputs."""
+    values, steps = plan.values, plan.steps
+    producer = {}
+    for st in steps:
+        producer.setdefault(_root(values, st.out), st)
+    readers = {}
+    for st in steps:
+        for r in st.reads():
+            readers.setdefault(_root(values, r), []).append(st)
+    placed = 0
+    for st in steps:
+        if st.op != 'concat':
+            continue
+        out = _root(values, st.out)
+        if values[out].slice_of is not None:
+            continue
+        off = 0
+        seen = set()
+        for i in st.ins:
+            c = values[i].shape[1]
+            r = _root(values, i)
+            v = values[r]
+            p = producer.get(r)
+            ok = (v.kind == 'act' and not v.is_output and v.slice_of is None and r not in seen and p is not None and
+                  p.op in writes_strided and not p.inplace and c % align == 0 and off % align == 0 and
+                  all(u.op in reads_strided for u in readers.get(r, [])) and
+                  not (p.op == 'upsample' and p.attrs.get('mode', 'nearest') != 'nearest') and
+                  not any(values[q].alias_of == r for q in range(len(values))))      # nothing aliases it in place
+            if ok and p.op == 'conv' and (p.attrs.get('group', 1) != 1):
+                ok = False
+            if ok:
+                v.slice_of = (out, off)
+                placed += 1
+            seen.add(r)
+            off += c
+    return placed
+
+
 def assign_buffers(plan, elem_bytes, storage_channels):
     """Liveness-based buffer reuse.  Values that alias (in-place relu, identity, flatten of 1x1 maps) share a
     buffer; graph inputs/outputs and weights are never recycled.  ``storage_channels(vid)`` gives the stored
     channel count (inputs may be channel-padded)."""
     values, steps = plan.values, plan.steps
-    root = lambda v: _root(values, v)
+    root = lambda v: _storage_root(values, v)
     for st in steps:                                   # aliases created by standalone steps
         if st.op in ('relu', 'clip', 'alias') or (st.op == 'flatten' and values[st.ins[0]].shape[2:] == (1, 1)):
             values[st.out].alias_of = st.ins[0]

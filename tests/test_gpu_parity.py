@@ -692,3 +692,56 @@ def test_pack_cache_roundtrip_and_sharing(planer, tmp_path):
     ex3 = net3.executor([x.shape], [x.dtype])
     assert ex3.pack_hits == 0 and ex3.pack_misses == ex.pack_misses
     assert not np.array_equal(net3(x), y0)
+
+
+def test_resnet18_fp16_batch128_distinct_images_vs_fp32_oracle(planer):
+    """BASELINE config 3 at its full batch on 128 DIFFERENT images: sampled rows of the logits against the fp32 oracle run
+    image by image (the forward has no cross-image term), north-star bar 1e-2; also uint8 pixels through the same batch."""
+    model, blob = cases.get_model('resnet18')
+    net = planer.from_model(model, blob, half=True)
+    onet = oracle.build_net(model, blob)
+    x = np.random.default_rng(31).standard_normal((128, 3, 224, 224)).astype(np.float16)
+    y = net(x)
+    assert y.shape == (128, 1000)
+    for i in (0, 37, 64, 127):
+        ref = onet(x[i:i + 1].astype(np.float32))
+        assert rel_err(y[i], ref[0]) <= 1e-2, i
+    x8 = np.random.default_rng(32).integers(0, 256, (128, 3, 224, 224), dtype=np.uint8)
+    y8 = net(x8)
+    for i in (5, 100):
+        ref = onet(x8[i:i + 1].astype(np.float32))
+        assert rel_err(y8[i], ref[0]) <= 1e-2, i
+
+
+def test_yolov3_fp16_batch32_distinct_images_vs_fp32_oracle(planer):
+    """BASELINE config 4 at its full batch (32 different 416x416 images): two sampled images against the fp32 oracle, all
+    three heads; the heads leave the graph as NCHW straight from the conv epilogue and the route / upsample values live inside
+    the concat buffers (zero-copy concat) -- both checked on the executor."""
+    model, blob = cases.get_model('yolov3')
+    net = planer.from_model(model, blob, half=True)
+    x = np.random.default_rng(41).standard_normal((32, 3, 416, 416)).astype(np.float16)
+    ys = net(x)
+    assert [t.shape for t in ys] == [(32, 255, 13, 13), (32, 255, 26, 26), (32, 255, 52, 52)]
+    ex = net.executor([(16, 3, 416, 416)], [np.float16])       # net(x) runs a 32-image host batch as two halves
+    assert ex.nchw_exits == 3 and ex.placed_concat_inputs == 4
+    assert 'to_nchw' not in ex.kinds and 'concat' not in ex.kinds
+    onet = oracle.build_net(model, blob)
+    for i in (3, 29):
+        refs = onet(x[i:i + 1].astype(np.float32))
+        for t, r in zip(ys, refs):
+            assert rel_err(t[i], r[0]) <= 1e-2, i
+
+
+def test_zero_copy_concat_and_nchw_exit_equal_the_copying_path(planer, monkeypatch):
+    """The same YOLOv3 (quarter width) forward with and without zero-copy concat / NCHW-exit folding: bit-identical."""
+    model, blob = cases.get_model('yolov3_quarter')
+    x = np.random.default_rng(43).standard_normal((3, 3, 96, 96)).astype(np.float16)
+    a = planer.from_model(model, blob, half=True)(x)
+    monkeypatch.setenv('PLNR_NO_ZERO_COPY_CONCAT', '1')
+    monkeypatch.setenv('PLNR_NO_NCHW_EXIT', '1')
+    net = planer.from_model(model, blob, half=True)
+    b = net(x)
+    ex = net.executor([x.shape], [x.dtype])
+    assert ex.nchw_exits == 0 and ex.placed_concat_inputs == 0
+    for s, t in zip(a, b):
+        assert np.array_equal(s, t)

@@ -42,7 +42,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_capi.Tensor) == 32
     assert ctypes.sizeof(_capi.ConvDesc) == 13 * 4
     assert ctypes.sizeof(_capi.Epilogue) == 40
-    assert _capi.Epilogue.act.offset == 24 and _capi.Epilogue.res_after_act.offset == 32
+    assert _capi.Epilogue.act.offset == 24 and _capi.Epilogue.res_after_act.offset == 32 and _capi.Epilogue.out_nchw.offset == 36
 
 
 def test_no_cpu_fallback(lib):
@@ -628,3 +628,47 @@ def test_shift_gemm_rejects_what_it_cannot_do(lib, monkeypatch):
                 ((1, 48, 12, 12), 8, (3, 3), 1, (1, 1, 1, 1), 1),     # Cin % 64 != 0
                 ((1, 64, 12, 300), 8, (3, 3), 2, (1, 1, 1, 1), 1)]:   # 2 * Wv > 256: the TMA box limit
         assert _shift_geometry(lib, *cfg)[0][0] == 0
+
+
+def test_zero_copy_concat_placement_and_liveness():
+    """P.place_concat_inputs: YOLOv3's four concat inputs (two nearest upsamples, two route convolutions that other
+    convolutions read too) are produced inside the concat buffers; the buffer of a concat is then live from its first
+    producer to the last reader of the concat or of any slice, and nothing else may take it in between."""
+    model, _ = cases.get_model('yolov3_quarter')
+    consts = {n: np.array([1, 1, 2, 2], np.float32) for n, s, d in model['inits'] if 'scales' in n}
+    gp = P.compile_graph(model, {'x': (1, 3, 64, 64)}, consts)
+    n_concat_inputs = sum(len(s.ins) for s in gp.steps if s.op == 'concat')
+    assert P.place_concat_inputs(gp) == n_concat_inputs == 4
+    P.assign_buffers(gp, 2, lambda v: gp.values[v].shape[1])
+    sroot = lambda v: P._storage_root(gp.values, v)
+    for s in gp.steps:
+        if s.op == 'concat':
+            off = 0
+            for i in s.ins:
+                v = gp.values[P._root(gp.values, i)]
+                assert v.slice_of == (P._root(gp.values, s.out), off) and sroot(i) == sroot(s.out)
+                assert P._root(gp.values, i) not in gp.buffer_of       # no buffer of its own
+                off += v.shape[1]
+    last = {}
+    for pos, s in enumerate(gp.steps):
+        for r in s.reads():
+            last[sroot(r)] = pos
+    tenant = {}
+    for pos, s in enumerate(gp.steps):
+        o = sroot(s.out)
+        if o in gp.buffer_of:
+            b = gp.buffer_of[o]
+            prev = tenant.get(b)
+            if prev is not None and prev != o:
+                assert last.get(prev, -1) < pos, (s.name, prev, o)
+            tenant[b] = o
+    # a value with a reader that cannot take a strided view (elementwise add) is not placed
+    b = zoo._Builder(3)
+    a1 = b.conv('x', 16, 16, 3, 1, 1, name='a1')
+    a2 = b.conv('x', 16, 16, 3, 1, 1, name='a2')
+    cat = b.op('concat', {'axis': 1}, [a1, a2], name='cat')
+    s_ = b.op('add', {}, [a1, 'x'], name='add')
+    model2, _ = b.finish(['x'], [cat, s_])
+    gp2 = P.compile_graph(model2, {'x': (1, 16, 8, 8)})
+    assert P.place_concat_inputs(gp2) == 1
+    assert gp2.values[P._root(gp2.values, [s for s in gp2.steps if s.name == 'a2'][0].out)].slice_of is not None
