@@ -403,7 +403,7 @@ class Executor:
                 a = st.attrs
                 g = a['group']
                 kh, kw = K.shape[2], K.shape[3]
-                if y.layout == 'nhwc' and y.ld != y.shape[1]:
+                if y.layout == 'nhwc' and y.ld != y.shape[1] and vals[self._root(st.out)].slice_of is None:
                     # channel-padded graph output (_out_cpad): run the kernel on ld channels, pad filter rows are zero
                     cop = y.ld
                     wp = self._packed('%s|pack|%d|%d' % (st.name, x.shape[1], cop), lambda: ops.pack_weight(K, x.shape[1], dt, co_pad=cop))
@@ -560,8 +560,11 @@ class Executor:
         else:
             import ctypes as C
             if self.graph is None:
-                for fn in self.launches:        # one eager pass first: validates every launch outside capture
-                    fn()
+                for fn, name in zip(self.launches, self.names):        # one eager pass first: validates every launch outside capture
+                    try:
+                        fn()
+                    except _capi.PlanerB200Error as e:
+                        raise _capi.PlanerB200Error('step %r: %s' % (name, e)) from None
                 B.synchronize()
                 lib, ctx = B.lib(), B.ctx()
                 _capi.check(lib.plnr_graph_begin(ctx), 'plnr_graph_begin')

@@ -100,8 +100,11 @@ def conv2d_into(x, w_packed, y, kh, kw, strides, dilations, pads, groups=1, scal
                        strides[0], strides[1], dilations[0], dilations[1], groups, algo)
     tx, ty = x.tensor(), (nchw_out_tensor(y) if out_nchw else y.tensor())
     ep, keep = _epilogue(scale, shift, residual, act, alpha, res_after_act, out_nchw)
-    _capi.check(B.lib().plnr_conv2d_fwd(B.ctx(), C.byref(d), C.byref(tx), w_packed.ptr, C.byref(ty), C.byref(ep)),
-                'plnr_conv2d_fwd')
+    rc = B.lib().plnr_conv2d_fwd(B.ctx(), C.byref(d), C.byref(tx), w_packed.ptr, C.byref(ty), C.byref(ep))
+    if rc != 0:
+        desc = lambda a: None if a is None else '%s %s ld=%s coff=%s' % (a.shape, a.layout, a.ld, a.coff)
+        _capi.check(rc, 'plnr_conv2d_fwd [x %s | y %s | residual %s | k %dx%d s %s]' % (desc(x), desc(y), desc(residual), kh, kw,
+                                                                                     tuple(strides)))
     return y
 
 
