@@ -78,12 +78,14 @@ static inline int plnr_after_launch(plnr_ctx* ctx, const char* what) {
   return PLNR_OK;
 }
 
-// PLNR_PDL=1 launches the tensor-core conv kernels with programmatic dependent launch (set-up overlapping the previous
-// kernel's tail).  Measured on ResNet-18 batch 128: no gain (every CTA needs the whole SM's shared memory, so a dependent
-// CTA cannot start before its predecessor on that SM exits) -- off by default, kept as an experiment switch.
+// The tensor-core conv kernels are launched with programmatic dependent launch: the next grid is scheduled while the
+// previous kernel of the stream drains, and everything it does before griddepcontrol.wait (barrier init, TMEM allocation,
+// tensor-map prefetch) overlaps that kernel's tail.  Every CTA needs the whole SM's shared memory, so a dependent CTA starts
+// when its predecessor on that SM exits: the gain is the launch latency, +0.7 % on the ResNet-18 batch-128 step
+// (profiles/r02_kernel_experiments.md 5).  PLNR_PDL=0 turns it off.
 static inline bool plnr_pdl_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("PLNR_PDL"); v = (e && atoi(e)) ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("PLNR_PDL"); v = (e && !atoi(e)) ? 0 : 1; }
   return v == 1;
 }
 

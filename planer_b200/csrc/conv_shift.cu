@@ -66,6 +66,7 @@ struct ShiftParams {
   const __half* res; int rld, rcoff;
   int act; float alpha; int res_after;
   int vec_ok;
+  int stage_wide;           // epilogue transposition stage: 2 KB per warp (a whole 32-column chunk per round trip) instead of 1 KB
   int y_nchw, ohw;          // 1: y is a dense NCHW array (graph exit folded into the epilogue); OH * OW
   int* err;
   long long* prof;
@@ -220,7 +221,8 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
     else { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), p.tmem_cols); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
-  if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all();      // the peer's barriers are initialised and its TMEM allocated before anything is sent to it
+  __syncthreads();                           // (also under CG == 2: a CTA barrier is what compute-sanitizer's racecheck models)
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   // programmatic dependent launch: let the next kernel of the stream start its own set-up, then wait until every
@@ -446,7 +448,7 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
     const int c_begin = alternate ? 0 : eg * half * 32, c_end = alternate ? 32 : min(nchunks, (eg + 1) * half) * 32;
     const bool has_res = p.res != nullptr;
     const uint32_t HvWv = (uint32_t)p.HvWv, uWv = (uint32_t)Wv, uMv = (uint32_t)p.Mv;
-    uint8_t* st_o = stage + (warp - 4) * 1024;
+    uint8_t* st_o = stage + (warp - 4) * (p.stage_wide ? 2048 : 1024);
     const uint32_t my_sw = (uint32_t)((lane >> 2) & 1);
     const int piece = lane & 1;
 
@@ -630,8 +632,9 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
           // loads per chunk instead of sixteen broadcast loads per row, and the math is 4 HFMA2 per row instead of
           // 8 FFMA + 8 FMNMX: the shared-memory pipe these loads shared with the MMA operand reads is what bounds the
           // Cout = 64 / 128 layers (profiles/r01_smem_budget.md).
-          auto chunk_math = [&](auto act_tag) {
+          auto chunk_math = [&](auto act_tag, auto wide_tag) {
             constexpr int kAct = decltype(act_tag)::value;      // 1 = ReLU, 2 = LeakyReLU (0 <= alpha <= 1), 0 = generic
+            constexpr bool kWide = decltype(wide_tag)::value != 0;
             const bool act_first = !has_res || p.res_after;
             const __half2 zero2 = __float2half2_rn(0.f), alpha2 = __float2half2_rn(p.alpha);
             auto act2 = [&](__half2 x) {
@@ -640,6 +643,67 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
               const float2 f = __half22float2(x);
               return __floats2half2_rn(plnr_apply_act(f.x, p.act, p.alpha), plnr_apply_act(f.y, p.act, p.alpha));
             };
+            auto finish = [&](uint4& val, const __half2* sch, const __half2* sfh, const uint4& res4) {
+              __half2* vh = reinterpret_cast<__half2*>(&val);
+              const __half2* rh = reinterpret_cast<const __half2*>(&res4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __half2 x;
+                if (kAct == 1 && act_first) x = __hfma2_relu(vh[e], sch[e], sfh[e]);
+                else {
+                  x = __hfma2(vh[e], sch[e], sfh[e]);
+                  if (act_first) x = act2(x);
+                }
+                if (has_res) {
+                  x = __hadd2(x, rh[e]);
+                  if (!p.res_after) x = act2(x);
+                }
+                vh[e] = x;
+              }
+            };
+            if (kWide) {
+              // 2 KB stage per warp: the whole 32-column chunk is transposed in ONE round trip (four STS, one warp barrier,
+              // four LDS) and the four 16-byte results are finished together -- twice the independent work per dependent
+              // step of this latency-bound chain (12 % issue utilisation with the two-round version, profiles/r02_kernel_experiments.md 6).
+              // Row of 64 B = four 16-byte slots, slot = piece ^ f(row), f = bit-reversed (row >> 1) & 3: conflict-free both ways.
+              const uint32_t wsw = (((uint32_t)lane >> 1) & 1u) << 1 | (((uint32_t)lane >> 2) & 1u);
+              const uint32_t rsw = (((uint32_t)lane >> 2) & 1u) << 1 | (((uint32_t)lane >> 3) & 1u);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 pk;
+                pk.x = pack_half2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+                pk.y = pack_half2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+                pk.z = pack_half2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+                pk.w = pack_half2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+                *reinterpret_cast<uint4*>(st_o + lane * 64 + (((uint32_t)q ^ wsw) << 4)) = pk;
+              }
+              uint4 sc4[2], sf4[2];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                sc4[h] = *reinterpret_cast<const uint4*>(ep_hscale + c0 + h * 16 + piece * 8);
+                sf4[h] = *reinterpret_cast<const uint4*>(ep_hshift + c0 + h * 16 + piece * 8);
+              }
+              __syncwarp();
+              uint4 val[4];
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const int row = 16 * i + (lane >> 1);
+                  val[2 * h + i] = *reinterpret_cast<const uint4*>(st_o + row * 64 + ((((uint32_t)(2 * h + piece)) ^ rsw) << 4));
+                }
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  finish(val[2 * h + i], reinterpret_cast<const __half2*>(&sc4[h]), reinterpret_cast<const __half2*>(&sf4[h]), rv[2 * h + i]);
+                  const bool ok = g.row[i] >= 0;                         // rim rows: computed, not stored (predicated store, no branch)
+                  __half* dst = p.y + (size_t)(ok ? g.row[i] : 0) * p.yld + p.ycoff + cb + h * 16 + piece * 8;
+                  if (ok) *reinterpret_cast<uint4*>(dst) = val[2 * h + i];
+                }
+              __syncwarp();                    // the stage is rewritten by the next chunk
+              return;
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -653,39 +717,29 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
               }
               const uint4 sc4 = *reinterpret_cast<const uint4*>(ep_hscale + c0 + h * 16 + piece * 8);
               const uint4 sf4 = *reinterpret_cast<const uint4*>(ep_hshift + c0 + h * 16 + piece * 8);
-              const __half2* sch = reinterpret_cast<const __half2*>(&sc4);
-              const __half2* sfh = reinterpret_cast<const __half2*>(&sf4);
               __syncwarp();
 #pragma unroll
               for (int i = 0; i < 2; ++i) {
                 const int row = 16 * i + (lane >> 1);
                 uint4 val = *reinterpret_cast<const uint4*>(st_o + row * 32 + ((((uint32_t)piece) ^ ((uint32_t)(row >> 2) & 1u)) << 4));
                 if (g.row[i] >= 0) {
-                  __half2* vh = reinterpret_cast<__half2*>(&val);
-                  const __half2* rh = reinterpret_cast<const __half2*>(&rv[2 * h + i]);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    __half2 x;
-                    if (kAct == 1 && act_first) x = __hfma2_relu(vh[e], sch[e], sfh[e]);
-                    else {
-                      x = __hfma2(vh[e], sch[e], sfh[e]);
-                      if (act_first) x = act2(x);
-                    }
-                    if (has_res) {
-                      x = __hadd2(x, rh[e]);
-                      if (!p.res_after) x = act2(x);
-                    }
-                    vh[e] = x;
-                  }
+                  finish(val, reinterpret_cast<const __half2*>(&sc4), reinterpret_cast<const __half2*>(&sf4), rv[2 * h + i]);
                   *reinterpret_cast<uint4*>(p.y + (size_t)g.row[i] * p.yld + p.ycoff + cb + h * 16 + piece * 8) = val;
                 }
               }
               __syncwarp();                    // the 1 KB stage is rewritten by the next half / chunk
             }
           };
-          if (p.act == PLNR_ACT_RELU) chunk_math(ActTag<1>{});
-          else if (p.act == PLNR_ACT_LEAKY && p.alpha >= 0.f && p.alpha <= 1.f) chunk_math(ActTag<2>{});
-          else chunk_math(ActTag<0>{});
+          const bool leaky01 = p.act == PLNR_ACT_LEAKY && p.alpha >= 0.f && p.alpha <= 1.f;
+          if (p.stage_wide) {
+            if (p.act == PLNR_ACT_RELU) chunk_math(ActTag<1>{}, ActTag<1>{});
+            else if (leaky01) chunk_math(ActTag<2>{}, ActTag<1>{});
+            else chunk_math(ActTag<0>{}, ActTag<1>{});
+          } else {
+            if (p.act == PLNR_ACT_RELU) chunk_math(ActTag<1>{}, ActTag<0>{});
+            else if (leaky01) chunk_math(ActTag<2>{}, ActTag<0>{});
+            else chunk_math(ActTag<0>{}, ActTag<0>{});
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) rv[i] = rvn[i];
           if (estamp && estamp_i < 1424) p.prof[estamp_i++] = clock64() - t_entry;
@@ -760,6 +814,7 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 static inline int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 
 struct ShiftPlan {
+  int stage_wide;
   int cg, n_tile, na, nb, b_resident, rows_max, Wv, Hv, halo;
   int cs, pv_t, pv_l;       // conv stride (1 | 2); virtual padding rows / columns of the (plane) grid
   uint32_t a_buf_bytes, b_stage_bytes;
@@ -830,7 +885,7 @@ static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
   pl.b_stage_bytes = (uint32_t)(pl.n_tile / pl.cg) * 128;
   const int kst = d->kh * d->kw * (x->c / 64) + c2 / 64;    // weight boxes per tile: (chunk, tap) + shortcut chunks
   const int num_n_tiles = (y->c + pl.n_tile - 1) / pl.n_tile;
-  const size_t fixed = kEpiBytes + 16 * kMaxA + 16 * kMaxB + 64 + kStageBytes + 1024;
+  size_t fixed = kEpiBytes + 16 * kMaxA + 16 * kMaxB + 64 + kStageBytes + 1024;
   const size_t budget = 232448;
   // resident weights: all (chunk, tap) boxes stay in shared memory for the whole kernel
   pl.na = 2;
@@ -838,6 +893,16 @@ static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
     return num_n_tiles == 1 && kst <= kMaxB &&
            fixed + (size_t)na_ * pl.a_buf_bytes + (size_t)kst * (size_t)(pl.n_tile / cg_) * 128 <= budget;
   };
+  // Epilogue stage: 2 KB per warp (one transposition round trip per 32-column chunk) unless those 8 KB are what keeps the
+  // weights resident (128 -> 128 channels at 28x28 as a CTA pair: 144 KB of filter + two A buffers fill the SM).
+  {
+    const bool res_narrow = resident_fits(1, 2) || (m_tiles_128 >= 2 && resident_fits(2, 2));
+    fixed += kStageBytes;
+    const bool res_wide = resident_fits(1, 2) || (m_tiles_128 >= 2 && resident_fits(2, 2));
+    pl.stage_wide = (res_wide || !res_narrow) ? 1 : 0;
+    if (const char* e = getenv("PLNR_SHIFT_STAGE_WIDE")) pl.stage_wide = atoi(e) ? 1 : 0;
+    if (!pl.stage_wide) fixed -= kStageBytes;
+  }
   if (forced == 0 && !resident_fits(1, 2) && m_tiles_128 >= 2 && pl.n_tile % 32 == 0 && resident_fits(2, 2)) {
     pl.cg = 2;
     pl.b_stage_bytes = (uint32_t)(pl.n_tile / 2) * 128;
@@ -987,6 +1052,7 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
   p.div_wv = make_fastdiv((uint32_t)p.Wv);
   p.div_mt = make_fastdiv((uint32_t)p.num_m_tiles);
   p.na = pl.na; p.nb = pl.nb; p.b_resident = pl.b_resident;
+  p.stage_wide = pl.stage_wide;
   p.a_buf_bytes = pl.a_buf_bytes; p.b_stage_bytes = pl.b_stage_bytes;
   p.idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)((kTileM * cg) >> 4) << 24);
   uint32_t cols = 32;
