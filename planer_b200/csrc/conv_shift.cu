@@ -228,7 +228,7 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
   // programmatic dependent launch: let the next kernel of the stream start its own set-up, then wait until every
   // kernel before this one has completed and flushed its results (no-ops when launched without the attribute)
   ptx::grid_launch_dependents();
-  ptx::grid_dependency_wait();
+  if (warp != 0) ptx::grid_dependency_wait();      // the producer warp first requests weights (below), then waits
   if (stamp && threadIdx.x == 0) {
     unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     p.prof[1400] = (long long)gt; p.prof[1401] = clock64() - t_entry;
@@ -242,6 +242,10 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
     const long long t_all0 = clock64();
     SegList segs;
     segs.init(p, unit, nunits);
+    // (Requesting the first weight boxes BEFORE this wait -- weights do not depend on the previous kernel -- was tried: fine
+    // in the single-CTA stacked kernel, intermittent launch failures in this kernel's CTA-pair configuration, removed:
+    // profiles/r02_kernel_experiments.md 8.)
+    ptx::grid_dependency_wait();
     for (int k = 0; k < segs.nseg; ++k) {
       const Seg sg = segs.at(k);
       const int tile = sg.tile;

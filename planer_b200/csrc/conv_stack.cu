@@ -147,13 +147,34 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // programmatic dependent launch (common.cuh): the next kernel may be scheduled from here on; this one touches nothing the
+  // previous kernel wrote before its warps pass griddepcontrol.wait below
+  ptx::grid_launch_dependents();
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     uint32_t ab = 0, aph = 0, bs = 0;
-    bool first = true;
     long long t_wait = 0;
     const long long t_all0 = clock64();
+    // this CTA's filter taps: loaded once, resident.  Weights do not depend on the previous kernel, so they are requested
+    // BEFORE the dependency wait: a CTA that starts in the previous kernel's tail has them (and L2 has them for everyone)
+    // by the time the activations may be read
+    if (m_first < p.num_m_tiles) {
+      for (int cc = 0; cc < p.cchunks + p.c2chunks; ++cc) {
+        const bool sc = cc >= p.cchunks;
+        const int ntaps = sc ? 1 : p.R * kS;
+        const int kbase = sc ? p.R * kS * p.C + (cc - p.cchunks) * 64 : cc * 64;
+        for (int tap = 0; tap < ntaps; ++tap, ++bs) {
+          if (ptx::elect_one()) {
+            const uint32_t full = bar_bfull + 8 * bs;
+            ptx::mbar_arrive_expect_tx(full, kBBox);
+            ptx::tma_load_2d(sB + bs * kBBox, &mapB, full, tap * p.C + kbase, n0);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    ptx::grid_dependency_wait();
     for (int m_idx = m_first; m_idx < p.num_m_tiles; m_idx += m_step) {
       const long long o0 = (long long)m_idx * kTilePos;
       const long long v0 = o0 / Wv;
@@ -181,20 +202,7 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         }
         __syncwarp();
         if (++ab == na) { ab = 0; aph ^= 1; }
-        if (first) {                                   // this CTA's filter taps: loaded once, resident
-          const int ntaps = sc ? 1 : p.R * kS;
-          const int kbase = sc ? p.R * kS * p.C + (cc - p.cchunks) * 64 : cc * 64;
-          for (int tap = 0; tap < ntaps; ++tap, ++bs) {
-            if (ptx::elect_one()) {
-              const uint32_t full = bar_bfull + 8 * bs;
-              ptx::mbar_arrive_expect_tx(full, kBBox);
-              ptx::tma_load_2d(sB + bs * kBBox, &mapB, full, tap * p.C + kbase, n0);
-            }
-            __syncwarp();
-          }
-        }
       }
-      first = false;
     }
     if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 0] = t_wait; p.prof[blockIdx.x * 8 + 1] = clock64() - t_all0; }
   } else if (warp == 1) {
@@ -259,6 +267,7 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 2] = t_full; p.prof[blockIdx.x * 8 + 3] = t_tempty; p.prof[blockIdx.x * 8 + 4] = clock64() - t_all0; }
   } else if (warp >= 4) {
     // ===================================== epilogue (16 warps) =================================
+    ptx::grid_dependency_wait();             // residual reads / output writes only after the previous kernel has completed
     // The epilogue of this kernel is a chain of dependent instructions (TMEM loads, shuffles, the boundary exchange):
     // spread over SIXTEEN warps -- four TMEM lane quarters x four 16-channel groups -- each warp's chain is half as long
     // as with eight, and the SM's issue slots (mostly idle in these kernels) absorb the extra warps.
@@ -598,6 +607,21 @@ int plnr_conv2d_stack(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
   int per_block = ctx->sm_count / pl.NT;                        // every output-channel block gets the same number of CTAs
   if (per_block > pl.num_m_tiles) per_block = pl.num_m_tiles;
   int grid = per_block * pl.NT;
-  kern<<<grid, kThreads, pl.smem_bytes, ctx->stream>>>(mapA, mapB, mapA2, p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = pl.smem_bytes;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = plnr_pdl_enabled() ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mapA, mapB, mapA2, p);
+  if (le != cudaSuccess) {
+    plnr_set_error("launch of conv_stack_f16_kernel failed: %s", cudaGetErrorString(le));
+    return PLNR_ERR_CUDA;
+  }
   return plnr_after_launch(ctx, "conv2d_stack");
 }
