@@ -220,7 +220,8 @@ def per_kernel_profile(net, x_dev, reps=3):
             lib.plnr_event_destroy(a); lib.plnr_event_destroy(b)
     fused = [f for f in ex.fused_stems.values()]
     in_kind = 'conv' if fused else 'input'
-    in_name = ('+'.join(fused[0]['conv'].fused + fused[0]['pool'].fused) + ' (one kernel, at input time)') if fused else 'input layout'
+    in_name = ('+'.join(fused[0]['conv'].fused + (fused[0]['pool'].fused if fused[0]['pool'] else [])) +
+               ' (one kernel, at input time)') if fused else 'input layout'
     return [{'kind': k, 'name': nm, 'ms': t, 'kernel': kn}
             for k, nm, t, kn in zip([in_kind] + list(ex.kinds), [in_name] + list(ex.names), best, kernels)]
 

@@ -137,6 +137,16 @@ int plnr_stem_pool_fwd(plnr_ctx* ctx, const void* x, int n, int c, int h, int w,
 int plnr_stem_pool_fwd_u8(plnr_ctx* ctx, const void* x, int n, int c, int h, int w, const void* w_packed,
                           const float* scale, const float* shift, int kh, int kw, int stride, int pad_t, int pad_l,
                           int pad_b, int pad_r, int act, int pool_k, int pool_stride, int pool_pad, const plnr_tensor* y);
+/* Small first layer on the CUDA cores (csrc/stem_direct.cu): 3x3 / stride-1 / pad-1 convolution of an NCHW image x (n, c <= 3,
+ * h, w; x_dtype PLNR_F16 or PLNR_U8) to y->c <= 32 channels (multiple of 8) + *scale + shift + activation -> pixel-major y.
+ * Replaces Conv2d (planer/layer.py:22-26 + planer/util.py:17-44) -> BatchNorm (:125-127) -> ReLU / LeakyReLU (:44-51) at
+ * the head of YOLOv3-style networks, where K = 27 and N = 32 leave the tensor cores nothing to do.  w_oihw: DEVICE pointer
+ * to the fp16 OIHW filter as stored by the model; scale / shift: DEVICE fp32 [y->c] or NULL.  All three are read back to the
+ * host once per pointer (first call, outside graph capture) and then travel in the kernel parameters. */
+int plnr_stem3x3_supported(int dtype, int c, int cout, int kh, int kw, int stride, int pad_t, int pad_l, int pad_b, int pad_r,
+                           int dil);
+int plnr_stem3x3_fwd(plnr_ctx* ctx, const void* x, int x_dtype, int n, int c, int h, int w, const void* w_oihw,
+                     const float* scale, const float* shift, int act, float alpha, const plnr_tensor* y);
 /* pixel-major view x -> NCHW dense y.  Graph exit: planer/net.py:100. */
 int plnr_nhwc_to_nchw(plnr_ctx* ctx, const plnr_tensor* x, int x_dtype, void* y, int y_dtype);
 /* flat cast, n elements (Net.half, planer/net.py:26-29). */

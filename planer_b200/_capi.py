@@ -57,6 +57,8 @@ PROTOTYPES = {
     'plnr_stem_pool_geometry': [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
     'plnr_stem_pool_fwd': [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P] + [C.c_int] * 11 + [_TP],
     'plnr_stem_pool_fwd_u8': [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P] + [C.c_int] * 11 + [_TP],
+    'plnr_stem3x3_supported': [C.c_int] * 11,
+    'plnr_stem3x3_fwd': [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_float, _TP],
     'plnr_nhwc_to_nchw': [_P, _TP, C.c_int, _P, C.c_int],
     'plnr_cast': [_P, _P, C.c_int, _P, C.c_int, C.c_int64],
     'plnr_pack_conv_weight': [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],

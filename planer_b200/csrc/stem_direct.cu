@@ -1,0 +1,169 @@
+// First layer of an image network with a SMALL filter bank: 3x3 / stride-1 / pad-1 convolution of a 1..4-channel NCHW image
+// (fp16 or uint8) to <= 32 channels, + scale / shift (bias, folded BatchNorm) + ReLU / LeakyReLU, written pixel-major (NHWC).
+//
+// Replaces, for YOLOv3's 3 -> 32 stem, the reference chain Conv2d (planer/layer.py:22-26 + planer/util.py:17-44) ->
+// BatchNorm (planer/layer.py:125-127) -> LeakyReLU (planer/layer.py:48-51) and this library's earlier two launches
+// (plnr_stem_pack + a tensor-core conv with K = 48, N = 32: 29 TFLOP/s, 12 % of the YOLOv3 step).  With K = 27 and
+// N = 32 the layer is 9.6 GFLOP against 16.6 MB read + 354 MB written per 32 images: it belongs on the CUDA cores, next to
+// the stores.  One thread = one output pixel, all 32 channels:
+//   * the filter lives in the KERNEL PARAMETERS (27 taps x 16 channel pairs of fp16 = 1.7 KB), so every HFMA2 takes its
+//     weight operand straight from the constant bank -- no shared memory, no weight loads;
+//   * the 27 input values of a pixel are 2-byte global loads, coalesced across the warp (consecutive pixels) and served by L1
+//     (neighbouring pixels share 6 of 9 positions);
+//   * products of one filter row (9 terms) accumulate in packed fp16, the three rows are added in fp32, the sum is rounded to
+//     fp16 once (the reference's conv output is an fp16 array), then scale / shift as one HFMA2 and the activation in fp16,
+//     like every other conv epilogue of this library;
+//   * a pixel's 32 channels are 64 contiguous bytes: four 16-byte stores, 2 KB contiguous per warp.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxCout = 32, kTaps = 27;
+
+struct Stem3Params {
+  const void* x;
+  int N, C, H, W;
+  __half* y; int yld, ycoff, Cout;
+  int act; float alpha;
+  __half2 w[kTaps][kMaxCout / 2];       // [(c*3 + r)*3 + s][channel pair], zero beyond C / Cout
+  __half2 scale[kMaxCout / 2], shift[kMaxCout / 2];
+};
+
+template <typename Tin> __device__ __forceinline__ __half ld_h(const Tin* p);
+template <> __device__ __forceinline__ __half ld_h<__half>(const __half* p) { return __ldg(p); }
+template <> __device__ __forceinline__ __half ld_h<uint8_t>(const uint8_t* p) { return __ushort2half_rn((unsigned short)__ldg(p)); }
+
+template <typename Tin, int kAct>
+__global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Stem3Params p) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)p.N * p.H * p.W;
+  if (pix >= total) return;
+  const int w_ = (int)(pix % p.W);
+  const long long t = pix / p.W;
+  const int h = (int)(t % p.H), n = (int)(t / p.H);
+  const Tin* x = reinterpret_cast<const Tin*>(p.x) + (size_t)n * p.C * p.H * p.W;
+  const __half zero = __float2half_rn(0.f);
+  float tot[kMaxCout];
+#pragma unroll
+  for (int j = 0; j < kMaxCout; ++j) tot[j] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int ih = h + r - 1;
+    const bool rok = ih >= 0 && ih < p.H;
+    __half2 acc[kMaxCout / 2];
+#pragma unroll
+    for (int j = 0; j < kMaxCout / 2; ++j) acc[j] = __half2half2(zero);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c < p.C) {
+        const Tin* row = x + ((size_t)c * p.H + (rok ? ih : 0)) * p.W;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int iw = w_ + s - 1;
+          const __half xv = (rok && iw >= 0 && iw < p.W) ? ld_h<Tin>(row + iw) : zero;
+          const __half2 x2 = __half2half2(xv);
+#pragma unroll
+          for (int j = 0; j < kMaxCout / 2; ++j) acc[j] = __hfma2(x2, p.w[(c * 3 + r) * 3 + s][j], acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxCout / 2; ++j) {
+      const float2 f = __half22float2(acc[j]);
+      tot[2 * j] += f.x; tot[2 * j + 1] += f.y;
+    }
+  }
+  __half* yrow = p.y + (size_t)pix * p.yld + p.ycoff;
+  const __half2 alpha2 = __float2half2_rn(p.alpha);
+#pragma unroll
+  for (int q = 0; q < kMaxCout / 8; ++q) {
+    if (q * 8 < p.Cout) {
+      uint4 out;
+      __half2* oh = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = q * 4 + e;
+        __half2 v = __floats2half2_rn(tot[2 * j], tot[2 * j + 1]);          // conv output rounded to fp16 once
+        if (kAct == 1) v = __hfma2_relu(v, p.scale[j], p.shift[j]);
+        else {
+          v = __hfma2(v, p.scale[j], p.shift[j]);
+          if (kAct == 2) v = __hmax2(v, __hmul2(v, alpha2));
+          else if (kAct == 3) {
+            const float2 f = __half22float2(v);
+            v = __floats2half2_rn(plnr_apply_act(f.x, p.act, p.alpha), plnr_apply_act(f.y, p.act, p.alpha));
+          }
+        }
+        oh[e] = v;
+      }
+      *reinterpret_cast<uint4*>(yrow + q * 8) = out;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int plnr_stem3x3_supported(int dtype, int c, int cout, int kh, int kw, int stride, int pad_t, int pad_l, int pad_b,
+                                      int pad_r, int dil) {
+  if (dtype != PLNR_F16) return 0;
+  if (c < 1 || c > 3 || cout < 8 || cout > kMaxCout || cout % 8 != 0) return 0;
+  if (kh != 3 || kw != 3 || stride != 1 || dil != 1) return 0;
+  return (pad_t == 1 && pad_l == 1 && pad_b == 1 && pad_r == 1) ? 1 : 0;
+}
+
+// w: DEVICE pointer to the OIHW fp16 filter (cout, c, 3, 3); scale / shift: DEVICE fp32 [cout] or NULL.  They are copied to
+// the host ONCE per (pointer, ctx) -- one synchronous 2 KB read at the first call, i.e. at executor build -- and travel in the
+// kernel parameters from then on, so the call is safe inside CUDA-graph capture after that first eager call.
+extern "C" int plnr_stem3x3_fwd(plnr_ctx* ctx, const void* x, int x_dtype, int n, int c, int h, int w, const void* w_oihw,
+                                const float* scale, const float* shift, int act, float alpha, const plnr_tensor* y) {
+  PLNR_REQUIRE(ctx && x && w_oihw && y && y->ptr, "stem3x3: NULL argument");
+  PLNR_REQUIRE(x_dtype == PLNR_F16 || x_dtype == PLNR_U8, "stem3x3: the image must be fp16 or uint8");
+  PLNR_REQUIRE(plnr_stem3x3_supported(PLNR_F16, c, y->c, 3, 3, 1, 1, 1, 1, 1, 1), "stem3x3: unsupported problem (c=%d cout=%d)", c, y->c);
+  PLNR_REQUIRE(y->n == n && y->h == h && y->w == w, "stem3x3: output is (%d,%d,%d), expected (%d,%d,%d)", y->n, y->h, y->w, n, h, w);
+  PLNR_REQUIRE((reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && y->ld % 8 == 0 && y->coff % 8 == 0,
+               "stem3x3: output rows must be 16-byte aligned");
+  const int cout = y->c;
+  std::string key(reinterpret_cast<const char*>(&w_oihw), sizeof(void*));
+  key.append(reinterpret_cast<const char*>(&scale), sizeof(void*));
+  key.append(reinterpret_cast<const char*>(&shift), sizeof(void*));
+  auto it = ctx->stem3_filters.find(key);
+  if (it == ctx->stem3_filters.end()) {
+    PLNR_REQUIRE(!ctx->capturing, "stem3x3: the first call for a filter must happen outside graph capture");
+    std::vector<char> blob(sizeof(__half) * (size_t)cout * c * 9 + sizeof(float) * 2 * (size_t)cout, 0);
+    PLNR_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLNR_CHECK_CUDA(cudaMemcpy(blob.data(), w_oihw, sizeof(__half) * (size_t)cout * c * 9, cudaMemcpyDeviceToHost));
+    float* sc = reinterpret_cast<float*>(blob.data() + sizeof(__half) * (size_t)cout * c * 9);
+    float* sf = sc + cout;
+    for (int i = 0; i < cout; ++i) { sc[i] = 1.f; sf[i] = 0.f; }
+    if (scale) PLNR_CHECK_CUDA(cudaMemcpy(sc, scale, sizeof(float) * cout, cudaMemcpyDeviceToHost));
+    if (shift) PLNR_CHECK_CUDA(cudaMemcpy(sf, shift, sizeof(float) * cout, cudaMemcpyDeviceToHost));
+    it = ctx->stem3_filters.emplace(key, std::move(blob)).first;
+  }
+  const __half* hw = reinterpret_cast<const __half*>(it->second.data());
+  const float* sc = reinterpret_cast<const float*>(it->second.data() + sizeof(__half) * (size_t)cout * c * 9);
+  const float* sf = sc + cout;
+
+  Stem3Params p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.N = n; p.C = c; p.H = h; p.W = w;
+  p.y = (__half*)y->ptr; p.yld = y->ld; p.ycoff = y->coff; p.Cout = cout;
+  p.act = act; p.alpha = alpha;
+  for (int ci = 0; ci < c; ++ci)
+    for (int r = 0; r < 3; ++r)
+      for (int s = 0; s < 3; ++s)
+        for (int co = 0; co < cout; ++co)
+          reinterpret_cast<__half*>(&p.w[(ci * 3 + r) * 3 + s][0])[co] = hw[((size_t)co * c + ci) * 9 + r * 3 + s];
+  for (int co = 0; co < kMaxCout; ++co) {
+    reinterpret_cast<__half*>(&p.scale[0])[co] = __float2half_rn(co < cout ? sc[co] : 0.f);
+    reinterpret_cast<__half*>(&p.shift[0])[co] = __float2half_rn(co < cout ? sf[co] : 0.f);
+  }
+  const long long total = (long long)n * h * w;
+  PLNR_REQUIRE(total > 0 && (total + 255) / 256 < (1ll << 31), "stem3x3: bad extents");
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  const int kact = act == PLNR_ACT_RELU ? 1 : (act == PLNR_ACT_LEAKY && alpha >= 0.f && alpha <= 1.f ? 2 : (act == PLNR_ACT_NONE ? 0 : 3));
+#define LAUNCH(T, A) stem3x3_kernel<T, A><<<grid, 256, 0, ctx->stream>>>(p)
+#define LAUNCH_T(T) do { if (kact == 1) LAUNCH(T, 1); else if (kact == 2) LAUNCH(T, 2); else if (kact == 0) LAUNCH(T, 0); else LAUNCH(T, 3); } while (0)
+  if (x_dtype == PLNR_U8) LAUNCH_T(uint8_t); else LAUNCH_T(__half);
+#undef LAUNCH_T
+#undef LAUNCH
+  return plnr_after_launch(ctx, "stem3x3");
+}

@@ -114,6 +114,27 @@ class Executor:
             return None
         return st
 
+    def _direct_stem_of(self, vid):
+        """The conv step when graph input ``vid`` feeds ONLY a 3x3 / stride-1 / pad-1 convolution with <= 3 input and <= 32
+        output channels (YOLOv3's first layer): csrc/stem_direct.cu computes conv + scale / shift + activation on the CUDA
+        cores straight from the caller's NCHW (fp16 / uint8) array.  None otherwise."""
+        v = self.values[vid]
+        if self.dtype != np.float16 or len(v.shape) != 4 or v.is_output or os.environ.get('PLNR_NO_DIRECT_STEM') == '1':
+            return None
+        users = [st for st in self.plan.steps if vid in [self._root(r) for r in st.reads()]]
+        if len(users) != 1 or users[0].op != 'conv' or self._root(users[0].ins[0]) != vid:
+            return None
+        st, a = users[0], users[0].attrs
+        if st.res is not None or st.shortcut is not None or a.get('flip') or a['group'] != 1:
+            return None
+        out = self.values[self._root(st.out)]
+        if out.is_output or out.slice_of is not None:
+            return None
+        k = self.values[st.w].shape
+        if not ops.stem3x3_supported(self.dtype, v.shape[1], k[0], k[2], k[3], a['strides'], a['dilations'], a['pads']):
+            return None
+        return st
+
     def _fused_stem_of(self, vid):
         """(conv step, maxpool step) when graph input ``vid`` feeds conv -> (bn) -> relu -> maxpool(3x3/s2/p1) and the
         fused first-layer kernel (csrc/stem_pool.cu) supports the shapes; else None."""
@@ -269,10 +290,14 @@ class Executor:
         for vid in self.input_ids:
             shp = vals[vid].shape
             fs = self._fused_stem_of(vid)
+            ds = self._direct_stem_of(vid) if fs is None else None
             st = self._stem_of(vid)
             if fs is not None:
                 self.fused_stems[vid] = dict(conv=fs[0], pool=fs[1], run=None)
                 a = None                                   # the kernel reads the caller's NCHW array in place
+            elif ds is not None:
+                self.fused_stems[vid] = dict(conv=ds, pool=None, run=None)       # small first layer on the CUDA cores, at input time
+                a = None
             elif st is not None:
                 kshape, at = vals[st.w].shape, st.attrs
                 g = ops.stem_geometry(shp[2], shp[3], kshape[2], kshape[3], at['strides'][0], at['pads'])
@@ -303,7 +328,7 @@ class Executor:
             self.input_bytes += self._nbytes(vid, self.input_dtypes[k].itemsize)
             fs = self.fused_stems.get(vid)
             if fs is not None:
-                self.input_bytes += self._nbytes(fs['pool'].out) + self._nbytes(fs['conv'].w)
+                self.input_bytes += self._nbytes((fs['pool'] or fs['conv']).out) + self._nbytes(fs['conv'].w)
             elif self.arr.get(vid) is not None:
                 a = self.arr[vid]
                 self.input_bytes += int(np.prod(a.shape)) * a.dtype.itemsize
@@ -358,6 +383,12 @@ class Executor:
                 self.nchw_exits += 1
                 return lambda: ops.conv2d_into(x, wp, flat, kh, kw, a['strides'], a['dilations'], a['pads'], 1, scale, shift,
                                                None, st.act, st.alpha, out_nchw=True)
+            if fused is not None and fused['pool'] is None:
+                y = alloc(st.out)
+                K16 = self._packed(st.name + '|cast', lambda: K.astype(np.float16))
+                self._keep += [K16, y]
+                fused['run'] = lambda xf: ops.stem3x3_into(xf, K16, scale, shift, y, st.act, st.alpha)
+                return None
             if fused is not None:
                 a = st.attrs
                 yp = alloc(fused['pool'].out)

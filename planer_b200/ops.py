@@ -408,6 +408,24 @@ def stem_pool_into(x_flat, w_packed, scale, shift, y, kh, kw, stride, pads, act=
     return y
 
 
+def stem3x3_supported(dtype, c, cout, kh, kw, strides, dilations, pads):
+    """True when the small-first-layer kernel (csrc/stem_direct.cu) applies: fp16 net, 3x3 / s1 / p1, c <= 3, cout <= 32."""
+    if strides[0] != strides[1] or dilations[0] != dilations[1]:
+        return False
+    return bool(B.lib().plnr_stem3x3_supported(_capi.dtype_code(dtype), c, cout, kh, kw, strides[0], pads[0], pads[1], pads[2],
+                                               pads[3], dilations[0]))
+
+
+def stem3x3_into(x_flat, K16, scale, shift, y, act=ACT_NONE, alpha=0.0):
+    """x_flat: NCHW image (float16 / uint8); K16: the OIHW filter as a flat float16 device array; y: nhwc output."""
+    n, c, h, w = x_flat.shape
+    t = y.tensor()
+    p = lambda a: a.ptr if a is not None else None
+    _capi.check(B.lib().plnr_stem3x3_fwd(B.ctx(), x_flat.ptr, _capi.src_dtype_code(x_flat.dtype), n, c, h, w, K16.ptr, p(scale),
+                                         p(shift), int(act), float(alpha), C.byref(t)), 'plnr_stem3x3_fwd')
+    return y
+
+
 def nhwc_to_nchw_into(x, y_flat):
     t = x.tensor()
     _capi.check(B.lib().plnr_nhwc_to_nchw(B.ctx(), C.byref(t), _capi.dtype_code(x.dtype), y_flat.ptr,

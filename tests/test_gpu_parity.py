@@ -745,3 +745,46 @@ def test_zero_copy_concat_and_nchw_exit_equal_the_copying_path(planer, monkeypat
     assert ex.nchw_exits == 0 and ex.placed_concat_inputs == 0
     for s, t in zip(a, b):
         assert np.array_equal(s, t)
+
+
+@pytest.mark.parametrize('cfg', [(2, 3, 33, 41, 32, 'leaky', np.float16), (1, 3, 64, 64, 16, 'relu', np.uint8),
+                                 (3, 1, 17, 19, 8, 'none', np.float16), (2, 2, 20, 24, 24, 'sigmoid', np.float16)])
+def test_small_first_layer_kernel_vs_oracle(planer, cfg):
+    """csrc/stem_direct.cu (3x3 / s1 / p1, <= 3 -> <= 32 channels, CUDA cores, filter in the kernel parameters) against the
+    oracle's conv -> batchnorm -> activation chain; odd image sizes, one to three input channels, uint8 pixels."""
+    from planer_b200 import ops, backend as B
+    n, c, h, w, cout, act, xdt = cfg
+    rng = np.random.default_rng(n * 100 + cout)
+    x = rng.integers(0, 256, (n, c, h, w), dtype=np.uint8) if xdt == np.uint8 else rng.standard_normal((n, c, h, w)).astype(np.float16)
+    K = (rng.standard_normal((cout, c, 3, 3)) * np.sqrt(2.0 / (c * 9))).astype(np.float16)
+    if xdt == np.uint8:
+        K = (K.astype(np.float32) / 64).astype(np.float16)
+    bk = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bb = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    ref = oracle.conv2d(x.astype(np.float32), K.astype(np.float32), None, 1, (1, 1), (1, 1), (1, 1, 1, 1))
+    ref = oracle.batchnorm(ref, bk.reshape(1, -1, 1, 1), bb.reshape(1, -1, 1, 1))
+    ref = {'leaky': lambda v: oracle.leakyrelu(v, 0.1), 'relu': oracle.relu, 'none': lambda v: v,
+           'sigmoid': oracle.sigmoid}[act](ref)
+    code = {'leaky': ops.ACT_LEAKY, 'relu': ops.ACT_RELU, 'none': ops.ACT_NONE, 'sigmoid': ops.ACT_SIGMOID}[act]
+    scale, shift = ops.fold_affine(None, B.asarray(bk), B.asarray(bb), cout)
+    y = B.empty((n, cout, h, w), np.float16, 'nhwc')
+    ops.stem3x3_into(B.asarray(x), B.asarray(K), scale, shift, y, code, 0.1)
+    B.synchronize()
+    assert rel_err(y.get(), ref) <= 5e-3
+
+
+def test_yolov3_first_layer_runs_on_the_direct_kernel(planer, monkeypatch):
+    """The planner hands YOLOv3's 3 -> 32 stem to csrc/stem_direct.cu (one input-time launch, no packing kernel); the
+    network output equals the packed tensor-core path to fp16 rounding of differently ordered sums."""
+    model, blob = cases.get_model('yolov3_quarter')
+    x = np.random.default_rng(47).standard_normal((2, 3, 96, 96)).astype(np.float16)
+    net = planer.from_model(model, blob, half=True)
+    a = net(x)
+    ex = net.executor([x.shape], [x.dtype])
+    assert len(ex.fused_stems) == 1 and list(ex.fused_stems.values())[0]['pool'] is None and not ex.stems
+    monkeypatch.setenv('PLNR_NO_DIRECT_STEM', '1')
+    net2 = planer.from_model(model, blob, half=True)
+    b = net2(x)
+    assert not net2.executor([x.shape], [x.dtype]).fused_stems
+    for s, t in zip(a, b):
+        assert rel_err(s, t) <= 3e-3
