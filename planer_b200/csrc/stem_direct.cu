@@ -5,7 +5,7 @@
 // BatchNorm (planer/layer.py:125-127) -> LeakyReLU (planer/layer.py:48-51) and this library's earlier two launches
 // (plnr_stem_pack + a tensor-core conv with K = 48, N = 32: 29 TFLOP/s, 12 % of the YOLOv3 step).  With K = 27 and
 // N = 32 the layer is 9.6 GFLOP against 16.6 MB read + 354 MB written per 32 images: it belongs on the CUDA cores, next to
-// the stores.  One thread = one output pixel, all 32 channels:
+// the stores.  One thread = four adjacent output pixels x 16 channels:
 //   * the filter lives in the KERNEL PARAMETERS (27 taps x 16 channel pairs of fp16 = 1.7 KB), so every HFMA2 takes its
 //     weight operand straight from the constant bank -- no shared memory, no weight loads;
 //   * the 27 input values of a pixel are 2-byte global loads, coalesced across the warp (consecutive pixels) and served by L1
@@ -13,7 +13,7 @@
 //   * products of one filter row (9 terms) accumulate in packed fp16, the three rows are added in fp32, the sum is rounded to
 //     fp16 once (the reference's conv output is an fp16 array), then scale / shift as one HFMA2 and the activation in fp16,
 //     like every other conv epilogue of this library;
-//   * a pixel's 32 channels are 64 contiguous bytes: four 16-byte stores, 2 KB contiguous per warp.
+//   * a pixel's 32 channels are 64 contiguous bytes, written by the two threads of a pixel group as 2 x 2 16-byte stores.
 #include "common.cuh"
 
 namespace {
@@ -25,7 +25,7 @@ struct Stem3Params {
   int N, C, H, W;
   __half* y; int yld, ycoff, Cout;
   int act; float alpha;
-  __half2 w[kTaps][kMaxCout / 2];       // [(c*3 + r)*3 + s][channel pair], zero beyond C / Cout
+  alignas(16) __half2 w[kTaps][kMaxCout / 2];       // [(c*3 + r)*3 + s][channel pair], zero beyond C / Cout (16-byte constant loads)
   __half2 scale[kMaxCout / 2], shift[kMaxCout / 2];
 };
 
@@ -33,69 +33,102 @@ template <typename Tin> __device__ __forceinline__ __half ld_h(const Tin* p);
 template <> __device__ __forceinline__ __half ld_h<__half>(const __half* p) { return __ldg(p); }
 template <> __device__ __forceinline__ __half ld_h<uint8_t>(const uint8_t* p) { return __ushort2half_rn((unsigned short)__ldg(p)); }
 
+// One thread = FOUR horizontally adjacent output pixels x 16 channels (one half of the filter bank): a weight pair fetched
+// from the constant bank feeds four HFMA2 instead of one (the one-pixel version spent 285 LDC on 467 HFMA2 per pixel and ran
+// at 26 TFLOP/s), and the six input values of a filter row serve all four pixels.
+constexpr int kPix = 4;
+
 template <typename Tin, int kAct>
-__global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Stem3Params p) {
-  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)p.N * p.H * p.W;
-  if (pix >= total) return;
-  const int w_ = (int)(pix % p.W);
-  const long long t = pix / p.W;
+__global__ void __launch_bounds__(256, 2) stem3x3_kernel(const __grid_constant__ Stem3Params p) {
+  const int half_ = threadIdx.x & 1;                         // channels [16 half_, 16 half_ + 16)
+  const long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+  const int gw = (p.W + kPix - 1) / kPix;                    // pixel groups per row
+  const long long total = (long long)p.N * p.H * gw;
+  if (grp >= total) return;
+  const int g_ = (int)(grp % gw);
+  const long long t = grp / gw;
   const int h = (int)(t % p.H), n = (int)(t / p.H);
+  const int w0 = g_ * kPix;
   const Tin* x = reinterpret_cast<const Tin*>(p.x) + (size_t)n * p.C * p.H * p.W;
   const __half zero = __float2half_rn(0.f);
-  float tot[kMaxCout];
+  float tot[kPix][16];
 #pragma unroll
-  for (int j = 0; j < kMaxCout; ++j) tot[j] = 0.f;
+  for (int i = 0; i < kPix; ++i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) tot[i][j] = 0.f;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     const int ih = h + r - 1;
     const bool rok = ih >= 0 && ih < p.H;
-    __half2 acc[kMaxCout / 2];
+    __half2 acc[kPix][8];
 #pragma unroll
-    for (int j = 0; j < kMaxCout / 2; ++j) acc[j] = __half2half2(zero);
+    for (int i = 0; i < kPix; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = __half2half2(zero);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       if (c < p.C) {
         const Tin* row = x + ((size_t)c * p.H + (rok ? ih : 0)) * p.W;
+        __half2 xv[kPix + 2];                                // columns w0 - 1 .. w0 + 4, broadcast to both halves of a pair
+#pragma unroll
+        for (int q = 0; q < kPix + 2; ++q) {
+          const int iw = w0 + q - 1;
+          xv[q] = __half2half2((rok && iw >= 0 && iw < p.W) ? ld_h<Tin>(row + iw) : zero);
+        }
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-          const int iw = w_ + s - 1;
-          const __half xv = (rok && iw >= 0 && iw < p.W) ? ld_h<Tin>(row + iw) : zero;
-          const __half2 x2 = __half2half2(xv);
+          // this thread's 8 weight pairs of the tap: 16-byte constant-bank loads
+          const uint4* wt = reinterpret_cast<const uint4*>(&p.w[(c * 3 + r) * 3 + s][half_ * 8]);
+          const uint4 wa = wt[0], wb = wt[1];
+          const __half2 wv[8] = {*reinterpret_cast<const __half2*>(&wa.x), *reinterpret_cast<const __half2*>(&wa.y),
+                                 *reinterpret_cast<const __half2*>(&wa.z), *reinterpret_cast<const __half2*>(&wa.w),
+                                 *reinterpret_cast<const __half2*>(&wb.x), *reinterpret_cast<const __half2*>(&wb.y),
+                                 *reinterpret_cast<const __half2*>(&wb.z), *reinterpret_cast<const __half2*>(&wb.w)};
 #pragma unroll
-          for (int j = 0; j < kMaxCout / 2; ++j) acc[j] = __hfma2(x2, p.w[(c * 3 + r) * 3 + s][j], acc[j]);
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int i = 0; i < kPix; ++i) acc[i][j] = __hfma2(xv[i + s], wv[j], acc[i][j]);
         }
       }
     }
 #pragma unroll
-    for (int j = 0; j < kMaxCout / 2; ++j) {
-      const float2 f = __half22float2(acc[j]);
-      tot[2 * j] += f.x; tot[2 * j + 1] += f.y;
-    }
+    for (int i = 0; i < kPix; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 f = __half22float2(acc[i][j]);
+        tot[i][2 * j] += f.x; tot[i][2 * j + 1] += f.y;
+      }
   }
-  __half* yrow = p.y + (size_t)pix * p.yld + p.ycoff;
   const __half2 alpha2 = __float2half2_rn(p.alpha);
+  const long long pix0 = ((long long)n * p.H + h) * p.W + w0;
 #pragma unroll
-  for (int q = 0; q < kMaxCout / 8; ++q) {
-    if (q * 8 < p.Cout) {
-      uint4 out;
-      __half2* oh = reinterpret_cast<__half2*>(&out);
+  for (int i = 0; i < kPix; ++i) {
+    if (w0 + i < p.W) {
+      __half* yrow = p.y + (size_t)(pix0 + i) * p.yld + p.ycoff + half_ * 16;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = q * 4 + e;
-        __half2 v = __floats2half2_rn(tot[2 * j], tot[2 * j + 1]);          // conv output rounded to fp16 once
-        if (kAct == 1) v = __hfma2_relu(v, p.scale[j], p.shift[j]);
-        else {
-          v = __hfma2(v, p.scale[j], p.shift[j]);
-          if (kAct == 2) v = __hmax2(v, __hmul2(v, alpha2));
-          else if (kAct == 3) {
-            const float2 f = __half22float2(v);
-            v = __floats2half2_rn(plnr_apply_act(f.x, p.act, p.alpha), plnr_apply_act(f.y, p.act, p.alpha));
+      for (int q = 0; q < 2; ++q) {
+        if (half_ * 16 + q * 8 < p.Cout) {
+          uint4 out;
+          __half2* oh = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = q * 4 + e;
+            __half2 v = __floats2half2_rn(tot[i][2 * j], tot[i][2 * j + 1]);          // conv output rounded to fp16 once
+            const __half2 sc = p.scale[half_ * 8 + j], sf = p.shift[half_ * 8 + j];
+            if (kAct == 1) v = __hfma2_relu(v, sc, sf);
+            else {
+              v = __hfma2(v, sc, sf);
+              if (kAct == 2) v = __hmax2(v, __hmul2(v, alpha2));
+              else if (kAct == 3) {
+                const float2 f = __half22float2(v);
+                v = __floats2half2_rn(plnr_apply_act(f.x, p.act, p.alpha), plnr_apply_act(f.y, p.act, p.alpha));
+              }
+            }
+            oh[e] = v;
           }
+          *reinterpret_cast<uint4*>(yrow + q * 8) = out;
         }
-        oh[e] = v;
       }
-      *reinterpret_cast<uint4*>(yrow + q * 8) = out;
     }
   }
 }
@@ -156,7 +189,7 @@ extern "C" int plnr_stem3x3_fwd(plnr_ctx* ctx, const void* x, int x_dtype, int n
     reinterpret_cast<__half*>(&p.scale[0])[co] = __float2half_rn(co < cout ? sc[co] : 0.f);
     reinterpret_cast<__half*>(&p.shift[0])[co] = __float2half_rn(co < cout ? sf[co] : 0.f);
   }
-  const long long total = (long long)n * h * w;
+  const long long total = (long long)n * h * ((w + kPix - 1) / kPix) * 2;          // threads: (group of four pixels) x (channel half)
   PLNR_REQUIRE(total > 0 && (total + 255) / 256 < (1ll << 31), "stem3x3: bad extents");
   const unsigned grid = (unsigned)((total + 255) / 256);
   const int kact = act == PLNR_ACT_RELU ? 1 : (act == PLNR_ACT_LEAKY && alpha >= 0.f && alpha <= 1.f ? 2 : (act == PLNR_ACT_NONE ? 0 : 3));
