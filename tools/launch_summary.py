@@ -31,7 +31,10 @@ with open('profiles/%s_launches_summary.md' % tag, 'w') as f:
     # one forward = from a stem_pool launch to the next
     idx = [i for i, (k, _) in enumerate(launches) if k.startswith('stem_pool')]
     if len(idx) >= 3:
-        fw = min((launches[a:b] for a, b in zip(idx[:-1], idx[1:])), key=len)     # a forward with no build kernels in between
+        # the LAST complete forward with no build kernels in between: the timed batch-128 step (earlier forwards are the
+        # bench's parity checks on small batches and the executor's first eager pass)
+        n_min = min(b - a for a, b in zip(idx[:-1], idx[1:]))
+        fw = [launches[a:b] for a, b in zip(idx[:-1], idx[1:]) if b - a == n_min][-1]
         f.write('\nOne forward (%d launches), us: %s = %.1f us\n' % (len(fw), ', '.join('%.1f' % v for _, v in fw), sum(v for _, v in fw)))
         conv = sum(v for k, v in fw if k.startswith(('conv_', 'stem_pool', 'gap_dense')))
         f.write('Share of the roofline kernel set (stem_pool + conv_stack + conv_shift + conv_igemm + gap_dense: every conv / dense layer) in that forward: %.1f%% '

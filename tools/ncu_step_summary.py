@@ -1,7 +1,7 @@
 """Summarise one steady-state step captured by tools/gpu_profile.sh (ncu --set full) into profiles/:
     python tools/ncu_step_summary.py gpurun_out/prof_step.ncu-rep r01b
 writes profiles/<tag>_step_full.md (per-kernel table) and profiles/<tag>_step_traffic.json (DRAM bytes per launch, read by bench.py)."""
-import csv, io, json, subprocess, sys
+import csv, hashlib, io, json, os, subprocess, sys
 
 rep, tag = sys.argv[1], sys.argv[2]
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
@@ -30,7 +30,11 @@ for r in data:
                  'tensor_pct': val(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')})
 tot = sum(k['us'] for k in kern)
 with open('profiles/%s_step_traffic.json' % tag, 'w') as f:
-    json.dump({'source': rep, 'kernels': kern}, f, indent=1)
+    # the capture is of the library that is in the tree NOW (gpurun ships the in-tree build): bench.py reports `traffic` only
+    # when the library it runs has this hash
+    lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'planer_b200', 'libplaner_b200.so')
+    sha = hashlib.sha256(open(lib, 'rb').read()).hexdigest()
+    json.dump({'source': rep, 'lib_sha256': sha, 'config': 'resnet18', 'kernels': kern}, f, indent=1)
 with open('profiles/%s_step_full.md' % tag, 'w') as f:
     f.write('# One steady-state step under `ncu --set full` (ResNet-18 fp16, batch 128, B200) -- %s\n\n' % tag)
     f.write('Command: tools/gpu_profile.sh (`ncu --set full --clock-control none --import-source on -k regex:conv_shift|conv_stack|'
