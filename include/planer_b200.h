@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PLNR_ABI_VERSION 1
+#define PLNR_ABI_VERSION 2
 
 enum { PLNR_F32 = 0, PLNR_F16 = 1, PLNR_U8 = 2 /* graph INPUTS only: uint8 images, converted by the input-time kernel */ };
 enum { PLNR_ACT_NONE = 0, PLNR_ACT_RELU = 1, PLNR_ACT_LEAKY = 2, PLNR_ACT_SIGMOID = 3 };
@@ -76,6 +76,13 @@ typedef struct {
   int32_t out_nchw;         /* 1: y->ptr is a DENSE NCHW array of y's logical shape -- the graph-exit transpose (planer/net.py:100
                              *    hands NCHW arrays back) folded into the epilogue.  No residual; only where
                              *    plnr_conv2d_out_nchw_supported says so (the shift-GEMM kernel). */
+  int32_t out_f32;          /* 1: the fp32 path on the tensor pipe -- desc.dtype is PLNR_F16 for the OPERANDS (x from plnr_split_f32,
+                             *    w_packed from plnr_pack_conv_weight_split), the fp32 accumulator is written as fp32: y and residual
+                             *    are fp32 tensors.  Runs the TMA-im2col kernel. */
+  float acc_scale;          /* accumulator multiplier applied before scale/shift (the inverse of the operands' power-of-two
+                             *    pre-scales); 0 means 1 */
+  const float* acc_scale_dev; /* NULL, or a DEVICE scalar multiplied in as well (the per-call activation pre-scale left by
+                             *    plnr_split_f32 in dyn[1]) */
 } plnr_epilogue;
 
 typedef struct {
@@ -140,9 +147,9 @@ int plnr_stem_pool_fwd_u8(plnr_ctx* ctx, const void* x, int n, int c, int h, int
 /* Small first layer on the CUDA cores (csrc/stem_direct.cu): 3x3 / stride-1 / pad-1 convolution of an NCHW image x (n, c <= 3,
  * h, w; x_dtype PLNR_F16 or PLNR_U8) to y->c <= 32 channels (multiple of 8) + *scale + shift + activation -> pixel-major y.
  * Replaces Conv2d (planer/layer.py:22-26 + planer/util.py:17-44) -> BatchNorm (:125-127) -> ReLU / LeakyReLU (:44-51) at
- * the head of YOLOv3-style networks, where K = 27 and N = 32 leave the tensor cores nothing to do.  w_oihw: DEVICE pointer
- * to the fp16 OIHW filter as stored by the model; scale / shift: DEVICE fp32 [y->c] or NULL.  All three are read back to the
- * host once per pointer (first call, outside graph capture) and then travel in the kernel parameters. */
+ * the head of YOLOv3-style networks, where K = 27 and N = 32 leave the tensor cores nothing to do.  w_oihw: HOST pointer
+ * to the fp16 OIHW filter (y->c, c, 3, 3); scale / shift: HOST fp32 [y->c] or NULL -- 1.7 KB that travel in the kernel
+ * parameters (the caller reads them back from the device once, at load time). */
 int plnr_stem3x3_supported(int dtype, int c, int cout, int kh, int kw, int stride, int pad_t, int pad_l, int pad_b, int pad_r,
                            int dil);
 int plnr_stem3x3_fwd(plnr_ctx* ctx, const void* x, int x_dtype, int n, int c, int h, int w, const void* w_oihw,
@@ -156,6 +163,20 @@ int plnr_cast(plnr_ctx* ctx, const void* x, int x_dtype, void* y, int y_dtype, i
  * contraction index is (r,s,c) with c innermost). */
 int plnr_pack_conv_weight(plnr_ctx* ctx, const void* w, int w_dtype, void* out, int out_dtype,
                           int cout, int cin_g, int kh, int kw, int cin_pad);
+/* The float32 Conv2d / Dense of a float32 net (planer/layer.py:22-26, :15-18 on float32 arrays) on the fp16 tensor pipe:
+ * both operands are split into two fp16 numbers, v * prescale = hi + lo, and ONE fp16 implicit GEMM over 3C channels per
+ * filter tap computes xh.wh + xh.wl + xl.wh with an fp32 accumulator (csrc/split_f32.cu).
+ *   plnr_split_f32:              x fp32 (n,h,w,C) view -> xs fp16 DENSE (n,h,w,cs), cs >= 3C: [hi C | hi C | lo C | pad];
+ *                                pad channels are left untouched (zero them once).  dyn == NULL: x is multiplied by
+ *                                `prescale`.  dyn = two device floats: the power-of-two pre-scale is derived from max|x| on the
+ *                                device (dyn[0] = max|x|, dyn[1] = 1 / prescale for plnr_epilogue.acc_scale_dev).
+ *   plnr_pack_conv_weight_split: OIHW fp32 -> [Cout][kh][kw][cs] fp16 with [hi C | lo C | hi C | pad] per tap (pad untouched).
+ *   plnr_absmax_f32:             out[0] = max |x[i]| (device scalar; the caller picks the weights' power-of-two pre-scale).
+ * Then plnr_conv2d_fwd(desc.dtype = PLNR_F16, x = xs, ep.out_f32 = 1, ep.acc_scale = 1 / prescale_w, ep.acc_scale_dev = dyn + 1). */
+int plnr_split_f32(plnr_ctx* ctx, const plnr_tensor* x, const plnr_tensor* xs, float prescale, float* dyn);
+int plnr_pack_conv_weight_split(plnr_ctx* ctx, const void* w, void* out, int cout, int cin, int kh, int kw, int cs,
+                                float prescale);
+int plnr_absmax_f32(plnr_ctx* ctx, const void* x, int64_t n, float* out);
 /* scale[c] = bn_k ? bn_k[c] : 1 ; shift[c] = (bias ? bias[c] : 0) * scale[c] + (bn_b ? bn_b[c] : 0).
  * Inputs have dtype `dtype`; outputs are fp32.  Folds planer/layer.py:26 and :125-127. */
 int plnr_fold_affine(plnr_ctx* ctx, const void* bias, const void* bn_k, const void* bn_b, int dtype,

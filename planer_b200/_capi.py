@@ -25,7 +25,8 @@ class Tensor(C.Structure):
 
 class Epilogue(C.Structure):
     _fields_ = [('scale', C.c_void_p), ('shift', C.c_void_p), ('residual', C.POINTER(Tensor)),
-                ('act', C.c_int32), ('alpha', C.c_float), ('res_after_act', C.c_int32), ('out_nchw', C.c_int32)]
+                ('act', C.c_int32), ('alpha', C.c_float), ('res_after_act', C.c_int32), ('out_nchw', C.c_int32),
+                ('out_f32', C.c_int32), ('acc_scale', C.c_float), ('acc_scale_dev', C.c_void_p)]
 
 
 class ConvDesc(C.Structure):
@@ -62,6 +63,9 @@ PROTOTYPES = {
     'plnr_nhwc_to_nchw': [_P, _TP, C.c_int, _P, C.c_int],
     'plnr_cast': [_P, _P, C.c_int, _P, C.c_int, C.c_int64],
     'plnr_pack_conv_weight': [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
+    'plnr_split_f32': [_P, _TP, _TP, C.c_float, _P],
+    'plnr_pack_conv_weight_split': [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float],
+    'plnr_absmax_f32': [_P, _P, C.c_int64, _P],
     'plnr_fold_affine': [_P, _P, _P, _P, C.c_int, _P, _P, C.c_int],
     'plnr_conv2d_fwd': [_P, C.POINTER(ConvDesc), _TP, _P, _TP, C.POINTER(Epilogue)],
     'plnr_conv2d_out_nchw_supported': [C.POINTER(ConvDesc), _TP, _TP],
@@ -118,8 +122,8 @@ def load():
         fn.restype = C.c_int
     lib.plnr_last_error.argtypes = []
     lib.plnr_last_error.restype = C.c_char_p
-    if lib.plnr_abi_version() != 1:
-        raise PlanerB200Error('ABI version mismatch: library %d, binding 1' % lib.plnr_abi_version())
+    if lib.plnr_abi_version() != 2:
+        raise PlanerB200Error('ABI version mismatch: library %d, binding 2' % lib.plnr_abi_version())
     _lib = lib
     return lib
 

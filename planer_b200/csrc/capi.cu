@@ -277,6 +277,11 @@ int plnr_conv2d_fwd(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x
     return plnr_conv2d_shift(ctx, d, x, w, y, ep);
   }
   bool tc_ok = plnr_conv2d_tcgen05_supported(d, x, y);
+  if (ep && ep->out_f32) {
+    PLNR_REQUIRE(d->dtype == PLNR_F16 && tc_ok && d->algo != PLNR_ALGO_DIRECT,
+                 "conv2d: out_f32 needs fp16 split operands on the tensor-core path (groups==1, Cin%%16==0, 16B-aligned x)");
+    return plnr_conv2d_tcgen05(ctx, d, x, w, y, ep);
+  }
   if (d->algo == PLNR_ALGO_TCGEN05 && !tc_ok) {
     plnr_set_error("conv2d: PLNR_ALGO_TCGEN05 requested but the problem is not eligible "
                    "(needs fp16, groups==1, Cin%%16==0, 16B-aligned views)");

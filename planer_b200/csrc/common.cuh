@@ -29,7 +29,6 @@ struct plnr_ctx {
   float* sk_ws = nullptr;          // stream-K workspace of the shift conv kernel: fp32 partial tiles, one slot per unit
   int* sk_flags = nullptr;         // ... and their ready flags (self-cleaning: the consumer resets them)
   std::unordered_map<long long, int> shift_max_units;   // (cta group, smem bytes) -> co-resident units of the shift conv kernel
-  std::unordered_map<std::string, std::vector<char>> stem3_filters;   // host copies of small first-layer filters (stem_direct.cu)
   const char* last_kernel = "";   // name handed to plnr_after_launch by the most recent launch (diagnostics)
   bool shift_attr_set = false;
   bool igemm_attr_set = false;     // cudaFuncSetAttribute(max dynamic smem) done for this device

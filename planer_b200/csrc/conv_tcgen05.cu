@@ -51,6 +51,9 @@ struct IgemmParams {
   const __half* res; int rld, rcoff;
   int act; float alpha; int res_after;
   int vec_ok;
+  int out_f32;       // plnr_epilogue.out_f32: y / residual are fp32 tensors (split-fp16 operands, split_f32.cu)
+  float acc_scale;   // accumulator multiplier (2^-(ex+ew) of the operand pre-scales), folded into the staged scale
+  const float* acc_scale_dev;   // ... times this device scalar (per-call activation pre-scale) when not NULL
   int* err;
   long long* prof;   // optional [grid][8] cycle counters per role (debug)
   int dbg;           // debug: bit0 = epilogue skips global loads/stores, bit1 = epilogue skips tcgen05.ld too
@@ -288,6 +291,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     const bool alternate = nchunks == 1;
     const int c_begin = alternate ? 0 : eg * half * 32, c_end = alternate ? 32 : min(nchunks, (eg + 1) * half) * 32;
     const bool has_res = p.res != nullptr;
+    const bool res16 = has_res && !p.out_f32;          // fp16 residual: read in the coalesced pattern, one chunk ahead
     const uint32_t uM = (uint32_t)p.M;
     uint8_t* st_o = stage + (warp - 4) * 2048;
     const uint32_t my_sw = (uint32_t)((lane >> 1) & 3);
@@ -317,7 +321,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           dst[i] = *reinterpret_cast<const uint4*>(p.res + (size_t)g.row[i] * p.rld + p.rcoff + cb + piece * 8);
     };
     Geo gn = tile_geo(unit < p.num_tiles ? unit : 0);
-    if (has_res && p.vec_ok && c_begin < c_end && unit < p.num_tiles && (!alternate || eg == 0)) {
+    if (res16 && p.vec_ok && c_begin < c_end && unit < p.num_tiles && (!alternate || eg == 0)) {
       const int cb = (int)fast_div((uint32_t)unit, p.div_mt) * p.n_tile + c_begin;
       if (cb + 32 <= p.Cout) fetch_res(gn, cb, rvp);
     }
@@ -332,10 +336,11 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         ebuf ^= 1u;
         float* dsc = epi + ebuf * 512, *dsf = dsc + 256;
         __half* hsc = reinterpret_cast<__half*>(epi + 1024) + ebuf * 512, *hsf = hsc + 256;
+        const float accs = p.acc_scale_dev ? p.acc_scale * __ldg(p.acc_scale_dev) : p.acc_scale;
         for (int i = et; i < p.n_tile; i += 256) {
           const int c = n0 + i;
           float sc = 0.f, sf = 0.f;
-          if (c < p.Cout) { sc = p.scale ? __ldg(p.scale + c) : 1.f; sf = p.shift ? __ldg(p.shift + c) : 0.f; }
+          if (c < p.Cout) { sc = (p.scale ? __ldg(p.scale + c) : 1.f) * accs; sf = p.shift ? __ldg(p.shift + c) : 0.f; }
           dsc[i] = sc; dsf[i] = sf;
           hsc[i] = __float2half_rn(sc); hsf[i] = __float2half_rn(sf);
         }
@@ -352,7 +357,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       const int tile_n = tile + nunits;
       if (tile_n < p.num_tiles) {
         gn = tile_geo(tile_n);
-        if (has_res && p.vec_ok && c_begin < c_end && (!alternate || ((it + 1) & 1u) == (uint32_t)eg)) {
+        if (res16 && p.vec_ok && c_begin < c_end && (!alternate || ((it + 1) & 1u) == (uint32_t)eg)) {
           const int cb = (int)fast_div((uint32_t)tile_n, p.div_mt) * p.n_tile + c_begin;
           if (cb + 32 <= p.Cout) fetch_res(gn, cb, rvp);
         }
@@ -374,8 +379,8 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(t_row + c0, v);
         const int cb = n0 + c0;
-        const bool fast = p.vec_ok && (cb + 32 <= p.Cout);
-        if (has_res && p.vec_ok && c0 + 32 < ce_ && cb + 64 <= p.Cout) fetch_res(g, cb + 32, rvn);   // one chunk ahead
+        const bool fast = !p.out_f32 && p.vec_ok && (cb + 32 <= p.Cout);
+        if (res16 && p.vec_ok && c0 + 32 < ce_ && cb + 64 <= p.Cout) fetch_res(g, cb + 32, rvn);   // one chunk ahead
         ptx::tmem_ld_wait();
         if (c0 + 32 >= ce_) {
           ptx::tc_fence_before();
@@ -449,6 +454,45 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           else chunk_math(ActTag<0>{});
 #pragma unroll
           for (int i = 0; i < 4; ++i) rv[i] = rvn[i];
+        } else if (p.out_f32) {
+          // fp32 result of the split-fp16 path: every thread finishes its own row (32 channels = 128 contiguous bytes),
+          // scale / shift / residual / activation in fp32 like the reference's float32 layers
+          if (g.own >= 0) {
+            float* yrow = reinterpret_cast<float*>(p.y) + (size_t)g.own * p.yld + p.ycoff;
+            const float* rrow = has_res ? reinterpret_cast<const float*>(p.res) + (size_t)g.own * p.rld + p.rcoff : nullptr;
+            if (p.vec_ok && cb + 32 <= p.Cout) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                const float4 sc = *reinterpret_cast<const float4*>(ep_scale + c0 + e);
+                const float4 sf = *reinterpret_cast<const float4*>(ep_shift + c0 + e);
+                float4 rf = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rrow) rf = *reinterpret_cast<const float4*>(rrow + cb + e);
+                float o[4] = {fmaf(__uint_as_float(v[e]), sc.x, sf.x), fmaf(__uint_as_float(v[e + 1]), sc.y, sf.y),
+                              fmaf(__uint_as_float(v[e + 2]), sc.z, sf.z), fmaf(__uint_as_float(v[e + 3]), sc.w, sf.w)};
+                const float r4[4] = {rf.x, rf.y, rf.z, rf.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (!p.res_after) o[j] += r4[j];
+                  o[j] = plnr_apply_act(o[j], p.act, p.alpha);
+                  if (p.res_after) o[j] += r4[j];
+                }
+                *reinterpret_cast<float4*>(yrow + cb + e) = make_float4(o[0], o[1], o[2], o[3]);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const int c = cb + e;
+                if (c < p.Cout) {
+                  float o1 = fmaf(__uint_as_float(v[e]), ep_scale[c0 + e], ep_shift[c0 + e]);
+                  const float rf = rrow ? rrow[c] : 0.f;
+                  if (!p.res_after) o1 += rf;
+                  o1 = plnr_apply_act(o1, p.act, p.alpha);
+                  if (p.res_after) o1 += rf;
+                  yrow[c] = o1;
+                }
+              }
+            }
+          }
         } else if (g.own >= 0) {
           __half* yrow = p.y + (size_t)g.own * p.yld + p.ycoff;
           const __half* rrow = has_res ? p.res + (size_t)g.own * p.rld + p.rcoff : nullptr;
@@ -562,7 +606,9 @@ bool plnr_conv2d_tcgen05_supported(const plnr_conv_desc* d, const plnr_tensor* x
 int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w,
                         const plnr_tensor* y, const plnr_epilogue* ep) {
   // stride-1 convolutions with Cin % 64 == 0 take the shift-GEMM kernel (conv_shift.cu): each input row is loaded once
-  if (plnr_conv2d_shift_supported(d, x, y)) return plnr_conv2d_shift(ctx, d, x, w, y, ep);
+  // (fp16 results only: the fp32 epilogue of the split-fp16 path lives in this kernel)
+  const bool out_f32 = ep && ep->out_f32;
+  if (!out_f32 && plnr_conv2d_shift_supported(d, x, y)) return plnr_conv2d_shift(ctx, d, x, w, y, ep);
   int rc = resolve_driver();
   if (rc != PLNR_OK) return rc;
   PLNR_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, "conv2d(tcgen05): packed weights must be 16-byte aligned");
@@ -609,14 +655,18 @@ int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tenso
   const size_t smem_bytes = (size_t)stages * stage_bytes + kEpiBytes + 16 * stages + 64 + kStageBytes + utab_bytes + 1024;
 
   p.y = (__half*)y->ptr; p.yld = y->ld; p.ycoff = y->coff; p.Cout = Cout;
-  bool vec = (y->ld % 8 == 0) && (y->coff % 8 == 0) && ((reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0);
+  p.out_f32 = out_f32 ? 1 : 0;
+  p.acc_scale = (ep && ep->acc_scale != 0.f) ? ep->acc_scale : 1.f;
+  p.acc_scale_dev = ep ? ep->acc_scale_dev : nullptr;
+  const int va = out_f32 ? 4 : 8;          // elements per 16-byte vector of y / residual
+  bool vec = (y->ld % va == 0) && (y->coff % va == 0) && ((reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0);
   if (ep) {
     p.scale = ep->scale; p.shift = ep->shift; p.act = ep->act; p.alpha = ep->alpha;
     p.res_after = ep->res_after_act;
     if (ep->residual) {
       const plnr_tensor* r = ep->residual;
       p.res = (const __half*)r->ptr; p.rld = r->ld; p.rcoff = r->coff;
-      vec = vec && (r->ld % 8 == 0) && (r->coff % 8 == 0) && ((reinterpret_cast<uintptr_t>(r->ptr) & 15) == 0);
+      vec = vec && (r->ld % va == 0) && (r->coff % va == 0) && ((reinterpret_cast<uintptr_t>(r->ptr) & 15) == 0);
     }
   }
   p.vec_ok = vec ? 1 : 0;

@@ -143,9 +143,9 @@ extern "C" int plnr_stem3x3_supported(int dtype, int c, int cout, int kh, int kw
   return (pad_t == 1 && pad_l == 1 && pad_b == 1 && pad_r == 1) ? 1 : 0;
 }
 
-// w: DEVICE pointer to the OIHW fp16 filter (cout, c, 3, 3); scale / shift: DEVICE fp32 [cout] or NULL.  They are copied to
-// the host ONCE per (pointer, ctx) -- one synchronous 2 KB read at the first call, i.e. at executor build -- and travel in the
-// kernel parameters from then on, so the call is safe inside CUDA-graph capture after that first eager call.
+// w_oihw: HOST pointer to the OIHW fp16 filter (cout, c, 3, 3); scale / shift: HOST fp32 [cout] or NULL.  They travel in the
+// kernel parameters, so the call is safe inside CUDA-graph capture (an earlier version cached a device read-back per
+// POINTER: a freed and re-used address then served a stale filter).
 extern "C" int plnr_stem3x3_fwd(plnr_ctx* ctx, const void* x, int x_dtype, int n, int c, int h, int w, const void* w_oihw,
                                 const float* scale, const float* shift, int act, float alpha, const plnr_tensor* y) {
   PLNR_REQUIRE(ctx && x && w_oihw && y && y->ptr, "stem3x3: NULL argument");
@@ -154,26 +154,16 @@ extern "C" int plnr_stem3x3_fwd(plnr_ctx* ctx, const void* x, int x_dtype, int n
   PLNR_REQUIRE(y->n == n && y->h == h && y->w == w, "stem3x3: output is (%d,%d,%d), expected (%d,%d,%d)", y->n, y->h, y->w, n, h, w);
   PLNR_REQUIRE((reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && y->ld % 8 == 0 && y->coff % 8 == 0,
                "stem3x3: output rows must be 16-byte aligned");
-  const int cout = y->c;
-  std::string key(reinterpret_cast<const char*>(&w_oihw), sizeof(void*));
-  key.append(reinterpret_cast<const char*>(&scale), sizeof(void*));
-  key.append(reinterpret_cast<const char*>(&shift), sizeof(void*));
-  auto it = ctx->stem3_filters.find(key);
-  if (it == ctx->stem3_filters.end()) {
-    PLNR_REQUIRE(!ctx->capturing, "stem3x3: the first call for a filter must happen outside graph capture");
-    std::vector<char> blob(sizeof(__half) * (size_t)cout * c * 9 + sizeof(float) * 2 * (size_t)cout, 0);
-    PLNR_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-    PLNR_CHECK_CUDA(cudaMemcpy(blob.data(), w_oihw, sizeof(__half) * (size_t)cout * c * 9, cudaMemcpyDeviceToHost));
-    float* sc = reinterpret_cast<float*>(blob.data() + sizeof(__half) * (size_t)cout * c * 9);
-    float* sf = sc + cout;
-    for (int i = 0; i < cout; ++i) { sc[i] = 1.f; sf[i] = 0.f; }
-    if (scale) PLNR_CHECK_CUDA(cudaMemcpy(sc, scale, sizeof(float) * cout, cudaMemcpyDeviceToHost));
-    if (shift) PLNR_CHECK_CUDA(cudaMemcpy(sf, shift, sizeof(float) * cout, cudaMemcpyDeviceToHost));
-    it = ctx->stem3_filters.emplace(key, std::move(blob)).first;
+  {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, w_oihw) == cudaSuccess)
+      PLNR_REQUIRE(pa.type != cudaMemoryTypeDevice, "stem3x3: w_oihw must be a HOST pointer (ABI 2)");
+    cudaGetLastError();
   }
-  const __half* hw = reinterpret_cast<const __half*>(it->second.data());
-  const float* sc = reinterpret_cast<const float*>(it->second.data() + sizeof(__half) * (size_t)cout * c * 9);
-  const float* sf = sc + cout;
+  const int cout = y->c;
+  const __half* hw = reinterpret_cast<const __half*>(w_oihw);
+  const float* sc = scale;
+  const float* sf = shift;
 
   Stem3Params p;
   memset(&p, 0, sizeof(p));
@@ -186,8 +176,8 @@ extern "C" int plnr_stem3x3_fwd(plnr_ctx* ctx, const void* x, int x_dtype, int n
         for (int co = 0; co < cout; ++co)
           reinterpret_cast<__half*>(&p.w[(ci * 3 + r) * 3 + s][0])[co] = hw[((size_t)co * c + ci) * 9 + r * 3 + s];
   for (int co = 0; co < kMaxCout; ++co) {
-    reinterpret_cast<__half*>(&p.scale[0])[co] = __float2half_rn(co < cout ? sc[co] : 0.f);
-    reinterpret_cast<__half*>(&p.shift[0])[co] = __float2half_rn(co < cout ? sf[co] : 0.f);
+    reinterpret_cast<__half*>(&p.scale[0])[co] = __float2half_rn(co < cout ? (sc ? sc[co] : 1.f) : 0.f);
+    reinterpret_cast<__half*>(&p.shift[0])[co] = __float2half_rn(co < cout ? (sf ? sf[co] : 0.f) : 0.f);
   }
   const long long total = (long long)n * h * ((w + kPix - 1) / kPix) * 2;          // threads: (group of four pixels) x (channel half)
   PLNR_REQUIRE(total > 0 && (total + 255) / 256 < (1ll << 31), "stem3x3: bad extents");

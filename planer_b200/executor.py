@@ -34,6 +34,7 @@ class Executor:
         self.input_ids = list(gplan.inputs)
         self.in_arrays, self.out_arrays, self.out_flat = [], [], []
         self._keep = []
+        self.split_convs = 0     # float32 convolutions routed to the tensor pipe (fp16 split operands)
         self._in_stage = {}       # graph input -> fp16 staging array (fp32 images on the fused first layer)
         self.pack_hits = self.pack_misses = 0
         self.nchw_exits = 0       # graph outputs written as NCHW by the producing conv's epilogue
@@ -387,7 +388,8 @@ class Executor:
                 y = alloc(st.out)
                 K16 = self._packed(st.name + '|cast', lambda: K.astype(np.float16))
                 self._keep += [K16, y]
-                fused['run'] = lambda xf: ops.stem3x3_into(xf, K16, scale, shift, y, st.act, st.alpha)
+                hK, hs, hf = ops.stem3x3_host_filter(K16, scale, shift)      # 1.7 KB, travel in the kernel parameters
+                fused['run'] = lambda xf: ops.stem3x3_into(xf, hK, hs, hf, y, st.act, st.alpha)
                 return None
             if fused is not None:
                 a = st.attrs
@@ -443,6 +445,14 @@ class Executor:
                     y = DeviceArray(y.buf, (y.shape[0], cop) + y.shape[2:], dt, 'nhwc', ld=cop, offset=y.offset)
                     self._keep += [wp, scale, shift]
                     return lambda: ops.conv2d_into(x, wp, y, kh, kw, a['strides'], a['dilations'], a['pads'], 1,
+                                                   scale, shift, res, st.act, st.alpha, res_after_act=st.res_after)
+                if dt == np.float32 and K.dtype == np.float32 and g == 1 and ops.split_conv_enabled():
+                    # float32 on the tensor pipe: fp16 (hi, lo) split operands, fp32 accumulator and epilogue (csrc/split_f32.cu)
+                    w16, meta = self._packed('%s|split|%d' % (st.name, x.shape[1]), lambda: ops.pack_weight_split(K))
+                    sw = ops.split_weight(w16, meta, x.shape[1])
+                    self._keep.append(sw)
+                    self.split_convs += 1
+                    return lambda: ops.conv2d_into(x, sw, y, kh, kw, a['strides'], a['dilations'], a['pads'], 1,
                                                    scale, shift, res, st.act, st.alpha, res_after_act=st.res_after)
                 wp = self._packed('%s|pack|%d' % (st.name, x.shape[1] // g), lambda: ops.pack_weight(K, x.shape[1] // g, dt))
                 self._keep.append(wp)

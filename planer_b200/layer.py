@@ -65,6 +65,15 @@ def _packed(K, cin_pad, dtype):
     return _pack_cache[key][0]
 
 
+def _packed_split(K):
+    key = (K.ptr, K.shape, 'split')
+    if key not in _pack_cache:
+        if len(_pack_cache) > 4096: _pack_cache.clear()
+        w16, meta = ops.pack_weight_split(K)
+        _pack_cache[key] = (ops.split_weight(w16, meta, K.shape[1]), K)
+    return _pack_cache[key][0]
+
+
 def Conv2d(x, K, B_=None, group=1, strides=(1, 1), dilations=(1, 1), pads=(0, 0, 0, 0)):
     """planer/layer.py:22-26.  x (N,C,H,W); K (Co,C/g,kh,kw); B_ (Co) or None; pads = (top,left,bottom,right)."""
     dt = _compute_dtype(x, K)
@@ -75,7 +84,10 @@ def Conv2d(x, K, B_=None, group=1, strides=(1, 1), dilations=(1, 1), pads=(0, 0,
     if cin != cg * group and not (group == 1 and cin >= cg):
         raise ValueError('Conv2d: input has %d channels, weight expects %d' % (x.shape[1], cg * group))
     y = B.empty(ops.conv_out_shape(x.shape, K.shape, strides, dilations, pads), dt, 'nhwc')
-    wp = _packed(K, cin // group, dt)
+    if dt == np.float32 and K.dtype == np.float32 and group == 1 and cin == cg and ops.split_conv_enabled():
+        wp = _packed_split(K)                # float32 on the tensor pipe (fp16 split operands, csrc/split_f32.cu)
+    else:
+        wp = _packed(K, cin // group, dt)
     scale = shift = None
     if B_ is not None:
         scale, shift = ops.fold_affine(B_, None, None, co)

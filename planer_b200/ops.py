@@ -33,10 +33,12 @@ def pool_out_shape(xshape, w, pads, strides):
             (ww + pads[1] + pads[3] - w[1] + strides[1]) // strides[1])
 
 
-def _epilogue(scale, shift, residual, act, alpha, res_after_act=False, out_nchw=False):
+def _epilogue(scale, shift, residual, act, alpha, res_after_act=False, out_nchw=False, out_f32=False, acc_scale=1.0,
+              acc_scale_dev=None):
     keep = []
     ep = _capi.Epilogue()
     ep.out_nchw = int(bool(out_nchw))
+    ep.out_f32, ep.acc_scale, ep.acc_scale_dev = int(bool(out_f32)), float(acc_scale), acc_scale_dev
     ep.scale = scale.ptr if scale is not None else None
     ep.shift = shift.ptr if shift is not None else None
     if residual is not None:
@@ -55,6 +57,76 @@ def pack_weight(K, cin_pad, dtype, co_pad=None):
                                               _capi.dtype_code(dtype), co, cg, kh, kw, cin_pad),
                 'plnr_pack_conv_weight')
     return out
+
+
+# ---- float32 convolutions on the fp16 tensor pipe (csrc/split_f32.cu) ---------------------------------------------------
+def split_conv_enabled():
+    """PLNR_F32_TENSOR=0 keeps float32 convolutions on the CUDA-core FFMA kernel (conv_direct.cu)."""
+    import os
+    return os.environ.get('PLNR_F32_TENSOR', '1') != '0'
+
+
+def split_channels(c):
+    """Stored channels of the split operand: [hi C | hi C | lo C] rounded up to the tensor-core kernel's multiple of 16."""
+    return (3 * c + 15) // 16 * 16
+
+
+class SplitWeight:
+    """A float32 filter split into fp16 (hi, lo) pairs for the tensor-core path: ``packed`` is [Cout][kh][kw][cs] fp16 with
+    [hi | lo | hi] per tap, ``prescale`` the power of two the filter was multiplied by.  Owns the fp16 staging tensors of
+    its input (one per input shape, zeroed once: the pad channels are never written) and the two device floats of the
+    per-call activation pre-scale."""
+
+    def __init__(self, packed, prescale, cin):
+        self.packed, self.prescale, self.cin = packed, float(prescale), int(cin)
+        self.cs = packed.shape[3]
+        self._stage = {}
+
+    def stage(self, x):
+        key = (x.shape[0], x.shape[2], x.shape[3])
+        if key not in self._stage:
+            if len(self._stage) >= 4:
+                self._stage.pop(next(iter(self._stage)))
+            xs = B.empty((x.shape[0], self.cs, x.shape[2], x.shape[3]), np.float16, 'nhwc')
+            _capi.check(B.lib().plnr_memset(B.ctx(), xs.ptr, 0, max(2 * x.shape[0] * x.shape[2] * x.shape[3] * self.cs, 1)), 'plnr_memset')
+            self._stage[key] = (xs, B.zeros((2,), np.float32))
+        return self._stage[key]
+
+
+def pack_weight_split(K):
+    """OIHW float32 filter -> (packed fp16 [Cout][kh][kw][cs], meta fp32 [prescale]) for ``SplitWeight``.  The pre-scale
+    puts max|w| into [2^13, 2^14) so that the low parts stay out of fp16's subnormal range."""
+    co, ci, kh, kw = K.shape
+    cs = split_channels(ci)
+    amax = B.empty((1,), np.float32)
+    _capi.check(B.lib().plnr_absmax_f32(B.ctx(), K.ptr, int(np.prod(K.shape)), amax.ptr), 'plnr_absmax_f32')
+    m = float(amax.get()[0])
+    e = 0 if not np.isfinite(m) or m <= 0 else 13 - int(np.floor(np.log2(m)))
+    prescale = 2.0 ** max(-100, min(100, e))
+    out = B.zeros((co, kh, kw, cs), np.float16)
+    _capi.check(B.lib().plnr_pack_conv_weight_split(B.ctx(), K.ptr, out.ptr, co, ci, kh, kw, cs, prescale),
+                'plnr_pack_conv_weight_split')
+    return out, B.asarray(np.array([prescale], np.float32))
+
+
+def split_weight(packed, meta, cin):
+    return SplitWeight(packed, float(meta.get()[0]), cin)
+
+
+def _conv2d_split_into(x, sw, y, kh, kw, strides, dilations, pads, scale, shift, residual, act, alpha, res_after_act):
+    """float32 x, y (and residual); fp16 split operands; three launches (max|x|, split, tensor-core conv with the fp32
+    epilogue)."""
+    xs, dyn = sw.stage(x)
+    tx, txs = x.tensor(), xs.tensor()
+    _capi.check(B.lib().plnr_split_f32(B.ctx(), C.byref(tx), C.byref(txs), 1.0, dyn.ptr), 'plnr_split_f32')
+    d = _capi.ConvDesc(_capi.dtype_code(np.float16), kh, kw, pads[0], pads[1], pads[2], pads[3],
+                       strides[0], strides[1], dilations[0], dilations[1], 1, ALGO_AUTO)
+    ty = y.tensor()
+    ep, keep = _epilogue(scale, shift, residual, act, alpha, res_after_act, out_f32=True,
+                         acc_scale=1.0 / sw.prescale, acc_scale_dev=dyn.ptr + 4)
+    _capi.check(B.lib().plnr_conv2d_fwd(B.ctx(), C.byref(d), C.byref(txs), sw.packed.ptr, C.byref(ty), C.byref(ep)),
+                'plnr_conv2d_fwd (float32 on the tensor pipe)')
+    return y
 
 
 def pad_vector(v, n):
@@ -95,7 +167,12 @@ def conv2d_out_nchw_supported(x, yshape, kh, kw, strides, dilations, pads):
 
 def conv2d_into(x, w_packed, y, kh, kw, strides, dilations, pads, groups=1, scale=None, shift=None,
                 residual=None, act=ACT_NONE, alpha=0.0, algo=ALGO_AUTO, res_after_act=False, out_nchw=False):
-    """``out_nchw``: y is a flat NCHW array and the epilogue writes it directly (plnr_epilogue.out_nchw)."""
+    """``out_nchw``: y is a flat NCHW array and the epilogue writes it directly (plnr_epilogue.out_nchw).  ``w_packed`` is
+    the array from ``pack_weight`` or, for float32 on the tensor pipe, a ``SplitWeight``."""
+    if isinstance(w_packed, SplitWeight):
+        assert groups == 1 and not out_nchw and x.dtype == np.float32 and y.dtype == np.float32
+        return _conv2d_split_into(x, w_packed, y, kh, kw, strides, dilations, pads, scale, shift, residual, act, alpha,
+                                  res_after_act)
     d = _capi.ConvDesc(_capi.dtype_code(x.dtype), kh, kw, pads[0], pads[1], pads[2], pads[3],
                        strides[0], strides[1], dilations[0], dilations[1], groups, algo)
     tx, ty = x.tensor(), (nchw_out_tensor(y) if out_nchw else y.tensor())
@@ -416,12 +493,21 @@ def stem3x3_supported(dtype, c, cout, kh, kw, strides, dilations, pads):
                                                pads[3], dilations[0]))
 
 
+def stem3x3_host_filter(K16, scale, shift):
+    """The small first-layer filter as the HOST arrays plnr_stem3x3_fwd takes (they travel in the kernel parameters): one
+    read-back at load time."""
+    host = lambda a, dt: None if a is None else np.ascontiguousarray(a.get() if isinstance(a, B.DeviceArray) else a, dtype=dt)
+    return host(K16, np.float16), host(scale, np.float32), host(shift, np.float32)
+
+
 def stem3x3_into(x_flat, K16, scale, shift, y, act=ACT_NONE, alpha=0.0):
-    """x_flat: NCHW image (float16 / uint8); K16: the OIHW filter as a flat float16 device array; y: nhwc output."""
+    """x_flat: NCHW image (float16 / uint8) on the device; K16 (OIHW float16), scale, shift: numpy arrays from
+    ``stem3x3_host_filter`` (device arrays are read back on every call); y: nhwc output."""
     n, c, h, w = x_flat.shape
     t = y.tensor()
-    p = lambda a: a.ptr if a is not None else None
-    _capi.check(B.lib().plnr_stem3x3_fwd(B.ctx(), x_flat.ptr, _capi.src_dtype_code(x_flat.dtype), n, c, h, w, K16.ptr, p(scale),
+    K16, scale, shift = stem3x3_host_filter(K16, scale, shift)
+    p = lambda a: a.ctypes.data if a is not None else None
+    _capi.check(B.lib().plnr_stem3x3_fwd(B.ctx(), x_flat.ptr, _capi.src_dtype_code(x_flat.dtype), n, c, h, w, p(K16), p(scale),
                                          p(shift), int(act), float(alpha), C.byref(t)), 'plnr_stem3x3_fwd')
     return y
 

@@ -107,6 +107,74 @@ CONV_SWEEP = [
 ]
 
 
+SPLIT_SWEEP = [
+    # n, cin, h, w, cout, k, stride, pad, dil, magnitude of x
+    (2, 3, 20, 22, 64, 7, 2, 3, 1, 1.0), (2, 64, 14, 14, 64, 3, 1, 1, 1, 1.0), (3, 64, 15, 13, 128, 3, 2, 1, 1, 1.0),
+    (1, 256, 7, 7, 512, 3, 1, 1, 1, 1.0), (2, 20, 10, 10, 50, 3, 1, 1, 1, 1.0), (1, 64, 13, 13, 255, 1, 1, 0, 1, 1.0),
+    (2, 64, 12, 12, 64, 3, 1, 2, 2, 1.0), (2, 7, 9, 9, 33, 5, 1, 2, 1, 1.0),
+    # activations far from 1: the low halves must stay representable (pre-scales, csrc/split_f32.cu)
+    (2, 64, 14, 14, 64, 3, 1, 1, 1, 1e-3), (2, 64, 14, 14, 64, 3, 1, 1, 1, 3e3), (2, 32, 8, 8, 32, 3, 1, 1, 1, 1e-5),
+]
+
+
+@pytest.mark.parametrize('cfg', SPLIT_SWEEP)
+@pytest.mark.parametrize('fused', [False, True])
+def test_conv_fp32_on_the_tensor_pipe_vs_oracle(planer, cfg, fused):
+    """float32 Conv2d through fp16 (hi, lo) split operands + fp32 accumulator (csrc/split_f32.cu, the out_f32 epilogue of the
+    im2col kernel) against the oracle's float64 evaluation: range-relative 2e-5 (the north star's bar is 1e-3; measured
+    ~3e-6, the CUDA-core fp32 kernel ~7e-7 on the same problems), whatever the magnitude of the activations."""
+    from planer_b200 import ops, backend as B
+    n, cin, h, w, cout, k, s, p, d, mag = cfg
+    rng = np.random.default_rng(hash(cfg) % (2 ** 31))
+    x = (rng.standard_normal((n, cin, h, w)) * mag).astype(np.float32)
+    K = (rng.standard_normal((cout, cin, k, k)) * np.sqrt(2.0 / (cin * k * k))).astype(np.float32)
+    bias = (rng.standard_normal(cout) * 0.1 * mag).astype(np.float32)
+    ref = oracle.conv2d(x.astype(np.float64), K.astype(np.float64), bias.astype(np.float64), 1, (s, s), (d, d), (p,) * 4)
+    r = None
+    if fused:
+        bk = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+        bb = (rng.standard_normal(cout) * 0.1 * mag).astype(np.float32)
+        ref = oracle.batchnorm(ref, bk.reshape(1, -1, 1, 1).astype(np.float64), bb.reshape(1, -1, 1, 1).astype(np.float64))
+        r = (rng.standard_normal(ref.shape) * mag).astype(np.float32)
+        ref = oracle.relu(oracle.add(ref, r.astype(np.float64)))
+        scale, shift = ops.fold_affine(B.asarray(bias), B.asarray(bk), B.asarray(bb), cout)
+    else:
+        scale, shift = ops.fold_affine(B.asarray(bias), None, None, cout)
+        scale = None
+    xd = B.to_nhwc(B.asarray(x))
+    Kd = B.asarray(K)
+    rd = B.to_nhwc(B.asarray(r)) if fused else None
+    act = ops.ACT_RELU if fused else ops.ACT_NONE
+    w16, meta = ops.pack_weight_split(Kd)
+    sw = ops.split_weight(w16, meta, cin)
+    y = B.empty(ref.shape, np.float32, 'nhwc')
+    ops.conv2d_into(xd, sw, y, k, k, (s, s), (d, d), (p,) * 4, 1, scale, shift, rd, act, 0.0)
+    y2 = B.empty(ref.shape, np.float32, 'nhwc')
+    ops.conv2d_into(xd, ops.pack_weight(Kd, cin, np.float32), y2, k, k, (s, s), (d, d), (p,) * 4, 1, scale, shift, rd, act, 0.0,
+                    ops.ALGO_DIRECT)
+    B.synchronize()
+    e_split, e_ffma = rel_err(y.get(), ref), rel_err(y2.get(), ref)
+    assert e_split <= 2e-5 and e_ffma <= 2e-5, (cfg, e_split, e_ffma)
+
+
+def test_fp32_net_runs_on_the_tensor_pipe_and_agrees_with_the_cuda_core_path(planer, monkeypatch):
+    """A float32 ResNet-18 forward takes the split-fp16 tensor-core path for every group-1 convolution by default;
+    PLNR_F32_TENSOR=0 keeps the FFMA kernel.  Both meet the 1e-3 bar on the reference fixture; they agree to 1e-4."""
+    from planer_b200 import backend as B
+    model, blob, x, _ = cases.make_graph_case('resnet18_small_f32')
+    ref = oracle.build_net(model, blob)(x.astype(np.float32))
+    outs = []
+    for flag in ('1', '0'):
+        monkeypatch.setenv('PLNR_F32_TENSOR', flag)
+        net = planer.from_model(model, blob)
+        y = net(x)
+        ex = list(net._executors.values())[0]
+        assert (ex.split_convs > 0) == (flag == '1')
+        outs.append(np.asarray(y))
+        assert rel_err(outs[-1], ref) <= 1e-3
+    assert rel_err(outs[0], outs[1]) <= 1e-4
+
+
 @pytest.mark.parametrize('cfg', CONV_SWEEP)
 @pytest.mark.parametrize('algo', ['tcgen05', 'direct'])
 def test_conv_fp16_kernels_vs_oracle(planer, cfg, algo):
