@@ -426,8 +426,14 @@ def main():
     all_ms = sum(r['ms'] for r in table)
     ms_step = ms_total / steps
     pk = peaks()
-    if not half:
-        # fp32 runs on the CUDA cores: 148 SMs x 128 FFMA/clk x 2 FLOP at the clock sampled under this load
+    split = (not half) and ex.split_convs > 0
+    if split:
+        # fp32 on the tensor pipe (csrc/split_f32.cu): every fp32 product is THREE fp16 tensor-core products, so the ceiling
+        # for ALGORITHMIC fp32 FLOPs is a third of the fp16 tensor peak
+        pk = dict(pk, tflops_sustained=pk['tflops_sustained'] / 3, tflops_burst=pk['tflops_burst'] / 3,
+                  source=pk['source'] + ' / 3 (fp32 as three fp16 products per multiply)')
+    elif not half:
+        # fp32 on the CUDA cores (PLNR_F32_TENSOR=0): 148 SMs x 128 FFMA/clk x 2 FLOP at the clock sampled under this load
         mhz = (clk or {}).get('sm_mhz') or 1965.0
         ffma = B.device_info()['sm_count'] * 128 * 2 * mhz * 1e6 / 1e12
         pk = dict(pk, tflops_sustained=ffma, tflops_burst=ffma, source='FFMA peak = SMs x 128 x 2 x sampled SM clock (%.0f MHz)' % mhz)
@@ -461,9 +467,11 @@ def main():
         else:
             traffic_src = ('null: the newest committed capture (profiles/%s) is of another build of libplaner_b200.so'
                            % cands[-1])
-    roofline = {'bound': 'tensor' if half else 'ffma',
+    roofline = {'bound': 'tensor' if (half or split) else 'ffma',
                 'kernel': 'whole step: every launch is a %s conv / dense kernel (%d conv+dense layers in %d launches)'
-                          % ('tcgen05' if half else 'CUDA-core FFMA', sum(1 for n in ex.plan.nodes if n.kind in ('conv', 'dense')), len(table)),
+                          % ('tcgen05' if half else ('tcgen05 split-fp16 (fp32 operands as hi+lo fp16 pairs, fp32 accumulate; + '
+                                                     'its absmax / split launches)' if split else 'CUDA-core FFMA'),
+                             sum(1 for n in ex.plan.nodes if n.kind in ('conv', 'dense')), len(table)),
                 'achieved': achieved, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved / pk['tflops_sustained'], 'traffic': traffic, 'traffic_source': traffic_src,
                 'peak_source': pk['source'] + ', sustained figure (kernels timed inside a long step)',

@@ -69,6 +69,60 @@ __global__ void nhwc_to_nchw_kernel(const Tin* __restrict__ x, Tout* __restrict_
   }
 }
 
+// fp16 pixel-major -> NCHW without shared memory: a thread loads an 8-pixel x 8-channel block as eight 16-byte vectors (one
+// per pixel), transposes it in registers (32 byte-permutes) and stores eight 16-byte vectors (one per channel: 8 consecutive
+// pixels).  A warp covers 8 pixel blocks x 4 channel groups, so a load instruction touches 64-byte runs and a store instruction
+// 128-byte runs: every sector moved is used in full.  (The 32x33 float tile above moves 2-byte elements: 0.28 of the copy
+// bandwidth; this one is bound by HBM.)  Stores fall back to narrower vectors when the NCHW row is not 16-byte aligned
+// (H*W not a multiple of 8).
+__global__ void __launch_bounds__(256) nhwc_to_nchw_h16_kernel(const __half* __restrict__ x, __half* __restrict__ y, int C, int HW,
+                                                                int ld, int coff, int PB8, int CG4, long long total) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int lane = (int)(idx & 31);
+  long long t = idx >> 5;
+  const int cg4 = (int)(t % CG4); t /= CG4;
+  const int pb8 = (int)(t % PB8);
+  const int n = (int)(t / PB8);
+  const int p0 = (pb8 * 8 + (lane & 7)) * 8;             // first pixel of this thread's block
+  const int c0 = (cg4 * 4 + (lane >> 3)) * 8;            // first channel
+  if (p0 >= HW || c0 >= C) return;
+  const __half* xb = x + ((size_t)n * HW + p0) * ld + coff + c0;
+  uint4 in[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    in[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (p0 + j < HW) in[j] = *reinterpret_cast<const uint4*>(xb + (size_t)j * ld);
+  }
+  const int npix = min(8, HW - p0);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {                          // channel c0 + k = half (k & 1) of word k / 2 of every pixel
+    uint32_t o[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const uint32_t w0 = reinterpret_cast<const uint32_t*>(&in[2 * a])[k >> 1];
+      const uint32_t w1 = reinterpret_cast<const uint32_t*>(&in[2 * a + 1])[k >> 1];
+      o[a] = __byte_perm(w0, w1, (k & 1) ? 0x7632 : 0x5410);
+    }
+    __half* dst = y + ((size_t)n * C + c0 + k) * HW + p0;
+    const uintptr_t ad = reinterpret_cast<uintptr_t>(dst);
+    if (npix == 8 && (ad & 15) == 0) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else if (npix == 8 && (ad & 7) == 0) {
+      *reinterpret_cast<uint2*>(dst) = make_uint2(o[0], o[1]);
+      *reinterpret_cast<uint2*>(dst + 4) = make_uint2(o[2], o[3]);
+    } else if (npix == 8 && (ad & 3) == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) *reinterpret_cast<uint32_t*>(dst + 2 * a) = o[a];
+    } else {
+      const __half* oh = reinterpret_cast<const __half*>(o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < npix) dst[j] = oh[j];
+    }
+  }
+}
+
 // Stem packing: NCHW input (few channels) -> pixel-major tensor whose "channels" are the horizontal filter taps x
 // vertical stride phases x input channels of one output column, so that a k x k / stride-s convolution becomes a
 // (T x 1) stride-1 convolution with 16/32/64 channels (one TMA row per pixel instead of k*k tiny ones).
@@ -293,6 +347,66 @@ __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, 
         *reinterpret_cast<Vec<T, V>*>(yb + ((size_t)oh * OW + ow0) * yld) = m0;
         if (ow0 + 1 < OW) *reinterpret_cast<Vec<T, V>*>(yb + ((size_t)oh * OW + ow0 + 1) * yld) = m1;
         m0 = VM::max2(floor_v, h0); m1 = VM::max2(floor_v, h1);
+      }
+    }
+  }
+}
+
+// 3x3 / stride-2 AVERAGE pooling with the same register blocking (a thread owns two adjacent output columns and a strip of
+// RB output rows; five loads per input row serve both): zero padding, divisor always 9 (planer/util.py:97-100), fp32 sums.
+template <typename T, int V, int RB>
+__global__ void avgpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int xld,
+                                    int xcoff, int OH, int OW, int yld, int ycoff, int pt, int pl) {
+  const int CV = C / V, OWP = (OW + 1) / 2, OHS = (OH + RB - 1) / RB;
+  const int64_t total = (int64_t)N * OHS * OWP * CV;
+  const float inv = 1.f / 9.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    int64_t t = i / CV;
+    const int owp = (int)(t % OWP); t /= OWP;
+    const int ohs = (int)(t % OHS);
+    const int n = (int)(t / OHS);
+    const int ow0 = 2 * owp, oh0 = ohs * RB;
+    const int nout = min(RB, OH - oh0);
+    const T* xb = x + (size_t)n * H * W * xld + xcoff + cv * V;
+    T* yb = y + (size_t)n * OH * OW * yld + ycoff + cv * V;
+    const int iw0 = 2 * ow0 - pl;
+    bool cok[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) cok[q] = iw0 + q >= 0 && iw0 + q < W;
+    float m0[V], m1[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) m0[k] = m1[k] = 0.f;
+    for (int r = 0; r <= 2 * nout; ++r) {
+      const int ih = 2 * oh0 - pt + r;
+      float h0[V], h1[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) h0[k] = h1[k] = 0.f;
+      if (ih >= 0 && ih < H) {
+        Vec<T, V> c[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const int iwc = min(max(iw0 + q, 0), W - 1);
+          c[q] = *reinterpret_cast<const Vec<T, V>*>(xb + ((size_t)ih * W + iwc) * xld);
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float f0 = cok[0] ? ld_f(&c[0].v[k]) : 0.f, f1 = cok[1] ? ld_f(&c[1].v[k]) : 0.f, f2 = cok[2] ? ld_f(&c[2].v[k]) : 0.f;
+          const float f3 = cok[3] ? ld_f(&c[3].v[k]) : 0.f, f4 = cok[4] ? ld_f(&c[4].v[k]) : 0.f;
+          h0[k] = f0 + f1 + f2; h1[k] = f2 + f3 + f4;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) { m0[k] += h0[k]; m1[k] += h1[k]; }
+      if (r >= 2 && (r & 1) == 0) {
+        const int oh = oh0 + (r >> 1) - 1;
+        Vec<T, V> o0, o1;
+#pragma unroll
+        for (int k = 0; k < V; ++k) { st_f(&o0.v[k], m0[k] * inv); st_f(&o1.v[k], m1[k] * inv); }
+        *reinterpret_cast<Vec<T, V>*>(yb + ((size_t)oh * OW + ow0) * yld) = o0;
+        if (ow0 + 1 < OW) *reinterpret_cast<Vec<T, V>*>(yb + ((size_t)oh * OW + ow0 + 1) * yld) = o1;
+#pragma unroll
+        for (int k = 0; k < V; ++k) { m0[k] = h0[k]; m1[k] = h1[k]; }
       }
     }
   }
@@ -1011,6 +1125,15 @@ int plnr_stem_pack(plnr_ctx* ctx, const void* x, int x_dtype, int n, int c, int 
 int plnr_nhwc_to_nchw(plnr_ctx* ctx, const plnr_tensor* x, int x_dtype, void* y, int y_dtype) {
   PLNR_REQUIRE(ctx && x && x->ptr && y, "nhwc_to_nchw: NULL argument");
   const int HW = x->h * x->w;
+  if (x_dtype == PLNR_F16 && y_dtype == PLNR_F16 && x->c % 8 == 0 && x->ld % 8 == 0 && x->coff % 8 == 0 && aligned16(x->ptr) &&
+      (reinterpret_cast<uintptr_t>(y) & 1) == 0 && !getenv("PLNR_TRANSPOSE_TILE")) {
+    const int PB8 = ((HW + 7) / 8 + 7) / 8, CG4 = (x->c / 8 + 3) / 4;
+    const long long total = (long long)x->n * PB8 * CG4 * 32;
+    PLNR_REQUIRE((total + 255) / 256 < (1ll << 31), "nhwc_to_nchw: tensor too large for one launch");
+    nhwc_to_nchw_h16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const __half*)x->ptr, (__half*)y, x->c, HW,
+                                                                                    x->ld, x->coff, PB8, CG4, total);
+    return plnr_after_launch(ctx, "nhwc_to_nchw");
+  }
   dim3 grid((HW + 31) / 32, (x->c + 31) / 32, x->n), block(32, 8);
   PLNR_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "nhwc_to_nchw: batch/channel count too large for one launch");
 #define LAUNCH(TI, TO) \
@@ -1122,7 +1245,12 @@ int plnr_avgpool2d(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const plnr_te
   DISPATCH_T(dtype, {
     constexpr int V = VecWidth<T>::value;
     if (view_vec_ok(x, V, sizeof(T)) && view_vec_ok(y, V, sizeof(T))) {
-      if (kh == 2 && kw == 2) AP_LAUNCH(V, 2, 2);
+      if (kh == 3 && kw == 3 && stride_h == 2 && stride_w == 2) {
+        constexpr int RB = 4;
+        const int64_t w2 = (int64_t)y->n * ((y->h + RB - 1) / RB) * ((y->w + 1) / 2) * (y->c / V);
+        avgpool3x3s2_kernel<T, V, RB><<<grid_for(w2, ctx->sm_count * 2), kThreads, 0, ctx->stream>>>(
+            (const T*)x->ptr, (T*)y->ptr, x->n, x->h, x->w, x->c, x->ld, x->coff, y->h, y->w, y->ld, y->coff, pad_t, pad_l);
+      } else if (kh == 2 && kw == 2) AP_LAUNCH(V, 2, 2);
       else if (kh == 3 && kw == 3) AP_LAUNCH(V, 3, 3);
       else AP_LAUNCH(V, 0, 0);
     } else {

@@ -856,3 +856,34 @@ def test_yolov3_first_layer_runs_on_the_direct_kernel(planer, monkeypatch):
     assert not net2.executor([x.shape], [x.dtype]).fused_stems
     for s, t in zip(a, b):
         assert rel_err(s, t) <= 3e-3
+
+
+@pytest.mark.parametrize('shape', [(2, 8, 7, 7), (3, 24, 26, 26), (2, 256, 52, 52), (1, 40, 5, 3), (2, 64, 13, 13), (1, 8, 1, 1)])
+def test_fp16_layout_exit_register_transpose_is_exact(planer, shape):
+    """plnr_nhwc_to_nchw, fp16 -> fp16 (nhwc_to_nchw_h16_kernel: 8x8 register transposes, 16-byte accesses on both sides):
+    bit-exact against numpy on dense tensors and on a channel slice of a wider buffer, for H*W that is / is not a multiple
+    of 8 (the stores then narrow to 8 / 4 / 2 bytes)."""
+    from planer_b200 import ops, backend as B
+    n, c, h, w = shape
+    x = np.random.default_rng(c * h).standard_normal(shape).astype(np.float16)
+    xd = B.to_nhwc(B.asarray(x))
+    assert np.array_equal(B.to_flat(xd).get(), x)
+    wide = np.random.default_rng(1).standard_normal((n, c + 16, h, w)).astype(np.float16)
+    wd = B.to_nhwc(B.asarray(wide))
+    out = B.empty(shape, np.float16)
+    ops.nhwc_to_nchw_into(ops.channel_slice(wd, 8, c), out)
+    assert np.array_equal(out.get(), wide[:, 8:8 + c])
+
+
+@pytest.mark.parametrize('cfg', [((2, 16, 13, 15), np.float16), ((1, 8, 112, 112), np.float16), ((2, 4, 9, 8), np.float32),
+                                 ((3, 24, 7, 7), np.float16)])
+def test_avgpool_3x3_s2_register_blocked_vs_oracle(planer, cfg):
+    """avgpool3x3s2_kernel (two output columns x four output rows per thread) against the oracle's AveragePool: zero padding,
+    divisor 9 everywhere (planer/util.py:97-100), odd and even extents."""
+    from planer_b200 import ops, backend as B
+    shape, dt = cfg
+    x = (np.random.default_rng(shape[2]).standard_normal(shape) + 0.5).astype(dt)
+    ref = oracle.avgpool(x.astype(np.float32), (3, 3), (1, 1, 1, 1), (2, 2))
+    y = B.empty(ref.shape, dt, 'nhwc')
+    ops.avgpool_into(B.to_nhwc(B.asarray(x)), y, (3, 3), (1, 1, 1, 1), (2, 2))
+    assert rel_err(y.get(), ref) <= TOL[np.dtype(dt)] / 5
