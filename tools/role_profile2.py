@@ -73,6 +73,12 @@ cfgs = {
     'l': ('layer4.0 256->512 s2', 128, 256, 14, 14, 512, 3, 2, False),
     'j': ('128->128 @14 x512 (layer2 FLOPs)', 512, 128, 14, 14, 128, 3, 1, False),
     'k': ('64->64 @28 x512 (layer1 FLOPs)', 512, 64, 28, 28, 64, 3, 1, False),
+    # YOLOv3-416 batch 32, the early (HBM-heavy) layers
+    'y': ('yolo 32->64 3x3 @208 +res', 32, 32, 208, 208, 64, 3, 1, True),
+    'z': ('yolo 32->64 3x3 s2 @416', 32, 32, 416, 416, 64, 3, 2, False),
+    'w': ('yolo 64->32 1x1 @208', 32, 64, 208, 208, 32, 1, 1, False),
+    'v': ('yolo 64->128 3x3 s2 @208', 32, 64, 208, 208, 128, 3, 2, False),
+    'u': ('yolo 128->64 1x1 @104', 32, 128, 104, 104, 64, 1, 1, False),
 }
 for key in (sys.argv[1] if len(sys.argv) > 1 else 'abcdefghi'):
     run(*cfgs[key])
