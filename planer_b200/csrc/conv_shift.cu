@@ -38,7 +38,7 @@ constexpr long long kWatchdogCycles = 4000000000ll;
 struct AMaps { CUtensorMap m[4]; };     // the A operand's tensor map with boxes of 1, 2, 4, 8 rows
 
 struct ShiftParams {
-  FastDiv div_hvwv, div_wv, div_mt;     // / (Hv*Wv), / Wv, / num_m_tiles
+  FastDiv div_hvwv, div_wv, div_mt, div_hv;     // / (Hv*Wv), / Wv, / num_m_tiles, / Hv
   int N, OH, OW, Hv, Wv, HvWv;
   int pad_t, pad_l;
   long long Mv;             // N * Hv * Wv virtual output positions
@@ -169,10 +169,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
 }
 
 // rows of the A buffer a CTA whose first position is o0 has to load: [v0, v0 + nrows)
-__device__ __forceinline__ void tile_rows(long long o0, int Wv, int halo, long long& v0, int& nrows, int& off) {
-  v0 = o0 / Wv;
-  off = (int)(o0 - v0 * Wv);
-  nrows = (int)((o0 + kTileM - 1 + halo) / Wv - v0) + 1;
+__device__ __forceinline__ void tile_rows(long long o0, int Wv, int halo, const FastDiv& div_wv, long long& v0, int& nrows, int& off) {
+  // every position (+ halo) is below 2^31 (make_plan), so the divisions are 32-bit multiply-highs: with 64-bit divisions
+  // the producer warp spent ~700 clk per tile on address arithmetic and paced layers with few MMAs per tile (YOLOv3's
+  // pointwise convolutions: 2300 clk per tile for four MMAs)
+  const uint32_t u0 = (uint32_t)o0;
+  const uint32_t q0 = fast_div(u0, div_wv);
+  v0 = (long long)q0;
+  off = (int)(u0 - q0 * (uint32_t)Wv);
+  nrows = (int)(fast_div(u0 + (uint32_t)(kTileM - 1 + halo), div_wv) - q0) + 1;
 }
 
 template <int CG>
@@ -249,14 +254,14 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
     for (int k = 0; k < segs.nseg; ++k) {
       const Seg sg = segs.at(k);
       const int tile = sg.tile;
-      const int m_idx = tile % p.num_m_tiles, n_idx = tile / p.num_m_tiles;
+      const int n_idx = (int)fast_div((uint32_t)tile, p.div_mt), m_idx = tile - n_idx * p.num_m_tiles;
       const long long o0 = ((long long)m_idx * CG + rank) * kTileM;
       long long v0; int nrows, off;
-      tile_rows(o0, Wv, p.halo, v0, nrows, off);
+      tile_rows(o0, Wv, p.halo, p.div_wv, v0, nrows, off);
       uint32_t a_bytes = (uint32_t)nrows * row_bytes;
       if (CG == 2) {                                     // the leader arms the barrier for both CTAs' rows
         long long v0p; int nrows_p, off_p;
-        tile_rows(o0 + (leader ? kTileM : -kTileM), Wv, p.halo, v0p, nrows_p, off_p);
+        tile_rows(o0 + (leader ? kTileM : -kTileM), Wv, p.halo, p.div_wv, v0p, nrows_p, off_p);
         a_bytes += (uint32_t)nrows_p * row_bytes;
       }
       const int n_row = n_idx * p.n_tile + (int)rank * (p.n_tile / CG);
@@ -269,7 +274,7 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
       for (int lu = 0; lu < nmain + p.c2chunks; ++lu) {
         // load unit = (64-channel chunk, plane) of the convolution, then the chunks of the fused shortcut
         const bool sc = lu >= nmain;
-        const int cc = sc ? lu - nmain : lu / p.nplanes;
+        const int cc = sc ? lu - nmain : (p.nplanes == 1 ? lu : lu / p.nplanes);
         const int pi = sc ? 0 : lu - cc * p.nplanes;
         // taps of this unit inside the segment's iteration range (iteration of tap t: cc * RS + t; shortcut chunks follow)
         int t0 = sc ? 0 : p.pl_first[pi], t1 = sc ? 1 : p.pl_first[pi + 1];
@@ -285,7 +290,7 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
           if (leader) ptx::mbar_arrive_expect_tx(full, a_bytes);
           uint32_t dst = sA + ab * p.a_buf_bytes + row0_off;
           long long v = v0;
-          int img = (int)(v / p.Hv), hrow = (int)(v - (long long)img * p.Hv);
+          int img = (int)fast_div((uint32_t)v, p.div_hv), hrow = (int)v - img * p.Hv;
           const int cs = sc ? p.s2 : p.cs, c0 = cc * 64;
           const int w0 = sc ? -p.pad_l * p.s2 : p.pl_w0[pi], h0 = sc ? -p.pad_t * p.s2 : p.pl_h0[pi];
           // The rows of one image go out as boxes of 8 / 4 / 2 / 1 rows: the issuing thread pays ~100-150 clk per TMA
@@ -364,10 +369,10 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
       uint32_t ridx = 0;                         // resident: running index of the next weight box
       for (int cc = 0; cc < nchunks_all; ++cc) { // cc = load unit: (chunk, plane), then the fused-shortcut chunks
         const bool sc = cc >= nmain;             // chunk of the fused 1x1 shortcut: one tap, the un-shifted view
-        const int pi = sc ? 0 : cc % p.nplanes;
+        const int pi = (sc || p.nplanes == 1) ? 0 : cc % p.nplanes;
         int t0 = sc ? 0 : p.pl_first[pi], t1 = sc ? 1 : p.pl_first[pi + 1];
         {                                        // the part of this unit inside the segment (see the producer)
-          const int ibase = sc ? cchunks * R * S + (cc - nmain) : (cc / p.nplanes) * R * S;
+          const int ibase = sc ? cchunks * R * S + (cc - nmain) : (p.nplanes == 1 ? cc : cc / p.nplanes) * R * S;
           const int nt = t1 - t0;
           t0 = max(t0, sg.it0 - ibase);
           t1 = min(t1, sg.it1 - ibase);
@@ -870,7 +875,7 @@ static ShiftPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
   }
   pl.a_buf_bytes = (uint32_t)round_up(need * 128, 1024);
   const long long Mv = (long long)x->n * pl.Hv * pl.Wv;
-  if (Mv >= (1ll << 31) - 512) return pl;
+  if (Mv + pl.halo + 1024 >= (1ll << 31)) return pl;       // positions (+ halo) stay below 2^31: 32-bit multiply-high divisions
   const double eff = (double)y->h * y->w / ((double)pl.Hv * pl.Wv);
   if (eff < 0.70) return pl;                              // small maps: too many discarded rim positions
   const int m_tiles_128 = (int)((Mv + kTileM - 1) / kTileM);
@@ -1055,6 +1060,7 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
   p.div_hvwv = make_fastdiv((uint32_t)p.HvWv);
   p.div_wv = make_fastdiv((uint32_t)p.Wv);
   p.div_mt = make_fastdiv((uint32_t)p.num_m_tiles);
+  p.div_hv = make_fastdiv((uint32_t)p.Hv);
   p.na = pl.na; p.nb = pl.nb; p.b_resident = pl.b_resident;
   p.stage_wide = pl.stage_wide;
   p.a_buf_bytes = pl.a_buf_bytes; p.b_stage_bytes = pl.b_stage_bytes;

@@ -607,6 +607,8 @@ int plnr_conv2d_tcgen05(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tenso
                         const plnr_tensor* y, const plnr_epilogue* ep) {
   // stride-1 convolutions with Cin % 64 == 0 take the shift-GEMM kernel (conv_shift.cu): each input row is loaded once
   // (fp16 results only: the fp32 epilogue of the split-fp16 path lives in this kernel)
+  // 1x1 / stride-1 convolutions with small filters: the lean resident-weight GEMM kernel (conv_pw.cu)
+  if (plnr_conv2d_pw_supported(d, x, y, ep)) return plnr_conv2d_pw(ctx, d, x, w, y, ep);
   const bool out_f32 = ep && ep->out_f32;
   if (!out_f32 && plnr_conv2d_shift_supported(d, x, y)) return plnr_conv2d_shift(ctx, d, x, w, y, ep);
   int rc = resolve_driver();

@@ -887,3 +887,51 @@ def test_avgpool_3x3_s2_register_blocked_vs_oracle(planer, cfg):
     y = B.empty(ref.shape, dt, 'nhwc')
     ops.avgpool_into(B.to_nhwc(B.asarray(x)), y, (3, 3), (1, 1, 1, 1), (2, 2))
     assert rel_err(y.get(), ref) <= TOL[np.dtype(dt)] / 5
+
+
+PW_SWEEP = [
+    # n, cin, h, w, cout, activation, output inside a wider (concat) buffer
+    (2, 64, 26, 26, 32, 'leaky', False), (3, 128, 13, 13, 64, 'leaky', True), (1, 256, 52, 52, 128, 'relu', False),
+    (2, 64, 7, 9, 24, 'none', False), (1, 192, 10, 10, 72, 'sigmoid', True), (5, 128, 5, 5, 256, 'leaky', False),
+    (1, 64, 1, 1, 8, 'relu', False), (4, 512, 8, 8, 64, 'leaky', False),
+]
+
+
+@pytest.mark.parametrize('cfg', PW_SWEEP)
+def test_pointwise_conv_kernel_vs_oracle_and_shift_kernel(planer, cfg, monkeypatch):
+    """conv_pw.cu (1x1 / stride-1 convolutions with a small resident filter as a GEMM over the pixel rows) against the oracle's
+    conv -> batchnorm -> activation chain and, bit for bit, against conv_shift.cu on the same problem (PLNR_PW=0): both
+    round the same fp32 sums to fp16 once and apply the same packed-fp16 epilogue.  Ragged row counts (M % 128 != 0),
+    channel counts that are not a multiple of 32, outputs written into a channel slice of a wider buffer."""
+    from planer_b200 import ops, backend as B
+    n, cin, h, w, cout, act, sliced = cfg
+    rng = np.random.default_rng(cin * 7 + cout)
+    x = rng.standard_normal((n, cin, h, w)).astype(np.float16)
+    K = (rng.standard_normal((cout, cin, 1, 1)) * np.sqrt(2.0 / cin)).astype(np.float16)
+    bk = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bb = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    ref = oracle.conv2d(x.astype(np.float32), K.astype(np.float32), None, 1, (1, 1), (1, 1), (0, 0, 0, 0))
+    ref = oracle.batchnorm(ref, bk.reshape(1, -1, 1, 1), bb.reshape(1, -1, 1, 1))
+    ref = {'leaky': lambda v: oracle.leakyrelu(v, 0.1), 'relu': oracle.relu, 'none': lambda v: v, 'sigmoid': oracle.sigmoid}[act](ref)
+    code = {'leaky': ops.ACT_LEAKY, 'relu': ops.ACT_RELU, 'none': ops.ACT_NONE, 'sigmoid': ops.ACT_SIGMOID}[act]
+    xd = B.to_nhwc(B.asarray(x))
+    wp = ops.pack_weight(B.asarray(K), cin, np.float16)
+    scale, shift = ops.fold_affine(None, B.asarray(bk), B.asarray(bb), cout)
+    outs = []
+    for flag in ('1', '0'):
+        monkeypatch.setenv('PLNR_PW', flag)
+        wide = B.to_nhwc(B.asarray(np.full((n, cout + 16, h, w), 7.0, np.float16)))
+        y = ops.channel_slice(wide, 8, cout) if sliced else B.empty(ref.shape, np.float16, 'nhwc')
+        ops.conv2d_into(xd, wp, y, 1, 1, (1, 1), (1, 1), (0, 0, 0, 0), 1, scale, shift, None, code, 0.1)
+        B.synchronize()
+        assert B.last_kernel() == ('conv2d_pw' if flag == '1' else 'conv2d_shift'), B.last_kernel()
+        got = y.get() if not sliced else wide.get()[:, 8:8 + cout]
+        assert rel_err(got, ref) <= 1e-2
+        if sliced:                                        # the neighbouring channels of the wide buffer are untouched
+            full = wide.get()
+            assert np.all(full[:, :8] == 7.0) and np.all(full[:, 8 + cout:] == 7.0)
+        outs.append(got)
+    if cout % 32 == 0:
+        assert np.array_equal(outs[0], outs[1])
+    else:          # conv_shift.cu finishes a partial 32-channel chunk in fp32 (one rounding), conv_pw.cu in packed fp16
+        assert rel_err(outs[0], outs[1]) <= 2e-3
