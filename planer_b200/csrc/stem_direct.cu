@@ -4,16 +4,16 @@
 // Replaces, for YOLOv3's 3 -> 32 stem, the reference chain Conv2d (planer/layer.py:22-26 + planer/util.py:17-44) ->
 // BatchNorm (planer/layer.py:125-127) -> LeakyReLU (planer/layer.py:48-51) and this library's earlier two launches
 // (plnr_stem_pack + a tensor-core conv with K = 48, N = 32: 29 TFLOP/s, 12 % of the YOLOv3 step).  With K = 27 and
-// N = 32 the layer is 9.6 GFLOP against 16.6 MB read + 354 MB written per 32 images: it belongs on the CUDA cores, next to
-// the stores.  One thread = four adjacent output pixels x 16 channels:
-//   * the filter lives in the KERNEL PARAMETERS (27 taps x 16 channel pairs of fp16 = 1.7 KB), so every HFMA2 takes its
-//     weight operand straight from the constant bank -- no shared memory, no weight loads;
-//   * the 27 input values of a pixel are 2-byte global loads, coalesced across the warp (consecutive pixels) and served by L1
-//     (neighbouring pixels share 6 of 9 positions);
-//   * products of one filter row (9 terms) accumulate in packed fp16, the three rows are added in fp32, the sum is rounded to
-//     fp16 once (the reference's conv output is an fp16 array), then scale / shift as one HFMA2 and the activation in fp16,
-//     like every other conv epilogue of this library;
-//   * a pixel's 32 channels are 64 contiguous bytes, written by the two threads of a pixel group as 2 x 2 16-byte stores.
+// N = 32 the layer is 9.6 GFLOP against 16.6 MB read + 354 MB written per 32 images: too small for a 128-row tcgen05 tile
+// pipeline, too many FLOPs for HFMA2 (the first version: 0.33 ms, instruction-bound).  It runs on the WARP-level tensor-core
+// instruction, straight from the NCHW image, next to the stores:
+//   * the filter travels in the KERNEL PARAMETERS (27 taps x 32 channels of fp16 = 1.7 KB), is staged once per block in shared
+//     memory and lives in 16 registers per lane as mma.sync B fragments;
+//   * the 27 input values of a pixel are 2-byte global loads gathered directly into A fragments (rows = 16 adjacent pixels),
+//     served by L1 (neighbouring pixels share 6 of 9 positions);
+//   * all 27 products accumulate in fp32, the sum is rounded to fp16 once (the reference's conv output is an fp16 array), then
+//     scale / shift as one HFMA2 and the activation in fp16, like every other conv epilogue of this library;
+//   * a pixel's 32 channels are 64 contiguous bytes, written by the four lanes of a quad as 4-byte pieces.
 #include "common.cuh"
 
 namespace {
@@ -33,88 +33,146 @@ template <typename Tin> __device__ __forceinline__ __half ld_h(const Tin* p);
 template <> __device__ __forceinline__ __half ld_h<__half>(const __half* p) { return __ldg(p); }
 template <> __device__ __forceinline__ __half ld_h<uint8_t>(const uint8_t* p) { return __ushort2half_rn((unsigned short)__ldg(p)); }
 
-// One thread = FOUR horizontally adjacent output pixels x 16 channels (one half of the filter bank): a weight pair fetched
-// from the constant bank feeds four HFMA2 instead of one (the one-pixel version spent 285 LDC on 467 HFMA2 per pixel and ran
-// at 26 TFLOP/s), and the six input values of a filter row serve all four pixels.
-constexpr int kPix = 4;
+// One WARP = 16 horizontally adjacent output pixels x 32 channels per trip, on the warp-level tensor-core instruction
+// (mma.sync.m16n8k16, fp16 x fp16 -> fp32): the 27 taps are the K dimension (padded to 32 = two K=16 steps), the 32 output
+// channels four N=8 blocks.  The first version of this kernel (four pixels x 16 channels per thread, HFMA2 with the filter in the
+// constant bank) executed 2200 instructions per thread of which 906 were HFMA2 and ran at 29 TFLOP/s, 0.33 ms for 32 x 416 x 416
+// (ncu: issue slots 58 % busy, FMA pipe 59 %): instruction-bound.  Here a warp spends ~215 instructions per 16 pixels: 16
+// two-byte loads per lane gather the A fragments (rows = pixels, neighbours hit L1), 8 mma.sync, and the epilogue of the other conv
+// kernels (fp32 sum rounded to fp16 once, scale / shift as one HFMA2, activation) on the C fragments.  The filter's B fragments
+// (16 registers) are read once per warp from shared memory, where the block stages the kernel parameters.  80 registers, three
+// blocks per SM: 0.24 ms for 32 x 416 x 416 (0.33 before).  What bounds it now is the L1 / LSU tag rate of its gathers (ncu: 49 %
+// excessive sectors -- every load request touches four lines, every 4-byte store request eight half-used sectors); staging the
+// input rows in shared memory and transposing the C fragments inside each quad for 16-byte stores is the next step.
+constexpr int kWarpsPerBlock = 8;
 
 template <typename Tin, int kAct>
-__global__ void __launch_bounds__(256, 2) stem3x3_kernel(const __grid_constant__ Stem3Params p) {
-  const int half_ = threadIdx.x & 1;                         // channels [16 half_, 16 half_ + 16)
-  const long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
-  const int gw = (p.W + kPix - 1) / kPix;                    // pixel groups per row
-  const long long total = (long long)p.N * p.H * gw;
-  if (grp >= total) return;
-  const int g_ = (int)(grp % gw);
-  const long long t = grp / gw;
-  const int h = (int)(t % p.H), n = (int)(t / p.H);
-  const int w0 = g_ * kPix;
-  const Tin* x = reinterpret_cast<const Tin*>(p.x) + (size_t)n * p.C * p.H * p.W;
-  const __half zero = __float2half_rn(0.f);
-  float tot[kPix][16];
-#pragma unroll
-  for (int i = 0; i < kPix; ++i)
-#pragma unroll
-    for (int j = 0; j < 16; ++j) tot[i][j] = 0.f;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int ih = h + r - 1;
-    const bool rok = ih >= 0 && ih < p.H;
-    __half2 acc[kPix][8];
-#pragma unroll
-    for (int i = 0; i < kPix; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = __half2half2(zero);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      if (c < p.C) {
-        const Tin* row = x + ((size_t)c * p.H + (rok ? ih : 0)) * p.W;
-        __half2 xv[kPix + 2];                                // columns w0 - 1 .. w0 + 4, broadcast to both halves of a pair
-#pragma unroll
-        for (int q = 0; q < kPix + 2; ++q) {
-          const int iw = w0 + q - 1;
-          xv[q] = __half2half2((rok && iw >= 0 && iw < p.W) ? ld_h<Tin>(row + iw) : zero);
-        }
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          // this thread's 8 weight pairs of the tap: 16-byte constant-bank loads
-          const uint4* wt = reinterpret_cast<const uint4*>(&p.w[(c * 3 + r) * 3 + s][half_ * 8]);
-          const uint4 wa = wt[0], wb = wt[1];
-          const __half2 wv[8] = {*reinterpret_cast<const __half2*>(&wa.x), *reinterpret_cast<const __half2*>(&wa.y),
-                                 *reinterpret_cast<const __half2*>(&wa.z), *reinterpret_cast<const __half2*>(&wa.w),
-                                 *reinterpret_cast<const __half2*>(&wb.x), *reinterpret_cast<const __half2*>(&wb.y),
-                                 *reinterpret_cast<const __half2*>(&wb.z), *reinterpret_cast<const __half2*>(&wb.w)};
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-#pragma unroll
-            for (int i = 0; i < kPix; ++i) acc[i][j] = __hfma2(xv[i + s], wv[j], acc[i][j]);
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < kPix; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 f = __half22float2(acc[i][j]);
-        tot[i][2 * j] += f.x; tot[i][2 * j + 1] += f.y;
-      }
+__global__ void __launch_bounds__(32 * kWarpsPerBlock, 3) stem3x3_kernel(const __grid_constant__ Stem3Params p, uint32_t num_tiles,
+                                                                      uint32_t tiles_per_row, FastDiv div_tpr, FastDiv div_h) {
+  __shared__ __half wsm[32][kMaxCout + 8];                   // [k (27 taps, zero-padded to 32)][channel], pitch 40: conflict-light
+  for (int i = threadIdx.x; i < 32 * kMaxCout; i += blockDim.x) {
+    const int k = i / kMaxCout, n = i - k * kMaxCout;
+    wsm[k][n] = k < kTaps ? reinterpret_cast<const __half*>(&p.w[k][0])[n] : __float2half_rn(0.f);
   }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tig = lane & 3;                 // fragment coordinates of mma.m16n8k16
+  // B fragments: b[ks][nb][0] = {W[16 ks + 2 tig][8 nb + gid], W[16 ks + 2 tig + 1][..]}, b[ks][nb][1] = the same at k + 8
+  uint32_t bfr[2][4][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int k = 16 * ks + 2 * tig + 8 * hh;
+        const __half2 v = __halves2half2(wsm[k][8 * nb + gid], wsm[k + 1][8 * nb + gid]);
+        bfr[ks][nb][hh] = *reinterpret_cast<const uint32_t*>(&v);
+      }
+  // this lane's eight k indices (two K=16 steps x {2 tig, 2 tig + 1, 2 tig + 8, 2 tig + 9}) decoded once: input offset
+  // relative to the output pixel, row / column displacement for the zero padding
+  // (kept small: koff + one bit mask; the border path re-derives row / column displacements from k)
+  int koff[8];
+  uint32_t kmask = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = 16 * (j >> 2) + 2 * tig + (j & 1) + 8 * ((j >> 1) & 1);
+    const int c = k / 9, r = (k - 9 * c) / 3, sx = k - 9 * c - 3 * r;
+    const bool ok = k < kTaps && c < p.C;
+    kmask |= (ok ? 1u : 0u) << j;
+    koff[j] = ok ? (c * p.H + (r - 1)) * p.W + (sx - 1) : 0;      // padded k: a valid address whose value is discarded
+  }
+  // scale / shift of this lane's channel pairs (8 nb + 2 tig, + 1)
+  __shared__ __half2 ssm[2][kMaxCout / 2];
+  if (threadIdx.x < kMaxCout / 2) { ssm[0][threadIdx.x] = p.scale[threadIdx.x]; ssm[1][threadIdx.x] = p.shift[threadIdx.x]; }
+  __syncthreads();
   const __half2 alpha2 = __float2half2_rn(p.alpha);
-  const long long pix0 = ((long long)n * p.H + h) * p.W + w0;
+  const __half zero = __float2half_rn(0.f);
+  const size_t img_stride = (size_t)p.C * p.H * p.W;
+
+  for (uint32_t tile = blockIdx.x * kWarpsPerBlock + warp; tile < num_tiles; tile += gridDim.x * kWarpsPerBlock) {
+    // tile -> (image, row, 16-pixel group) by multiply-high divisions (the 64-bit % and / of the first version of this loop
+    // were a quarter of its 444 instructions)
+    const uint32_t t2 = fast_div(tile, div_tpr);
+    const int tw = (int)(tile - t2 * tiles_per_row);
+    const int n = (int)fast_div(t2, div_h);
+    const int h = (int)(t2 - (uint32_t)n * (uint32_t)p.H);
+    const int w0 = tw * 16;
+    // interior tiles (91 % at 416 x 416) need no padding tests: all 27 taps of all 16 pixels are inside the image
+    const bool interior = h >= 1 && h + 1 < p.H && w0 >= 1 && w0 + 16 < p.W;
+    const Tin* xc = reinterpret_cast<const Tin*>(p.x) + (size_t)n * img_stride + (size_t)h * p.W + w0;
+    // A fragments: registers {a0, a1, a2, a3} of step ks = (pixel gid, k 2tig..), (pixel gid + 8, same k), (gid, k + 8), (gid + 8, k + 8)
+    uint32_t afr[2][4];
+    if (interior) {
+      // every load is unconditional (no branches): a padded k reads the pixel itself and is replaced by zero
 #pragma unroll
-  for (int i = 0; i < kPix; ++i) {
-    if (w0 + i < p.W) {
-      __half* yrow = p.y + (size_t)(pix0 + i) * p.yld + p.ycoff + half_ * 16;
+      for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (half_ * 16 + q * 8 < p.Cout) {
-          uint4 out;
-          __half2* oh = reinterpret_cast<__half2*>(&out);
+        for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = q * 4 + e;
-            __half2 v = __floats2half2_rn(tot[i][2 * j], tot[i][2 * j + 1]);          // conv output rounded to fp16 once
-            const __half2 sc = p.scale[half_ * 8 + j], sf = p.shift[half_ * 8 + j];
+          for (int pp = 0; pp < 2; ++pp) {
+            const int pix = gid + 8 * pp;
+            __half v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int j = 4 * ks + 2 * hh + e;
+              const __half t = ld_h<Tin>(xc + pix + koff[j]);
+              v[e] = ((kmask >> j) & 1u) ? t : zero;
+            }
+            const __half2 pk = __halves2half2(v[0], v[1]);
+            afr[ks][2 * hh + pp] = *reinterpret_cast<const uint32_t*>(&pk);
+          }
+    } else {
+      // image border: coordinates clamped into the image (the load stays unconditional), taps outside contribute zero
+      const Tin* xi = reinterpret_cast<const Tin*>(p.x) + (size_t)n * img_stride;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int pp = 0; pp < 2; ++pp) {
+            const int pix = gid + 8 * pp;
+            __half v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int j = 4 * ks + 2 * hh + e;
+              const int k = 16 * ks + 2 * tig + e + 8 * hh;
+              const int c = k / 9, r = (k - 9 * c) / 3, sx = k - 9 * c - 3 * r;
+              const bool kvalid = (kmask >> j) & 1u;
+              const int ih = h + r - 1, iw = w0 + pix + sx - 1;
+              const bool ok = kvalid && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
+              const int ihc = min(max(ih, 0), p.H - 1), iwc = min(max(iw, 0), p.W - 1);
+              const int cofs = kvalid ? c * p.H * p.W : 0;                   // channel plane offset of this k (0 when padded)
+              const __half t = ld_h<Tin>(xi + cofs + (size_t)ihc * p.W + iwc);
+              v[e] = ok ? t : zero;
+            }
+            const __half2 pk = __halves2half2(v[0], v[1]);
+            afr[ks][2 * hh + pp] = *reinterpret_cast<const uint32_t*>(&pk);
+          }
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nb][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(acc[nb][0]), "+f"(acc[nb][1]), "+f"(acc[nb][2]), "+f"(acc[nb][3])
+                     : "r"(afr[ks][0]), "r"(afr[ks][1]), "r"(afr[ks][2]), "r"(afr[ks][3]), "r"(bfr[ks][nb][0]), "r"(bfr[ks][nb][1]));
+    }
+    // C fragment: (pixel gid, channels 8 nb + 2 tig, + 1) in acc[nb][0..1], (pixel gid + 8, same channels) in acc[nb][2..3]
+    const long long pix0 = ((long long)n * p.H + h) * p.W + w0;
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp) {
+      const int pix = gid + 8 * pp;
+      if (w0 + pix < p.W) {
+        __half* yrow = p.y + (size_t)(pix0 + pix) * p.yld + p.ycoff;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+          if (8 * nb + 2 * tig < p.Cout) {
+            __half2 v = __floats2half2_rn(acc[nb][2 * pp], acc[nb][2 * pp + 1]);      // conv output rounded to fp16 once
+            const __half2 sc = ssm[0][4 * nb + tig], sf = ssm[1][4 * nb + tig];
             if (kAct == 1) v = __hfma2_relu(v, sc, sf);
             else {
               v = __hfma2(v, sc, sf);
@@ -124,9 +182,8 @@ __global__ void __launch_bounds__(256, 2) stem3x3_kernel(const __grid_constant__
                 v = __floats2half2_rn(plnr_apply_act(f.x, p.act, p.alpha), plnr_apply_act(f.y, p.act, p.alpha));
               }
             }
-            oh[e] = v;
+            *reinterpret_cast<__half2*>(yrow + 8 * nb + 2 * tig) = v;
           }
-          *reinterpret_cast<uint4*>(yrow + q * 8) = out;
         }
       }
     }
@@ -179,11 +236,14 @@ extern "C" int plnr_stem3x3_fwd(plnr_ctx* ctx, const void* x, int x_dtype, int n
     reinterpret_cast<__half*>(&p.scale[0])[co] = __float2half_rn(co < cout ? (sc ? sc[co] : 1.f) : 0.f);
     reinterpret_cast<__half*>(&p.shift[0])[co] = __float2half_rn(co < cout ? (sf ? sf[co] : 0.f) : 0.f);
   }
-  const long long total = (long long)n * h * ((w + kPix - 1) / kPix) * 2;          // threads: (group of four pixels) x (channel half)
-  PLNR_REQUIRE(total > 0 && (total + 255) / 256 < (1ll << 31), "stem3x3: bad extents");
-  const unsigned grid = (unsigned)((total + 255) / 256);
+  const int tiles_per_row = (w + 15) / 16;
+  const long long num_tiles = (long long)n * h * tiles_per_row;                    // one warp trip = 16 pixels of one row
+  PLNR_REQUIRE(num_tiles > 0 && num_tiles < (1ll << 31), "stem3x3: bad extents");
+  long long blocks = (num_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const long long cap = (long long)ctx->sm_count * 32;                             // grid-stride: the B fragments are set up once per warp
+  const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
   const int kact = act == PLNR_ACT_RELU ? 1 : (act == PLNR_ACT_LEAKY && alpha >= 0.f && alpha <= 1.f ? 2 : (act == PLNR_ACT_NONE ? 0 : 3));
-#define LAUNCH(T, A) stem3x3_kernel<T, A><<<grid, 256, 0, ctx->stream>>>(p)
+#define LAUNCH(T, A) stem3x3_kernel<T, A><<<grid, 32 * kWarpsPerBlock, 0, ctx->stream>>>(p, (uint32_t)num_tiles, (uint32_t)tiles_per_row, make_fastdiv((uint32_t)tiles_per_row), make_fastdiv((uint32_t)h))
 #define LAUNCH_T(T) do { if (kact == 1) LAUNCH(T, 1); else if (kact == 2) LAUNCH(T, 2); else if (kact == 0) LAUNCH(T, 0); else LAUNCH(T, 3); } while (0)
   if (x_dtype == PLNR_U8) LAUNCH_T(uint8_t); else LAUNCH_T(__half);
 #undef LAUNCH_T
