@@ -1,7 +1,7 @@
 #!/bin/bash
 # compute-sanitizer over the conv-kernel parity tests (mbarrier rings, TMEM hand-offs, stream-K flags): racecheck, synccheck, memcheck
 mkdir -p gpurun_out
-SEL='conv_fp16_kernels_vs_oracle or stream_k or stride2 or stacked_conv or test_op_vs_reference_golden or readme'
+SEL='conv_fp16_kernels_vs_oracle or stream_k or stride2 or stacked_conv or test_op_vs_reference_golden or readme or pointwise or small_first_layer or fp32_on_the_tensor_pipe or register_transpose or avgpool_3x3'
 for tool in memcheck racecheck synccheck; do
   echo "=== compute-sanitizer --tool $tool ===" 
   timeout 1500 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 9 \
