@@ -1,9 +1,11 @@
-// Pointwise (1x1 / stride 1 / no padding) fp16 convolution with SMALL filters: a plain GEMM  y[M, Cout] = x[M, Cin] . W^T
-// over the M = N*H*W pixel rows, weights resident in shared memory, activations streamed through a deep TMA ring.
+// Pointwise (1x1 / stride 1 / no padding) fp16 convolution as a plain GEMM  y[M, Cout] = x[M, Cin] . W^T  over the
+// M = N*H*W pixel rows: the filter (or a slice of 128 / 64 output channels of it, pinned to the CTA) stays RESIDENT in shared
+// memory, the activations stream through a deep TMA ring.
 //
-// Replaces, for the 1x1 bottleneck layers of Darknet-style networks (YOLOv3: 64 -> 32 @208x208, 128 -> 64 @104x104,
-// 256 -> 128 @52x52 at batch 32), the same reference code as conv_shift.cu: Conv2d (planer/layer.py:22-26 +
-// planer/util.py:17-44) -> BatchNorm (planer/layer.py:125-127) -> LeakyReLU / ReLU (planer/layer.py:44-51).
+// Replaces, for the 1x1 bottleneck layers of Darknet-style networks (YOLOv3 at batch 32: 64 -> 32 @208x208, 128 -> 64 @104x104,
+// 256 -> 128 @52x52, and on few rows 512 -> 256 @26x26, 1024 -> 512 @13x13), the same reference code as conv_shift.cu: Conv2d
+// (planer/layer.py:22-26 + planer/util.py:17-44) -> BatchNorm (planer/layer.py:125-127) -> LeakyReLU / ReLU
+// (planer/layer.py:44-51).
 //
 // Why a separate kernel.  These layers have FOUR to SIXTEEN tcgen05.mma per 128-pixel tile and are bound by HBM (41 us of
 // traffic for 64 -> 32 @208 x32), but ran at 40 % of that roofline through conv_shift.cu: role counters showed every role
@@ -27,13 +29,14 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kThreads = 384;
 constexpr int kMaxStages = 8;
-constexpr int kMaxChunks = 8;                        // Cin <= 512
+constexpr int kMaxChunks = 16;                       // Cin <= 1024
 constexpr uint32_t kAStage = kTileM * 128;           // 128 rows x 64 channels x fp16
 constexpr uint32_t kStageBytes = 8 * 2048;           // epilogue transposition stage: 32 rows x 64 B per warp
 constexpr long long kWatchdogCycles = 4000000000ll;
 
 struct PwParams {
   int M, Cout, cchunks, n_tile, num_tiles, stages;
+  int num_n;         // output-channel blocks of n_tile channels; block b % num_n is PINNED to CTA b (its filter slice stays resident)
   uint32_t b_chunk_bytes, idesc, tmem_cols;
   __half* y; int yld, ycoff;
   const float* scale; const float* shift;
@@ -84,6 +87,9 @@ conv_pw_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   __half* ssh = reinterpret_cast<__half*>(base_ptr + off_ss);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTA b serves output-channel block b % num_n (its filter slice is loaded once) and the row tiles b / num_n + k * (grid / num_n)
+  const int n_idx = (int)blockIdx.x % p.num_n, n0 = n_idx * p.n_tile;
+  const int t_first = (int)blockIdx.x / p.num_n, t_step = (int)gridDim.x / p.num_n;
   const int nchunks = p.n_tile >> 5;
   const bool alternate = nchunks == 1;               // one 32-column chunk per tile: the two column groups take tiles in turn
 
@@ -101,7 +107,7 @@ conv_pw_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (warp == 3) {
     for (int i = lane; i < p.n_tile; i += 32) {
       float sc = 0.f, sf = 0.f;
-      if (i < p.Cout) { sc = p.scale ? __ldg(p.scale + i) : 1.f; sf = p.shift ? __ldg(p.shift + i) : 0.f; }
+      if (n0 + i < p.Cout) { sc = p.scale ? __ldg(p.scale + n0 + i) : 1.f; sf = p.shift ? __ldg(p.shift + n0 + i) : 0.f; }
       ssh[i] = __float2half_rn(sc);
       ssh[p.n_tile + i] = __float2half_rn(sf);
     }
@@ -114,17 +120,17 @@ conv_pw_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if ((int)blockIdx.x < p.num_tiles) {
+    if (t_first < p.num_tiles) {
       // the filter does not depend on the previous kernel: requested before the dependency wait
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(bar_bfull, (uint32_t)p.cchunks * p.b_chunk_bytes);
-        for (int cc = 0; cc < p.cchunks; ++cc) ptx::tma_load_2d(sB + cc * p.b_chunk_bytes, &mapB, bar_bfull, cc * 64, 0);
+        for (int cc = 0; cc < p.cchunks; ++cc) ptx::tma_load_2d(sB + cc * p.b_chunk_bytes, &mapB, bar_bfull, cc * 64, n0);
       }
       __syncwarp();
     }
     ptx::grid_dependency_wait();
     uint32_t s = 0, ph = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = t_first; tile < p.num_tiles; tile += t_step) {
       const int row0 = tile * kTileM;
       for (int cc = 0; cc < p.cchunks; ++cc) {
         mbar_wait(bar_empty + 8 * s, ph ^ 1, p.err, 0);
@@ -145,7 +151,7 @@ conv_pw_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const uint32_t a_step = kAStage >> 4, b_step = p.b_chunk_bytes >> 4;
     const bool elected = ptx::elect_one();
     const int cchunks = p.cchunks;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = t_first; tile < p.num_tiles; tile += t_step, ++it) {
       const uint32_t a = it & 1, tph = (it >> 1) & 1;
       mbar_wait(bar_tempty + 8 * a, tph ^ 1, p.err, 1);
       if (it == 0) mbar_wait(bar_bfull, 0, p.err, 5);
@@ -182,7 +188,7 @@ conv_pw_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       return __floats2half2_rn(plnr_apply_act(f.x, p.act, p.alpha), plnr_apply_act(f.y, p.act, p.alpha));
     };
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = t_first; tile < p.num_tiles; tile += t_step, ++it) {
       const uint32_t a = it & 1, tph = (it >> 1) & 1;
       if (alternate && (it & 1u) != (uint32_t)eg) continue;           // the other group's tile (it drains accumulator a alone)
       const int row_base = tile * kTileM + ew * 32;
@@ -220,7 +226,7 @@ conv_pw_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         for (int i = 0; i < 4; ++i) {
           uint4 val = *reinterpret_cast<const uint4*>(st_r + i * 512);
           const int row = row_base + 8 * i + rrow;
-          if (row < p.M && ch + 8 <= p.Cout) {
+          if (row < p.M && n0 + ch + 8 <= p.Cout) {
             __half2* vh = reinterpret_cast<__half2*>(&val);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -229,7 +235,7 @@ conv_pw_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
               else x = act2(__hfma2(vh[e], sch[e], sfh[e]));
               vh[e] = x;
             }
-            *reinterpret_cast<uint4*>(p.y + (size_t)row * p.yld + p.ycoff + ch) = val;
+            *reinterpret_cast<uint4*>(p.y + (size_t)row * p.yld + p.ycoff + n0 + ch) = val;
           }
         }
         __syncwarp();                                // the stage is rewritten by the next chunk
@@ -271,7 +277,7 @@ static void small_tensor_fixup(CUtensorMap* m, uint64_t tensor_bytes) {
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-struct PwPlan { bool ok; int n_tile, cchunks, stages; uint32_t b_chunk_bytes; size_t smem_bytes; };
+struct PwPlan { bool ok; int n_tile, num_n, cchunks, stages; uint32_t b_chunk_bytes; size_t smem_bytes; };
 
 static PwPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y, const plnr_epilogue* ep) {
   PwPlan pl;
@@ -283,14 +289,23 @@ static PwPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const pln
   if (d->pad_t || d->pad_l || d->pad_b || d->pad_r) return pl;
   if (ep && (ep->residual || ep->out_nchw || ep->out_f32)) return pl;
   if (x->c % 64 != 0 || x->c > 64 * kMaxChunks || x->ld % 8 != 0 || x->coff % 8 != 0 || (reinterpret_cast<uintptr_t>(x->ptr) & 15)) return pl;
-  if (y->c % 8 != 0 || y->c > 256 || y->ld % 8 != 0 || y->coff % 8 != 0 || (reinterpret_cast<uintptr_t>(y->ptr) & 15)) return pl;
+  if (y->c % 8 != 0 || y->ld % 8 != 0 || y->coff % 8 != 0 || (reinterpret_cast<uintptr_t>(y->ptr) & 15)) return pl;
   const long long M = (long long)x->n * x->h * x->w;
   if (M < 1 || M >= (1ll << 31) - 256) return pl;
-  pl.n_tile = round_up(y->c, 32);
   pl.cchunks = x->c / 64;
+  // output-channel block: all channels when their filter fits beside the A ring, else slices of 128 / 64 channels pinned to
+  // CTAs (the slice stays resident; the activations, the small operand of such layers, are re-read per slice from L2)
+  const size_t kMaxB = 128 * 1024;
+  pl.n_tile = round_up(y->c, 32) <= 256 ? round_up(y->c, 32) : 256;
+  while (pl.n_tile > 64 && (size_t)pl.cchunks * pl.n_tile * 128 > kMaxB) pl.n_tile = pl.n_tile > 128 ? 128 : 64;
+  pl.num_n = (y->c + pl.n_tile - 1) / pl.n_tile;
   pl.b_chunk_bytes = (uint32_t)pl.n_tile * 128u;
   const size_t b_bytes = (size_t)pl.cchunks * pl.b_chunk_bytes;
-  if (b_bytes > 64 * 1024) return pl;                 // larger filters: enough MMAs per tile for conv_shift.cu
+  if (b_bytes > kMaxB || pl.num_n > 16) return pl;
+  // Large filters are worth it only where the rows are few: with many row tiles per CTA conv_shift.cu's streamed N = 256 CTA
+  // pairs run at the tensor floor, while few tiles leave it re-streaming the whole filter per tile (YOLOv3 512 -> 256 @26x26:
+  // 23 us there for 6 us of traffic)
+  if ((size_t)x->c * y->c * 2 > 64 * 1024 && M > 65536) return pl;
   const size_t fixed = kStageBytes + 1024 + 16 * kMaxStages + 8 + 32 + 64 + 1024;
   size_t room = 232448 - fixed - b_bytes;
   int stages = (int)(room / kAStage);
@@ -321,6 +336,7 @@ int plnr_conv2d_pw(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x,
   p.M = x->n * x->h * x->w; p.Cout = y->c; p.cchunks = pl.cchunks; p.n_tile = pl.n_tile;
   p.num_tiles = (p.M + kTileM - 1) / kTileM;
   p.stages = pl.stages;
+  p.num_n = pl.num_n;
   p.b_chunk_bytes = pl.b_chunk_bytes;
   p.idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
   uint32_t cols = 32;
@@ -363,8 +379,10 @@ int plnr_conv2d_pw(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x,
     PLNR_CHECK_CUDA(cudaFuncSetAttribute(kerns[kact], cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set[kact] = true;
   }
-  int grid = ctx->sm_count;
-  if (grid > p.num_tiles) grid = p.num_tiles;
+  int per_n = ctx->sm_count / pl.num_n;                       // every output-channel block gets the same number of CTAs
+  if (per_n > p.num_tiles) per_n = p.num_tiles;
+  if (per_n < 1) per_n = 1;
+  const int grid = per_n * pl.num_n;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);

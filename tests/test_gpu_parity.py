@@ -894,6 +894,9 @@ PW_SWEEP = [
     (2, 64, 26, 26, 32, 'leaky', False), (3, 128, 13, 13, 64, 'leaky', True), (1, 256, 52, 52, 128, 'relu', False),
     (2, 64, 7, 9, 24, 'none', False), (1, 192, 10, 10, 72, 'sigmoid', True), (5, 128, 5, 5, 256, 'leaky', False),
     (1, 64, 1, 1, 8, 'relu', False), (4, 512, 8, 8, 64, 'leaky', False),
+    # larger filters on few rows: slices of 128 / 64 output channels pinned to CTAs (the slice stays resident)
+    (2, 512, 26, 26, 256, 'leaky', False), (2, 1024, 13, 13, 512, 'leaky', False), (1, 768, 13, 13, 256, 'leaky', True),
+    (3, 384, 9, 7, 200, 'relu', False),
 ]
 
 
