@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_h16_kernel(const __half* __r
       const uint32_t w1 = reinterpret_cast<const uint32_t*>(&in[2 * a + 1])[k >> 1];
       o[a] = __byte_perm(w0, w1, (k & 1) ? 0x7632 : 0x5410);
     }
+    if (c0 + k >= C) break;                              // channel count not a multiple of 8: the row's pad channels are dropped
     __half* dst = y + ((size_t)n * C + c0 + k) * HW + p0;
     const uintptr_t ad = reinterpret_cast<uintptr_t>(dst);
     if (npix == 8 && (ad & 15) == 0) {
@@ -1125,9 +1126,11 @@ int plnr_stem_pack(plnr_ctx* ctx, const void* x, int x_dtype, int n, int c, int 
 int plnr_nhwc_to_nchw(plnr_ctx* ctx, const plnr_tensor* x, int x_dtype, void* y, int y_dtype) {
   PLNR_REQUIRE(ctx && x && x->ptr && y, "nhwc_to_nchw: NULL argument");
   const int HW = x->h * x->w;
-  if (x_dtype == PLNR_F16 && y_dtype == PLNR_F16 && x->c % 8 == 0 && x->ld % 8 == 0 && x->coff % 8 == 0 && aligned16(x->ptr) &&
-      (reinterpret_cast<uintptr_t>(y) & 1) == 0 && !getenv("PLNR_TRANSPOSE_TILE")) {
-    const int PB8 = ((HW + 7) / 8 + 7) / 8, CG4 = (x->c / 8 + 3) / 4;
+  // (a channel count that is not a multiple of 8 -- YOLO's 255-channel heads in rows padded to 256 -- reads the pad channels
+  // of the last 16-byte vector, which must lie inside the row: coff + roundup(c, 8) <= ld)
+  if (x_dtype == PLNR_F16 && y_dtype == PLNR_F16 && x->ld % 8 == 0 && x->coff % 8 == 0 && aligned16(x->ptr) &&
+      x->coff + (x->c + 7) / 8 * 8 <= x->ld && (reinterpret_cast<uintptr_t>(y) & 1) == 0 && !getenv("PLNR_TRANSPOSE_TILE")) {
+    const int PB8 = ((HW + 7) / 8 + 7) / 8, CG4 = ((x->c + 7) / 8 + 3) / 4;
     const long long total = (long long)x->n * PB8 * CG4 * 32;
     PLNR_REQUIRE((total + 255) / 256 < (1ll << 31), "nhwc_to_nchw: tensor too large for one launch");
     nhwc_to_nchw_h16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const __half*)x->ptr, (__half*)y, x->c, HW,
