@@ -39,7 +39,7 @@ constexpr uint32_t kBBox = kNT * 128;          // one (chunk, tap) weight box
 constexpr long long kWatchdogCycles = 4000000000ll;
 
 struct StackParams {
-  FastDiv div_hvwv, div_wv, div_mt;
+  FastDiv div_hvwv, div_wv, div_mt, div_hv;
   int N, OH, OW, Hv, Wv, HvWv;
   int pad_t, pad_l;
   long long Mv;
@@ -176,10 +176,12 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     }
     ptx::grid_dependency_wait();
     for (int m_idx = m_first; m_idx < p.num_m_tiles; m_idx += m_step) {
-      const long long o0 = (long long)m_idx * kTilePos;
-      const long long v0 = o0 / Wv;
-      const int off = (int)(o0 - v0 * Wv);
-      const int nrows = (int)((o0 + kTileM - 1 + p.halo) / Wv - v0) + 1;
+      // every position (+ halo) is below 2^31 (make_plan): 32-bit multiply-high divisions instead of three 64-bit ones per tile
+      const uint32_t o0 = (uint32_t)m_idx * (uint32_t)kTilePos;
+      const uint32_t v0 = fast_div(o0, p.div_wv);
+      const int off = (int)(o0 - v0 * (uint32_t)Wv);
+      const int nrows = (int)(fast_div(o0 + (uint32_t)(kTileM - 1 + p.halo), p.div_wv) - v0) + 1;
+      const int img0 = (int)fast_div(v0, p.div_hv), hrow0 = (int)v0 - img0 * p.Hv;
       const uint32_t a_bytes = (uint32_t)nrows * row_bytes;
       const uint32_t row0_off = (uint32_t)(Wv - off) * 128u;       // position o0 lands at row offset Wv of the buffer
       for (int cc = 0; cc < p.cchunks + p.c2chunks; ++cc) {
@@ -191,7 +193,7 @@ conv_stack_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           const uint32_t full = bar_afull + 8 * ab;
           ptx::mbar_arrive_expect_tx(full, a_bytes);
           uint32_t dst = sA + ab * p.a_buf_bytes + row0_off;
-          int img = (int)(v0 / p.Hv), hrow = (int)(v0 - (long long)img * p.Hv);
+          int img = img0, hrow = hrow0;
           const CUtensorMap* mA = sc ? &mapA2 : &mapA;
           const int cs = sc ? p.s2 : 1, c0 = (sc ? cc - p.cchunks : cc) * 64;
           for (int i = 0; i < nrows; ++i) {
@@ -492,7 +494,7 @@ static StackPlan make_plan(const plnr_conv_desc* d, const plnr_tensor* x, const 
   }
   pl.a_buf_bytes = (uint32_t)round_up(need * 128, 1024);
   const long long Mv = (long long)x->n * pl.Hv * pl.Wv;
-  if (Mv >= (1ll << 31) - 512) return pl;
+  if (Mv + pl.halo + 1024 >= (1ll << 31)) return pl;
   const double eff = (double)y->h * y->w / ((double)pl.Hv * pl.Wv);
   if (eff < 0.70) return pl;
   // 64 input channels = ONE k-chunk per tile: 12 MMAs cannot hide the two-shift epilogue (measured: layer1, epilogue-bound)
@@ -547,6 +549,7 @@ int plnr_conv2d_stack(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
   p.div_hvwv = make_fastdiv((uint32_t)p.HvWv);
   p.div_wv = make_fastdiv((uint32_t)p.Wv);
   p.div_mt = make_fastdiv((uint32_t)p.num_m_tiles);
+  p.div_hv = make_fastdiv((uint32_t)p.Hv);
   p.na = pl.na; p.nb = pl.nb; p.a_buf_bytes = pl.a_buf_bytes;
   p.y = (__half*)y->ptr; p.yld = y->ld; p.ycoff = y->coff; p.Cout = y->c;
   if (ep) {
