@@ -781,6 +781,27 @@ def test_resnet18_fp16_batch128_distinct_images_vs_fp32_oracle(planer):
         assert rel_err(y8[i], ref[0]) <= 1e-2, i
 
 
+def test_resnet18_fp32_tensor_path_batch32_and_batch1_vs_oracle(planer):
+    """BASELINE config 2 (ResNet-18 float32) on the tensor pipe (fp16 split operands, csrc/split_f32.cu): batch 1 against the
+    reference fixture and a batch of 32 DIFFERENT images against the fp32 oracle run image by image, at a tenth of the north
+    star's 1e-3 bar; every group-1 convolution of the plan must have taken the tensor path."""
+    model, blob = cases.get_model('resnet18')
+    net = planer.from_model(model, blob)
+    onet = oracle.build_net(model, blob)
+    g = np.load(os.path.join(GOLD, 'graphs.npz'))
+    x1 = np.random.default_rng(1).standard_normal((1, 3, 224, 224)).astype(np.float32)
+    y1 = net(x1)
+    assert rel_err(y1, g['resnet18_f32_n1.out0']) <= 1e-4
+    ex = net.executor([x1.shape], [x1.dtype])
+    assert ex.split_convs == 20                      # 17 main-path + 3 shortcut convolutions
+    x = np.random.default_rng(33).standard_normal((32, 3, 224, 224)).astype(np.float32)
+    y = net(x)
+    assert y.shape == (32, 1000) and y.dtype == np.float32
+    for i in (0, 13, 31):
+        ref = onet(x[i:i + 1])
+        assert rel_err(y[i], ref[0]) <= 1e-4, i
+
+
 def test_yolov3_fp16_batch32_distinct_images_vs_fp32_oracle(planer):
     """BASELINE config 4 at its full batch (32 different 416x416 images): two sampled images against the fp32 oracle, all
     three heads; the pointwise heads run the resident-filter GEMM kernel into rows padded to 256 channels and leave through the
