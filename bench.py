@@ -76,6 +76,19 @@ def lib_sha256():
     return h.hexdigest()
 
 
+def src_sha256():
+    """Hash of the CUDA sources + the C header the library is built from: identifies the build when the .so itself was rebuilt
+    on another box (-lineinfo embeds the source paths, so the binary hash then differs for identical code)."""
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, 'planer_b200', 'csrc')
+    files = sorted(os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(('.cu', '.cuh')))
+    for fn in files + [os.path.join(ROOT, 'include', 'planer_b200.h')]:
+        h.update(os.path.basename(fn).encode())
+        with open(fn, 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -460,10 +473,10 @@ def main():
     if cands and batch == cfg['batch']:
         with open(os.path.join(ROOT, 'profiles', cands[-1])) as f:
             tj = json.load(f)
-        if tj.get('lib_sha256') == sha and tj.get('config', 'resnet18') == args.config:
+        if (tj.get('lib_sha256') == sha or tj.get('src_sha256') == src_sha256()) and tj.get('config', 'resnet18') == args.config:
             traffic = sum(int((k['dram_read_mb'] + k['dram_write_mb']) * 1e6) for k in tj['kernels'])
             traffic_src = ('dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of one step, ncu --set full of '
-                           'THIS binary (profiles/%s, lib sha256 %s)' % (cands[-1], sha[:12]))
+                           'THIS build (profiles/%s: same library or same CUDA sources, lib sha256 %s)' % (cands[-1], sha[:12]))
         else:
             traffic_src = ('null: the newest committed capture (profiles/%s) is of another build of libplaner_b200.so'
                            % cands[-1])

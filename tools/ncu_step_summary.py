@@ -34,7 +34,13 @@ with open('profiles/%s_step_traffic.json' % tag, 'w') as f:
     # when the library it runs has this hash
     lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'planer_b200', 'libplaner_b200.so')
     sha = hashlib.sha256(open(lib, 'rb').read()).hexdigest()
-    json.dump({'source': rep, 'lib_sha256': sha, 'config': 'resnet18', 'kernels': kern}, f, indent=1)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hs = hashlib.sha256()                      # same definition as bench.py:src_sha256
+    csrc = os.path.join(root, 'planer_b200', 'csrc')
+    for fn in sorted(os.path.join(csrc, f_) for f_ in os.listdir(csrc) if f_.endswith(('.cu', '.cuh'))) + [os.path.join(root, 'include', 'planer_b200.h')]:
+        hs.update(os.path.basename(fn).encode())
+        hs.update(open(fn, 'rb').read())
+    json.dump({'source': rep, 'lib_sha256': sha, 'src_sha256': hs.hexdigest(), 'config': 'resnet18', 'kernels': kern}, f, indent=1)
 with open('profiles/%s_step_full.md' % tag, 'w') as f:
     f.write('# One steady-state step under `ncu --set full` (ResNet-18 fp16, batch 128, B200) -- %s\n\n' % tag)
     f.write('Command: tools/gpu_profile.sh (`ncu --set full --clock-control none --import-source on -k regex:conv_shift|conv_stack|'
