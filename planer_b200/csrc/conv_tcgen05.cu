@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                       const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
+  const long long t_entry = clock64();
+  const bool stamp = p.prof && blockIdx.x == 0;      // debug: phase time stamps of CTA 0 at prof[1400..] (tools/role_profile2.py)
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;           // 128B-swizzle atoms need 1024-byte alignment
   uint8_t* base_ptr = smem_raw + (base - raw);
@@ -147,6 +149,10 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   // kernel before this one has completed and flushed its results (no-ops when launched without the attribute)
   ptx::grid_launch_dependents();
   ptx::grid_dependency_wait();
+  if (stamp && threadIdx.x == 0) {
+    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.prof[1400] = (long long)gt; p.prof[1401] = clock64() - t_entry;
+  }
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -223,6 +229,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         uint32_t acc = 0u;
         for (int j = 0; j < kstages; ++j) {
           mbar_wait(bar_full + 8 * s, ph, p.err, 2);      // TMA bytes (of both CTAs) have landed
+          if (stamp && it == 0 && j == 0 && lane == 0) p.prof[1402] = clock64() - t_entry;
           ptx::tc_fence_after();
           if (elected) {
             ptx::umma_f16_x4<CG>(d_tmem, a_lo0 + s * a_step, b_lo0 + s * b_step, desc_hi, idesc, acc);
@@ -271,6 +278,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       if (trace) p.prof[1200 + it * 4 + 3] = clock64() - t_all0;
     }
     if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 2] = t_full; p.prof[blockIdx.x * 8 + 3] = t_tempty; p.prof[blockIdx.x * 8 + 4] = clock64() - t_all0; }
+    if (stamp && lane == 0) p.prof[1403] = clock64() - t_entry;
   } else if (warp >= 4) {
     // ===================================== epilogue ===========================================
     // A thread owns one accumulator ROW (TMEM lane) and 32 channels per chunk; rows are transposed through a per-warp
@@ -512,15 +520,21 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       }
     }
     if (p.prof && threadIdx.x == 128) { p.prof[blockIdx.x * 8 + 5] = t_tfull; p.prof[blockIdx.x * 8 + 6] = clock64() - t_all0; }
+    if (stamp && threadIdx.x == 128) p.prof[1404] = clock64() - t_entry;
   }
 
   // ---- teardown: everyone (in both CTAs) is done with TMEM before the allocator warps free it ----
   ptx::tc_fence_before();
   if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+  if (stamp && threadIdx.x == 0) p.prof[1405] = clock64() - t_entry;
   if (warp == 2) {
     ptx::tc_fence_after();
     if (CG == 2) ptx::tmem_dealloc_pair(tmem_base, p.tmem_cols);
     else ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+    if (stamp && lane == 0) {
+      unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      p.prof[1406] = clock64() - t_entry; p.prof[1407] = (long long)gt;
+    }
   }
 }
 
