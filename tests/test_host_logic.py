@@ -673,3 +673,34 @@ def test_zero_copy_concat_placement_and_liveness():
     gp2 = P.compile_graph(model2, {'x': (1, 16, 8, 8)})
     assert P.place_concat_inputs(gp2) == 1
     assert gp2.values[P._root(gp2.values, [s for s in gp2.steps if s.name == 'a2'][0].out)].slice_of is not None
+
+
+def test_fp16_split_arithmetic_reproduces_a_float32_dot_product():
+    """The algebra of csrc/split_f32.cu, emulated in numpy (no GPU): both operands scaled by a power of two into
+    [2^13, 2^14), split into fp16 (hi, lo), and  xh.wh + xh.wl + xl.wh  accumulated in fp32 reproduce a float32 dot product to
+    ~1e-6 of its range for tensors of any magnitude (1e-5 .. 3e3 here) -- the bar of the float32 path is 1e-3."""
+    rng = np.random.default_rng(7)
+
+    def prescale(a):
+        m = float(np.abs(a).max())
+        return 2.0 ** (13 - int(np.floor(np.log2(m)))) if m > 0 else 1.0
+
+    def split(a, s):
+        v = (a * np.float32(s)).astype(np.float32)
+        hi = v.astype(np.float16)
+        lo = (v - hi.astype(np.float32)).astype(np.float16)
+        assert np.isfinite(hi.astype(np.float32)).all()
+        return hi.astype(np.float32), lo.astype(np.float32)
+
+    for mag in (1.0, 1e-5, 3e3):
+        x = (rng.standard_normal((64, 576)) * mag).astype(np.float32)
+        w = (rng.standard_normal((576, 32)) * np.sqrt(2.0 / 576)).astype(np.float32)
+        sx, sw = prescale(x), prescale(w)
+        xh, xl = split(x, sx)
+        wh, wl = split(w, sw)
+        acc = (xh @ wh + xh @ wl + xl @ wh).astype(np.float32)              # every fp16 x fp16 product is exact in fp32
+        got = acc * np.float32(1.0 / (sx * sw))
+        ref = x.astype(np.float64) @ w.astype(np.float64)
+        assert np.abs(got - ref).max() / np.abs(ref).max() <= 2e-6, mag
+        # dropping the low halves (plain fp16 operands) is three orders of magnitude worse
+        assert np.abs(xh @ wh / (sx * sw) - ref).max() / np.abs(ref).max() >= 1e-4
