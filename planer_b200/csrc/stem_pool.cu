@@ -264,9 +264,9 @@ __global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const StemParams
         q[k] = make_uint4(0u, 0u, 0u, 0u);
         if (ld_goff[k] >= 0 && ih >= 0 && ih < p.H) {
           if (U8)       // uint8 image: 8-byte loads, converted here so that staging and gather are those of the fp16 path
-            q[k] = u8x8_to_h8(__ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(p.x) + row0 + ld_goff[k])));
+            q[k] = u8x8_to_h8(__ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(p.x) + row0 + ld_goff[k])));
           else
-            q[k] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.x) + row0 + ld_goff[k]));
+            q[k] = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.x) + row0 + ld_goff[k]));
         }
       }
     };
