@@ -964,3 +964,65 @@ def test_pointwise_conv_kernel_vs_oracle_and_shift_kernel(planer, cfg, monkeypat
         assert np.array_equal(outs[0], outs[1])
     else:          # conv_shift.cu finishes a partial 32-channel chunk in fp32 (one rounding), conv_pw.cu in packed fp16
         assert rel_err(outs[0], outs[1]) <= 2e-3
+
+
+def _random_conv_cases(count, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < count:
+        k = int(rng.choice([1, 1, 3, 3, 3, 5]))
+        cfg = dict(n=int(rng.integers(1, 4)), cin=int(rng.choice([3, 16, 32, 64, 64, 128, 192, 256])),
+                   cout=int(rng.choice([8, 24, 32, 64, 64, 96, 128, 255, 256])), k=k, s=int(rng.choice([1, 1, 2])),
+                   p=int(rng.choice([0, k // 2])), d=int(rng.choice([1, 1, 2])), h=int(rng.integers(5, 41)), w=int(rng.integers(5, 41)),
+                   act=str(rng.choice(['none', 'relu', 'leaky', 'sigmoid'])), res=bool(rng.integers(0, 2)), bn=bool(rng.integers(0, 2)),
+                   f32=bool(rng.integers(0, 4) == 0))
+        if (cfg['h'] + 2 * cfg['p'] - (k - 1) * cfg['d'] - 1) < 0 or (cfg['w'] + 2 * cfg['p'] - (k - 1) * cfg['d'] - 1) < 0:
+            continue
+        out.append(cfg)
+    return out
+
+
+@pytest.mark.parametrize('cfg', _random_conv_cases(int(os.environ.get('PLNR_RANDOM_CONVS', '48')), int(os.environ.get('PLNR_RANDOM_SEED', '2024'))), ids=lambda c: '%(n)dx%(cin)dx%(h)dx%(w)d-%(cout)d-k%(k)ds%(s)dp%(p)dd%(d)d-%(act)s%(res)d%(bn)d%(f32)d' % c)
+def test_random_convolutions_through_the_dispatcher_vs_oracle(planer, cfg):
+    """A seeded random sweep over shapes, strides, dilations, paddings, activations, residuals and dtypes through
+    plnr_conv2d_fwd's own kernel choice (pointwise GEMM, stacked taps, shift GEMM, TMA-im2col, fp16-split fp32, CUDA cores)
+    against the oracle: whatever kernel the dispatcher picks must meet the north star's bar."""
+    from planer_b200 import ops, backend as B
+    n, cin, cout, k, s, p, d, h, w = (cfg[x] for x in ('n', 'cin', 'cout', 'k', 's', 'p', 'd', 'h', 'w'))
+    dt = np.float32 if cfg['f32'] else np.float16
+    rng = np.random.default_rng(cin * 1000 + cout + h * w)
+    x = rng.standard_normal((n, cin, h, w)).astype(dt)
+    K = (rng.standard_normal((cout, cin, k, k)) * np.sqrt(2.0 / (cin * k * k))).astype(dt)
+    bias = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    ref = oracle.conv2d(x.astype(np.float64), K.astype(np.float64), bias.astype(np.float64), 1, (s, s), (d, d), (p,) * 4)
+    bk = bb = None
+    if cfg['bn']:
+        bk = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+        bb = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+        ref = oracle.batchnorm(ref, bk.reshape(1, -1, 1, 1).astype(np.float64), bb.reshape(1, -1, 1, 1).astype(np.float64))
+    r = None
+    if cfg['res']:
+        r = rng.standard_normal(ref.shape).astype(dt)
+        ref = oracle.add(ref, r.astype(np.float64))
+    ref = {'leaky': lambda v: oracle.leakyrelu(v, 0.1), 'relu': oracle.relu, 'none': lambda v: v, 'sigmoid': oracle.sigmoid}[cfg['act']](ref)
+    code = {'leaky': ops.ACT_LEAKY, 'relu': ops.ACT_RELU, 'none': ops.ACT_NONE, 'sigmoid': ops.ACT_SIGMOID}[cfg['act']]
+    pad16 = dt == np.float16 and cin % 16 != 0
+    xd = B.to_nhwc(B.asarray(x))
+    if pad16:                                            # the eager layer pads few-channel fp16 inputs to 16 channels (layer.py)
+        xp = np.zeros((n, 16, h, w), dt); xp[:, :cin] = x
+        xd = B.to_nhwc(B.asarray(xp))
+    Kd = B.asarray(K)
+    if dt == np.float32 and ops.split_conv_enabled():
+        w16, meta = ops.pack_weight_split(Kd)
+        wp = ops.split_weight(w16, meta, cin)
+    else:
+        wp = ops.pack_weight(Kd, xd.shape[1], dt)
+    scale, shift = ops.fold_affine(B.asarray(bias), None if bk is None else B.asarray(bk), None if bb is None else B.asarray(bb), cout)
+    if bk is None:
+        scale = None
+    y = B.empty(ref.shape, dt, 'nhwc')
+    rd = None if r is None else B.to_nhwc(B.asarray(r))
+    ops.conv2d_into(xd, wp, y, k, k, (s, s), (d, d), (p,) * 4, 1, scale, shift, rd, code, 0.1)
+    B.synchronize()
+    tol = 1e-3 if dt == np.float32 else 1e-2
+    assert rel_err(y.get(), ref) <= tol, (cfg, B.last_kernel(), rel_err(y.get(), ref))
