@@ -91,12 +91,22 @@ class Executor:
             return False
         return ops.conv2d_out_nchw_supported(x, v.shape, K.shape[2], K.shape[3], a['strides'], a['dilations'], a['pads'])
 
+    def _is_side_operand(self, vid):
+        """True when ``vid`` is also the residual / shortcut operand of some step (``out = x + conv(x)`` on a graph input): its
+        stored layout must then stay the logical one -- no channel padding, no first-layer packing."""
+        for st in self.plan.steps:
+            if st.res is not None and self._root(st.res) == vid:
+                return True
+            if st.shortcut is not None and self._root(st.shortcut[0]) == vid:
+                return True
+        return False
+
     def _input_cpad(self, vid):
         """Graph inputs feeding only group-1 convs are channel-padded to a multiple of 16 in fp16 so that the
         first layer runs on the tensor cores (Cin=3 -> 16; the packed weights carry zeros there)."""
         c = self.values[vid].shape[1]
-        if self.dtype != np.float16 or c % 16 == 0 or self.values[vid].is_output:
-            return c                 # an input that is also returned keeps its logical channels
+        if self.dtype != np.float16 or c % 16 == 0 or self.values[vid].is_output or self._is_side_operand(vid):
+            return c                 # an input that is also returned (or added to a conv result) keeps its logical channels
         for st in self.plan.steps:
             if vid in [self._root(r) for r in st.reads()]:
                 if not (st.op == 'conv' and st.attrs['group'] == 1 and self._root(st.ins[0]) == vid):
@@ -111,6 +121,8 @@ class Executor:
             return None
         users = [st for st in self.plan.steps if vid in [self._root(r) for r in st.reads()]]
         if len(users) != 1 or users[0].op != 'conv' or self._root(users[0].ins[0]) != vid or v.is_output:
+            return None
+        if self._is_side_operand(vid):
             return None
         st, a = users[0], users[0].attrs
         kshape = self.values[st.w].shape
@@ -464,7 +476,7 @@ class Executor:
                 self._keep.append(wp)
                 return lambda: ops.conv2d_into(x, wp, y, kh, kw, a['strides'], a['dilations'], a['pads'], g,
                                                scale, shift, res, st.act, st.alpha, res_after_act=st.res_after)
-            Kc = self._packed(st.name + '|cast', lambda: K.astype(dt))
+            Kc = self._packed(st.name + '|cast', lambda: _aligned_cast(K, dt))
             self._keep.append(Kc)
             if x.layout != 'flat':
                 raise NotImplementedError('dense %r needs a 2-D input (got %s)' % (st.name, x.shape))
@@ -552,7 +564,7 @@ class Executor:
                     scale, shift = self._packed(dn.name + '|fold', lambda: ops.fold_affine(bias, bn_k, bn_b, K.shape[0]))
                     if bn_k is None:
                         scale = None
-                Kc = self._packed(dn.name + '|cast', lambda: K.astype(dt))
+                Kc = self._packed(dn.name + '|cast', lambda: _aligned_cast(K, dt))
                 y = alloc(dn.out)
                 self._keep += [scale, shift, Kc]
                 self.fused_dense |= {id(fl), id(dn)}
@@ -637,6 +649,14 @@ class Executor:
 
 def x_dtype_ok(dt):
     return np.dtype(dt) == np.float16
+
+
+def _aligned_cast(K, dt):
+    """K in the compute dtype at a 16-byte-aligned address: ``astype`` of an array that already has the dtype returns the
+    array itself, i.e. a view into the weight blob at whatever byte offset the model file gave it (planer/net.py:83-88 packs
+    the inits back to back) -- the vector loads of the dense kernels need alignment."""
+    Kc = K.astype(dt)
+    return B.clone(Kc) if Kc.ptr % 16 else Kc
 
 
 def _dense(a):

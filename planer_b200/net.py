@@ -200,6 +200,10 @@ class Net:
                 consts[xs[1]] = self.host_const(xs[1])
             if kinds.get(first) == 'resize' and not isinstance(xs, str) and len(xs) > 2 and xs[2] in self.inits:
                 consts[xs[2]] = self.host_const(xs[2])
+            if kinds.get(first) == 'clip' and not isinstance(xs, str):
+                for name in xs[1:3]:                       # bounds given as inputs (the reference passes them on to Clip(x, min, max))
+                    if name in self.inits:
+                        consts[name] = self.host_const(name)
         if not self._pack_store and getattr(self, '_pack_path', None) and not getattr(self, '_pack_tried', False):
             from . import io as _io
             self._pack_tried = True

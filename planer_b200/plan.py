@@ -143,6 +143,15 @@ def infer(values, nodes, host_consts=None):
             nd.flops = 2 * m * nn * kk
         elif k in ('relu', 'leakyrelu', 'sigmoid', 'batchnorm', 'identity', 'hardsigmoid', 'clip'):
             out = sh[0]
+            if k == 'clip' and len(nd.ins) > 1:
+                # bounds as inputs: the reference's interpreter hands every input to Clip(x, min, max) (planer/net.py:54-58), so an
+                # IR with constant-init bounds is valid there; anything but constants is rejected instead of silently ignored
+                nd.attrs = dict(nd.attrs)
+                for key, vid in zip(('min', 'max'), nd.ins[1:3]):
+                    name = values[vid].name
+                    if name not in host_consts:
+                        raise NotImplementedError('clip %r: bound %r must be a constant init' % (nd.name, name))
+                    nd.attrs[key] = float(np.asarray(host_consts[name], np.float64).reshape(-1)[0])
         elif k == 'softmax':
             ax = a.get('axis', -1)
             if not ((len(sh[0]) == 4 and ax in (1, -3)) or (len(sh[0]) == 2 and ax in (1, -1))):
@@ -348,7 +357,7 @@ def fuse(values, nodes, outputs):
             st = emit(Step('scale_shift', nd.name, [x], out))
             st.bn = (nd.ins[1], nd.ins[2])
         elif k == 'clip':
-            st = emit(Step('clip', nd.name, [x], out, nd.attrs))
+            st = emit(Step('clip', nd.name, [x], out, nd.attrs))       # bounds given as inputs were resolved by infer()
             st.inplace = True
         elif k in ('maxpool', 'averagepool', 'zero_stuff', 'hardsigmoid', 'softmax'):
             emit(Step(k, nd.name, [x], out, nd.attrs))
