@@ -1048,7 +1048,7 @@ def _random_graph(seed):
         return b.op(kind, {'alpha': 0.1} if kind == 'leakyrelu' else {}, [y])
 
     for step in range(int(rng.integers(5, 10))):
-        kind = str(rng.choice(['conv', 'conv', 'res', 'dark', 'pool', 'upcat', 'gconv', 'dconv', 'clip', 'avg']))
+        kind = str(rng.choice(['conv', 'conv', 'res', 'dark', 'pool', 'upcat', 'gconv', 'dconv', 'clip', 'avg', 'alias', 'hsig', 'convt', 'fork']))
         if kind == 'conv':
             co, k = int(rng.choice([16, 32, 64, 128])), int(rng.choice([1, 3, 3, 5]))
             s = 2 if (h >= 16 and rng.integers(0, 3) == 0) else 1
@@ -1067,6 +1067,21 @@ def _random_graph(seed):
             x = b.op('clip', {}, [x, b.init('clip%d.min' % step, np.array(-0.5, np.float32)), b.init('clip%d.max' % step, np.array(2.0, np.float32))])
         elif kind == 'avg' and h >= 8:
             x = b.op('averagepool', {'w': [2, 2], 'pads': [0, 0, 0, 0], 'strides': [2, 2]}, [x]); h, w = h // 2, w // 2
+        elif kind == 'alias':                         # the reference's ReLU works IN PLACE: x is mutated too, so this is 2 relu(x)
+            y = b.op('relu', {}, [x])
+            x = b.op('add', {}, [x, y])
+        elif kind == 'hsig':
+            x = b.op('hardsigmoid', {'alpha': 0.2, 'beta': 0.5}, [x])
+        elif kind == 'convt' and h <= 16:             # ConvTranspose2d k4 / s2 / p1: doubles the extent
+            co = int(rng.choice([16, 32]))
+            wt = (rng.standard_normal((c, co, 4, 4)) * np.sqrt(1.0 / (c * 4))).astype(np.float32)
+            x = b.op('convtranspose', {'strides': [2, 2], 'dilations': [1, 1], 'pads': [1, 1, 1, 1], 'output_padding': [0, 0], 'group': 1},
+                     [x, b.init('ct%d.weight' % step, wt), b.init('ct%d.bias' % step, (rng.standard_normal(co) * 0.1).astype(np.float32))])
+            c, h, w = co, 2 * h, 2 * w
+        elif kind == 'fork':                          # two convolutions read the same tensor, their results are added
+            y1 = b.op('relu', {}, [b.conv(x, c, c, 3, bias=True)])
+            y2 = b.bn(b.conv(x, c, c, 1), c, gamma_scale=0.5)
+            x = b.op('add', {}, [y1, y2])
         elif kind == 'res':        # relu(x + bn(conv3x3(x)))
             y = b.bn(b.conv(x, c, c, 3), c, gamma_scale=0.5)
             x = b.op('relu', {}, [b.op('add', {}, [y, x])])
@@ -1104,7 +1119,7 @@ def _random_graph(seed):
 def test_random_graphs_planner_and_executor_vs_oracle(planer, seed, half):
     """Random DAGs through the planner (fusion of batchnorm / add / activation into conv epilogues, in-place aliasing, zero-copy
     concat, exit layout) and the CUDA-graph executor against the oracle's layer-by-layer interpreter: float32 (convolutions on
-    the tensor pipe through fp16 split operands) at 1e-3, float16 at 1e-2 against the fp32 oracle."""
+    the tensor pipe through fp16 split operands) at 1e-3, float16 at 2e-2 against the fp32 oracle."""
     model, blob, cin, size = _random_graph(1000 + seed)
     x = np.random.default_rng(seed).standard_normal((2, cin, size, size)).astype(np.float32)
     refs = oracle.build_net(model, blob)(x.copy())
@@ -1115,4 +1130,6 @@ def test_random_graphs_planner_and_executor_vs_oracle(planer, seed, half):
     assert len(ys) == len(refs)
     for y, r in zip(ys, refs):
         assert y.shape == r.shape
-        assert rel_err(y, r) <= (1e-2 if half else 1e-3), (seed, half, rel_err(y, r))
+        # float16 against the FLOAT32 oracle: a chain of up to ten random layers drifts past the 1e-2 that holds layer by layer
+        # (1 of 600 graphs reached 1.1e-2, its float32 twin 1e-6); 2e-2 still separates rounding from any logic error (>= 0.4)
+        assert rel_err(y, r) <= (2e-2 if half else 1e-3), (seed, half, rel_err(y, r))
