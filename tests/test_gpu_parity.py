@@ -1036,7 +1036,11 @@ def _random_graph(seed):
     rng = np.random.default_rng(seed)
     b = _Builder(seed)
     cin = int(rng.choice([3, 16, 32]))
-    h = w = size = int(rng.choice([32, 48, 64]))
+    if rng.integers(0, 3) == 0:                       # odd, non-square extents
+        h, w = int(rng.integers(17, 50)), int(rng.integers(17, 50))
+    else:
+        h = w = int(rng.choice([32, 48, 64]))
+    size = (h, w)
     x, c = 'x', cin
     seen = {}                      # (h, w) -> (name, channels) of an earlier tensor to concatenate with
     mid = None
@@ -1121,7 +1125,10 @@ def test_random_graphs_planner_and_executor_vs_oracle(planer, seed, half):
     concat, exit layout) and the CUDA-graph executor against the oracle's layer-by-layer interpreter: float32 (convolutions on
     the tensor pipe through fp16 split operands) at 1e-3, float16 at 2e-2 against the fp32 oracle."""
     model, blob, cin, size = _random_graph(1000 + seed)
-    x = np.random.default_rng(seed).standard_normal((2, cin, size, size)).astype(np.float32)
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((int(rng.integers(1, 5)), cin) + tuple(size)).astype(np.float32)
+    if rng.integers(0, 4) == 0:                       # 8-bit pixels (the first-layer kernels convert while staging)
+        x = rng.integers(0, 256, x.shape).astype(np.float32) / 64
     refs = oracle.build_net(model, blob)(x.copy())
     refs = refs if isinstance(refs, tuple) else (refs,)
     net = planer.from_model(model, blob, half=half)
