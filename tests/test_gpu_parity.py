@@ -1140,3 +1140,74 @@ def test_random_graphs_planner_and_executor_vs_oracle(planer, seed, half):
         # float16 against the FLOAT32 oracle: a chain of up to ten random layers drifts past the 1e-2 that holds layer by layer
         # (1 of 600 graphs reached 1.1e-2, its float32 twin 1e-6); 2e-2 still separates rounding from any logic error (>= 0.4)
         assert rel_err(y, r) <= (2e-2 if half else 1e-3), (seed, half, rel_err(y, r))
+
+
+def _random_op_cases(count, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    kinds = ['maxpool', 'averagepool', 'upsample', 'upsample_linear', 'concat', 'softmax', 'gap', 'eltwise', 'batchnorm', 'resize']
+    while len(out) < count:
+        out.append(dict(kind=str(rng.choice(kinds)), n=int(rng.integers(1, 4)), c=int(rng.choice([1, 3, 5, 8, 12, 16, 21, 32, 40, 64])),
+                        h=int(rng.integers(3, 30)), w=int(rng.integers(3, 30)), f16=bool(rng.integers(0, 2)), seed=int(rng.integers(0, 1 << 30))))
+    return out
+
+
+@pytest.mark.parametrize('cfg', _random_op_cases(int(os.environ.get('PLNR_RANDOM_OPS', '60')), 77),
+                         ids=lambda c: '%(kind)s-%(n)dx%(c)dx%(h)dx%(w)d-%(f16)d-%(seed)d' % c)
+def test_random_operators_of_the_eager_table_vs_oracle(planer, cfg):
+    """The HBM-bound operators through ``layer_map`` on random shapes -- channel counts that are not a multiple of the 16-byte
+    vector width, odd extents, random windows / strides / paddings / factors -- against the oracle, float32 and float16."""
+    rng = np.random.default_rng(cfg['seed'])
+    n, c, h, w, kind = cfg['n'], cfg['c'], cfg['h'], cfg['w'], cfg['kind']
+    dt = np.float16 if cfg['f16'] else np.float32
+    x = rng.standard_normal((n, c, h, w)).astype(dt)
+    dev = lambda a: planer.b200.asarray(a)
+    lm = planer.layer_map
+    if kind in ('maxpool', 'averagepool'):
+        k = int(rng.choice([2, 3])); s = int(rng.choice([1, 2])); p = int(rng.integers(0, k // 2 + 1))
+        if h + 2 * p < k or w + 2 * p < k:
+            pytest.skip('window larger than the padded image')
+        kw = {'w': (k, k), 'pads': (p, p, p, p), 'strides': (s, s)}
+        ref = (oracle.maxpool if kind == 'maxpool' else oracle.avgpool)(x.astype(np.float32) if False else x.copy(), **kw)
+        y = lm[kind](dev(x), **kw)
+    elif kind in ('upsample', 'upsample_linear'):
+        lo = 1 if kind == 'upsample' else 2          # the reference's bilinear path needs both factors >= 2 (planer/util.py:133-153)
+        f = np.array([1, 1, int(rng.integers(lo, 4)), int(rng.integers(lo, 4))], np.float32)
+        mode = 'nearest' if kind == 'upsample' else 'linear'
+        ref = oracle.upsample(x.copy(), f, mode=mode)
+        y = lm['upsample'](dev(x), f, mode=mode)
+    elif kind == 'resize':
+        if cfg['f16']:
+            pytest.skip('the reference indexes out of range on float16 coordinates (DESIGN 3)')
+        f = np.array([1, 1, float(rng.uniform(0.6, 2.5)), float(rng.uniform(0.6, 2.5))], np.float32)
+        ref = oracle.resize(x.copy(), np.zeros(0, np.float32), f, mode='linear')
+        y = lm['resize'](dev(x), np.zeros(0, np.float32), f, mode='linear')
+    elif kind == 'concat':
+        c2 = int(rng.choice([1, 3, 8, 16, 24]))
+        x2 = rng.standard_normal((n, c2, h, w)).astype(dt)
+        ref = oracle.concat(x.copy(), x2.copy(), axis=1)
+        y = lm['concat'](dev(x), dev(x2), axis=1)
+    elif kind == 'softmax':
+        ref = oracle.softmax(x.copy(), axis=1)
+        y = lm['softmax'](dev(x), axis=1)
+    elif kind == 'gap':
+        ref = oracle.gap(x.copy())
+        y = lm['gap'](dev(x))
+    elif kind == 'batchnorm':
+        K = rng.uniform(0.5, 1.5, (1, c, 1, 1)).astype(dt); Bv = rng.standard_normal((1, c, 1, 1)).astype(dt)
+        ref = oracle.batchnorm(x.copy(), K, Bv)
+        y = lm['batchnorm'](dev(x), dev(K), dev(Bv))
+    else:
+        op = str(rng.choice(['relu', 'leakyrelu', 'sigmoid', 'add', 'hardsigmoid', 'clip']))
+        if op == 'add':
+            x2 = rng.standard_normal(x.shape).astype(dt)
+            ref = oracle.add(x.copy(), x2); y = lm['add'](dev(x), dev(x2))
+        elif op == 'leakyrelu':
+            ref = oracle.leakyrelu(x.copy(), 0.1); y = lm['leakyrelu'](dev(x), alpha=0.1)
+        elif op == 'clip':
+            ref = oracle.clip(x.copy(), -0.5, 1.5); y = lm['clip'](dev(x), min=-0.5, max=1.5)
+        else:
+            ref = getattr(oracle, op)(x.copy()); y = lm[op](dev(x))
+    got = y.get()
+    assert got.shape == np.asarray(ref).shape, (got.shape, np.asarray(ref).shape)
+    assert rel_err(got, ref) <= TOL[np.dtype(dt)], (cfg, rel_err(got, ref))
