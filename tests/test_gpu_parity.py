@@ -1211,3 +1211,41 @@ def test_random_operators_of_the_eager_table_vs_oracle(planer, cfg):
     got = y.get()
     assert got.shape == np.asarray(ref).shape, (got.shape, np.asarray(ref).shape)
     assert rel_err(got, ref) <= TOL[np.dtype(dt)], (cfg, rel_err(got, ref))
+
+
+def test_call_and_map_with_changing_batch_sizes_and_dtypes(planer):
+    """A stateful sequence on ONE Net: blocking calls and pipelined streams with batch sizes and input dtypes changing from
+    call to call (executor LRU of four signatures, pinned result rings, the chunked upload of large host batches).  Every
+    image's result must equal what the same image gives alone (the forward has no cross-image term), whatever came before."""
+    model, blob = cases.get_model('resnet18')             # full ResNet-18 on 112 x 112 images
+    net = planer.from_model(model, blob, half=True)
+    net.max_executors = 3
+    rng = np.random.default_rng(5)
+    pool16 = rng.standard_normal((160, 3, 112, 112)).astype(np.float16)     # 128+ images = more than 8 MB: the chunked upload path
+    pool8 = rng.integers(0, 256, (160, 3, 112, 112), dtype=np.uint8)
+    single = {}
+
+    def alone(kind, i):
+        if (kind, i) not in single:
+            src = pool16 if kind == 'f16' else pool8
+            single[(kind, i)] = np.asarray(net(src[i:i + 1].copy()))[0].astype(np.float32)
+        return single[(kind, i)]
+
+    sizes = [1, 2, 3, 5, 8, 16, 33, 64, 96, 128, 160]
+    for step in range(24):
+        kind = 'f16' if rng.integers(0, 2) else 'u8'
+        src = pool16 if kind == 'f16' else pool8
+        n = int(rng.choice(sizes))
+        i0 = int(rng.integers(0, 160 - n + 1))
+        if rng.integers(0, 3) == 0:
+            batches = [np.ascontiguousarray(src[i0:i0 + n]) for _ in range(3)]
+            outs = [np.asarray(y) for y in net.map(iter(batches))]
+            assert len(outs) == 3 and all(np.array_equal(outs[0], o) for o in outs)
+            y = outs[0]
+        else:
+            y = np.asarray(net(np.ascontiguousarray(src[i0:i0 + n])))
+        assert y.shape[0] == n
+        for j in sorted({0, n // 2, n - 1}):
+            ref = alone(kind, i0 + j)
+            scale = max(float(np.abs(ref).max()), 1e-6)
+            assert float(np.abs(y[j].astype(np.float32) - ref).max()) / scale <= 4e-3, (step, kind, n, j)
