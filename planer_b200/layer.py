@@ -155,7 +155,9 @@ def Clip(x, min=0, max=1):
     """planer/layer.py:247-251: np.minimum(x, max, out=x); np.maximum(x, min, out=x) -- IN PLACE, returns its input (the
     numexpr branch of the reference, which allocates, is not the path the oracle pins)."""
     d = _dense_rows(x)           # x itself when it is dense; a dense copy of a strided view / NCHW graph input otherwise
-    return ops.unary2(ops.EW_CLIP, d, d, min, max)
+    # bounds that arrive as inputs (constant inits of the graph, uploaded like every init) are read back: two scalars
+    scalar = lambda v: float(np.asarray(v.get() if isinstance(v, DeviceArray) else v, np.float64).reshape(-1)[0])
+    return ops.unary2(ops.EW_CLIP, d, d, scalar(min), scalar(max))
 
 
 def Softmax(x, axis=-1):

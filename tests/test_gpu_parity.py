@@ -1249,3 +1249,38 @@ def test_call_and_map_with_changing_batch_sizes_and_dtypes(planer):
             ref = alone(kind, i0 + j)
             scale = max(float(np.abs(ref).max()), 1e-6)
             assert float(np.abs(y[j].astype(np.float32) - ref).max()) / scale <= 4e-3, (step, kind, n, j)
+
+
+@pytest.mark.parametrize('seed', list(range(int(os.environ.get('PLNR_RANDOM_DROPIN', '8')))))
+def test_random_graphs_through_the_reference_net_numpy_vs_b200(planer, seed):
+    """Random DAGs run by the UNMODIFIED reference's own Net twice: on numpy (the reference itself -- not the oracle) and, after
+    ``planer_b200.install(planer)``, on the B200 kernels behind its plug points (planer/__init__.py:22-38, planer/layer.py:262-281).
+    float32, 1e-3."""
+    import numpy
+    ref = _import_reference()
+    model, blob, cin, size = _random_graph(5000 + seed)
+    x = np.random.default_rng(seed).standard_normal((2, cin) + tuple(size)).astype(np.float32)
+
+    def run_reference_net():
+        net = ref.Net()
+        net.load_json(model['input'], model['inits'], model['layers'], model['flow'])
+        net.load_weights(blob)
+        y = net(x.copy())
+        return y if isinstance(y, tuple) else (y,)
+
+    ref.core(numpy, True)
+    if hasattr(ref.util, 'clear_buf'):
+        ref.util.clear_buf()
+    want = [np.asarray(t).copy() for t in run_reference_net()]
+    saved = dict(ref.layer.layer_map)
+    try:
+        planer.install(ref)
+        got = run_reference_net()
+        assert len(got) == len(want)
+        for g, w_ in zip(got, want):
+            assert isinstance(g, numpy.ndarray) and g.shape == w_.shape
+            assert rel_err(g, w_) <= 1e-3, (seed, rel_err(g, w_))
+    finally:
+        ref.core(numpy, True)
+        ref.layer.layer_map.clear()
+        ref.layer.layer_map.update(saved)
