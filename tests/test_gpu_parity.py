@@ -1054,7 +1054,7 @@ def _random_graph(seed):
     for step in range(int(rng.integers(5, 10))):
         kind = str(rng.choice(['conv', 'conv', 'res', 'dark', 'pool', 'upcat', 'gconv', 'dconv', 'clip', 'avg', 'alias', 'hsig', 'convt', 'fork']))
         if kind == 'conv':
-            co, k = int(rng.choice([16, 32, 64, 128])), int(rng.choice([1, 3, 3, 5]))
+            co, k = int(rng.choice([16, 32, 64, 128] + ([256, 512] if h <= 16 else []))), int(rng.choice([1, 3, 3, 5]))
             s = 2 if (h >= 16 and rng.integers(0, 3) == 0) else 1
             y = b.conv(x, c, co, k, stride=s, bias=bool(rng.integers(0, 2)))
             if rng.integers(0, 2):
