@@ -704,3 +704,44 @@ def test_fp16_split_arithmetic_reproduces_a_float32_dot_product():
         assert np.abs(got - ref).max() / np.abs(ref).max() <= 2e-6, mag
         # dropping the low halves (plain fp16 operands) is three orders of magnitude worse
         assert np.abs(xh @ wh / (sx * sw) - ref).max() / np.abs(ref).max() >= 1e-4
+
+
+def test_tile_decorator_random_cases_equal_the_reference_itself():
+    """planer_b200.util.tile against the UNMODIFIED reference's decorator (baseline/_ref, planer/util.py:291-348) on random image
+    sizes, windows, margins, sampling factors and per-window functions: bit-identical, also with ``batched=True``."""
+    ref_root = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_root, 'planer')):
+        pytest.skip('baseline/_ref is not in this checkout')
+    import sys
+    if not os.access(os.path.expanduser('~'), os.W_OK):
+        os.environ['HOME'] = '/tmp'
+    sys.path.insert(0, ref_root)
+    try:
+        import planer as ref
+    finally:
+        sys.path.remove(ref_root)
+    from planer_b200 import util
+    rng = np.random.default_rng(11)
+    quiet = lambda *a: None
+    skipped = 0
+    for case in range(60):
+        rgb = bool(rng.integers(0, 2))
+        shape = (int(rng.integers(20, 200)), int(rng.integers(20, 200))) + ((3,) if rgb else ())
+        img = (rng.standard_normal(shape) * 10).astype(np.float32)
+        kind = str(rng.choice(['same', 'up2', 'down2'] + (['gray'] if rgb else [])))
+        kw = dict(window=int(rng.choice([16, 24, 32, 48, 64, 256])), margin=float(rng.choice([0.1, 0.25, 0.3])) if rng.integers(0, 2) else int(rng.integers(1, 8)),
+                  glob=int(rng.choice([1, 8, 16])), progress=quiet)
+        if rng.integers(0, 3) == 0:
+            kw['sample'] = float(rng.choice([0.5, 0.75, 1.5]))
+        fn = cases.tile_fn(kind)
+        try:
+            want = ref.util.tile(**kw)(fn)(img.copy())
+        except Exception:          # parameter combinations the reference itself cannot run (odd extents under a /2 function, ...)
+            skipped += 1
+            continue
+        got = util.tile(**kw)(fn)(img.copy())
+        assert got.shape == want.shape and got.dtype == want.dtype, (case, kw, shape, kind)
+        assert np.array_equal(got, want), (case, kw, shape, kind)
+        stacked = lambda ws, fn=fn: np.stack([fn(w_) for w_ in ws])
+        assert np.array_equal(util.tile(batched=True, **kw)(stacked)(img.copy()), want), (case, kw, shape, kind)
+    assert skipped <= 30, skipped
