@@ -63,8 +63,9 @@ def conv2d(x, K, B=None, group=1, strides=(1, 1), dilations=(1, 1), pads=(0, 0, 
       * result dtype is the matmul dtype (fp16 in -> fp16 out, fp32 accumulate inside numpy).
       * bias is added afterwards with ``np.add(out, B.reshape(1,-1,1,1), out=out)``
         (layer.py:26): a second rounding in fp16.
-    Returned array is C-contiguous NCHW (the reference returns a transposed view of the same
-    values, util.py:44).
+    Returned array is the same TRANSPOSED VIEW of the (Co, N, oh, ow) GEMM result the reference returns (util.py:44): the
+    memory layout is part of the parity contract, because numpy's pairwise summation (GlobalAveragePool) and the BLAS path
+    matmul picks (Dense after gap -> flatten) depend on the strides of what they are handed.
     """
     sh, sw = strides
     dh, dw = dilations
@@ -84,7 +85,7 @@ def conv2d(x, K, B=None, group=1, strides=(1, 1), dilations=(1, 1), pads=(0, 0, 
     else:
         out = np.matmul(K.reshape(group, co // group, -1),
                         col.reshape(group, (c // group) * kh * kw, -1))
-    out = np.ascontiguousarray(out.reshape(co, n, oh, ow).transpose(1, 0, 2, 3))
+    out = out.reshape(co, n, oh, ow).transpose(1, 0, 2, 3)
     if B is not None:
         np.add(out, B.reshape(1, -1, 1, 1), out=out)
     return out

@@ -219,3 +219,96 @@ TILE_CASES = {
 def make_tile_case(name):
     shape, kw, kind = TILE_CASES[name]
     return _rng(name).standard_normal(shape).astype('float32') * 10, dict(kw), tile_fn(kind)
+
+
+# ---------------------------------------------------------------------------------------------
+# random DAGs of the hot-path operators (GPU parity sweeps, oracle-vs-reference sweep)
+# ---------------------------------------------------------------------------------------------
+def random_graph(seed):
+    """A random DAG of the hot-path operators built with the zoo's IR builder: plain / strided convolutions with optional
+    batchnorm and activation, ResNet- and Darknet-style residual blocks, pooling, nearest upsampling + concatenation with an
+    earlier tensor, a second graph output taken from the middle."""
+    from planer_b200.zoo import _Builder
+    rng = np.random.default_rng(seed)
+    b = _Builder(seed)
+    cin = int(rng.choice([3, 16, 32]))
+    if rng.integers(0, 3) == 0:                       # odd, non-square extents
+        h, w = int(rng.integers(17, 50)), int(rng.integers(17, 50))
+    else:
+        h = w = int(rng.choice([32, 48, 64]))
+    size = (h, w)
+    x, c = 'x', cin
+    seen = {}                      # (h, w) -> (name, channels) of an earlier tensor to concatenate with
+    mid = None
+
+    def act(y):
+        kind = str(rng.choice(['relu', 'leakyrelu', 'sigmoid', 'none']))
+        if kind == 'none':
+            return y
+        return b.op(kind, {'alpha': 0.1} if kind == 'leakyrelu' else {}, [y])
+
+    for step in range(int(rng.integers(5, 10))):
+        kind = str(rng.choice(['conv', 'conv', 'res', 'dark', 'pool', 'upcat', 'gconv', 'dconv', 'clip', 'avg', 'alias', 'hsig', 'convt', 'fork']))
+        if kind == 'conv':
+            co, k = int(rng.choice([16, 32, 64, 128] + ([256, 512] if h <= 16 else []))), int(rng.choice([1, 3, 3, 5]))
+            s = 2 if (h >= 16 and rng.integers(0, 3) == 0) else 1
+            y = b.conv(x, c, co, k, stride=s, bias=bool(rng.integers(0, 2)))
+            if rng.integers(0, 2):
+                y = b.bn(y, co)
+            x, c = act(y), co
+            if s == 2:
+                h, w = (h + 1) // 2, (w + 1) // 2
+        elif kind == 'gconv' and c % 4 == 0:          # grouped 3x3 convolution (CUDA-core kernel) + relu
+            x = b.op('relu', {}, [b.conv(x, c, c, 3, group=4, bias=True)])
+        elif kind == 'dconv':                         # dilated 3x3 convolution + batchnorm
+            co = int(rng.choice([32, 64]))
+            x, c = b.bn(b.conv(x, c, co, 3, dil=2), co), co
+        elif kind == 'clip':
+            x = b.op('clip', {}, [x, b.init('clip%d.min' % step, np.array(-0.5, np.float32)), b.init('clip%d.max' % step, np.array(2.0, np.float32))])
+        elif kind == 'avg' and h >= 8:
+            x = b.op('averagepool', {'w': [2, 2], 'pads': [0, 0, 0, 0], 'strides': [2, 2]}, [x]); h, w = h // 2, w // 2
+        elif kind == 'alias':                         # the reference's ReLU works IN PLACE: x is mutated too, so this is 2 relu(x)
+            y = b.op('relu', {}, [x])
+            x = b.op('add', {}, [x, y])
+        elif kind == 'hsig':
+            x = b.op('hardsigmoid', {'alpha': 0.2, 'beta': 0.5}, [x])
+        elif kind == 'convt' and h <= 16:             # ConvTranspose2d k4 / s2 / p1: doubles the extent
+            co = int(rng.choice([16, 32]))
+            wt = (rng.standard_normal((c, co, 4, 4)) * np.sqrt(1.0 / (c * 4))).astype(np.float32)
+            x = b.op('convtranspose', {'strides': [2, 2], 'dilations': [1, 1], 'pads': [1, 1, 1, 1], 'output_padding': [0, 0], 'group': 1},
+                     [x, b.init('ct%d.weight' % step, wt), b.init('ct%d.bias' % step, (rng.standard_normal(co) * 0.1).astype(np.float32))])
+            c, h, w = co, 2 * h, 2 * w
+        elif kind == 'fork':                          # two convolutions read the same tensor, their results are added
+            y1 = b.op('relu', {}, [b.conv(x, c, c, 3, bias=True)])
+            y2 = b.bn(b.conv(x, c, c, 1), c, gamma_scale=0.5)
+            x = b.op('add', {}, [y1, y2])
+        elif kind == 'res':        # relu(x + bn(conv3x3(x)))
+            y = b.bn(b.conv(x, c, c, 3), c, gamma_scale=0.5)
+            x = b.op('relu', {}, [b.op('add', {}, [y, x])])
+        elif kind == 'dark':       # x + leaky(bn(conv3x3(leaky(bn(conv1x1(x))))))
+            cm = max(8, c // 2)
+            y = b.op('leakyrelu', {'alpha': 0.1}, [b.bn(b.conv(x, c, cm, 1), cm)])
+            y = b.op('leakyrelu', {'alpha': 0.1}, [b.bn(b.conv(y, cm, c, 3), c, gamma_scale=0.5)])
+            x = b.op('add', {}, [x, y])
+        elif kind == 'pool' and h >= 8:
+            seen[(h, w)] = (x, c)
+            if rng.integers(0, 2):
+                x = b.op('maxpool', {'w': [2, 2], 'pads': [0, 0, 0, 0], 'strides': [2, 2]}, [x]); h, w = h // 2, w // 2
+            else:
+                x = b.op('maxpool', {'w': [3, 3], 'pads': [1, 1, 1, 1], 'strides': [2, 2]}, [x]); h, w = (h + 1) // 2, (w + 1) // 2
+        elif kind == 'upcat' and (2 * h, 2 * w) in seen:
+            other, oc = seen[(2 * h, 2 * w)]
+            y = b.op('upsample', {'mode': 'nearest'}, [x, b.init('up%d.scales' % step, np.array([1, 1, 2, 2], np.float32))])
+            x, c = b.op('concat', {'axis': 1}, [y, other]), c + oc
+            h, w = 2 * h, 2 * w
+        if mid is None and step >= 2 and rng.integers(0, 2):
+            mid = x
+    if rng.integers(0, 3) == 0:                       # classifier tail: gap -> flatten -> dense
+        nc = int(rng.choice([10, 100]))
+        y = b.op('flatten', {}, [b.op('gap', {}, [x])])
+        wd = (rng.standard_normal((nc, c)) * np.sqrt(1.0 / c)).astype(np.float32)
+        x = b.op('dense', {'shp': [c, nc]}, [y, b.init('fc.weight', wd), b.init('fc.bias', (rng.standard_normal(nc) * 0.1).astype(np.float32))])
+        mid = None if mid is None else mid
+    outs = [x] if mid is None or mid == x else [x, mid]
+    model, blob = b.finish(['x'], outs)
+    return model, blob, cin, size

@@ -76,3 +76,38 @@ def test_batchnorm_fold_matches_formula():
     x = rng.standard_normal((2, 8, 3, 3)).astype(np.float32)
     ref = g.reshape(1, -1, 1, 1) * (x - m.reshape(1, -1, 1, 1)) / np.sqrt(v.reshape(1, -1, 1, 1) + 1e-5) + b.reshape(1, -1, 1, 1)
     assert np.allclose(oracle.batchnorm(x, k, s), ref, atol=1e-5)
+
+
+def test_oracle_equals_the_reference_itself_on_random_graphs():
+    """The oracle's interpreter against the UNMODIFIED reference's Net (baseline/_ref, numpy backend) on random DAGs of the
+    hot-path operators (the generator of tests/test_gpu_parity.py): BIT-exact, like on the committed fixtures."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_root = os.path.join(root, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_root, 'planer')):
+        pytest.skip('baseline/_ref is not in this checkout')
+    if not os.access(os.path.expanduser('~'), os.W_OK):
+        os.environ['HOME'] = '/tmp'
+    sys.path.insert(0, ref_root)
+    try:
+        import planer as ref
+    finally:
+        sys.path.remove(ref_root)
+    _random_graph = cases.random_graph
+    import numpy
+    ref.core(numpy, True)
+    for seed in range(24):
+        model, blob, cin, size = _random_graph(9000 + seed)
+        x = np.random.default_rng(seed).standard_normal((2, cin) + tuple(size)).astype(np.float32)
+        net = ref.Net()
+        net.load_json(model['input'], model['inits'], model['layers'], model['flow'])
+        net.load_weights(blob)
+        if hasattr(ref.util, 'clear_buf'):
+            ref.util.clear_buf()
+        want = net(x.copy())
+        want = want if isinstance(want, tuple) else (want,)
+        got = oracle.build_net(model, blob)(x.copy())
+        got = got if isinstance(got, tuple) else (got,)
+        assert len(got) == len(want)
+        for g, w_ in zip(got, want):
+            assert np.array_equal(np.asarray(g), np.asarray(w_)), (seed, float(np.abs(np.asarray(g) - np.asarray(w_)).max()))
