@@ -13,7 +13,7 @@
 //     served by L1 (neighbouring pixels share 6 of 9 positions);
 //   * all 27 products accumulate in fp32, the sum is rounded to fp16 once (the reference's conv output is an fp16 array), then
 //     scale / shift as one HFMA2 and the activation in fp16, like every other conv epilogue of this library;
-//   * a pixel's 32 channels are 64 contiguous bytes, written by the four lanes of a quad as 4-byte pieces.
+//   * a pixel's 32 channels are 64 contiguous bytes, written by the four lanes of a quad as 16-byte pieces (stem3_tap).
 #include "common.cuh"
 
 namespace {
@@ -41,10 +41,28 @@ template <> __device__ __forceinline__ __half ld_h<uint8_t>(const uint8_t* p) { 
 // two-byte loads per lane gather the A fragments (rows = pixels, neighbours hit L1), 8 mma.sync, and the epilogue of the other conv
 // kernels (fp32 sum rounded to fp16 once, scale / shift as one HFMA2, activation) on the C fragments.  The filter's B fragments
 // (16 registers) are read once per warp from shared memory, where the block stages the kernel parameters.  80 registers, three
-// blocks per SM: 0.24 ms for 32 x 416 x 416 (0.33 before).  What bounds it now is the L1 / LSU tag rate of its gathers (ncu: 49 %
-// excessive sectors -- every load request touches four lines, every 4-byte store request eight half-used sectors); staging the
-// input rows in shared memory and transposing the C fragments inside each quad for 16-byte stores is the next step.
+// blocks per SM: 0.24 ms for 32 x 416 x 416 (0.33 before); that version was bound by the L1 / LSU tag rate of its gathers (ncu:
+// 49 % excessive sectors -- every load request touched four lines, every 4-byte store request eight half-used sectors).  The
+// fragment orders below (stem3_tap) fix both without shared memory or shuffles: 0.18 ms.
 constexpr int kWarpsPerBlock = 8;
+
+// Order of the contraction index and of the output channels inside the fragments.  ANY order works as long as the A gather
+// and the filter staging agree, so both are chosen for the memory system (v4; profiles/r02_kernel_experiments.md 17):
+//   * k = 16 ks + 8 hh + 2 tig + e.  The load instruction j = 4 ks + 2 hh + e of a warp covers lanes tig = 0..3 of eight
+//     adjacent pixels; it reads input row j = (channel j / 3, filter row j % 3) at horizontal taps s = tig for tig < 3 -- ten
+//     adjacent 2-byte values, one or two sectors of ONE line, where the natural order k = (c*3 + r)*3 + s touched three or
+//     four lines per instruction.  The ninth row (c = 2, r = 2) rides in the tig = 3 lanes of j = 0..2, the other tig = 3
+//     slots are zero padding.
+//   * MMA column 8 nb + 2 tig + e holds output channel 8 tig + 2 nb + e: a lane's four N blocks are EIGHT CONSECUTIVE
+//     channels = one 16-byte store, a quad writes a whole 64-byte pixel and a warp instruction 512 contiguous bytes (before:
+//     eight 4-byte stores per lane, each warp instruction half-filling eight sectors).
+__device__ __forceinline__ bool stem3_tap(int j, int tig, int& c, int& r, int& sx) {
+  int row, s;
+  if (tig < 3) { row = j; s = tig; }
+  else { row = 8; s = j; if (j >= 3) { c = r = sx = 0; return false; } }
+  c = row / 3; r = row - 3 * c; sx = s;
+  return true;
+}
 
 template <typename Tin, int kAct>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, 3) stem3x3_kernel(const __grid_constant__ Stem3Params p, uint32_t num_tiles,
@@ -52,12 +70,15 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock, 3) stem3x3_kernel(const _
   __shared__ __half wsm[32][kMaxCout + 8];                   // [k (27 taps, zero-padded to 32)][channel], pitch 40: conflict-light
   for (int i = threadIdx.x; i < 32 * kMaxCout; i += blockDim.x) {
     const int k = i / kMaxCout, n = i - k * kMaxCout;
-    wsm[k][n] = k < kTaps ? reinterpret_cast<const __half*>(&p.w[k][0])[n] : __float2half_rn(0.f);
+    int c, r, sx;
+    const bool ok = stem3_tap(4 * (k >> 4) + 2 * ((k >> 3) & 1) + (k & 1), (k >> 1) & 3, c, r, sx);
+    wsm[k][n] = ok ? reinterpret_cast<const __half*>(&p.w[(c * 3 + r) * 3 + sx][0])[n] : __float2half_rn(0.f);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;                 // fragment coordinates of mma.m16n8k16
-  // B fragments: b[ks][nb][0] = {W[16 ks + 2 tig][8 nb + gid], W[16 ks + 2 tig + 1][..]}, b[ks][nb][1] = the same at k + 8
+  // B fragments: b[ks][nb][0] = {W[16 ks + 2 tig][ch], W[16 ks + 2 tig + 1][ch]}, b[ks][nb][1] = the same at k + 8, where
+  // ch = 8 (gid / 2) + 2 nb + gid % 2 is the output channel of MMA column 8 nb + gid
   uint32_t bfr[2][4][2];
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks)
@@ -66,7 +87,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock, 3) stem3x3_kernel(const _
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int k = 16 * ks + 2 * tig + 8 * hh;
-        const __half2 v = __halves2half2(wsm[k][8 * nb + gid], wsm[k + 1][8 * nb + gid]);
+        const int ch = 8 * (gid >> 1) + 2 * nb + (gid & 1);
+        const __half2 v = __halves2half2(wsm[k][ch], wsm[k + 1][ch]);
         bfr[ks][nb][hh] = *reinterpret_cast<const uint32_t*>(&v);
       }
   // this lane's eight k indices (two K=16 steps x {2 tig, 2 tig + 1, 2 tig + 8, 2 tig + 9}) decoded once: input offset
@@ -76,13 +98,13 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock, 3) stem3x3_kernel(const _
   uint32_t kmask = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int k = 16 * (j >> 2) + 2 * tig + (j & 1) + 8 * ((j >> 1) & 1);
-    const int c = k / 9, r = (k - 9 * c) / 3, sx = k - 9 * c - 3 * r;
-    const bool ok = k < kTaps && c < p.C;
+    int c, r, sx;
+    const bool ok = stem3_tap(j, tig, c, r, sx) && c < p.C;
     kmask |= (ok ? 1u : 0u) << j;
     koff[j] = ok ? (c * p.H + (r - 1)) * p.W + (sx - 1) : 0;      // padded k: a valid address whose value is discarded
+    if (!ok && tig == 3 && j >= 3 && j / 3 < p.C) koff[j] = ((j / 3) * p.H + (j % 3 - 1)) * p.W;   // ... in the sector its quad reads anyway
   }
-  // scale / shift of this lane's channel pairs (8 nb + 2 tig, + 1)
+  // scale / shift of this lane's channel pairs (8 tig + 2 nb, + 1)
   __shared__ __half2 ssm[2][kMaxCout / 2];
   if (threadIdx.x < kMaxCout / 2) { ssm[0][threadIdx.x] = p.scale[threadIdx.x]; ssm[1][threadIdx.x] = p.shift[threadIdx.x]; }
   __syncthreads();
@@ -136,8 +158,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock, 3) stem3x3_kernel(const _
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int j = 4 * ks + 2 * hh + e;
-              const int k = 16 * ks + 2 * tig + e + 8 * hh;
-              const int c = k / 9, r = (k - 9 * c) / 3, sx = k - 9 * c - 3 * r;
+              int c, r, sx;
+              stem3_tap(j, tig, c, r, sx);
               const bool kvalid = (kmask >> j) & 1u;
               const int ih = h + r - 1, iw = w0 + pix + sx - 1;
               const bool ok = kvalid && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
@@ -161,18 +183,20 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock, 3) stem3x3_kernel(const _
                      : "+f"(acc[nb][0]), "+f"(acc[nb][1]), "+f"(acc[nb][2]), "+f"(acc[nb][3])
                      : "r"(afr[ks][0]), "r"(afr[ks][1]), "r"(afr[ks][2]), "r"(afr[ks][3]), "r"(bfr[ks][nb][0]), "r"(bfr[ks][nb][1]));
     }
-    // C fragment: (pixel gid, channels 8 nb + 2 tig, + 1) in acc[nb][0..1], (pixel gid + 8, same channels) in acc[nb][2..3]
+    // C fragment: (pixel gid, channels 8 tig + 2 nb, + 1) in acc[nb][0..1], (pixel gid + 8, same channels) in acc[nb][2..3]:
+    // the four N blocks of a lane are eight consecutive channels, one 16-byte store per pixel
     const long long pix0 = ((long long)n * p.H + h) * p.W + w0;
+    if (8 * tig < p.Cout) {
 #pragma unroll
-    for (int pp = 0; pp < 2; ++pp) {
-      const int pix = gid + 8 * pp;
-      if (w0 + pix < p.W) {
-        __half* yrow = p.y + (size_t)(pix0 + pix) * p.yld + p.ycoff;
+      for (int pp = 0; pp < 2; ++pp) {
+        const int pix = gid + 8 * pp;
+        if (w0 + pix < p.W) {
+          uint4 out;
+          uint32_t* o = reinterpret_cast<uint32_t*>(&out);
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) {
-          if (8 * nb + 2 * tig < p.Cout) {
+          for (int nb = 0; nb < 4; ++nb) {
             __half2 v = __floats2half2_rn(acc[nb][2 * pp], acc[nb][2 * pp + 1]);      // conv output rounded to fp16 once
-            const __half2 sc = ssm[0][4 * nb + tig], sf = ssm[1][4 * nb + tig];
+            const __half2 sc = ssm[0][4 * tig + nb], sf = ssm[1][4 * tig + nb];
             if (kAct == 1) v = __hfma2_relu(v, sc, sf);
             else {
               v = __hfma2(v, sc, sf);
@@ -182,8 +206,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock, 3) stem3x3_kernel(const _
                 v = __floats2half2_rn(plnr_apply_act(f.x, p.act, p.alpha), plnr_apply_act(f.y, p.act, p.alpha));
               }
             }
-            *reinterpret_cast<__half2*>(yrow + 8 * nb + 2 * tig) = v;
+            o[nb] = *reinterpret_cast<const uint32_t*>(&v);
           }
+          *reinterpret_cast<uint4*>(p.y + (size_t)(pix0 + pix) * p.yld + p.ycoff + 8 * tig) = out;
         }
       }
     }
