@@ -78,9 +78,8 @@ def test_batchnorm_fold_matches_formula():
     assert np.allclose(oracle.batchnorm(x, k, s), ref, atol=1e-5)
 
 
-def test_oracle_equals_the_reference_itself_on_random_graphs():
-    """The oracle's interpreter against the UNMODIFIED reference's Net (baseline/_ref, numpy backend) on random DAGs of the
-    hot-path operators (the generator of tests/test_gpu_parity.py): BIT-exact, like on the committed fixtures."""
+def _reference_module():
+    """The UNMODIFIED reference, pip-installed into baseline/_ref by __graft_entry__.build() (numpy backend)."""
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     ref_root = os.path.join(root, 'baseline', '_ref')
@@ -93,21 +92,32 @@ def test_oracle_equals_the_reference_itself_on_random_graphs():
         import planer as ref
     finally:
         sys.path.remove(ref_root)
-    _random_graph = cases.random_graph
     import numpy
     ref.core(numpy, True)
-    for seed in range(24):
-        model, blob, cin, size = _random_graph(9000 + seed)
-        x = np.random.default_rng(seed).standard_normal((2, cin) + tuple(size)).astype(np.float32)
+    return ref
+
+
+@pytest.mark.parametrize('half,count,batch', [(False, 24, 2), (True, 8, 1)])
+def test_oracle_equals_the_reference_itself_on_random_graphs(half, count, batch):
+    """The oracle's interpreter against the UNMODIFIED reference's Net (baseline/_ref, numpy backend) on random DAGs of the
+    hot-path operators (the generator of tests/test_gpu_parity.py): BIT-exact, like on the committed fixtures -- in float32
+    and after ``Net.half()`` (numpy's float16 matmul has no BLAS: fewer, single-image graphs)."""
+    ref = _reference_module()
+    for seed in range(count):
+        model, blob, cin, size = cases.random_graph((9100 if half else 9000) + seed)
+        x = np.random.default_rng(seed).standard_normal((batch, cin) + tuple(size)).astype(np.float16 if half else np.float32)
         net = ref.Net()
         net.load_json(model['input'], model['inits'], model['layers'], model['flow'])
         net.load_weights(blob)
+        if half:
+            net.half()
         if hasattr(ref.util, 'clear_buf'):
             ref.util.clear_buf()
         want = net(x.copy())
         want = want if isinstance(want, tuple) else (want,)
-        got = oracle.build_net(model, blob)(x.copy())
+        got = oracle.build_net(model, blob, half=half)(x.copy())
         got = got if isinstance(got, tuple) else (got,)
         assert len(got) == len(want)
         for g, w_ in zip(got, want):
-            assert np.array_equal(np.asarray(g), np.asarray(w_)), (seed, float(np.abs(np.asarray(g) - np.asarray(w_)).max()))
+            g, w_ = np.asarray(g), np.asarray(w_)
+            assert g.dtype == w_.dtype and np.array_equal(g, w_), (seed, float(np.abs(g.astype(np.float32) - w_.astype(np.float32)).max()))
