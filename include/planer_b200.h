@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PLNR_ABI_VERSION 2
+#define PLNR_ABI_VERSION 3
 
 enum { PLNR_F32 = 0, PLNR_F16 = 1, PLNR_U8 = 2 /* graph INPUTS only: uint8 images, converted by the input-time kernel */ };
 enum { PLNR_ACT_NONE = 0, PLNR_ACT_RELU = 1, PLNR_ACT_LEAKY = 2, PLNR_ACT_SIGMOID = 3 };
@@ -83,6 +83,11 @@ typedef struct {
                              *    pre-scales); 0 means 1 */
   const float* acc_scale_dev; /* NULL, or a DEVICE scalar multiplied in as well (the per-call activation pre-scale left by
                              *    plnr_split_f32 in dyn[1]) */
+  float* pool_sum;          /* (ABI 3) NULL, or the GlobalAveragePool that consumes this conv's output folded into its epilogue
+                             *    (planer/layer.py:77-78 after :22-26/:125-127/:93-95/:44-46): fp32 [n][parts][cout] with parts =
+                             *    plnr_conv2d_pool_parts(...) > 0 -- the SUM of the finished (fp16-rounded) outputs over each
+                             *    32-position part of an image, one writer per element (deterministic); y is NOT written.
+                             *    plnr_pooled_dense_fwd adds the parts, divides by h*w and applies the Dense layer. */
 } plnr_epilogue;
 
 typedef struct {
@@ -192,6 +197,9 @@ int plnr_fold_affine(plnr_ctx* ctx, const void* bias, const void* bn_k, const vo
 int plnr_conv2d_fwd(plnr_ctx* ctx, const plnr_conv_desc* desc, const plnr_tensor* x, const void* w_packed,
                     const plnr_tensor* y, const plnr_epilogue* ep);
 int plnr_conv2d_out_nchw_supported(const plnr_conv_desc* desc, const plnr_tensor* x, const plnr_tensor* y);
+/* parts per image of plnr_epilogue.pool_sum for this problem, or 0 when the pooling fold does not apply (needs the fp16
+ * stride-1 shift-GEMM kernel, cout % 32 == 0 and a padded image grid of a multiple of 32 positions, e.g. 7x7 + pad 1). */
+int plnr_conv2d_pool_parts(const plnr_conv_desc* desc, const plnr_tensor* x, const plnr_tensor* y);
 /* Conv2d + fused 1x1 shortcut convolution: y = act((conv(x, W) + conv1x1_stride(x2, W2)) * scale + shift).  Replaces the
  * tail of a down-sampling residual block -- Conv2d -> BatchNorm on the main path, Conv2d(1x1, stride) -> BatchNorm on
  * the shortcut, Add, ReLU (planer/layer.py:22-26, :125-127, :93-95, :44-46) -- by ONE launch: the shortcut's k-chunks
@@ -253,6 +261,10 @@ int plnr_global_avgpool(plnr_ctx* ctx, int dtype, const plnr_tensor* x, void* y)
  * scale[o] + shift[o]); w is the reference's (out, in) matrix in dtype `dtype`; y is (n, out_features) of the same dtype. */
 int plnr_gap_dense_fwd(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const void* w, const float* scale,
                        const float* shift, void* y, int out_features, int act, float alpha);
+/* The same tail when the pooling was folded into the producing convolution (plnr_epilogue.pool_sum): pool is fp32
+ * [n][parts][c] of partial sums, hw the number of pooled positions (planer/layer.py:77-78 divides by h*w); fp16 w / y. */
+int plnr_pooled_dense_fwd(plnr_ctx* ctx, const float* pool, int n, int parts, int c, int hw, const void* w, const float* scale,
+                          const float* shift, void* y, int out_features, int act, float alpha);
 
 /* ---- CUDA-graph capture of a planned forward (replaces the Python interpreter loop of
  *      planer/net.py:43-70 by one replayable launch) ------------------------------------- */

@@ -26,7 +26,7 @@ class Tensor(C.Structure):
 class Epilogue(C.Structure):
     _fields_ = [('scale', C.c_void_p), ('shift', C.c_void_p), ('residual', C.POINTER(Tensor)),
                 ('act', C.c_int32), ('alpha', C.c_float), ('res_after_act', C.c_int32), ('out_nchw', C.c_int32),
-                ('out_f32', C.c_int32), ('acc_scale', C.c_float), ('acc_scale_dev', C.c_void_p)]
+                ('out_f32', C.c_int32), ('acc_scale', C.c_float), ('acc_scale_dev', C.c_void_p), ('pool_sum', C.c_void_p)]
 
 
 class ConvDesc(C.Structure):
@@ -69,6 +69,7 @@ PROTOTYPES = {
     'plnr_fold_affine': [_P, _P, _P, _P, C.c_int, _P, _P, C.c_int],
     'plnr_conv2d_fwd': [_P, C.POINTER(ConvDesc), _TP, _P, _TP, C.POINTER(Epilogue)],
     'plnr_conv2d_out_nchw_supported': [C.POINTER(ConvDesc), _TP, _TP],
+    'plnr_conv2d_pool_parts': [C.POINTER(ConvDesc), _TP, _TP],
     'plnr_conv2d_shortcut_supported': [C.POINTER(ConvDesc), _TP, _TP, C.c_int, _TP],
     'plnr_conv2d_shortcut_fwd': [_P, C.POINTER(ConvDesc), _TP, _P, _TP, C.c_int, _TP, C.POINTER(Epilogue)],
     'plnr_dense_fwd': [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(Epilogue), C.c_int],
@@ -85,6 +86,7 @@ PROTOTYPES = {
     'plnr_softmax': [_P, C.c_int, _P, _P, C.c_int64, C.c_int],
     'plnr_global_avgpool': [_P, C.c_int, _TP, _P],
     'plnr_gap_dense_fwd': [_P, C.c_int, _TP, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float],
+    'plnr_pooled_dense_fwd': [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float],
     'plnr_graph_begin': [_P],
     'plnr_graph_end': [_P, C.POINTER(_P)],
     'plnr_graph_launch': [_P, _P],
@@ -122,8 +124,8 @@ def load():
         fn.restype = C.c_int
     lib.plnr_last_error.argtypes = []
     lib.plnr_last_error.restype = C.c_char_p
-    if lib.plnr_abi_version() != 2:
-        raise PlanerB200Error('ABI version mismatch: library %d, binding 2' % lib.plnr_abi_version())
+    if lib.plnr_abi_version() != 3:
+        raise PlanerB200Error('ABI version mismatch: library %d, binding 3' % lib.plnr_abi_version())
     _lib = lib
     return lib
 

@@ -276,6 +276,11 @@ int plnr_conv2d_fwd(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x
                  "conv2d: out_nchw needs the shift-GEMM kernel (plnr_conv2d_out_nchw_supported)");
     return plnr_conv2d_shift(ctx, d, x, w, y, ep);
   }
+  if (ep && ep->pool_sum) {
+    PLNR_REQUIRE(d->algo != PLNR_ALGO_DIRECT && plnr_conv2d_pool_parts(d, x, y) > 0,
+                 "conv2d: pool_sum needs the shift-GEMM kernel with whole 32-position parts per image (plnr_conv2d_pool_parts)");
+    return plnr_conv2d_shift(ctx, d, x, w, y, ep);
+  }
   bool tc_ok = plnr_conv2d_tcgen05_supported(d, x, y);
   if (ep && ep->out_f32) {
     PLNR_REQUIRE(d->dtype == PLNR_F16 && tc_ok && d->algo != PLNR_ALGO_DIRECT,
@@ -294,6 +299,11 @@ int plnr_conv2d_fwd(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x
 int plnr_conv2d_out_nchw_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y) {
   if (!d || !x || !y || d->dtype != PLNR_F16 || d->groups != 1 || d->algo == PLNR_ALGO_DIRECT) return 0;
   return plnr_conv2d_shift_supported(d, x, y) ? 1 : 0;
+}
+
+int plnr_conv2d_pool_parts(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y) {
+  if (!d || !x || !y || d->dtype != PLNR_F16 || d->groups != 1 || d->algo == PLNR_ALGO_DIRECT) return 0;
+  return plnr_conv2d_shift_pool_parts(d, x, y);
 }
 
 int plnr_conv2d_shortcut_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* x2, int stride2,

@@ -145,6 +145,7 @@ bool plnr_conv2d_stack_supported(const plnr_conv_desc* d, const plnr_tensor* x, 
 bool plnr_conv2d_shift_shortcut_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* x2, int s2,
                                           const plnr_tensor* y);
 bool plnr_conv2d_shift_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y);
+int plnr_conv2d_shift_pool_parts(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y);
 // pointwise convolutions with small resident filters (conv_pw.cu)
 bool plnr_conv2d_pw_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y, const plnr_epilogue* ep);
 int plnr_conv2d_pw(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w, const plnr_tensor* y,

@@ -68,6 +68,10 @@ struct ShiftParams {
   int vec_ok;
   int stage_wide;           // epilogue transposition stage: 2 KB per warp (a whole 32-column chunk per round trip) instead of 1 KB
   int y_nchw, ohw;          // 1: y is a dense NCHW array (graph exit folded into the epilogue); OH * OW
+  // Global-average-pool fold (plnr_epilogue.pool_sum): instead of storing y, every epilogue warp writes the fp32 SUM of its
+  // 32 accumulator rows (all of one image: HvWv % 32 == 0), finished values, rim rows excluded, to
+  // pool[(image * pool_parts + (position in the image) / 32) * Cout + channel] -- one writer per element, no atomics
+  float* pool; int pool_parts;
   int* err;
   long long* prof;
   // stream-K (see SegList): iterations per tile = weight boxes per tile; fp32 partial tiles and their ready flags
@@ -180,7 +184,9 @@ __device__ __forceinline__ void tile_rows(long long o0, int Wv, int halo, const 
   nrows = (int)(fast_div(u0 + (uint32_t)(kTileM - 1 + halo), div_wv) - q0) + 1;
 }
 
-template <int CG>
+// POOL: the instantiation whose epilogue folds GlobalAveragePool (ShiftParams::pool); a separate instantiation so that the
+// register allocation of every other launch is exactly what it was without the fold (168 registers, no spills)
+template <int CG, bool POOL = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant__ CUtensorMap mapB,
                       const __grid_constant__ CUtensorMap mapA2, const ShiftParams p) {
@@ -701,6 +707,58 @@ conv_shift_f16_kernel(const __grid_constant__ AMaps mapsA, const __grid_constant
                   const int row = 16 * i + (lane >> 1);
                   val[2 * h + i] = *reinterpret_cast<const uint4*>(st_o + row * 64 + ((((uint32_t)(2 * h + piece)) ^ rsw) << 4));
                 }
+              if (POOL && p.pool) {
+                // GlobalAveragePool folded into this epilogue (the layer's only consumer): the lane's two rows are added in
+                // fp32, then a reduce-scatter over the sixteen lanes that hold the same channels (lane bits 1..4: 8 + 4 + 2 + 1
+                // shuffles) leaves every lane with the 32-row sum of ONE channel of the chunk; nothing is stored to y.
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                  for (int i = 0; i < 2; ++i)
+                    finish(val[2 * h + i], reinterpret_cast<const __half2*>(&sc4[h]), reinterpret_cast<const __half2*>(&sf4[h]), rv[2 * h + i]);
+                float s16[16];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const __half2* r0 = reinterpret_cast<const __half2*>(&val[2 * h]);
+                  const __half2* r1 = reinterpret_cast<const __half2*>(&val[2 * h + 1]);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 a0 = __half22float2(r0[e]), a1 = __half22float2(r1[e]);
+                    s16[h * 8 + 2 * e] = (g.row[0] >= 0 ? a0.x : 0.f) + (g.row[1] >= 0 ? a1.x : 0.f);
+                    s16[h * 8 + 2 * e + 1] = (g.row[0] >= 0 ? a0.y : 0.f) + (g.row[1] >= 0 ? a1.y : 0.f);
+                  }
+                }
+                float s8[8], s4[4], s2[2];
+                const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float got = __shfl_xor_sync(0xffffffffu, b4 ? s16[j] : s16[j + 8], 16);
+                  s8[j] = (b4 ? s16[j + 8] : s16[j]) + got;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float got = __shfl_xor_sync(0xffffffffu, b3 ? s8[j] : s8[j + 4], 8);
+                  s4[j] = (b3 ? s8[j + 4] : s8[j]) + got;
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const float got = __shfl_xor_sync(0xffffffffu, b2 ? s4[j] : s4[j + 2], 4);
+                  s2[j] = (b2 ? s4[j + 2] : s4[j]) + got;
+                }
+                const float tot = (b1 ? s2[1] : s2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? s2[0] : s2[1], 2);
+                // the kept value: 16-channel half b4, element 4 b3 + 2 b2 + b1 of this lane's 8-channel piece
+                const int ch = cb + (b4 ? 16 : 0) + piece * 8 + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+                // (image, 32-row part) this warp's rows belong to
+                const uint32_t m_idx_ = (uint32_t)tile - (uint32_t)n_idx * (uint32_t)p.num_m_tiles;
+                const uint32_t ob = (m_idx_ * CG + rank) * kTileM + (uint32_t)(ew * 32);
+                if (ob < uMv) {
+                  const uint32_t img = fast_div(ob, p.div_hvwv);
+                  const uint32_t pool_row = img * (uint32_t)p.pool_parts + ((ob - img * HvWv) >> 5);
+                  p.pool[(size_t)pool_row * p.Cout + ch] = tot;
+                }
+                __syncwarp();
+                return;
+              }
 #pragma unroll
               for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -1018,6 +1076,17 @@ bool plnr_conv2d_shift_supported(const plnr_conv_desc* d, const plnr_tensor* x, 
   return make_plan(d, x, y, 148).ok;
 }
 
+// GlobalAveragePool fold: 32-row parts per image (> 0) when the shift kernel runs the problem with the wide epilogue stage and
+// every TMEM lane quarter (32 consecutive virtual positions) lies inside ONE image; 0 otherwise.
+int plnr_conv2d_shift_pool_parts(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* y) {
+  if (const char* e = getenv("PLNR_NO_POOL_FOLD")) { if (atoi(e)) return 0; }
+  if (!plnr_conv2d_shift_supported(d, x, y)) return 0;
+  const ShiftPlan pl = make_plan(d, x, y, 148);
+  if (!pl.ok || !pl.stage_wide || pl.cs != 1 || y->c % 32 != 0 || (pl.Hv * pl.Wv) % 32 != 0) return 0;
+  if (y->ld % 8 != 0 || y->coff % 8 != 0) return 0;
+  return pl.Hv * pl.Wv / 32;
+}
+
 // The fused shortcut: x2 is the block input, (n, c2, >= (y.h-1)*s2+1, >= (y.w-1)*s2+1); its 1x1 / stride-s2 convolution is
 // accumulated into the same TMEM tile as extra k-chunks (weights appended to the packed filter along K).
 bool plnr_conv2d_shift_shortcut_supported(const plnr_conv_desc* d, const plnr_tensor* x, const plnr_tensor* x2, int s2,
@@ -1033,7 +1102,7 @@ bool plnr_conv2d_shift_shortcut_supported(const plnr_conv_desc* d, const plnr_te
 int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor* x, const void* w,
                       const plnr_tensor* y, const plnr_epilogue* ep, const plnr_tensor* x2, int s2) {
   // 3-wide filters over 64-channel output blocks whose taps fit in shared memory: the stacked variant (conv_stack.cu)
-  if (!(ep && ep->out_nchw) && plnr_conv2d_stack_supported(d, x, y, ep, x2, s2)) return plnr_conv2d_stack(ctx, d, x, w, y, ep, x2, s2);
+  if (!(ep && (ep->out_nchw || ep->pool_sum)) && plnr_conv2d_stack_supported(d, x, y, ep, x2, s2)) return plnr_conv2d_stack(ctx, d, x, w, y, ep, x2, s2);
   int rc = resolve_driver();
   if (rc != PLNR_OK) return rc;
   const int c2 = x2 ? x2->c : 0;
@@ -1082,6 +1151,12 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
   if (ep && ep->out_nchw) {          // every thread stores its own pixel, channel by channel: lanes = consecutive pixels of a plane
     PLNR_REQUIRE(!ep->residual, "conv2d(shift): out_nchw cannot be combined with a residual operand");
     p.y_nchw = 1; p.ohw = y->h * y->w; p.vec_ok = 0;
+  }
+  if (ep && ep->pool_sum) {          // GlobalAveragePool folded into the epilogue (plnr_conv2d_pool_parts)
+    const int parts = plnr_conv2d_shift_pool_parts(d, x, y);
+    PLNR_REQUIRE(parts > 0 && !ep->out_nchw && p.vec_ok && pl.stage_wide,
+                 "conv2d(shift): pool_sum needs plnr_conv2d_pool_parts > 0, 16-byte-aligned views, no out_nchw");
+    p.pool = ep->pool_sum; p.pool_parts = parts;
   }
   p.err = ctx->dev_error;
   p.prof = ctx->prof;
@@ -1150,6 +1225,8 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
   if (!ctx->shift_attr_set) {
     PLNR_CHECK_CUDA(cudaFuncSetAttribute(conv_shift_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     PLNR_CHECK_CUDA(cudaFuncSetAttribute(conv_shift_f16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    PLNR_CHECK_CUDA((cudaFuncSetAttribute(conv_shift_f16_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)));
+    PLNR_CHECK_CUDA((cudaFuncSetAttribute(conv_shift_f16_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)));
     ctx->shift_attr_set = true;
   }
   // Persistent grid = the number of units (CTAs / CTA pairs) that can be RESIDENT AT ONCE.  For pairs that is not
@@ -1191,7 +1268,7 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
     if (const char* e = getenv("PLNR_STREAMK")) mode = atoi(e);
     const double waves = (double)p.num_tiles / units;
     const double dp_rounds = (double)((p.num_tiles + units - 1) / units);
-    const bool legal = !p.b_resident && p.n_tile >= 64 && (long long)p.num_tiles * p.ipt >= 4ll * units && p.num_tiles >= 2 &&
+    const bool legal = !p.pool && !p.b_resident && p.n_tile >= 64 && (long long)p.num_tiles * p.ipt >= 4ll * units && p.num_tiles >= 2 &&
                        !(ctx->capturing && !ctx->sk_ws);
     if (legal && mode > 0 && (mode >= 2 || dp_rounds / (waves + 0.12) >= 1.06)) {
       const size_t ws_bytes = (size_t)units * cg * kTileM * 256 * sizeof(float);
@@ -1223,8 +1300,11 @@ int plnr_conv2d_shift(plnr_ctx* ctx, const plnr_conv_desc* d, const plnr_tensor*
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = plnr_pdl_enabled() ? 2 : 1;
-  cudaError_t le = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<2>, mapsA, mapB, mapA2, p)
-                           : cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<1>, mapsA, mapB, mapA2, p);
+  cudaError_t le;
+  if (p.pool) le = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<2, true>, mapsA, mapB, mapA2, p)
+                           : cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<1, true>, mapsA, mapB, mapA2, p);
+  else le = cg == 2 ? cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<2>, mapsA, mapB, mapA2, p)
+                    : cudaLaunchKernelEx(&cfg, conv_shift_f16_kernel<1>, mapsA, mapB, mapA2, p);
   if (le != cudaSuccess) {
     plnr_set_error("launch of conv_shift_f16_kernel<%d> failed: %s", cg, cudaGetErrorString(le));
     return PLNR_ERR_CUDA;

@@ -1068,6 +1068,108 @@ __global__ void __launch_bounds__(512) gap_dense_mma_kernel(const __half* __rest
   }
 }
 
+// The same tail when GlobalAveragePool was folded into the producing convolution's epilogue (plnr_epilogue.pool_sum,
+// conv_shift.cu): `pre` holds fp32 partial sums [image][part][channel].  Phase 1 adds the parts, divides by the number of pooled
+// positions and rounds to fp16 (the reference's GlobalAveragePool returns an fp16 array: planer/layer.py:77-78) -- 16 KB of
+// reads per CTA instead of re-pooling 400 KB of activations.  Phase 2 is gap_dense_mma_kernel's product with the K range of a
+// 16-feature block split over two warps when there are warps to spare (all loads of a warp in flight at once: the phase is
+// a chain of L2 latencies, not of bytes), partial accumulators added through shared memory in a fixed order.
+template <int IMGS>
+__global__ void __launch_bounds__(512) pooled_dense_mma_kernel(const float* __restrict__ pre, const __half* __restrict__ w,
+                                                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                __half* __restrict__ y, int N, int P, float inv, int C, int OUT,
+                                                                int och, int act, float alpha) {
+  static_assert(IMGS == 8, "the n8 dimension of mma.m16n8k16 is the image group");
+  extern __shared__ __align__(16) uint8_t pd_smem[];
+  __half* pooled = reinterpret_cast<__half*>(pd_smem);          // [8][C + 8]
+  const int pitch = C + 8;
+  float* red = reinterpret_cast<float*>(pd_smem + (((size_t)IMGS * pitch * sizeof(__half)) + 15) / 16 * 16);   // [warp][4][32]
+  const int n0 = blockIdx.x * IMGS, o0 = blockIdx.y * och;
+  const int o_end = min(o0 + och, OUT);
+  const int C4 = C >> 2;
+  for (int idx = threadIdx.x; idx < IMGS * C4; idx += blockDim.x) {
+    const int img = idx / C4, c4 = idx - img * C4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + img < N) {
+      const float4* src = reinterpret_cast<const float4*>(pre + (size_t)(n0 + img) * P * C) + c4;
+      for (int pp = 0; pp < P; ++pp) {
+        const float4 v = __ldcg(src + (size_t)pp * C4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    __half2* dst = reinterpret_cast<__half2*>(pooled + img * pitch + c4 * 4);
+    dst[0] = __floats2half2_rn(acc.x * inv, acc.y * inv);
+    dst[1] = __floats2half2_rn(acc.z * inv, acc.w * inv);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int gid = lane >> 2, tig = lane & 3;               // fragment coordinates of mma.m16n8k16
+  const int blocks = (o_end - o0 + 15) >> 4;
+  const int ks = (nwarps >= 2 * blocks && C % 32 == 0) ? 2 : 1;      // K halves per 16-feature block
+  const int Kper = C / ks;
+  for (int base = 0; base < blocks * ks; base += nwarps) {
+    const int wi = base + warp;
+    const bool active = wi < blocks * ks;
+    const int blk = wi / ks, kh = wi - blk * ks;
+    const int m0 = o0 + blk * 16;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    if (active) {
+      const int r0 = min(m0 + gid, OUT - 1), r1 = min(m0 + gid + 8, OUT - 1);
+      const uint32_t* w0 = reinterpret_cast<const uint32_t*>(w + (size_t)r0 * C + kh * Kper) + tig;
+      const uint32_t* w1 = reinterpret_cast<const uint32_t*>(w + (size_t)r1 * C + kh * Kper) + tig;
+      const uint32_t* pb = reinterpret_cast<const uint32_t*>(pooled + gid * pitch + kh * Kper) + tig;
+      constexpr int U = 16;                                 // k-steps of 16 whose loads are in flight together
+      for (int k0 = 0; k0 < Kper; k0 += 16 * U) {
+        uint32_t a[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int kw = (k0 + 16 * u) >> 1;                // 32-bit word index of column k
+          if (k0 + 16 * u < Kper) {
+            a[u][0] = __ldg(w0 + kw); a[u][1] = __ldg(w1 + kw); a[u][2] = __ldg(w0 + kw + 4); a[u][3] = __ldg(w1 + kw + 4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (k0 + 16 * u < Kper) {
+            const int kw = (k0 + 16 * u) >> 1;
+            const uint32_t b0 = pb[kw], b1 = pb[kw + 4];
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)
+                         : "r"(a[u][0]), "r"(a[u][1]), "r"(a[u][2]), "r"(a[u][3]), "r"(b0), "r"(b1));
+          }
+        }
+      }
+    }
+    if (ks == 2) {                                          // upper K half -> shared memory -> added by the lower half's warp
+      if (active && kh == 1) {
+        float* r = red + warp * 128;
+        r[lane] = d0; r[32 + lane] = d1; r[64 + lane] = d2; r[96 + lane] = d3;
+      }
+      __syncthreads();
+      if (active && kh == 0) {
+        const float* r = red + (warp + 1) * 128;
+        d0 += r[lane]; d1 += r[32 + lane]; d2 += r[64 + lane]; d3 += r[96 + lane];
+      }
+      __syncthreads();
+    }
+    if (active && kh == 0) {
+      // D fragment: (feature m0 + gid, images 2*tig, 2*tig + 1) and (feature m0 + gid + 8, same images)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int f = m0 + gid + 8 * h;
+        if (f < o_end) {
+          const float sc = scale ? scale[f] : 1.f, sf = shift ? shift[f] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int n = n0 + 2 * tig + j;
+            if (n < N) y[(size_t)n * OUT + f] = __float2half_rn(plnr_apply_act(fmaf(h ? (j ? d3 : d2) : (j ? d1 : d0), sc, sf), act, alpha));
+          }
+        }
+      }
+    }
+  }
+}
+
 static inline bool view_vec_ok(const plnr_tensor* t, int V, size_t esz) {
   return t->c % V == 0 && t->ld % V == 0 && t->coff % V == 0 && aligned16(t->ptr) && (V * esz == 16);
 }
@@ -1498,6 +1600,27 @@ int plnr_gap_dense_fwd(plnr_ctx* ctx, int dtype, const plnr_tensor* x, const voi
         (const T*)x->ptr, (const T*)w, scale, shift, (T*)y, x->n, HW, x->c, x->ld, x->coff, out_features, och, act, alpha);
   })
   return plnr_after_launch(ctx, "gap_dense");
+}
+
+int plnr_pooled_dense_fwd(plnr_ctx* ctx, const float* pool, int n, int parts, int c, int hw, const void* w, const float* scale,
+                          const float* shift, void* y, int out_features, int act, float alpha) {
+  PLNR_REQUIRE(ctx && pool && w && y, "pooled_dense: NULL argument");
+  PLNR_REQUIRE(n >= 1 && parts >= 1 && hw >= 1 && out_features >= 1, "pooled_dense: empty problem");
+  PLNR_REQUIRE(c % 16 == 0 && aligned16(w) && aligned16(pool), "pooled_dense: channels (%d) must be a multiple of 16 and pointers "
+               "16-byte aligned", c);
+  constexpr int IMGS8 = 8;
+  const size_t smem = ((size_t)IMGS8 * (c + 8) * sizeof(__half) + 15) / 16 * 16 + 16 * 128 * sizeof(float);
+  PLNR_REQUIRE(smem <= 48 * 1024, "pooled_dense: %d channels do not fit the pooled-vector stage", c);
+  const int gx = (n + IMGS8 - 1) / IMGS8;
+  int gy = ctx->sm_count / gx;
+  if (gy < 1) gy = 1;
+  int och = (out_features + gy - 1) / gy;
+  och = (och + 15) / 16 * 16;
+  if (och < 128 && out_features > och) och = 128 < out_features ? 128 : (out_features + 15) / 16 * 16;   // eight blocks x two K halves = 16 warps
+  gy = (out_features + och - 1) / och;
+  pooled_dense_mma_kernel<IMGS8><<<dim3(gx, gy), 512, smem, ctx->stream>>>(
+      pool, (const __half*)w, scale, shift, (__half*)y, n, parts, 1.f / (float)hw, c, out_features, och, act, alpha);
+  return plnr_after_launch(ctx, "pooled_dense");
 }
 
 }  // extern "C"

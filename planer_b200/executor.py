@@ -38,6 +38,7 @@ class Executor:
         self._in_stage = {}       # graph input -> fp16 staging array (fp32 images on the fused first layer)
         self.pack_hits = self.pack_misses = 0
         self.nchw_exits = 0       # graph outputs written as NCHW by the producing conv's epilogue
+        self.pool_folds = {}      # root of a conv output -> (fp32 partial-sum array, h*w): GlobalAveragePool folded into that conv
         self._build()
 
     # ------------------------------------------------------------------------------------------
@@ -221,6 +222,22 @@ class Executor:
         if c % (16 // self.dtype.itemsize) != 0 or c * 8 * 4 > 96 * 1024:
             return None
         return chain
+
+    def _pool_fold_of(self, st, x, K):
+        """GlobalAveragePool folded into the epilogue of the convolution that feeds it (plnr_epilogue.pool_sum): applies when
+        the conv's output is read by ONE step, a gap that heads a gap -> flatten -> dense tail, is not a graph output, and the
+        library says the kernel it will run can pool (fp16 stride-1 shift GEMM, image grid of whole 32-position parts -- the
+        7x7 map of a 224x224 ResNet).  Returns the parts per image or 0."""
+        if self.dtype != np.float16 or st.attrs.get('group', 1) != 1 or st.shortcut is not None or self.values[st.out].is_output:
+            return 0
+        if os.environ.get('PLNR_NO_POOL_FOLD') == '1' or self.values[self._root(st.out)].slice_of is not None:
+            return 0
+        root = self._root(st.out)
+        users = [u for u in self.plan.steps if u is not st and root in [self._root(r) for r in u.reads()]]
+        if len(users) != 1 or users[0].op != 'gap' or self._gap_dense_tail(users[0]) is None:
+            return 0
+        a = st.attrs
+        return ops.conv2d_pool_parts(x, self.values[st.out].shape, K.shape[2], K.shape[3], a['strides'], a['dilations'], a['pads'])
 
     def _packed(self, key, build):
         """One-off weight artefact of this net (packed filter, folded scale / shift, ...): taken from the Net's pack store when
@@ -474,6 +491,15 @@ class Executor:
                                                    scale, shift, res, st.act, st.alpha, res_after_act=st.res_after)
                 wp = self._packed('%s|pack|%d' % (st.name, x.shape[1] // g), lambda: ops.pack_weight(K, x.shape[1] // g, dt))
                 self._keep.append(wp)
+                parts = self._pool_fold_of(st, x, K)
+                if parts > 0:
+                    # the only reader is gap -> flatten -> dense: the epilogue writes per-part sums instead of the activation
+                    n_, c_, h_, w_ = vals[st.out].shape
+                    pool = B.empty((n_, parts, c_), np.float32)
+                    self.pool_folds[self._root(st.out)] = (pool, h_ * w_)
+                    self._keep.append(pool)
+                    return lambda: ops.conv2d_into(x, wp, y, kh, kw, a['strides'], a['dilations'], a['pads'], g,
+                                                   scale, shift, res, st.act, st.alpha, res_after_act=st.res_after, pool_sum=pool)
                 return lambda: ops.conv2d_into(x, wp, y, kh, kw, a['strides'], a['dilations'], a['pads'], g,
                                                scale, shift, res, st.act, st.alpha, res_after_act=st.res_after)
             Kc = self._packed(st.name + '|cast', lambda: _aligned_cast(K, dt))
@@ -570,6 +596,11 @@ class Executor:
                 self.fused_dense |= {id(fl), id(dn)}
                 self.names_override = '+'.join(st.fused + dn.fused)
                 self._io_override = self._nbytes(st.ins[0]) + self._nbytes(dn.out) + self._nbytes(dn.w)
+                fold = self.pool_folds.get(self._root(st.ins[0]))
+                if fold is not None:
+                    pool, hw = fold
+                    self._io_override = pool.nbytes + self._nbytes(dn.out) + self._nbytes(dn.w)
+                    return lambda: ops.pooled_dense_into(pool, hw, Kc, y, scale, shift, dn.act, dn.alpha)
                 return lambda: ops.gap_dense_into(x, Kc, y, scale, shift, dn.act, dn.alpha)
             x, y = self._view(st.ins[0]), alloc(st.out)
             return lambda: ops.gap_into(x, y)

@@ -34,10 +34,11 @@ def pool_out_shape(xshape, w, pads, strides):
 
 
 def _epilogue(scale, shift, residual, act, alpha, res_after_act=False, out_nchw=False, out_f32=False, acc_scale=1.0,
-              acc_scale_dev=None):
+              acc_scale_dev=None, pool_sum=None):
     keep = []
     ep = _capi.Epilogue()
     ep.out_nchw = int(bool(out_nchw))
+    ep.pool_sum = pool_sum.ptr if pool_sum is not None else None
     ep.out_f32, ep.acc_scale, ep.acc_scale_dev = int(bool(out_f32)), float(acc_scale), acc_scale_dev
     ep.scale = scale.ptr if scale is not None else None
     ep.shift = shift.ptr if shift is not None else None
@@ -165,18 +166,30 @@ def conv2d_out_nchw_supported(x, yshape, kh, kw, strides, dilations, pads):
     return bool(B.lib().plnr_conv2d_out_nchw_supported(C.byref(d), C.byref(tx), C.byref(ty)))
 
 
+def conv2d_pool_parts(x, yshape, kh, kw, strides, dilations, pads):
+    """32-position parts per image when GlobalAveragePool can be folded into this convolution's epilogue
+    (plnr_epilogue.pool_sum), 0 when it cannot."""
+    d = _capi.ConvDesc(_capi.dtype_code(x.dtype), kh, kw, pads[0], pads[1], pads[2], pads[3],
+                       strides[0], strides[1], dilations[0], dilations[1], 1, ALGO_AUTO)
+    tx = x.tensor()
+    ty = _capi.Tensor(256, yshape[0], yshape[2], yshape[3], yshape[1], yshape[1], 0)
+    return int(B.lib().plnr_conv2d_pool_parts(C.byref(d), C.byref(tx), C.byref(ty)))
+
+
 def conv2d_into(x, w_packed, y, kh, kw, strides, dilations, pads, groups=1, scale=None, shift=None,
-                residual=None, act=ACT_NONE, alpha=0.0, algo=ALGO_AUTO, res_after_act=False, out_nchw=False):
-    """``out_nchw``: y is a flat NCHW array and the epilogue writes it directly (plnr_epilogue.out_nchw).  ``w_packed`` is
-    the array from ``pack_weight`` or, for float32 on the tensor pipe, a ``SplitWeight``."""
+                residual=None, act=ACT_NONE, alpha=0.0, algo=ALGO_AUTO, res_after_act=False, out_nchw=False, pool_sum=None):
+    """``out_nchw``: y is a flat NCHW array and the epilogue writes it directly (plnr_epilogue.out_nchw).  ``pool_sum``: a
+    float32 (n, parts, cout) array that receives the partial sums of the GlobalAveragePool consuming this layer INSTEAD of y
+    (plnr_epilogue.pool_sum; parts from ``conv2d_pool_parts``).  ``w_packed`` is the array from ``pack_weight`` or, for
+    float32 on the tensor pipe, a ``SplitWeight``."""
     if isinstance(w_packed, SplitWeight):
-        assert groups == 1 and not out_nchw and x.dtype == np.float32 and y.dtype == np.float32
+        assert groups == 1 and not out_nchw and pool_sum is None and x.dtype == np.float32 and y.dtype == np.float32
         return _conv2d_split_into(x, w_packed, y, kh, kw, strides, dilations, pads, scale, shift, residual, act, alpha,
                                   res_after_act)
     d = _capi.ConvDesc(_capi.dtype_code(x.dtype), kh, kw, pads[0], pads[1], pads[2], pads[3],
                        strides[0], strides[1], dilations[0], dilations[1], groups, algo)
     tx, ty = x.tensor(), (nchw_out_tensor(y) if out_nchw else y.tensor())
-    ep, keep = _epilogue(scale, shift, residual, act, alpha, res_after_act, out_nchw)
+    ep, keep = _epilogue(scale, shift, residual, act, alpha, res_after_act, out_nchw, pool_sum=pool_sum)
     rc = B.lib().plnr_conv2d_fwd(B.ctx(), C.byref(d), C.byref(tx), w_packed.ptr, C.byref(ty), C.byref(ep))
     if rc != 0:
         desc = lambda a: None if a is None else '%s %s ld=%s coff=%s' % (a.shape, a.layout, a.ld, a.coff)
@@ -393,6 +406,16 @@ def gap_dense_into(x, w, y, scale=None, shift=None, act=ACT_NONE, alpha=0.0):
     p = lambda a: a.ptr if a is not None else None
     _capi.check(B.lib().plnr_gap_dense_fwd(B.ctx(), _capi.dtype_code(x.dtype), C.byref(tx), w.ptr, p(scale), p(shift), y.ptr,
                                            w.shape[0], act, float(alpha)), 'plnr_gap_dense_fwd')
+    return y
+
+
+def pooled_dense_into(pool, hw, w, y, scale=None, shift=None, act=ACT_NONE, alpha=0.0):
+    """The gap -> flatten -> dense tail after a convolution that pooled in its epilogue: pool float32 (n, parts, c) partial
+    sums, hw pooled positions per image, w (out, c) fp16, y flat (n, out) fp16."""
+    p = lambda a: a.ptr if a is not None else None
+    n, parts, c = pool.shape
+    _capi.check(B.lib().plnr_pooled_dense_fwd(B.ctx(), pool.ptr, n, parts, c, int(hw), w.ptr, p(scale), p(shift), y.ptr,
+                                              w.shape[0], act, float(alpha)), 'plnr_pooled_dense_fwd')
     return y
 
 

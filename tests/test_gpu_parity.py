@@ -1197,3 +1197,69 @@ def test_random_graphs_through_the_reference_net_numpy_vs_b200(planer, seed):
         ref.core(numpy, True)
         ref.layer.layer_map.clear()
         ref.layer.layer_map.update(saved)
+
+
+@pytest.mark.parametrize('cfg', [(5, 64, 7, 7, 64, True), (16, 256, 7, 7, 512, True), (3, 128, 7, 7, 128, False),
+                                 (9, 64, 3, 15, 96, True)])
+def test_pooling_folded_into_the_conv_epilogue(planer, cfg):
+    """plnr_epilogue.pool_sum: the conv's epilogue writes, per image and 32-position part of the padded image grid, the fp32 sum
+    of its finished fp16 outputs instead of the activation.  Against the sums of the unfused launch's own output (fp32 addition
+    in another order; the unfused launch may be the stacked-tap kernel, whose accumulation order moves single outputs by one
+    fp16 ulp: 2e-4 of the largest sum, where a dropped or doubled row would show as 2e-2), on single CTAs and CTA pairs, a
+    ragged last tile, with the residual path; then the pooled dense tail against the gap -> flatten -> dense kernel."""
+    from planer_b200 import ops, backend as B
+    n, cin, h, w, cout, with_res = cfg
+    rng = np.random.default_rng(91)
+    x = rng.standard_normal((n, cin, h, w)).astype(np.float16)
+    K = (rng.standard_normal((cout, cin, 3, 3)) * np.sqrt(2.0 / (cin * 9))).astype(np.float16)
+    bk = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bb = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    r = rng.standard_normal((n, cout, h, w)).astype(np.float16) if with_res else None
+    xd = B.to_nhwc(B.asarray(x))
+    wp = ops.pack_weight(B.asarray(K), cin, np.float16)
+    scale, shift = B.asarray(bk), B.asarray(bb)
+    rd = B.to_nhwc(B.asarray(r)) if with_res else None
+    parts = ops.conv2d_pool_parts(xd, (n, cout, h, w), 3, 3, (1, 1), (1, 1), (1, 1, 1, 1))
+    assert parts == (h + 1) * (w + 1) // 32 and parts > 0
+    y = B.empty((n, cout, h, w), np.float16, 'nhwc')
+    ops.conv2d_into(xd, wp, y, 3, 3, (1, 1), (1, 1), (1, 1, 1, 1), 1, scale, shift, rd, ops.ACT_RELU)
+    pool = B.zeros((n, parts, cout), np.float32)
+    y2 = B.to_nhwc(B.asarray(np.zeros((n, cout, h, w), np.float16)))
+    ops.conv2d_into(xd, wp, y2, 3, 3, (1, 1), (1, 1), (1, 1, 1, 1), 1, scale, shift, rd, ops.ACT_RELU, pool_sum=pool)
+    B.synchronize()
+    assert B.last_kernel() == 'conv2d_shift'
+    want = y.get().astype(np.float32).sum(axis=(2, 3))
+    got = pool.get().sum(axis=1)
+    assert np.abs(got - want).max() <= 2e-4 * max(1.0, np.abs(want).max()), float(np.abs(got - want).max())
+    assert not y2.get().any()                                   # the activation itself is not written
+    # the tail: pooled dense == gap_dense on the stored activation (both round the mean to fp16 before the product)
+    out = 40
+    Kd = (rng.standard_normal((out, cout)) * 0.2).astype(np.float16)
+    bias = B.asarray(rng.standard_normal(out).astype(np.float32))
+    a, b = B.empty((n, out), np.float16), B.empty((n, out), np.float16)
+    ops.gap_dense_into(y, B.asarray(Kd), a, None, bias)
+    ops.pooled_dense_into(pool, h * w, B.asarray(Kd), b, None, bias)
+    B.synchronize()
+    assert rel_err(b.get(), a.get().astype(np.float32)) <= 2e-3
+
+
+def test_resnet18_tail_pools_in_the_last_conv(planer, monkeypatch):
+    """ResNet-18 at 224 x 224: layer4.1.conv2's epilogue pools (7 x 7 + padding = 64 positions = two parts per image), the
+    tail kernel starts from the partial sums; logits equal the unfolded path to fp16 rounding of the pooled mean."""
+    model, blob = cases.get_model('resnet18')
+    x = np.random.default_rng(5).standard_normal((4, 3, 224, 224)).astype(np.float16)
+    net = planer.from_model(model, blob, half=True)
+    a = net(x)
+    ex = net.executor([x.shape], [x.dtype])
+    assert len(ex.pool_folds) == 1
+    monkeypatch.setenv('PLNR_NO_POOL_FOLD', '1')
+    net2 = planer.from_model(model, blob, half=True)
+    b = net2(x)
+    assert len(net2.executor([x.shape], [x.dtype]).pool_folds) == 0
+    assert rel_err(a, b.astype(np.float32)) <= 2e-3
+    # another input size: 8 x 8 maps (81 padded positions) cannot fold and take the separate tail kernel
+    monkeypatch.delenv('PLNR_NO_POOL_FOLD')
+    x3 = np.random.default_rng(6).standard_normal((2, 3, 256, 256)).astype(np.float16)
+    net3 = planer.from_model(model, blob, half=True)
+    c = net3(x3)
+    assert len(net3.executor([x3.shape], [x3.dtype]).pool_folds) == 0 and np.isfinite(c).all()

@@ -35,13 +35,13 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(raw, name), 'header declares %s but the library does not export it' % name
     assert declared - {'plnr_last_error'} == set(_capi.PROTOTYPES), 'ctypes binding and header differ'
-    assert lib.plnr_abi_version() == 2
+    assert lib.plnr_abi_version() == 3
 
 
 def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_capi.Tensor) == 32
     assert ctypes.sizeof(_capi.ConvDesc) == 13 * 4
-    assert ctypes.sizeof(_capi.Epilogue) == 56 and _capi.Epilogue.acc_scale_dev.offset == 48
+    assert ctypes.sizeof(_capi.Epilogue) == 64 and _capi.Epilogue.acc_scale_dev.offset == 48 and _capi.Epilogue.pool_sum.offset == 56
     assert _capi.Epilogue.act.offset == 24 and _capi.Epilogue.res_after_act.offset == 32 and _capi.Epilogue.out_nchw.offset == 36
     assert _capi.Epilogue.out_f32.offset == 40 and _capi.Epilogue.acc_scale.offset == 44
 

@@ -36,8 +36,8 @@ with open('profiles/%s_launches_summary.md' % tag, 'w') as f:
         n_min = min(b - a for a, b in zip(idx[:-1], idx[1:]))
         fw = [launches[a:b] for a, b in zip(idx[:-1], idx[1:]) if b - a == n_min][-1]
         f.write('\nOne forward (%d launches), us: %s = %.1f us\n' % (len(fw), ', '.join('%.1f' % v for _, v in fw), sum(v for _, v in fw)))
-        conv = sum(v for k, v in fw if k.startswith(('conv_', 'stem_pool', 'gap_dense')))
-        f.write('Share of the roofline kernel set (stem_pool + conv_stack + conv_shift + conv_igemm + gap_dense: every conv / dense layer) in that forward: %.1f%% '
+        conv = sum(v for k, v in fw if k.startswith(('conv_', 'stem_pool', 'gap_dense', 'pooled_dense')))
+        f.write('Share of the roofline kernel set (stem_pool + conv_stack + conv_shift + conv_igemm + gap_dense | pooled_dense: every conv / dense layer) in that forward: %.1f%% '
                 '(bench.py `roofline.kernel_share_of_step`, timed live with CUDA events, must agree with this share).\n'
                 % (100 * conv / sum(v for _, v in fw)))
 print('wrote profiles/%s_launches_summary.md (%d launches)' % (tag, len(launches)))

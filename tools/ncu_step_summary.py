@@ -44,7 +44,7 @@ with open('profiles/%s_step_traffic.json' % tag, 'w') as f:
 with open('profiles/%s_step_full.md' % tag, 'w') as f:
     f.write('# One steady-state step under `ncu --set full` (ResNet-18 fp16, batch 128, B200) -- %s\n\n' % tag)
     f.write('Command: tools/gpu_profile.sh (`ncu --set full --clock-control none --import-source on -k regex:conv_shift|conv_stack|'
-            'conv_igemm|stem_pool|gap_dense -s 36 -c 18 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --min-warm-sec 0`).\n'
+            'conv_igemm|stem_pool|gap_dense|pooled_dense -s 36 -c 18 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --min-warm-sec 0`).\n'
             'Durations are cold-cache and serialised: compare shares.  Metrics: `gpu__time_duration.sum`, `dram__bytes_read.sum`, '
             '`dram__bytes_write.sum`, `sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active`.\n\n')
     f.write('| # | kernel | grid | us | share | DRAM read MB | DRAM write MB | tensor pipe active % |\n|---|---|---|---|---|---|---|---|\n')
