@@ -1199,8 +1199,9 @@ def test_random_graphs_through_the_reference_net_numpy_vs_b200(planer, seed):
         ref.layer.layer_map.update(saved)
 
 
-@pytest.mark.parametrize('cfg', [(5, 64, 7, 7, 64, True), (16, 256, 7, 7, 512, True), (3, 128, 7, 7, 128, False),
-                                 (9, 64, 3, 15, 96, True)])
+@pytest.mark.parametrize('cfg', [(5, 64, 7, 7, 64, True, 3), (16, 256, 7, 7, 512, True, 3), (3, 128, 7, 7, 128, False, 3),
+                                 (9, 64, 3, 15, 96, True, 3), (4, 64, 15, 15, 32, False, 3), (2, 128, 31, 31, 64, True, 3),
+                                 (6, 64, 8, 8, 256, False, 1), (3, 64, 14, 14, 160, True, 5)])
 def test_pooling_folded_into_the_conv_epilogue(planer, cfg):
     """plnr_epilogue.pool_sum: the conv's epilogue writes, per image and 32-position part of the padded image grid, the fp32 sum
     of its finished fp16 outputs instead of the activation.  Against the sums of the unfused launch's own output (fp32 addition
@@ -1208,10 +1209,12 @@ def test_pooling_folded_into_the_conv_epilogue(planer, cfg):
     fp16 ulp: 2e-4 of the largest sum, where a dropped or doubled row would show as 2e-2), on single CTAs and CTA pairs, a
     ragged last tile, with the residual path; then the pooled dense tail against the gap -> flatten -> dense kernel."""
     from planer_b200 import ops, backend as B
-    n, cin, h, w, cout, with_res = cfg
+    n, cin, h, w, cout, with_res, k = cfg
+    pd = k // 2
+    pads = (pd, pd, pd, pd)
     rng = np.random.default_rng(91)
     x = rng.standard_normal((n, cin, h, w)).astype(np.float16)
-    K = (rng.standard_normal((cout, cin, 3, 3)) * np.sqrt(2.0 / (cin * 9))).astype(np.float16)
+    K = (rng.standard_normal((cout, cin, k, k)) * np.sqrt(2.0 / (cin * k * k))).astype(np.float16)
     bk = rng.uniform(0.5, 1.5, cout).astype(np.float32)
     bb = (rng.standard_normal(cout) * 0.1).astype(np.float32)
     r = rng.standard_normal((n, cout, h, w)).astype(np.float16) if with_res else None
@@ -1219,13 +1222,13 @@ def test_pooling_folded_into_the_conv_epilogue(planer, cfg):
     wp = ops.pack_weight(B.asarray(K), cin, np.float16)
     scale, shift = B.asarray(bk), B.asarray(bb)
     rd = B.to_nhwc(B.asarray(r)) if with_res else None
-    parts = ops.conv2d_pool_parts(xd, (n, cout, h, w), 3, 3, (1, 1), (1, 1), (1, 1, 1, 1))
-    assert parts == (h + 1) * (w + 1) // 32 and parts > 0
+    parts = ops.conv2d_pool_parts(xd, (n, cout, h, w), k, k, (1, 1), (1, 1), pads)
+    assert parts == (h + pd) * (w + pd) // 32 and parts > 0
     y = B.empty((n, cout, h, w), np.float16, 'nhwc')
-    ops.conv2d_into(xd, wp, y, 3, 3, (1, 1), (1, 1), (1, 1, 1, 1), 1, scale, shift, rd, ops.ACT_RELU)
+    ops.conv2d_into(xd, wp, y, k, k, (1, 1), (1, 1), pads, 1, scale, shift, rd, ops.ACT_RELU)
     pool = B.zeros((n, parts, cout), np.float32)
     y2 = B.to_nhwc(B.asarray(np.zeros((n, cout, h, w), np.float16)))
-    ops.conv2d_into(xd, wp, y2, 3, 3, (1, 1), (1, 1), (1, 1, 1, 1), 1, scale, shift, rd, ops.ACT_RELU, pool_sum=pool)
+    ops.conv2d_into(xd, wp, y2, k, k, (1, 1), (1, 1), pads, 1, scale, shift, rd, ops.ACT_RELU, pool_sum=pool)
     B.synchronize()
     assert B.last_kernel() == 'conv2d_shift'
     want = y.get().astype(np.float32).sum(axis=(2, 3))
