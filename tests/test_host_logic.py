@@ -745,3 +745,29 @@ def test_tile_decorator_random_cases_equal_the_reference_itself():
         stacked = lambda ws, fn=fn: np.stack([fn(w_) for w_ in ws])
         assert np.array_equal(util.tile(batched=True, **kw)(stacked)(img.copy()), want), (case, kw, shape, kind)
     assert skipped <= 30, skipped
+
+
+def test_pool_fold_applies_only_to_whole_32_position_parts(lib, monkeypatch):
+    """plnr_conv2d_pool_parts (host logic of plnr_epilogue.pool_sum): the GlobalAveragePool fold needs the fp16 stride-1
+    shift-GEMM kernel, output channels in whole 32-column chunks and a padded image grid of whole 32-position parts, so that
+    every TMEM lane quarter of a tile lies inside one image."""
+    def parts(xs, cout, k, stride=1, pad=None, dtype=np.float16, groups=1):
+        n, c, h, w = xs
+        pad = k // 2 if pad is None else pad
+        oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        d = _capi.ConvDesc(_capi.dtype_code(np.dtype(dtype)), k, k, pad, pad, pad, pad, stride, stride, 1, 1, groups, 0)
+        tx = _capi.Tensor(256, n, h, w, c, c, 0)
+        ty = _capi.Tensor(256, n, oh, ow, cout, cout, 0)
+        return lib.plnr_conv2d_pool_parts(ctypes.byref(d), ctypes.byref(tx), ctypes.byref(ty))
+    assert parts((128, 512, 7, 7), 512, 3) == 2               # ResNet-18 at 224 x 224: (7 + 1) x (7 + 1) = 64 positions
+    assert parts((4, 64, 15, 15), 32, 3) == 8
+    assert parts((2, 128, 31, 31), 64, 3) == 32
+    assert parts((6, 64, 8, 8), 256, 1) == 2                  # 1 x 1 without padding: the grid is the image
+    assert parts((2, 512, 8, 8), 512, 3) == 0                 # 256 x 256 inputs: 81 positions per image
+    assert parts((2, 512, 7, 7), 1000, 3) == 0                # output channels not in whole 32-column chunks
+    assert parts((2, 48, 7, 7), 64, 3) == 0                   # input channels not in 64-channel chunks: another kernel
+    assert parts((2, 64, 14, 14), 64, 3, stride=2) == 0       # strided: the im2col kernel
+    assert parts((2, 64, 7, 7), 64, 3, dtype=np.float32) == 0
+    assert parts((2, 64, 7, 7), 64, 3, groups=2) == 0
+    monkeypatch.setenv('PLNR_NO_POOL_FOLD', '1')
+    assert parts((128, 512, 7, 7), 512, 3) == 0
