@@ -121,3 +121,83 @@ def test_oracle_equals_the_reference_itself_on_random_graphs(half, count, batch)
         for g, w_ in zip(got, want):
             g, w_ = np.asarray(g), np.asarray(w_)
             assert g.dtype == w_.dtype and np.array_equal(g, w_), (seed, float(np.abs(g.astype(np.float32) - w_.astype(np.float32)).max()))
+
+
+def _op_case(rng):
+    """One random call of a hot-path operator: (name, attrs, arrays) -- shapes with odd extents and channel counts."""
+    n, c, h, w = int(rng.integers(1, 4)), int(rng.choice([1, 3, 5, 8, 12, 16, 21, 32])), int(rng.integers(3, 24)), int(rng.integers(3, 24))
+    dt = np.float16 if rng.integers(0, 2) else np.float32
+    x = rng.standard_normal((n, c, h, w)).astype(dt)
+    kind = str(rng.choice(['maxpool', 'averagepool', 'upsample', 'upsample_linear', 'resize', 'concat', 'softmax', 'gap', 'batchnorm',
+                           'relu', 'leakyrelu', 'sigmoid', 'add', 'hardsigmoid', 'clip', 'conv', 'convtranspose', 'dense', 'flatten']))
+    if kind in ('maxpool', 'averagepool'):
+        k = int(rng.choice([2, 3])); s = int(rng.choice([1, 2])); p = int(rng.integers(0, k // 2 + 1))
+        if h + 2 * p < k or w + 2 * p < k:
+            return None
+        return kind, {'w': (k, k), 'pads': (p, p, p, p), 'strides': (s, s)}, [x]
+    if kind in ('upsample', 'upsample_linear'):
+        lo = 1 if kind == 'upsample' else 2
+        f = np.array([1, 1, int(rng.integers(lo, 4)), int(rng.integers(lo, 4))], np.float32)
+        return 'upsample', {'mode': 'nearest' if kind == 'upsample' else 'linear'}, [x, f]
+    if kind == 'resize':
+        if dt == np.float16:
+            return None                               # the reference indexes out of range on float16 coordinates (DESIGN 3)
+        f = np.array([1, 1, float(rng.uniform(0.6, 2.5)), float(rng.uniform(0.6, 2.5))], np.float32)
+        return 'resize', {'mode': 'linear'}, [x, np.zeros(0, np.float32), f]
+    if kind == 'concat':
+        x2 = rng.standard_normal((n, int(rng.choice([1, 3, 8])), h, w)).astype(dt)
+        return 'concat', {'axis': 1}, [x, x2]
+    if kind == 'softmax':
+        return 'softmax', {'axis': 1}, [x]
+    if kind == 'batchnorm':
+        return 'batchnorm', {}, [x, rng.uniform(0.5, 1.5, (1, c, 1, 1)).astype(dt), rng.standard_normal((1, c, 1, 1)).astype(dt)]
+    if kind == 'add':
+        return 'add', {}, [x, rng.standard_normal(x.shape).astype(dt)]
+    if kind == 'leakyrelu':
+        return 'leakyrelu', {'alpha': 0.1}, [x]
+    if kind == 'clip':
+        return 'clip', {'min': -0.5, 'max': 1.5}, [x]
+    if kind == 'hardsigmoid':
+        return 'hardsigmoid', {'alpha': 0.2, 'beta': 0.5}, [x]
+    if kind == 'conv':
+        co, k = int(rng.choice([4, 8, 16])), int(rng.choice([1, 3, 5]))
+        g = 2 if (c % 2 == 0 and co % 2 == 0 and rng.integers(0, 3) == 0) else 1
+        s, d = int(rng.choice([1, 2])), int(rng.choice([1, 2]))
+        p = int(rng.integers(0, k // 2 + 1)) * d
+        if h + 2 * p < (k - 1) * d + 1 or w + 2 * p < (k - 1) * d + 1:
+            return None
+        K = (rng.standard_normal((co, c // g, k, k)) * 0.2).astype(dt)
+        arrs = [x, K] + ([rng.standard_normal(co).astype(dt)] if rng.integers(0, 2) else [])
+        return 'conv', {'group': g, 'strides': (s, s), 'dilations': (d, d), 'pads': (p, p, p, p)}, arrs
+    if kind == 'convtranspose':
+        co = int(rng.choice([4, 8]))
+        K = (rng.standard_normal((c, co, 4, 4)) * 0.2).astype(dt)
+        return 'convtranspose', {'strides': (2, 2), 'dilations': (1, 1), 'pads': (1, 1, 1, 1), 'output_padding': (0, 0), 'group': 1}, \
+            [x, K, rng.standard_normal(co).astype(dt)]
+    if kind == 'dense':
+        xf = rng.standard_normal((n, c * 4)).astype(dt)
+        return 'dense', {}, [xf, (rng.standard_normal((10, c * 4)) * 0.2).astype(dt), rng.standard_normal(10).astype(dt)]
+    return kind, {}, [x]                              # relu, sigmoid, gap, flatten
+
+
+def test_oracle_operators_equal_the_reference_itself_on_random_calls():
+    """Every operator of the oracle's table against the UNMODIFIED reference's own layer (baseline/_ref, numpy backend) on 400
+    random calls -- odd extents, channel counts off the vector width, random windows / strides / dilations / groups / factors,
+    float32 and float16: BIT-exact, dtype included."""
+    ref = _reference_module()
+    rng = np.random.default_rng(20261017)
+    done = {}
+    for _ in range(400):
+        case = _op_case(rng)
+        if case is None:
+            continue
+        name, attrs, arrs = case
+        if hasattr(ref.util, 'clear_buf'):
+            ref.util.clear_buf()                      # the reference's im2col scratch keeps the previous call's dtype (App. D Q6)
+        want = ref.layer_map[name](*[a.copy() for a in arrs], **attrs)       # what Net wraps: planer/net.py:17, layer.py:6-13
+        got = oracle.layer_map[name](*[a.copy() for a in arrs], **attrs)
+        want, got = np.asarray(want), np.asarray(got)
+        assert got.shape == want.shape and got.dtype == want.dtype, (name, attrs, got.shape, want.shape, got.dtype, want.dtype)
+        assert np.array_equal(got, want, equal_nan=True), (name, attrs, [a.shape for a in arrs], str(arrs[0].dtype))
+        done[name] = done.get(name, 0) + 1
+    assert len(done) >= 17, done
